@@ -1,0 +1,73 @@
+// assigs.h -- host side of the assignment tables: the per-solver slot state machine
+// (reference OneSolverAssigs / HostAssigs, gpuShareLib/Assigs.{cuh,cu}; rules restated in
+// SURVEY.md Appendix A).  A solver owns 32 assignment slots (slot = assignment id % 32); a
+// frozen slot holds the solver's whole partial assignment at trySendAssignment time.  Per run
+// the GPU thread ships one VarUpdate (all 32 slots of one variable) per variable touched since
+// the previous run, plus the masks the kernels need.
+#pragma once
+#include "common.h"
+#include "mem.h"
+#include <memory>
+#include <mutex>
+#include <vector>
+
+namespace gss {
+
+struct AssigIds {
+    int64_t start = 0;
+    int32_t count = 0;
+};
+
+class SolverAssigs {
+public:
+    explicit SolverAssigs(int varCount);
+    void setVarCount(int varCount);
+
+    void lock() { lock_.lock(); }
+    bool tryLock() { return lock_.try_lock(); }
+    void unlock() { lock_.unlock(); }
+
+    // all *Locked methods need the lock (reference Assigs.cu:163-201)
+    void setVarLocked(int var, uint8_t val);
+    bool isAssignmentAvailableLocked() const { return currentId_ != firstIdUsed_ + kSlots; }
+    int64_t assignmentDoneLocked();
+    void getCurrentAssignment(uint8_t *assig);
+
+    // Collect this solver's share of a run (reference copyUpdatesLocked, Assigs.cu:243-300).
+    // Appends the updates to `updates` and fills `p` and `ids`.  When fullRebuild is set the
+    // update list covers EVERY variable (the device tables are being re-created).
+    void collectLocked(HostBuf<VarUpdate> &updates, SolverRunParams &p, AssigIds &ids, bool fullRebuild);
+
+    void setAggBits(int start, int end) { startAggBit_ = start; endAggBit_ = end; }
+    int64_t updatesSent() const { return updatesSent_; }
+    int varCount() const { return (int)lastVarVal_.size(); }
+
+private:
+    static uint32_t maskFromTo(int64_t fromId, int64_t toId);
+
+    std::mutex lock_;
+    uint32_t notCompletedMask_ = ~0u; // slots that are free or still being written
+    int64_t updatesSent_ = 0;
+    std::vector<uint8_t> lastVarVal_; // the solver's current value of every variable
+    std::vector<VarUpdate> updates_;  // one per variable touched in the batch being built
+    std::vector<int32_t> varToUpdatePos_;
+    int64_t firstIdUsed_ = 0; // first assignment id not yet shipped to the GPU
+    int64_t currentId_ = 0;   // id of the assignment being written
+    int startAggBit_ = 0, endAggBit_ = 0;
+};
+
+class HostAssigs {
+public:
+    HostAssigs();
+    void setVarCount(int varCount);
+    void growSolvers(int count); // reference growSolverAssigs, Assigs.cu:402-426
+    int solverCount() const { return (int)solvers_.size(); }
+    int varCount() const { return varCount_; }
+    SolverAssigs &solver(int s) { return *solvers_[s]; }
+
+private:
+    int varCount_ = 0;
+    std::vector<std::unique_ptr<SolverAssigs>> solvers_;
+};
+
+} // namespace gss

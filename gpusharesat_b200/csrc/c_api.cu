@@ -1,0 +1,90 @@
+// c_api.cu -- the extern "C" boundary declared in include/gpushare_b200.h.  Thin forwarding
+// only; every function names the GpuClauseSharer.h method it stands for in the header.
+#include "../../include/gpushare_b200.h"
+#include "sharer.h"
+
+using gss::Sharer;
+
+struct gss_sharer {
+    Sharer impl;
+    gss_sharer(const gss_options &o, gss_log_fn log, void *ctx) : impl(o, log, ctx) {}
+};
+
+extern "C" {
+
+void gss_options_default(gss_options *o) {
+    // GpuClauseSharerOptions(), GpuClauseSharer.h:49-58
+    o->gpuBlockCountGuideline = -1;
+    o->gpuThreadsPerBlockGuideline = -1;
+    o->minGpuLatencyMicros = -1;
+    o->verbosity = 1;
+    o->clauseActivityDecay = -1;
+    o->quickProf = 1;
+    o->initReportCountPerCategory = -1;
+    o->maxPageLockedMemory = -1;
+}
+
+gss_sharer *gss_create(const gss_options *opts, gss_log_fn log, void *log_ctx) {
+    gss_options o;
+    if (opts) o = *opts; else gss_options_default(&o);
+    return new gss_sharer(o, log, log_ctx);
+}
+
+void gss_destroy(gss_sharer *h) { delete h; }
+
+void gss_gpu_run(gss_sharer *h) { h->impl.gpuRun(); }
+void gss_reduce_db(gss_sharer *h) { h->impl.reduceDb(); }
+int64_t gss_get_added_clause_count(gss_sharer *h) { return h->impl.addedClauseCount(); }
+int64_t gss_get_added_clause_count_at_last_reduce_db(gss_sharer *h) { return h->impl.addedClauseCountAtLastReduceDb(); }
+int gss_has_run_out_of_gpu_memory_once(gss_sharer *h) { return h->impl.hasRunOutOfGpuMemoryOnce() ? 1 : 0; }
+void gss_get_gpu_mem_info(gss_sharer *h, size_t *free_bytes, size_t *total_bytes) { h->impl.gpuMemInfo(free_bytes, total_bytes); }
+int gss_get_global_stat_count(gss_sharer *) { return gss::G_COUNT; }
+int64_t gss_get_global_stat(gss_sharer *h, int stat) {
+    if (stat < 0 || stat >= gss::G_COUNT) return 0;
+    return h->impl.globalStat(stat);
+}
+const char *gss_get_global_stat_name(gss_sharer *, int stat) {
+    return (stat < 0 || stat >= gss::G_COUNT) ? nullptr : gss::kGlobalStatNames[stat];
+}
+void gss_write_clauses_in_cnf(gss_sharer *h, FILE *file) { h->impl.writeClausesInCnf(file); }
+void gss_set_var_count(gss_sharer *h, int n) { h->impl.setVarCount(n); }
+void gss_set_cpu_solver_count(gss_sharer *h, int n) { h->impl.setCpuSolverCount(n); }
+
+int64_t gss_add_clause(gss_sharer *h, int solver_id, const int *lits, int count) { return h->impl.addClause(solver_id, lits, count); }
+
+int gss_try_set_solver_values(gss_sharer *h, int s, const int *lits, int count) { return h->impl.trySetSolverValues(s, lits, count) ? 1 : 0; }
+void gss_unset_solver_values(gss_sharer *h, int s, const int *lits, int count) { h->impl.unsetSolverValues(s, lits, count); }
+int64_t gss_try_send_assignment(gss_sharer *h, int s) { return h->impl.trySendAssignment(s); }
+int gss_pop_reported_clause(gss_sharer *h, int s, int **lits, int *count, int64_t *id) {
+    int *l = nullptr;
+    int c = 0;
+    int64_t i = 0;
+    if (!h->impl.popReportedClause(s, l, c, i)) return 0;
+    *lits = l;
+    *count = c;
+    *id = i;
+    return 1;
+}
+int64_t gss_get_last_assig_all_reported(gss_sharer *h, int s) { return h->impl.lastAssigAllReported(s); }
+void gss_get_current_assignment(gss_sharer *h, int s, uint8_t *assig) { h->impl.currentAssignment(s, assig); }
+int gss_get_one_solver_stat_count(gss_sharer *) { return gss::S_COUNT; }
+int64_t gss_get_one_solver_stat(gss_sharer *h, int s, int stat) {
+    if (stat < 0 || stat >= gss::S_COUNT) return 0;
+    return h->impl.oneSolverStat(s, stat);
+}
+const char *gss_get_one_solver_stat_name(gss_sharer *, int stat) {
+    return (stat < 0 || stat >= gss::S_COUNT) ? nullptr : gss::kOneSolverStatNames[stat];
+}
+
+int64_t gss_debug_last_hits(gss_sharer *h, gss_hit *out, int64_t cap) { return h->impl.lastHits(out, cap); }
+int64_t gss_add_clauses_bulk(gss_sharer *h, const int64_t *offsets, const int *lits, int64_t n) { return h->impl.addClausesBulk(offsets, lits, n); }
+void gss_set_max_clause_len(gss_sharer *h, int max_len) { h->impl.setMaxClauseLen(max_len); }
+void gss_debug_set_dense(gss_sharer *h, int dense) { h->impl.setDense(dense != 0); }
+double gss_debug_time_check(gss_sharer *h, int iters, int dense) { return h->impl.timeCheck(iters, dense != 0); }
+int gss_debug_last_run_times(gss_sharer *h, double out_us[3]) { return h->impl.lastRunTimes(out_us); }
+void gss_debug_last_run_bytes(gss_sharer *h, int64_t *h2d, int64_t *d2h) { h->impl.lastRunBytes(h2d, d2h); }
+int64_t gss_debug_kernel_launches(gss_sharer *h) { return h->impl.kernelLaunches(); }
+void gss_debug_db_size(gss_sharer *h, int64_t *nclauses, int64_t *nlits) { h->impl.dbSize(nclauses, nlits); }
+const char *gss_version(void) { return "gpushare_b200 0.1 sm_100a"; }
+
+} // extern "C"

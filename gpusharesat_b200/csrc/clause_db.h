@@ -1,0 +1,114 @@
+// clause_db.h -- host + device clause database (replaces the reference's Clauses/ClauseUpdates,
+// gpuShareLib/Clauses.{cuh,cu}, ClauseUpdates.{cuh,cu}).
+//
+// Layout (B200-first, not the reference's 32-interleave): one arena per clause length s, made of
+// tiles of 128 clauses.  Inside a tile literal i of clause c sits at word i*128 + c, so one warp
+// reads a whole literal row (512 B) with one 128-bit load per lane and every lane carries four
+// clauses.  No padding literals: the clause count masks the tail of the last tile.  The host
+// mirror has the same layout, so new clauses are uploaded with one plain async copy of the
+// touched tiles per length -- no staging format and no scatter kernel (reference:
+// ClauseUpdates + initClauses, GpuRunner.cu:64-66).
+#pragma once
+#include "common.h"
+#include "mem.h"
+#include <memory>
+#include <mutex>
+#include <vector>
+
+namespace gss {
+
+struct ClauseMeta {
+    int64_t id;     // GpuClauseId handed out by addClause
+    float activity; // bumped per hit, decayed per added clause (Clauses.cu:200-237)
+};
+
+// One non-empty clause length, as the kernels see it.
+struct LenDir {
+    const int32_t *base; // device arena of this length
+    int32_t len;
+    int32_t count;   // clauses of this length
+    int32_t tileEnd; // cumulative tile count including this length (lengths in descending order)
+    int32_t pad;
+};
+
+struct DbStats {
+    int64_t clauses = 0, lengthSum = 0, added = 0;
+};
+
+class ClauseDb {
+public:
+    ClauseDb(double activityDecay, const Logger &logger, size_t pinnedLimitBytes);
+
+    void setMaxLen(int maxLen);
+    int maxLen() const { return maxLen_; }
+
+    // ---- any thread (locked): reference HostClauses::addClause, Clauses.cu:349-356 ----
+    int64_t addClause(const int *lits, int n);
+    int64_t addClausesBulk(const int64_t *offsets, const int *lits, int64_t nclauses);
+
+    // ---- GPU thread only ----
+    // move pending clauses into the host mirror (reference getUpdatesForDevice, Clauses.cu:318-346)
+    void drainPending();
+    // copy the tiles touched since the last upload; false when device memory ran out
+    bool uploadDirty(cudaStream_t stream, int64_t *bytesCopied);
+    // directory of non-empty lengths, longest first; returns the total tile count
+    int buildDirectory(std::vector<LenDir> &dir) const;
+
+    void getClause(int len, int idx, std::vector<int> &lits, int64_t &id) const;
+    int64_t clauseId(int len, int idx) const { return perLen_[len]->meta[idx].id; }
+    float activity(int len, int idx) const { return perLen_[len]->meta[idx].activity; }
+    void bumpActivity(int len, int idx); // Clauses.cu:231-237
+    int count(int len) const { return len <= maxLen_ ? (int)perLen_[len]->meta.size() : 0; }
+
+    // reference HostClauses::reduceDb (actOnly), Clauses.cu:426-465 / 249-282
+    void reduceDb(cudaStream_t stream);
+    // reference approxNthAct, Clauses.cu:492-525
+    float approxNthAct(int64_t n) const;
+    void writeCnf(FILE *f, int varCount) const; // Clauses.cu:527-549
+
+    const DbStats &stats() const { return stats_; }
+    int64_t addedAtLastReduceDb() const { return addedAtLastReduce_; }
+    int64_t reduceDbCount() const { return reduceDbs_; }
+    // largest variable index referenced by any clause + 1 (tables must cover it)
+    int maxVarPlusOne() const { return maxVarPlusOne_; }
+
+private:
+    struct PerLen {
+        HostBuf<int32_t> lits;    // tiled host mirror
+        std::vector<ClauseMeta> meta;
+        DevBuf<int32_t> dev;
+        int64_t dirtyFrom = 0;    // first clause index not yet on the device
+        bool fullReupload = false;
+    };
+    static size_t wordsFor(int len, int64_t count) {
+        return (size_t)((count + kTileClauses - 1) / kTileClauses) * kTileClauses * (size_t)len;
+    }
+    static size_t wordPos(int len, int64_t idx, int i) {
+        return (size_t)(idx / kTileClauses) * kTileClauses * (size_t)len + (size_t)i * kTileClauses +
+               (size_t)(idx % kTileClauses);
+    }
+    void appendToMirror(const int *lits, int n, int64_t id);
+    void rescaleActivity();
+
+    int maxLen_ = kDefaultMaxClauseLen;
+    std::vector<std::unique_ptr<PerLen>> perLen_;
+    const Logger &logger_;
+    size_t pinnedLimit_;
+
+    // pending clauses, shared with solver threads
+    std::mutex pendingLock_;
+    std::vector<int> pendingLits_;
+    std::vector<int> pendingLens_;
+    int64_t nextId_ = 0;      // guarded by pendingLock_
+    int64_t pendingFirstId_ = 0;
+    bool frozenMaxLen_ = false;
+
+    float actIncr_ = 1.0f;
+    float actDecay_;
+    DbStats stats_;
+    int64_t addedAtLastReduce_ = 0;
+    int64_t reduceDbs_ = 0;
+    int maxVarPlusOne_ = 0;
+};
+
+} // namespace gss

@@ -1,0 +1,92 @@
+// common.h -- shared types and helpers of the B200 clause sharer (host + device).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <sstream>
+#include <string>
+
+namespace gss {
+
+// ---- literal encoding: same as the reference (gpuShareLib/SolverTypes.h:44-60) ----
+// lit = 2*var + sign, sign 1 = negated
+__host__ __device__ inline int litVar(int lit) { return lit >> 1; }
+__host__ __device__ inline int litSign(int lit) { return lit & 1; }
+
+// value of a variable, same numbering as the reference's lbool (SolverTypes.h:77-80)
+enum : uint8_t { V_TRUE = 0, V_FALSE = 1, V_UNDEF = 2 };
+
+constexpr int kSlots = 32;          // assignment slots per solver (one 32-bit word)
+constexpr int kTileClauses = 128;   // clauses per tile: one warp x int4
+constexpr int kDefaultMaxClauseLen = 100; // reference MAX_CL_SIZE (BaseTypes.cuh:28)
+constexpr int kMaxSolversPerGroup = 32;   // one aggregate word / one lane per solver
+
+// One delta record: the 32 slots of one variable of one solver (reference VarUpdate,
+// gpuShareLib/Assigs.cuh:122-125).  tru is garbage where def is 0.
+struct VarUpdate {
+    int32_t var;
+    uint32_t def;
+    uint32_t tru;
+};
+
+// What the check kernels emit (reference ReportedClause, BaseTypes.cuh:146-151)
+struct HitRecord {
+    uint32_t mask;
+    int32_t solver;
+    int32_t len;
+    int32_t idx; // index of the clause inside its length array
+};
+
+// A clause that survived the aggregate filter
+struct Survivor {
+    int32_t dirIdx; // index into the run's length directory
+    int32_t idx;    // index of the clause inside its length array
+    uint32_t aggBits;
+    uint32_t pad;
+};
+
+// Per-solver parameters of one run (reference DOneSolverAssigs + AggCorresp,
+// gpuShareLib/Assigs.cuh:77-80,105-111)
+struct SolverRunParams {
+    uint32_t startVals;  // frozen slots = the ones to test
+    uint32_t lastMask;   // the slot every other slot collapses to after the run
+    uint32_t allAggBits; // aggregate bits owned by this solver
+    uint32_t usedAggBits; // aggregate bits in use this run
+    int32_t updStart;    // range of this solver's updates in the update array
+    int32_t updCount;
+    int32_t nGroups;     // number of (aggregate bit, slot mask) pairs
+    int32_t pad;
+    uint32_t groupAggBit[kSlots];
+    uint32_t groupSlotMask[kSlots];
+};
+
+struct Logger {
+    int verbosity = 1;
+    std::function<void(const std::string &)> fn;
+    void log(int level, const std::string &s) const {
+        if (level <= verbosity && fn) fn(s);
+    }
+};
+
+[[noreturn]] inline void die(const char *file, int line, const std::string &msg) {
+    // same contract as the reference's THROW() (gpuShareLib/Assert.h:44-48): print and exit(1)
+    fprintf(stderr, "gpushare_b200 fatal: %s (%s:%d)\n", msg.c_str(), file, line);
+    fflush(stderr);
+    exit(1);
+}
+
+#define GSS_DIE(msg) ::gss::die(__FILE__, __LINE__, (msg))
+#define GSS_CHECK(cond)                                        \
+    do {                                                       \
+        if (!(cond)) GSS_DIE(std::string("check failed: ") + #cond); \
+    } while (0)
+#define GSS_CUDA(call)                                                            \
+    do {                                                                          \
+        cudaError_t e__ = (call);                                                 \
+        if (e__ != cudaSuccess)                                                   \
+            GSS_DIE(std::string("CUDA error ") + cudaGetErrorString(e__) + " in " + #call); \
+    } while (0)
+
+} // namespace gss

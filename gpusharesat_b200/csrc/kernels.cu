@@ -1,0 +1,373 @@
+// kernels.cu -- hand-written sm_100a kernels of the clause check (see kernels.cuh for the data
+// layout).  The recurrence is the reference's ReportComputer (gpuShareLib/GpuRunner.cu:34-57):
+//     justOne = (allFalse & undef) | (justOne & false);   allFalse &= false;
+// i.e. three LOP3 per (literal, 32-slot word); a clause is reported where allFalse|justOne != 0.
+//
+// Kernel inventory
+//   k_fill_tables    initial table contents (everything undefined)
+//   k_apply_updates  per-run assignment deltas -> T2 rows + the solver's aggregate bits in A1
+//   k_collapse       after a run: every slot := the solver's last slot (reference
+//                    dSetAllAssigsToLast, Assigs.cu:127-141), run at the START of the next run so
+//                    that a run whose hit buffer overflowed can simply be re-launched
+//   k_filter         level 1: one warp per 128-clause tile, lane = 4 clauses (LDG.128 literal
+//                    rows, LDG.64 gathers from the L2-resident A1), ballot early exit per row,
+//                    warp-aggregated survivor append
+//   k_exact          level 2: one warp per survivor, lane = solver (coalesced 256 B T2 rows),
+//                    warp-aggregated hit append
+//   k_check_dense    bench-only: every (literal, solver word) pair, no filter, no early exit
+#include "kernels.cuh"
+
+namespace gss {
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+// ---- cache-hinted loads ----
+// literal rows are streamed once: evict-first so they do not push the assignment tables out of L2
+__device__ __forceinline__ int4 ldStream128(const int32_t *p) { return __ldcs(reinterpret_cast<const int4 *>(p)); }
+__device__ __forceinline__ int ldStream32(const int32_t *p) { return __ldcs(p); }
+__device__ __forceinline__ uint2 ldTable(const uint2 *p) { return __ldg(p); }
+
+__device__ __forceinline__ void step(uint32_t &all, uint32_t &one, uint32_t f, uint32_t u) {
+    one = (all & u) | (one & f); // 2 LOP3
+    all &= f;                    // 1 LOP3
+}
+
+// set the bits of `mask` in *p to `bits` (bits is a subset of mask); other solvers own the other bits
+__device__ __forceinline__ void mergeBits(uint32_t *p, uint32_t mask, uint32_t bits) {
+    uint32_t clear = mask & ~bits;
+    if (clear) atomicAnd(p, ~clear);
+    if (bits) atomicOr(p, bits);
+}
+
+__device__ __forceinline__ void writeAggregates(const DeviceTables &t, int solver, int var, uint32_t mask, uint32_t T,
+                                                uint32_t F, uint32_t U) {
+    uint2 *a = t.a1 + (size_t)(solver / kMaxSolversPerGroup) * 2 * (size_t)t.varCap + 2 * (size_t)var;
+    // positive literal (2v) is false where the variable is false; negated (2v+1) where it is true
+    mergeBits(&a[0].x, mask, F);
+    mergeBits(&a[0].y, mask, U);
+    mergeBits(&a[1].x, mask, T);
+    mergeBits(&a[1].y, mask, U);
+}
+
+__global__ void k_fill_tables(DeviceTables t, int varFrom) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t nVars = (size_t)(t.varCap - varFrom);
+    // A1: F = 0 (cannot be false), U = ~0 (can be undefined)  (reference MultiAgg{0,~0,0})
+    for (int g = 0; g < t.nGroups; g++) {
+        uint2 *a = t.a1 + (size_t)g * 2 * t.varCap + 2 * (size_t)varFrom;
+        for (size_t i = i0; i < 2 * nVars; i += stride) a[i] = make_uint2(0u, ~0u);
+    }
+    // T2: undefined everywhere  (reference MultiLBool{0,0})
+    uint2 *r = t.t2 + (size_t)varFrom * t.solverStride;
+    for (size_t i = i0; i < nVars * t.solverStride; i += stride) r[i] = make_uint2(0u, 0u);
+}
+
+// blockIdx.y = solver.  (reference dUpdateAssigs, Assigs.cu:100-116)
+__global__ void __launch_bounds__(256) k_apply_updates(const VarUpdate *__restrict__ upd,
+                                                       const SolverRunParams *__restrict__ params, DeviceTables t) {
+    __shared__ uint32_t sAgg[kSlots], sSlot[kSlots];
+    const int s = blockIdx.y;
+    const SolverRunParams &p = params[s];
+    const int n = p.updCount, nGroups = p.nGroups;
+    if (n == 0) return;
+    if (threadIdx.x < kSlots) {
+        sAgg[threadIdx.x] = p.groupAggBit[threadIdx.x];
+        sSlot[threadIdx.x] = p.groupSlotMask[threadIdx.x];
+    }
+    __syncthreads();
+    const uint32_t used = p.usedAggBits;
+    const VarUpdate *u = upd + p.updStart;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        VarUpdate vu = u[i];
+        t.t2[(size_t)vu.var * t.solverStride + s] = make_uint2(vu.def, vu.tru);
+        if (used) {
+            uint32_t bt = vu.tru & vu.def, bf = ~vu.tru & vu.def, bu = ~vu.def;
+            uint32_t T = 0, F = 0, U = 0;
+            for (int g = 0; g < nGroups; g++) {
+                uint32_t m = sSlot[g], bit = sAgg[g];
+                if (bt & m) T |= bit;
+                if (bf & m) F |= bit;
+                if (bu & m) U |= bit;
+            }
+            writeAggregates(t, s, vu.var, used, T, F, U);
+        }
+    }
+}
+
+// blockIdx.y = solver.  (reference dSetAllAssigsToLast, Assigs.cu:127-141)
+__global__ void __launch_bounds__(256) k_collapse(const VarUpdate *__restrict__ upd,
+                                                  const SolverRunParams *__restrict__ params, DeviceTables t) {
+    const int s = blockIdx.y;
+    const SolverRunParams &p = params[s];
+    const int n = p.updCount;
+    const uint32_t last = p.lastMask, allAgg = p.allAggBits;
+    const VarUpdate *u = upd + p.updStart;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        VarUpdate vu = u[i];
+        uint32_t def = (vu.def & last) ? ~0u : 0u, tru = (vu.tru & last) ? ~0u : 0u;
+        t.t2[(size_t)vu.var * t.solverStride + s] = make_uint2(def, tru);
+        if (allAgg) writeAggregates(t, s, vu.var, allAgg, (def & tru) ? allAgg : 0u, (def & ~tru) ? allAgg : 0u,
+                                    def ? 0u : allAgg);
+    }
+}
+
+// directory lookup: first entry whose cumulative tile count exceeds `tile`
+__device__ __forceinline__ int findDir(const int *sTileEnd, int nDir, int tile) {
+    int lo = 0, hi = nDir - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (tile < sTileEnd[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Level 1.  One warp per tile; lane l owns clauses 4l..4l+3 of the tile.  Per literal row: one
+// LDG.128 (512 B per warp, fully coalesced), four LDG.64 gathers, twelve LOP3, one vote.
+// (reference pass 1 of dFindClauses, GpuRunner.cu:148-172: one clause per thread, 4 B loads,
+// 12 B gathers with a sign select, no early exit across the warp)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_filter(CheckArgs a) {
+    extern __shared__ int sTileEnd[];
+    for (int i = threadIdx.x; i < a.nDir; i += blockDim.x) sTileEnd[i] = a.dir[i].tileEnd;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warpsPerBlock = blockDim.x >> 5;
+    const int warp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
+    const int nWarps = gridDim.x * warpsPerBlock;
+    const uint2 *__restrict__ a1 = a.tables.a1 + (size_t)(a.groupBase / kMaxSolversPerGroup) * 2 * (size_t)a.tables.varCap;
+    const uint32_t start = a.aggStart;
+
+    for (int tile = warp; tile < a.totalTiles; tile += nWarps) {
+        const int k = findDir(sTileEnd, a.nDir, tile);
+        const LenDir d = a.dir[k];
+        const int tileInLen = tile - (k ? sTileEnd[k - 1] : 0);
+        const int len = d.len;
+        const int32_t *row = d.base + (size_t)tileInLen * kTileClauses * len + lane * 4;
+        const int c0 = tileInLen * kTileClauses + lane * 4;
+        const int nValid = d.count - c0; // clauses of this lane that exist (may be <= 0 or >= 4)
+
+        uint32_t all0 = nValid > 0 ? start : 0u, all1 = nValid > 1 ? start : 0u;
+        uint32_t all2 = nValid > 2 ? start : 0u, all3 = nValid > 3 ? start : 0u;
+        uint32_t one0 = 0, one1 = 0, one2 = 0, one3 = 0;
+
+        int4 lits = ldStream128(row);
+        uint32_t alive = 0;
+        for (int i = 0; i < len; i++) {
+            int4 next = lits;
+            if (i + 1 < len) next = ldStream128(row + (size_t)(i + 1) * kTileClauses); // overlaps the gathers
+            uint2 g0 = ldTable(a1 + lits.x), g1 = ldTable(a1 + lits.y);
+            uint2 g2 = ldTable(a1 + lits.z), g3 = ldTable(a1 + lits.w);
+            step(all0, one0, g0.x, g0.y);
+            step(all1, one1, g1.x, g1.y);
+            step(all2, one2, g2.x, g2.y);
+            step(all3, one3, g3.x, g3.y);
+            alive = (all0 | one0) | (all1 | one1) | (all2 | one2) | (all3 | one3);
+            if (!__any_sync(FULL, alive)) break; // all 128 clauses are dead: skip the remaining rows
+            lits = next;
+        }
+        if (!__any_sync(FULL, alive)) continue;
+
+        // warp-aggregated append of the survivors (rare)
+        const uint32_t m0 = all0 | one0, m1 = all1 | one1, m2 = all2 | one2, m3 = all3 | one3;
+        const int cnt = (m0 != 0) + (m1 != 0) + (m2 != 0) + (m3 != 0);
+        int incl = cnt;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            int n = __shfl_up_sync(FULL, incl, dlt);
+            if (lane >= dlt) incl += n;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(&a.counters->nSurvivors[a.groupBase / kMaxSolversPerGroup], (unsigned int)total);
+        base = __shfl_sync(FULL, base, 0);
+        unsigned int pos = base + (unsigned int)(incl - cnt);
+        if (m0) { if (pos < a.survCap) a.survivors[pos] = Survivor{k, c0 + 0, m0, 0u}; pos++; }
+        if (m1) { if (pos < a.survCap) a.survivors[pos] = Survivor{k, c0 + 1, m1, 0u}; pos++; }
+        if (m2) { if (pos < a.survCap) a.survivors[pos] = Survivor{k, c0 + 2, m2, 0u}; pos++; }
+        if (m3) { if (pos < a.survCap) a.survivors[pos] = Survivor{k, c0 + 3, m3, 0u}; pos++; }
+    }
+}
+
+// append one hit per lane with a non-zero mask; one atomic per warp
+__device__ __forceinline__ void reportHits(const CheckArgs &a, uint32_t m, int solver, int len, int idx, int lane) {
+    const unsigned hitLanes = __ballot_sync(FULL, m != 0);
+    if (!hitLanes) return;
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(&a.counters->nHits, (unsigned int)__popc(hitLanes));
+    base = __shfl_sync(FULL, base, 0);
+    if (m) {
+        unsigned int pos = base + __popc(hitLanes & ((1u << lane) - 1));
+        if (pos < a.hitCap) a.hits[pos] = HitRecord{m, solver, len, idx};
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Level 2.  One warp per survivor, lane = solver of the group.  Per literal: one uniform 4 B
+// load and one coalesced T2 row (8 B per lane).  (reference dCheckOneClauseAllSolvers /
+// dCheckOneClauseOneSolver, GpuRunner.cu:68-131: serial per thread, one solver after the other)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_exact(CheckArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int warpsPerBlock = blockDim.x >> 5;
+    const int warp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
+    const int nWarps = gridDim.x * warpsPerBlock;
+    const bool active = lane < a.groupSolvers;
+    const int solver = a.groupBase + (active ? lane : 0);
+    const uint32_t myStart = active ? a.params[solver].startVals : 0u;
+    const uint32_t myAgg = active ? a.params[solver].allAggBits : 0u;
+    const uint2 *__restrict__ t2 = a.tables.t2 + solver;
+    const size_t stride = (size_t)a.tables.solverStride;
+
+    unsigned int n = a.counters->nSurvivors[a.groupBase / kMaxSolversPerGroup];
+    if (n > a.survCap) n = a.survCap;
+    unsigned long long tests = 0;
+    for (unsigned int sIdx = warp; sIdx < n; sIdx += nWarps) {
+        const Survivor sv = a.survivors[sIdx];
+        const LenDir d = a.dir[sv.dirIdx];
+        const int len = d.len;
+        const int32_t *lp = d.base + (size_t)(sv.idx / kTileClauses) * kTileClauses * len + (sv.idx % kTileClauses);
+        uint32_t all = (sv.aggBits & myAgg) ? myStart : 0u, one = 0;
+        tests += __popc(__ballot_sync(FULL, all != 0));
+        for (int i = 0; i < len; i++) {
+            const int lit = __ldg(lp + (size_t)i * kTileClauses);
+            const uint2 e = ldTable(t2 + (size_t)(lit >> 1) * stride);
+            const uint32_t f = e.x & ((lit & 1) ? e.y : ~e.y);
+            step(all, one, f, ~e.x);
+            if (!__any_sync(FULL, all | one)) break;
+        }
+        reportHits(a, all | one, solver, len, sv.idx, lane);
+    }
+    if (lane == 0 && tests) atomicAdd(&a.counters->exactTests, tests);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense mode (bench only).  One warp per quarter tile (32 clauses), lane = solver.  The 32
+// clauses are advanced together, so 32 independent T2 row gathers are in flight per warp.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_check_dense(CheckArgs a) {
+    extern __shared__ int sTileEnd[];
+    for (int i = threadIdx.x; i < a.nDir; i += blockDim.x) sTileEnd[i] = a.dir[i].tileEnd;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warpsPerBlock = blockDim.x >> 5;
+    const int warp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
+    const int nWarps = gridDim.x * warpsPerBlock;
+    const bool active = lane < a.groupSolvers;
+    const int solver = a.groupBase + (active ? lane : 0);
+    const uint32_t myStart = active ? a.params[solver].startVals : 0u;
+    const uint2 *__restrict__ t2 = a.tables.t2 + solver;
+    const size_t stride = (size_t)a.tables.solverStride;
+
+    const long long nWork = (long long)a.totalTiles * 4;
+    for (long long w = warp; w < nWork; w += nWarps) {
+        const int tile = (int)(w >> 2), q = (int)(w & 3);
+        const int k = findDir(sTileEnd, a.nDir, tile);
+        const LenDir d = a.dir[k];
+        const int tileInLen = tile - (k ? sTileEnd[k - 1] : 0);
+        const int len = d.len;
+        const int c0 = tileInLen * kTileClauses + q * 32;
+        const int nValid = d.count - c0;
+        if (nValid <= 0) continue;
+        const int32_t *col = d.base + (size_t)tileInLen * kTileClauses * len + q * 32 + lane;
+
+        uint32_t all[32], one[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) { all[c] = c < nValid ? myStart : 0u; one[c] = 0u; }
+        for (int i = 0; i < len; i++) {
+            const int word = ldStream32(col + (size_t)i * kTileClauses); // literal i of clause c0+lane
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const int lit = __shfl_sync(FULL, word, c);
+                const uint2 e = ldTable(t2 + (size_t)(lit >> 1) * stride);
+                const uint32_t f = e.x & ((lit & 1) ? e.y : ~e.y);
+                step(all[c], one[c], f, ~e.x);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; c++) reportHits(a, all[c] | one[c], solver, len, c0 + c, lane);
+    }
+}
+
+int resolveBlocks(const void *kernel, int threads, size_t smem, int numSMs, int requested, long long work) {
+    int perSM = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, smem);
+    if (perSM < 1) perSM = 1;
+    long long blocks = requested > 0 ? requested : (long long)perSM * numSMs;
+    if (work >= 0 && blocks > work) blocks = work;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+inline void checkLaunch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) GSS_DIE(std::string("kernel launch failed: ") + what + ": " + cudaGetErrorString(e));
+}
+
+} // namespace
+
+void launchFillTables(const DeviceTables &t, int varFrom, cudaStream_t s, int64_t *launches) {
+    if (t.varCap <= varFrom) return;
+    k_fill_tables<<<592, 256, 0, s>>>(t, varFrom);
+    checkLaunch("k_fill_tables");
+    ++*launches;
+}
+
+static dim3 updateGrid(int nSolvers, int maxUpdPerSolver, int numSMs) {
+    int bx = (maxUpdPerSolver + 255) / 256;
+    int cap = std::max(1, numSMs * 8 / std::max(1, nSolvers));
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    return dim3(bx, nSolvers, 1);
+}
+
+void launchApplyUpdates(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
+                        const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches) {
+    if (nSolvers == 0 || maxUpdPerSolver == 0) return;
+    k_apply_updates<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(upd, params, t);
+    checkLaunch("k_apply_updates");
+    ++*launches;
+}
+
+void launchCollapse(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
+                    const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches) {
+    if (nSolvers == 0 || maxUpdPerSolver == 0) return;
+    k_collapse<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(upd, params, t);
+    checkLaunch("k_collapse");
+    ++*launches;
+}
+
+void launchCheck(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches) {
+    if (a.totalTiles == 0) return;
+    int threads = dims.threads;
+    size_t smem = (size_t)a.nDir * sizeof(int);
+    int warpsPerBlock = threads / 32;
+    int blocks = resolveBlocks((const void *)k_filter, threads, smem, numSMs, dims.blocks,
+                               ((long long)a.totalTiles + warpsPerBlock - 1) / warpsPerBlock);
+    k_filter<<<blocks, threads, smem, s>>>(a);
+    checkLaunch("k_filter");
+    ++*launches;
+    // the survivor count is only known on the device: a fixed grid strides over it
+    int blocks2 = resolveBlocks((const void *)k_exact, threads, 0, numSMs, dims.blocks, -1);
+    k_exact<<<blocks2, threads, 0, s>>>(a);
+    checkLaunch("k_exact");
+    ++*launches;
+}
+
+void launchCheckDense(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches) {
+    if (a.totalTiles == 0) return;
+    int threads = 128;
+    size_t smem = (size_t)a.nDir * sizeof(int);
+    int blocks = resolveBlocks((const void *)k_check_dense, threads, smem, numSMs, dims.blocks,
+                               ((long long)a.totalTiles * 4 + 3) / 4);
+    k_check_dense<<<blocks, threads, smem, s>>>(a);
+    checkLaunch("k_check_dense");
+    ++*launches;
+}
+
+} // namespace gss

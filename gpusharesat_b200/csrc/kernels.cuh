@@ -1,0 +1,67 @@
+// kernels.cuh -- launch interface of the sm_100a kernels (kernels.cu).
+//
+// Device data (all 32-bit integer / bitwise work, no tensor cores -- this is not a contraction):
+//   A1  level-1 table, per solver group: one {F, U} pair per LITERAL (8 B, one LDG.64, no sign
+//       select).  Bit b of F: "the literal can be false in some slot summarised by aggregate bit
+//       b"; U: "its variable can be undefined".  16 B per variable -> 16 MB for 1 M variables,
+//       L2 resident.  (reference: MultiAgg, 12 B per variable + sign select, Assigs.cuh:44-48)
+//   T2  level-2 table: {def, tru} per (variable, solver), row-major by variable so the 32 solver
+//       words of a variable are one coalesced 256 B row (lane = solver).  (reference: one
+//       MultiLBool array per solver, Assigs.cuh:105-111)
+//   clause arenas: see clause_db.h (128-clause tiles, literal-row major, LDG.128 per lane).
+#pragma once
+#include "clause_db.h"
+#include "common.h"
+
+namespace gss {
+
+struct DeviceTables {
+    uint2 *a1 = nullptr; // [nGroups][2 * varCap]
+    uint2 *t2 = nullptr; // [varCap][solverStride]
+    int varCap = 0;
+    int solverStride = 0;
+    int nGroups = 0;
+};
+
+constexpr int kMaxGroups = 8; // solver groups of 32 (256 solver threads)
+
+// device-side counters of one run
+struct Counters {
+    unsigned int nHits;
+    unsigned int pad;
+    unsigned long long exactTests;        // (clause, solver) pairs the exact pass looked at
+    unsigned int nSurvivors[kMaxGroups];  // per solver group
+};
+
+struct LaunchDims {
+    int blocks = 0;  // <= 0: derive from occupancy
+    int threads = 256;
+};
+
+struct CheckArgs {
+    const LenDir *dir; // device copy of the length directory
+    int nDir;
+    int totalTiles;
+    const SolverRunParams *params; // device, all solvers
+    int groupBase;                 // first solver of this group
+    int groupSolvers;              // solvers in this group (<= 32)
+    uint32_t aggStart;             // aggregate bits in use by this group this run
+    DeviceTables tables;
+    Survivor *survivors;           // this group's survivor list
+    unsigned int survCap;
+    HitRecord *hits;
+    unsigned int hitCap;
+    Counters *counters;
+};
+
+void launchFillTables(const DeviceTables &t, int varFrom, cudaStream_t s, int64_t *launches);
+void launchApplyUpdates(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
+                        const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches);
+void launchCollapse(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
+                    const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches);
+// production: aggregate filter + survivor compaction, then the exact pass on the survivors
+void launchCheck(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
+// bench-only dense mode: no filter, no early exit
+void launchCheckDense(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
+
+} // namespace gss

@@ -1,0 +1,97 @@
+// reported.h -- host side hand-over of hits to the solver threads (reference Reported /
+// ClauseBatch / ConcurrentQueue, gpuShareLib/Reported.{cuh,cu}, ConcurrentQueue.h; rules
+// restated in SURVEY.md Appendix B).  Pure CPU logic; observable behaviour follows the
+// reference call for call, including its re-report suppression rules.
+#pragma once
+#include "assigs.h"
+#include "clause_db.h"
+#include "common.h"
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <queue>
+#include <set>
+#include <vector>
+
+namespace gss {
+
+// The clauses reported to one solver by one GPU run.
+struct ClauseBatch {
+    struct Entry {
+        int64_t id;
+        int32_t pos; // start in lits
+    };
+    std::vector<int> lits;
+    std::vector<Entry> entries;
+    size_t next = 0;
+    AssigIds ids;
+    uint32_t hadSomeReported = 0;
+    int64_t assigWhichKnowsAboutThese = 0;
+
+    void clear() {
+        lits.clear();
+        entries.clear();
+        next = 0;
+        hadSomeReported = 0;
+    }
+    bool pop(int *&outLits, int &count, int64_t &id) {
+        if (next >= entries.size()) return false;
+        const Entry &e = entries[next];
+        int end = next + 1 < entries.size() ? entries[next + 1].pos : (int)lits.size();
+        outLits = lits.data() + e.pos;
+        count = end - e.pos;
+        id = e.id;
+        next++;
+        return true;
+    }
+};
+
+// Batches of one solver.  Producer: the GPU thread (begin/publish).  Consumer: that solver's
+// thread (takeNext / oldest / retireOldest).  Three cursors like the reference's
+// ConcurrentQueue: retired < handed-over < published.
+class BatchQueue {
+public:
+    ClauseBatch &begin();  // a cleared batch, not yet visible to the consumer
+    void publish();        // make the batch returned by begin() visible
+    bool takeNext(ClauseBatch *&b);
+    bool oldest(ClauseBatch *&b);
+    void retireOldest();
+
+private:
+    std::mutex lock_;
+    std::deque<std::unique_ptr<ClauseBatch>> live_; // [retired .. published (+1 being built))
+    std::vector<std::unique_ptr<ClauseBatch>> spare_;
+    size_t taken_ = 0;     // index in live_ of the next batch to hand over
+    size_t published_ = 0; // number of visible batches in live_
+};
+
+class Reported {
+public:
+    Reported(ClauseDb &db, std::vector<std::vector<uint64_t>> &oneSolverStats) : db_(db), stats_(oneSolverStats) {}
+    void setSolverCount(int n);
+
+    void clauseWasAdded(int solver, int64_t clauseId);                 // Reported.cu:97-103
+    void assigWasSent(int solver, int64_t id) { lastSent_[solver] = id; } // Reported.cuh:118
+    // GPU thread: Reported.cu:160-204
+    void fill(const std::vector<AssigIds> &ids, const HitRecord *hits, size_t nHits);
+    // solver thread: Reported.cu:105-158
+    bool pop(int solver, int *&lits, int &count, int64_t &id);
+    int64_t lastAssigAllReported(int solver) const { return lastAllReported_[solver]; }
+
+private:
+    struct DontImport {
+        int64_t clauseId;
+        int64_t assigId;
+    };
+    ClauseDb &db_;
+    std::vector<std::vector<uint64_t>> &stats_;
+    std::vector<std::unique_ptr<BatchQueue>> queues_;
+    std::vector<std::set<int64_t>> notAgain_; // solver-thread private
+    std::vector<ClauseBatch *> current_;      // solver-thread private
+    std::vector<int64_t> lastSent_;
+    std::vector<int64_t> lastAllReported_;
+    std::vector<std::queue<DontImport>> dontImport_;
+    std::vector<int> tmpLits_;
+};
+
+} // namespace gss

@@ -1,0 +1,499 @@
+// sharer.cu -- see sharer.h.  The run pipeline keeps the reference's shape (start run k+1,
+// then hand run k's hits to the solvers while the GPU works: GpuRunner.cu:211-261) with three
+// differences: (1) the post-run "collapse to last slot" is deferred to the start of the next run,
+// so the tables of a finished run stay intact and a run whose survivor/hit buffer overflowed is
+// simply re-launched with larger buffers -- hits are never dropped (reference: Reporter.cuh:46-48
+// drops them); (2) new clauses go up as plain copies of the touched tiles; (3) counters are 64-bit.
+#include "sharer.h"
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <thread>
+
+namespace gss {
+
+static inline int64_t nowMicros() {
+    return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct TimeAdder { // reference TimeGauge, gpuShareLib/Profiler.h:28-46
+    uint64_t &acc;
+    bool on;
+    int64_t t0;
+    TimeAdder(uint64_t &a, bool enabled) : acc(a), on(enabled), t0(enabled ? nowMicros() : 0) {}
+    ~TimeAdder() { if (on) acc += (uint64_t)(nowMicros() - t0); }
+};
+
+Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
+    logger_.verbosity = o.verbosity;
+    if (log) logger_.fn = [log, logCtx](const std::string &s) { log(s.c_str(), logCtx); };
+
+    // no CPU fallback: without a usable device the library refuses to work
+    int nDev = 0;
+    cudaError_t e = cudaGetDeviceCount(&nDev);
+    if (e != cudaSuccess || nDev == 0)
+        GSS_DIE(std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); gpushare_b200 has no CPU fallback");
+    const char *envDev = getenv("GPUSHARE_DEVICE");
+    if (envDev) device_ = atoi(envDev);
+    else GSS_CUDA(cudaGetDevice(&device_));
+    GSS_CUDA(cudaSetDevice(device_));
+    cudaDeviceProp props;
+    GSS_CUDA(cudaGetDeviceProperties(&props, device_));
+    numSMs_ = props.multiProcessorCount;
+
+    // defaults: GpuClauseSharerImpl.cu:41-63
+    if (opts_.minGpuLatencyMicros < 0) opts_.minGpuLatencyMicros = 50;
+    if (opts_.clauseActivityDecay < 0) opts_.clauseActivityDecay = 0.99999;
+    size_t pinnedLimit;
+    if (opts_.maxPageLockedMemory < 0) {
+        size_t freeB, totalB;
+        GSS_CUDA(cudaMemGetInfo(&freeB, &totalB));
+        pinnedLimit = totalB / 3;
+    } else {
+        pinnedLimit = (size_t)opts_.maxPageLockedMemory;
+    }
+    if (opts_.clauseActivityDecay >= 1) GSS_DIE("Clause activity decay must be strictly smaller than 1");
+    if (opts_.initReportCountPerCategory < 0) opts_.initReportCountPerCategory = 10;
+    if (opts_.initReportCountPerCategory == 0) GSS_DIE("initReportCountPerCategory must not be 0");
+    if (opts_.gpuThreadsPerBlockGuideline == 0) GSS_DIE("gpuThreadsPerBlockGuideline must not be 0");
+    if (opts_.gpuBlockCountGuideline == 0) GSS_DIE("gpuBlockCountGuideline must not be 0");
+
+    // The guidelines only steer the grid (GpuClauseSharer.h:26-29); -1 lets occupancy decide.
+    dims_.blocks = opts_.gpuBlockCountGuideline > 0 ? opts_.gpuBlockCountGuideline : 0;
+    int thr = opts_.gpuThreadsPerBlockGuideline > 0 ? opts_.gpuThreadsPerBlockGuideline : 256;
+    thr = std::max(32, std::min(256, (thr / 32) * 32));
+    dims_.threads = thr;
+    int categories = opts_.gpuBlockCountGuideline > 0 ? opts_.gpuBlockCountGuideline : 2 * numSMs_;
+    hitCap_ = (size_t)opts_.initReportCountPerCategory * (size_t)categories;
+    survCap_ = hitCap_;
+
+    GSS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto &s : slots_) {
+        GSS_CUDA(cudaEventCreate(&s.evStart));
+        GSS_CUDA(cudaEventCreate(&s.evBeforeCheck));
+        GSS_CUDA(cudaEventCreate(&s.evAfterCheck));
+        GSS_CUDA(cudaEventCreate(&s.evEnd));
+        s.headHost.setPinnedLimit(pinnedLimit);
+        s.updHost.setPinnedLimit(pinnedLimit);
+        s.resHost.setPinnedLimit(pinnedLimit);
+    }
+    db_ = std::make_unique<ClauseDb>(opts_.clauseActivityDecay, logger_, pinnedLimit);
+    assigs_ = std::make_unique<HostAssigs>();
+    reported_ = std::make_unique<Reported>(*db_, oneSolverStats_);
+    setCpuSolverCount(1);
+    logger_.log(1, std::string("c gpushare_b200 on ") + props.name + ", " + std::to_string(numSMs_) + " SMs\n");
+}
+
+Sharer::~Sharer() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    for (auto &s : slots_) {
+        cudaEventDestroy(s.evStart);
+        cudaEventDestroy(s.evBeforeCheck);
+        cudaEventDestroy(s.evAfterCheck);
+        cudaEventDestroy(s.evEnd);
+    }
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Sharer::useDevice() { GSS_CUDA(cudaSetDevice(device_)); }
+
+void Sharer::gpuMemInfo(size_t *freeB, size_t *totalB) {
+    useDevice();
+    GSS_CUDA(cudaMemGetInfo(freeB, totalB));
+}
+
+void Sharer::setVarCount(int n) {
+    varCount_ = std::max(varCount_, n);
+    assigs_->setVarCount(n);
+}
+
+void Sharer::setCpuSolverCount(int n) {
+    // GpuClauseSharerImpl.cu:96-103
+    if (n > kMaxGroups * kMaxSolversPerGroup) GSS_DIE("too many cpu solvers (max 256)");
+    assigs_->growSolvers(n);
+    reported_->setSolverCount(n);
+    if ((int)toUnset_.size() < n) toUnset_.resize(n);
+    size_t c = oneSolverStats_.size();
+    if ((size_t)n > c) {
+        oneSolverStats_.resize(n);
+        for (size_t i = c; i < (size_t)n; i++) oneSolverStats_[i].assign(S_COUNT, 0);
+    }
+}
+
+int64_t Sharer::addClause(int solver, const int *lits, int n) {
+    int64_t id = db_->addClause(lits, n);
+    // GpuClauseSharerImpl.cu:124-128 registers the echo suppression even for a rejected clause
+    if (solver != -1) reported_->clauseWasAdded(solver, id);
+    return id;
+}
+
+int64_t Sharer::addClausesBulk(const int64_t *offsets, const int *lits, int64_t n) {
+    return db_->addClausesBulk(offsets, lits, n);
+}
+
+void Sharer::unsetPendingLocked(int solver) {
+    std::vector<int> &u = toUnset_[solver];
+    SolverAssigs &sa = assigs_->solver(solver);
+    for (int l : u) sa.setVarLocked(litVar(l), V_UNDEF);
+    oneSolverStats_[solver][S_varUpdatesSentToGpu] += u.size();
+    u.clear();
+}
+
+bool Sharer::trySetSolverValues(int solver, const int *lits, int n) {
+    // GpuClauseSharerImpl.cu:130-147: all or nothing
+    SolverAssigs &sa = assigs_->solver(solver);
+    bool ok = false;
+    sa.lock();
+    if (sa.isAssignmentAvailableLocked()) {
+        unsetPendingLocked(solver);
+        for (int i = 0; i < n; i++) sa.setVarLocked(litVar(lits[i]), litSign(lits[i]) ? V_FALSE : V_TRUE);
+        oneSolverStats_[solver][S_varUpdatesSentToGpu] += n;
+        ok = true;
+    } else {
+        oneSolverStats_[solver][S_failuresToFindAssig]++;
+    }
+    sa.unlock();
+    return ok;
+}
+
+void Sharer::unsetSolverValues(int solver, const int *lits, int n) {
+    // GpuClauseSharerImpl.cu:159-176: buffered when no slot is free
+    SolverAssigs &sa = assigs_->solver(solver);
+    sa.lock();
+    if (sa.isAssignmentAvailableLocked()) {
+        unsetPendingLocked(solver);
+        for (int i = 0; i < n; i++) sa.setVarLocked(litVar(lits[i]), V_UNDEF);
+        oneSolverStats_[solver][S_varUpdatesSentToGpu] += n;
+    } else {
+        toUnset_[solver].insert(toUnset_[solver].end(), lits, lits + n);
+    }
+    sa.unlock();
+}
+
+int64_t Sharer::trySendAssignment(int solver) {
+    // GpuClauseSharerImpl.cu:178-191
+    SolverAssigs &sa = assigs_->solver(solver);
+    int64_t r = -1;
+    sa.lock();
+    if (sa.isAssignmentAvailableLocked()) {
+        r = sa.assignmentDoneLocked();
+        oneSolverStats_[solver][S_assigsSentToGpu]++;
+        reported_->assigWasSent(solver, r);
+    } else {
+        oneSolverStats_[solver][S_failuresToFindAssig]++;
+    }
+    sa.unlock();
+    return r;
+}
+
+bool Sharer::popReportedClause(int solver, int *&lits, int &count, int64_t &id) {
+    return reported_->pop(solver, lits, count, id);
+}
+
+void Sharer::currentAssignment(int solver, uint8_t *assig) {
+    // GpuClauseSharerImpl.cu:238-244: pending unsets are overlaid
+    assigs_->solver(solver).getCurrentAssignment(assig);
+    for (int l : toUnset_[solver]) assig[litVar(l)] = V_UNDEF;
+}
+
+int64_t Sharer::globalStat(int stat) {
+    switch (stat) {
+    case G_gpuClauses: return db_->stats().clauses;
+    case G_gpuClauseLengthSum: return db_->stats().lengthSum;
+    case G_gpuClausesAdded: return db_->stats().added;
+    case G_gpuReduceDbs: return db_->reduceDbCount();
+    default: return (int64_t)globalStats_[stat];
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// run pipeline
+// --------------------------------------------------------------------------------------------
+
+void Sharer::gpuRun() {
+    // GpuClauseSharerImpl.cu:83-94
+    int64_t t0 = nowMicros();
+    wholeRun(true);
+    int64_t passed = nowMicros() - t0;
+    if (passed < opts_.minGpuLatencyMicros)
+        std::this_thread::sleep_for(std::chrono::microseconds(opts_.minGpuLatencyMicros - passed));
+}
+
+void Sharer::reduceDb() {
+    // GpuClauseSharerImpl.cu:105-110: no run may be in flight, clause indices change
+    wholeRun(false);
+    useDevice();
+    TimeAdder t(globalStats_[G_timeSpentReduceGpuDb], true);
+    db_->reduceDb(stream_);
+    lastStarted_ = -1;
+}
+
+void Sharer::wholeRun(bool canStart) {
+    useDevice();
+    RunSlot *prev = cur_ >= 0 ? &slots_[cur_] : nullptr;
+    if (prev) finishRun(*prev); // run k is complete and every hit is on the host
+    int startedSlot = -1;
+    bool outOfMemory = false;
+    if (canStart) {
+        int next = cur_ >= 0 ? 1 - cur_ : (collapseSlot_ >= 0 ? 1 - collapseSlot_ : 0);
+        db_->drainPending();
+        if (db_->stats().clauses > 0) { // GpuRunner.cu:284-288: nothing starts on an empty database
+            if (startRun(slots_[next])) startedSlot = next;
+            else outOfMemory = true;
+        }
+    }
+    if (prev) processResults(*prev); // overlaps with run k+1 on the GPU
+    cur_ = startedSlot;
+    if (outOfMemory) {
+        // GpuRunner.cu:243-246
+        logger_.log(1, "c gpushare_b200: out of GPU memory, reducing the clause database\n");
+        TimeAdder t(globalStats_[G_timeSpentReduceGpuDb], true);
+        db_->reduceDb(stream_);
+        lastStarted_ = -1;
+        ranOutOfMemory_ = true;
+    }
+}
+
+bool Sharer::ensureTables(bool &rebuild) {
+    int needVars = std::max(std::max(varCount_, db_->maxVarPlusOne()), 1);
+    int nSolvers = assigs_->solverCount();
+    rebuild = false;
+    if (tablesValid_ && needVars <= tables_.varCap && nSolvers == tableSolvers_) return true;
+    // (Re)create the tables; their contents are rebuilt from the host state by a full update
+    // list in this run (SolverAssigs::collectLocked with fullRebuild).
+    int stride = nSolvers <= 2 ? nSolvers : (nSolvers + 3) / 4 * 4;
+    int groups = (nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
+    int varCap = tablesValid_ ? std::max(needVars, tables_.varCap) : needVars;
+    if (!a1_.tryReserve((size_t)groups * 2 * varCap, 0, stream_, true)) return false;
+    if (!t2_.tryReserve((size_t)varCap * stride, 0, stream_, true)) return false;
+    tables_.a1 = a1_.data();
+    tables_.t2 = t2_.data();
+    tables_.varCap = varCap;
+    tables_.solverStride = stride;
+    tables_.nGroups = groups;
+    tableSolvers_ = nSolvers;
+    tablesValid_ = true;
+    launchFillTables(tables_, 0, stream_, &launches_);
+    collapseSlot_ = -1; // superseded by the rebuild
+    rebuild = true;
+    return true;
+}
+
+void Sharer::ensureResultBuffers() {
+    int groups = std::max(1, tables_.nGroups);
+    resDev_.reserve(sizeof(Counters) + hitCap_ * sizeof(HitRecord), 0, stream_);
+    survDev_.reserve((size_t)groups * survCap_, 0, stream_);
+}
+
+CheckArgs Sharer::checkArgs(const RunSlot &slot, int g) const {
+    CheckArgs a;
+    a.dir = slot.dirDev();
+    a.nDir = slot.nDir;
+    a.totalTiles = slot.totalTiles;
+    a.params = slot.paramsDev();
+    a.groupBase = g * kMaxSolversPerGroup;
+    a.groupSolvers = std::min(kMaxSolversPerGroup, slot.nSolvers - a.groupBase);
+    a.aggStart = slot.aggStart[g];
+    a.tables = tables_;
+    a.survivors = const_cast<Survivor *>(survDev_.data()) + (size_t)g * survCap_;
+    a.survCap = (unsigned int)survCap_;
+    a.hits = (HitRecord *)(const_cast<uint8_t *>(resDev_.data()) + sizeof(Counters));
+    a.hitCap = (unsigned int)hitCap_;
+    a.counters = (Counters *)const_cast<uint8_t *>(resDev_.data());
+    return a;
+}
+
+void Sharer::launchCheckKernels(RunSlot &slot, bool dense) {
+    GSS_CUDA(cudaMemsetAsync(resDev_.data(), 0, sizeof(Counters), stream_));
+    int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
+    for (int g = 0; g < groups; g++) {
+        if (slot.aggStart[g] == 0) continue; // no frozen slot in this group
+        CheckArgs a = checkArgs(slot, g);
+        if (dense) launchCheckDense(a, dims_, numSMs_, stream_, &launches_);
+        else launchCheck(a, dims_, numSMs_, stream_, &launches_);
+    }
+}
+
+void Sharer::enqueueResultCopy(RunSlot &slot) {
+    size_t bytes = sizeof(Counters) + resultChunk() * sizeof(HitRecord);
+    slot.resHost.resize(bytes);
+    GSS_CUDA(cudaMemcpyAsync(slot.resHost.data(), resDev_.data(), bytes, cudaMemcpyDeviceToHost, stream_));
+    lastD2H_ = (int64_t)bytes;
+}
+
+bool Sharer::startRun(RunSlot &slot) {
+    int64_t h2d = 0;
+    GSS_CUDA(cudaEventRecord(slot.evStart, stream_));
+    bool rebuild = false;
+    if (!ensureTables(rebuild)) return false;
+    if (!db_->uploadDirty(stream_, &h2d)) return false;
+
+    std::vector<LenDir> dir;
+    slot.totalTiles = db_->buildDirectory(dir);
+    slot.nDir = (int)dir.size();
+    slot.nSolvers = assigs_->solverCount();
+    slot.dirBytes = ((size_t)slot.nDir * sizeof(LenDir) + 15) / 16 * 16;
+    slot.headHost.resize(slot.dirBytes + (size_t)slot.nSolvers * sizeof(SolverRunParams));
+    memcpy(slot.headHost.data(), dir.data(), dir.size() * sizeof(LenDir));
+    SolverRunParams *params = (SolverRunParams *)(slot.headHost.data() + slot.dirBytes);
+
+    // reference HostAssigs::fillAssigsAsync, Assigs.cu:326-372
+    slot.updHost.clear();
+    slot.ids.assign(slot.nSolvers, AssigIds{});
+    int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
+    slot.aggStart.assign(groups, 0u);
+    slot.assigCount = 0;
+    slot.maxUpd = 0;
+    {
+        TimeAdder t(globalStats_[G_timeSpentFillingAssigs], opts_.quickProf != 0);
+        for (int s = 0; s < slot.nSolvers; s++) {
+            SolverAssigs &sa = assigs_->solver(s);
+            SolverRunParams &p = params[s];
+            memset(&p, 0, sizeof(p));
+            p.updStart = (int32_t)slot.updHost.size();
+            // a solver busy writing its assignment is skipped for this run (Assigs.cu:350);
+            // during a table rebuild every solver must contribute, so wait for it
+            bool locked = rebuild ? (sa.lock(), true) : sa.tryLock();
+            if (!locked) continue;
+            sa.collectLocked(slot.updHost, p, slot.ids[s], rebuild);
+            sa.unlock();
+            slot.aggStart[s / kMaxSolversPerGroup] |= p.usedAggBits;
+            slot.assigCount += slot.ids[s].count;
+            slot.maxUpd = std::max(slot.maxUpd, (int)p.updCount);
+        }
+    }
+    slot.nUpdates = (int64_t)slot.updHost.size();
+    slot.dense = dense_;
+
+    slot.headDev.reserve(slot.headHost.size(), 0, stream_);
+    GSS_CUDA(cudaMemcpyAsync(slot.headDev.data(), slot.headHost.data(), slot.headHost.size(), cudaMemcpyHostToDevice, stream_));
+    h2d += (int64_t)slot.headHost.size();
+    if (slot.nUpdates) {
+        slot.updDev.reserve((size_t)slot.nUpdates, 0, stream_);
+        GSS_CUDA(cudaMemcpyAsync(slot.updDev.data(), slot.updHost.data(), (size_t)slot.nUpdates * sizeof(VarUpdate),
+                                 cudaMemcpyHostToDevice, stream_));
+        h2d += slot.nUpdates * (int64_t)sizeof(VarUpdate);
+    }
+    ensureResultBuffers();
+
+    // the previous batch collapses to its last slot first (deferred dSetAllAssigsToLast)
+    if (collapseSlot_ >= 0) {
+        RunSlot &c = slots_[collapseSlot_];
+        launchCollapse(c.updDev.data(), c.paramsDev(), c.nSolvers, c.maxUpd, tables_, numSMs_, stream_, &launches_);
+        collapseSlot_ = -1;
+    }
+    launchApplyUpdates(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, tables_, numSMs_, stream_, &launches_);
+    GSS_CUDA(cudaEventRecord(slot.evBeforeCheck, stream_));
+    launchCheckKernels(slot, slot.dense);
+    GSS_CUDA(cudaEventRecord(slot.evAfterCheck, stream_));
+    enqueueResultCopy(slot);
+    GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
+    slot.inFlight = true;
+    if (slot.nUpdates) collapseSlot_ = (int)(&slot - slots_);
+    lastStarted_ = (int)(&slot - slots_);
+    lastH2D_ = h2d;
+    return true;
+}
+
+void Sharer::finishRun(RunSlot &slot) {
+    GSS_CUDA(cudaEventSynchronize(slot.evEnd));
+    float msApply = 0, msCheck = 0, msTotal = 0;
+    cudaEventElapsedTime(&msApply, slot.evStart, slot.evBeforeCheck);
+    cudaEventElapsedTime(&msCheck, slot.evBeforeCheck, slot.evAfterCheck);
+    cudaEventElapsedTime(&msTotal, slot.evStart, slot.evEnd);
+    lastTimes_[0] = msApply * 1000.0;
+    lastTimes_[1] = msCheck * 1000.0;
+    lastTimes_[2] = msTotal * 1000.0;
+    haveTimes_ = true;
+    if (opts_.quickProf) globalStats_[G_timeSpentTestingClauses] += (uint64_t)(msCheck * 1000.0f);
+
+    Counters c;
+    for (int attempt = 0;; attempt++) {
+        memcpy(&c, slot.resHost.data(), sizeof(c));
+        size_t maxSurv = 0;
+        for (int g = 0; g < kMaxGroups; g++) maxSurv = std::max(maxSurv, (size_t)c.nSurvivors[g]);
+        if (c.nHits <= hitCap_ && maxSurv <= survCap_) break;
+        GSS_CHECK(attempt < 8);
+        // Overflow: the tables of this run are still intact (collapse is deferred), so grow the
+        // buffers and run the check again.  Nothing is dropped.
+        if (c.nHits > hitCap_) hitCap_ = std::max(hitCap_ * 2, (size_t)c.nHits + c.nHits / 4);
+        if (maxSurv > survCap_) survCap_ = std::max(survCap_ * 2, maxSurv + maxSurv / 4);
+        hitCap_ = std::max(hitCap_, survCap_ / 4);
+        ensureResultBuffers();
+        launchCheckKernels(slot, slot.dense);
+        enqueueResultCopy(slot);
+        GSS_CUDA(cudaStreamSynchronize(stream_));
+    }
+    hits_.resize(c.nHits);
+    size_t first = std::min((size_t)c.nHits, (slot.resHost.size() - sizeof(Counters)) / sizeof(HitRecord));
+    if (first) memcpy(hits_.data(), slot.resHost.data() + sizeof(Counters), first * sizeof(HitRecord));
+    if (c.nHits > first) {
+        size_t rest = c.nHits - first;
+        GSS_CUDA(cudaMemcpyAsync(hits_.data() + first, resDev_.data() + sizeof(Counters) + first * sizeof(HitRecord),
+                                 rest * sizeof(HitRecord), cudaMemcpyDeviceToHost, stream_));
+        GSS_CUDA(cudaStreamSynchronize(stream_));
+        lastD2H_ += (int64_t)(rest * sizeof(HitRecord));
+    }
+    globalStats_[G_clauseTestsOnAssigs] += c.exactTests;
+    slot.inFlight = false;
+}
+
+void Sharer::processResults(RunSlot &slot) {
+    // reference gatherGpuRunResults, GpuRunner.cu:360-383 (64-bit arithmetic)
+    int64_t clCount = db_->stats().clauses;
+    globalStats_[G_gpuRuns]++;
+    globalStats_[G_totalAssigClauseTested] += (uint64_t)clCount * (uint64_t)slot.assigCount;
+    globalStats_[G_clauseTestsOnGroups] += (uint64_t)clCount;
+    globalStats_[G_gpuReports] += hits_.size();
+    lastHits_.resize(hits_.size());
+    for (size_t i = 0; i < hits_.size(); i++) {
+        const HitRecord &h = hits_[i];
+        db_->bumpActivity(h.len, h.idx);
+        lastHits_[i] = gss_hit{db_->clauseId(h.len, h.idx), h.solver, h.mask};
+    }
+    std::sort(lastHits_.begin(), lastHits_.end(), [](const gss_hit &a, const gss_hit &b) {
+        return a.clause_id != b.clause_id ? a.clause_id < b.clause_id : a.solver_id < b.solver_id;
+    });
+    TimeAdder t(globalStats_[G_timeSpentFillingReported], opts_.quickProf != 0);
+    reported_->fill(slot.ids, hits_.data(), hits_.size());
+}
+
+int64_t Sharer::lastHits(gss_hit *out, int64_t cap) {
+    int64_t n = (int64_t)lastHits_.size();
+    if (out && cap > 0) memcpy(out, lastHits_.data(), (size_t)std::min(n, cap) * sizeof(gss_hit));
+    return n;
+}
+
+double Sharer::timeCheck(int iters, bool dense) {
+    useDevice();
+    if (lastStarted_ < 0 || iters < 1) return -1.0;
+    RunSlot &slot = slots_[lastStarted_];
+    GSS_CUDA(cudaStreamSynchronize(stream_));
+    cudaEvent_t e0, e1;
+    GSS_CUDA(cudaEventCreate(&e0));
+    GSS_CUDA(cudaEventCreate(&e1));
+    launchCheckKernels(slot, dense); // warm-up, also sizes nothing: overflow is handled by finishRun
+    GSS_CUDA(cudaEventRecord(e0, stream_));
+    for (int i = 0; i < iters; i++) launchCheckKernels(slot, dense);
+    GSS_CUDA(cudaEventRecord(e1, stream_));
+    enqueueResultCopy(slot);
+    GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
+    GSS_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    GSS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    slot.dense = dense;
+    return (double)ms * 1000.0 / iters;
+}
+
+int Sharer::lastRunTimes(double out[3]) {
+    if (!haveTimes_) return 0;
+    out[0] = lastTimes_[0];
+    out[1] = lastTimes_[1];
+    out[2] = lastTimes_[2];
+    return 1;
+}
+
+} // namespace gss

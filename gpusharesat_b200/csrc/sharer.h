@@ -1,0 +1,122 @@
+// sharer.h -- the engine behind the C ABI: owns the clause database, the assignment state
+// machines, the device tables and the run pipeline (replaces the reference's
+// GpuClauseSharerImpl + GpuRunner, gpuShareLib/GpuClauseSharerImpl.cu, GpuRunner.cu).
+#pragma once
+#include "../../include/gpushare_b200.h"
+#include "assigs.h"
+#include "clause_db.h"
+#include "kernels.cuh"
+#include "reported.h"
+#include "stats.h"
+#include <memory>
+#include <vector>
+
+namespace gss {
+
+class Sharer {
+public:
+    Sharer(const gss_options &opts, gss_log_fn log, void *logCtx);
+    ~Sharer();
+
+    // ---- GpuClauseSharer.h API (see include/gpushare_b200.h for the line map) ----
+    void gpuRun();
+    void reduceDb();
+    int64_t addedClauseCount() { return db_->stats().added; }
+    int64_t addedClauseCountAtLastReduceDb() { return db_->addedAtLastReduceDb(); }
+    bool hasRunOutOfGpuMemoryOnce() const { return ranOutOfMemory_; }
+    void gpuMemInfo(size_t *freeB, size_t *totalB);
+    int64_t globalStat(int stat);
+    void writeClausesInCnf(FILE *f) { db_->writeCnf(f, varCount_); }
+    void setVarCount(int n);
+    void setCpuSolverCount(int n);
+    int64_t addClause(int solver, const int *lits, int n);
+    bool trySetSolverValues(int solver, const int *lits, int n);
+    void unsetSolverValues(int solver, const int *lits, int n);
+    int64_t trySendAssignment(int solver);
+    bool popReportedClause(int solver, int *&lits, int &count, int64_t &id);
+    int64_t lastAssigAllReported(int solver) { return reported_->lastAssigAllReported(solver); }
+    void currentAssignment(int solver, uint8_t *assig);
+    int64_t oneSolverStat(int solver, int stat) { return (int64_t)oneSolverStats_[solver][stat]; }
+
+    // ---- parity / bench hooks ----
+    int64_t lastHits(gss_hit *out, int64_t cap);
+    int64_t addClausesBulk(const int64_t *offsets, const int *lits, int64_t n);
+    void setMaxClauseLen(int n) { db_->setMaxLen(n); }
+    void setDense(bool d) { dense_ = d; }
+    double timeCheck(int iters, bool dense);
+    int lastRunTimes(double out[3]);
+    void lastRunBytes(int64_t *h2d, int64_t *d2h) { *h2d = lastH2D_; *d2h = lastD2H_; }
+    int64_t kernelLaunches() const { return launches_; }
+    void dbSize(int64_t *ncl, int64_t *nlits) { *ncl = db_->stats().clauses; *nlits = db_->stats().lengthSum; }
+
+private:
+    struct RunSlot {
+        HostBuf<uint8_t> headHost; // [LenDir x nDir][SolverRunParams x nSolvers]
+        HostBuf<VarUpdate> updHost;
+        DevBuf<uint8_t> headDev;
+        DevBuf<VarUpdate> updDev;
+        HostBuf<uint8_t> resHost;  // [Counters][HitRecord x chunk]
+        std::vector<AssigIds> ids;
+        std::vector<uint32_t> aggStart; // per solver group
+        int nDir = 0, totalTiles = 0, nSolvers = 0, maxUpd = 0, assigCount = 0;
+        int64_t nUpdates = 0;
+        bool dense = false;
+        bool inFlight = false;
+        cudaEvent_t evStart = nullptr, evBeforeCheck = nullptr, evAfterCheck = nullptr, evEnd = nullptr;
+        const LenDir *dirDev() const { return (const LenDir *)headDev.data(); }
+        const SolverRunParams *paramsDev() const { return (const SolverRunParams *)(headDev.data() + dirBytes); }
+        size_t dirBytes = 0;
+    };
+
+    void useDevice();
+    void wholeRun(bool canStart);
+    bool startRun(RunSlot &slot);      // false: nothing started
+    void finishRun(RunSlot &slot);     // wait, re-run on overflow, pull every hit to the host
+    void processResults(RunSlot &slot);
+    void launchCheckKernels(RunSlot &slot, bool dense);
+    void enqueueResultCopy(RunSlot &slot);
+    bool ensureTables(bool &rebuild);
+    void ensureResultBuffers();
+    void unsetPendingLocked(int solver);
+    CheckArgs checkArgs(const RunSlot &slot, int group) const;
+    size_t resultChunk() const { return hitCap_ < 4096 ? hitCap_ : 4096; }
+
+    gss_options opts_;
+    Logger logger_;
+    int device_ = 0, numSMs_ = 1;
+    cudaStream_t stream_ = nullptr;
+    LaunchDims dims_;
+
+    std::unique_ptr<ClauseDb> db_;
+    std::unique_ptr<HostAssigs> assigs_;
+    std::unique_ptr<Reported> reported_;
+    std::vector<std::vector<uint64_t>> oneSolverStats_;
+    std::vector<std::vector<int>> toUnset_;
+    uint64_t globalStats_[G_COUNT] = {};
+    int varCount_ = 0;
+
+    // device state
+    DeviceTables tables_;
+    DevBuf<uint2> a1_, t2_;
+    bool tablesValid_ = false;
+    int tableSolvers_ = 0;
+    DevBuf<uint8_t> resDev_; // [Counters][HitRecord x hitCap]
+    DevBuf<Survivor> survDev_; // [nGroups][survCap]
+    size_t hitCap_ = 0, survCap_ = 0;
+
+    RunSlot slots_[2];
+    int cur_ = -1;          // slot of the run in flight
+    int collapseSlot_ = -1; // slot whose updates still have to be collapsed on the device
+    int lastStarted_ = -1;  // slot whose tables are still intact (for timeCheck)
+
+    std::vector<HitRecord> hits_;   // hits of the run being processed
+    std::vector<gss_hit> lastHits_; // sorted, for gss_debug_last_hits
+    bool dense_ = false;
+    bool ranOutOfMemory_ = false;
+    int64_t launches_ = 0;
+    int64_t lastH2D_ = 0, lastD2H_ = 0;
+    double lastTimes_[3] = {0, 0, 0};
+    bool haveTimes_ = false;
+};
+
+} // namespace gss

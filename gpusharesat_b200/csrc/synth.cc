@@ -1,0 +1,134 @@
+// synth.cc -- deterministic synthetic inputs (see include/gpushare_b200_synth.h)
+#include "../../include/gpushare_b200_synth.h"
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+namespace {
+
+struct SplitMix64 {
+    uint64_t s;
+    explicit SplitMix64(uint64_t seed) : s(seed) {}
+    uint64_t next() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    // uniform in [0, n)
+    uint32_t below(uint32_t n) { return (uint32_t)(((next() >> 32) * (uint64_t)n) >> 32); }
+    double unit() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+// Glucose::luby(2, x) restated (glucose-syrup/core/Solver.cc:1967-1979): 2^seq
+inline int lubyPow2(int64_t x) {
+    int64_t size = 1;
+    int seq = 0;
+    while (size < x + 1) { seq++; size = 2 * size + 1; }
+    while (size - 1 != x) {
+        size = (size - 1) >> 1;
+        seq--;
+        x = x % size;
+    }
+    return 1 << seq;
+}
+
+inline int clauseLen(int64_t i, int maxLen) {
+    int l = 1 + lubyPow2(i);
+    return l < maxLen ? l : maxLen;
+}
+
+} // namespace
+
+struct gss_synth_stream {
+    int nvars;
+    std::vector<uint8_t> sigma, vals;
+    double pUndef;
+    int perStep;
+    SplitMix64 rng;
+    bool first = true;
+    std::vector<int> touched;
+    std::vector<uint8_t> mark;
+    gss_synth_stream(int n, uint64_t seed) : nvars(n), rng(seed) {}
+};
+
+extern "C" {
+
+int64_t gss_synth_total_lits(int64_t nclauses, int max_len) {
+    int64_t t = 0;
+    for (int64_t i = 0; i < nclauses; i++) t += clauseLen(i, max_len);
+    return t;
+}
+
+void gss_synth_sigma(int nvars, uint64_t seed, uint8_t *sigma) {
+    SplitMix64 r(seed);
+    for (int v = 0; v < nvars; v++) sigma[v] = (uint8_t)(r.next() & 1);
+}
+
+void gss_synth_clauses(int64_t nclauses, int nvars, int max_len, const uint8_t *sigma, double p_agree,
+                       uint64_t seed, int64_t *offsets, int32_t *lits) {
+    SplitMix64 r(seed);
+    int64_t pos = 0;
+    for (int64_t c = 0; c < nclauses; c++) {
+        offsets[c] = pos;
+        int len = clauseLen(c, max_len);
+        for (int i = 0; i < len; i++) {
+            int v = (int)r.below((uint32_t)nvars);
+            int sign;
+            if (sigma) {
+                bool agree = r.unit() < p_agree;
+                // literal true under sigma: positive when sigma says true (0), negated otherwise
+                int trueSign = sigma[v] == 0 ? 0 : 1;
+                sign = agree ? trueSign : 1 - trueSign;
+            } else {
+                sign = (int)(r.next() & 1);
+            }
+            lits[pos++] = 2 * v + sign;
+        }
+    }
+    offsets[nclauses] = pos;
+}
+
+gss_synth_stream *gss_synth_stream_create(int nvars, const uint8_t *sigma, double p_undef, double churn, uint64_t seed) {
+    gss_synth_stream *s = new gss_synth_stream(nvars, seed);
+    s->sigma.assign(sigma, sigma + nvars);
+    s->vals.assign(nvars, 2);
+    s->pUndef = p_undef;
+    s->perStep = (int)std::ceil(churn * nvars);
+    s->mark.assign(nvars, 0);
+    return s;
+}
+
+void gss_synth_stream_destroy(gss_synth_stream *s) { delete s; }
+
+const uint8_t *gss_synth_stream_values(gss_synth_stream *s) { return s->vals.data(); }
+
+void gss_synth_stream_next(gss_synth_stream *s, int32_t *set_lits, int32_t *n_set, int32_t *unset_lits, int32_t *n_unset) {
+    int ns = 0, nu = 0;
+    if (s->first) {
+        s->first = false;
+        for (int v = 0; v < s->nvars; v++) {
+            uint8_t nv = s->rng.unit() < s->pUndef ? 2 : s->sigma[v];
+            s->vals[v] = nv;
+            if (nv != 2) set_lits[ns++] = 2 * v + (nv == 1 ? 1 : 0);
+        }
+    } else {
+        s->touched.clear();
+        for (int k = 0; k < s->perStep; k++) {
+            int v = (int)s->rng.below((uint32_t)s->nvars);
+            uint8_t nv = s->rng.unit() < s->pUndef ? 2 : s->sigma[v];
+            if (s->mark[v]) continue; // one change per variable per step
+            if (nv == s->vals[v]) continue;
+            s->mark[v] = 1;
+            s->touched.push_back(v);
+            s->vals[v] = nv;
+            if (nv == 2) unset_lits[nu++] = 2 * v; // the sign is irrelevant for an unset
+            else set_lits[ns++] = 2 * v + (nv == 1 ? 1 : 0);
+        }
+        for (int v : s->touched) s->mark[v] = 0;
+    }
+    *n_set = ns;
+    *n_unset = nu;
+}
+
+} // extern "C"

@@ -1,0 +1,148 @@
+/*
+ * gpushare_b200.h -- C ABI of the B200-native clause sharer (libgpushare_b200.so).
+ *
+ * This is the drop-in boundary for GpuShareSat's one hot path: checking every clause of the
+ * GPU clause database against up to 1024 bit-packed partial assignments and reporting
+ * (clause, solver, assignment-mask) hits.  Every entry point below replaces exactly one
+ * virtual method of the reference's abstract class `GpuShare::GpuClauseSharer`
+ * (/root/reference/gpuShareLib/GpuClauseSharer.h); the cited line is the declaration it
+ * stands for.  A ~100-line C++ shim (gpusharesat_b200/shim/GpuClauseSharerShim.cc, see
+ * INTEGRATION.md) implements the reference's class and factory on top of these calls, so
+ * glucose-syrup and rel-newtech link the library unchanged.
+ *
+ * Conventions: plain C types only; no exceptions cross the boundary; `int` 0/1 where the
+ * C++ API returns bool; contract violations print to stderr and exit(1) exactly like the
+ * reference (gpuShareLib/Assert.h:44-48).  There is NO CPU fallback: gss_create() fails
+ * loudly (exit 1) when no CUDA device is usable.
+ *
+ * Threading is the reference's (GpuClauseSharer.h:79,114,124): the "GPU thread" calls
+ * gss_gpu_run / gss_reduce_db / stats; each solver thread calls the per-solver functions
+ * for its own solver id; gss_add_clause may be called from any thread.
+ */
+#ifndef GPUSHARE_B200_H
+#define GPUSHARE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gss_sharer gss_sharer; /* opaque handle */
+
+/* Field for field GpuShare::GpuClauseSharerOptions (GpuClauseSharer.h:25-59); -1 = default.
+ * gpuBlockCountGuideline/gpuThreadsPerBlockGuideline only steer the grid size (a guideline in
+ * the reference too); initReportCountPerCategory * block guideline sizes the first hit buffer
+ * (hits are never dropped here: an overflowing run is re-run with a larger buffer). */
+typedef struct gss_options {
+    int    gpuBlockCountGuideline;
+    int    gpuThreadsPerBlockGuideline;
+    int    minGpuLatencyMicros;
+    int    verbosity;
+    double clauseActivityDecay;
+    int    quickProf;                  /* bool */
+    int    initReportCountPerCategory;
+    int    maxPageLockedMemory;
+} gss_options;
+
+typedef void (*gss_log_fn)(const char *msg, void *ctx);
+
+/* GpuClauseSharerOptions() constructor defaults (GpuClauseSharer.h:49-58) */
+void gss_options_default(gss_options *opts);
+
+/* makeGpuClauseSharerPtr (GpuClauseSharer.h:165, GpuClauseSharerImpl.cu:15).  The device is
+ * the calling thread's current CUDA device unless GPUSHARE_DEVICE is set. */
+gss_sharer *gss_create(const gss_options *opts, gss_log_fn log, void *log_ctx);
+/* virtual ~GpuClauseSharer (GpuClauseSharer.h:161) */
+void gss_destroy(gss_sharer *h);
+
+/* ---- GPU-thread methods ---- */
+void    gss_gpu_run(gss_sharer *h);                              /* gpuRun            :83  */
+void    gss_reduce_db(gss_sharer *h);                            /* reduceDb          :87  */
+int64_t gss_get_added_clause_count(gss_sharer *h);               /* getAddedClauseCount :90 */
+int64_t gss_get_added_clause_count_at_last_reduce_db(gss_sharer *h); /* :92 */
+int     gss_has_run_out_of_gpu_memory_once(gss_sharer *h);       /* :95 */
+void    gss_get_gpu_mem_info(gss_sharer *h, size_t *free_bytes, size_t *total_bytes); /* :97 */
+int     gss_get_global_stat_count(gss_sharer *h);                /* :99  */
+int64_t gss_get_global_stat(gss_sharer *h, int stat);            /* :101 (GlobalStats.h order) */
+const char *gss_get_global_stat_name(gss_sharer *h, int stat);   /* :120 */
+void    gss_write_clauses_in_cnf(gss_sharer *h, FILE *file);     /* :103 */
+void    gss_set_var_count(gss_sharer *h, int new_count);         /* :105 */
+void    gss_set_cpu_solver_count(gss_sharer *h, int count);      /* :112 (not thread safe) */
+
+/* ---- any thread ---- */
+/* addClause :109 -- returns the clause id, or -1 when the clause is longer than the maximum
+ * clause length (reference: MAX_CL_SIZE 100, Clauses.cu:350).  lits are borrowed. */
+int64_t gss_add_clause(gss_sharer *h, int solver_id, const int *lits, int count);
+
+/* ---- per-solver-thread methods ---- */
+int     gss_try_set_solver_values(gss_sharer *h, int solver_id, const int *lits, int count); /* :129 */
+void    gss_unset_solver_values(gss_sharer *h, int solver_id, const int *lits, int count);   /* :134 */
+int64_t gss_try_send_assignment(gss_sharer *h, int solver_id);                                /* :139 */
+/* popReportedClause :148 -- *lits points into library memory private to this solver, writable
+ * (callers permute it in place), valid until the next pop for the same solver. */
+int     gss_pop_reported_clause(gss_sharer *h, int solver_id, int **lits, int *count, int64_t *gpu_clause_id);
+int64_t gss_get_last_assig_all_reported(gss_sharer *h, int solver_id);                        /* :151 */
+void    gss_get_current_assignment(gss_sharer *h, int solver_id, uint8_t *assig);             /* :155 */
+int     gss_get_one_solver_stat_count(gss_sharer *h);                                         /* :122 */
+int64_t gss_get_one_solver_stat(gss_sharer *h, int solver_id, int stat);                      /* :159 */
+const char *gss_get_one_solver_stat_name(gss_sharer *h, int stat);                            /* :118 */
+
+/* ------------------------------------------------------------------------------------------
+ * Additions that are NOT part of GpuClauseSharer.h: parity / bench hooks and the knobs the
+ * reference hard-codes.  The C++ shim does not use them.
+ * ---------------------------------------------------------------------------------------- */
+
+/* one hit exactly as the kernels produce it (cf. ReportedClause, BaseTypes.cuh:146-151) */
+typedef struct gss_hit {
+    int64_t  clause_id; /* id returned by gss_add_clause */
+    int32_t  solver_id;
+    uint32_t mask;      /* bit p <=> fires on assignment slot p (= assignment id % 32) */
+} gss_hit;
+
+/* Hits of the most recently gathered run, sorted by (clause_id, solver_id).  Returns the
+ * number of hits of that run; at most cap are written.  GPU thread only. */
+int64_t gss_debug_last_hits(gss_sharer *h, gss_hit *out, int64_t cap);
+
+/* Same as n calls of gss_add_clause(h, -1, ...) on CSR input, under one lock.  Returns the id
+ * of the first clause added (ids are consecutive), or -1 if any clause is too long (none added). */
+int64_t gss_add_clauses_bulk(gss_sharer *h, const int64_t *offsets, const int *lits, int64_t nclauses);
+
+/* Maximum clause length accepted by gss_add_clause (default 100 = the reference's
+ * MAX_CL_SIZE, BaseTypes.cuh:28).  Must be called before the first clause is added. */
+void gss_set_max_clause_len(gss_sharer *h, int max_len);
+
+/* kernel mode for the NEXT runs: 0 production (two-level filter + early exit, default),
+ * 1 dense (bench only: no filter, no early exit, every (literal, 32-slot word) pair is
+ * evaluated).  Hit sets are identical in both modes. */
+void gss_debug_set_dense(gss_sharer *h, int dense);
+
+/* Re-launch the check kernels `iters` times on the tables of the last started run (the
+ * assignment tables stay intact until the next run starts) and return the average device
+ * time of one sweep in microseconds (CUDA events on the library's stream).  The hit buffer
+ * of the last iteration replaces the run's hits.  GPU thread only; waits for the run. */
+double gss_debug_time_check(gss_sharer *h, int iters, int dense);
+
+/* Device time in microseconds of the phases of the last gathered run: [0] upload+apply
+ * (collapse of the previous batch, clause upload, delta apply), [1] check kernels, [2] total
+ * from first H2D to last D2H.  Returns 0 if no run has been gathered. */
+int gss_debug_last_run_times(gss_sharer *h, double out_us[3]);
+
+/* bytes moved by the last started run: host->device and device->host */
+void gss_debug_last_run_bytes(gss_sharer *h, int64_t *h2d, int64_t *d2h);
+
+/* number of kernel launches issued by the library so far */
+int64_t gss_debug_kernel_launches(gss_sharer *h);
+
+/* Sum of clause lengths / clause count currently in the database */
+void gss_debug_db_size(gss_sharer *h, int64_t *nclauses, int64_t *nlits);
+
+/* library build info: "gpushare_b200 <version> sm_100a" */
+const char *gss_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUSHARE_B200_H */
