@@ -74,6 +74,7 @@ SIGNATURES = {
     "gss_debug_set_dense": (None, [_P, _I]),
     "gss_debug_time_check": (C.c_double, [_P, _I, _I]),
     "gss_debug_last_run_times": (_I, [_P, C.POINTER(C.c_double)]),
+    "gss_debug_lop3_peak": (C.c_double, [_P]),
     "gss_debug_last_run_bytes": (None, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "gss_debug_kernel_launches": (_L, [_P]),
     "gss_debug_db_size": (None, [_P, C.POINTER(_L), C.POINTER(_L)]),
@@ -314,10 +315,13 @@ class GpuClauseSharer:
         return self._lib.gss_debug_time_check(self._h, int(iters), 1 if dense else 0)
 
     def debugLastRunTimes(self):
-        t = (C.c_double * 3)()
+        t = (C.c_double * 4)()
         if not self._lib.gss_debug_last_run_times(self._h, t):
             return None
         return list(t)
+
+    def debugLop3Peak(self):
+        return self._lib.gss_debug_lop3_peak(self._h)
 
     def debugLastRunBytes(self):
         a, b = C.c_int64(), C.c_int64()

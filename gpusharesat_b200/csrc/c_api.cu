@@ -81,7 +81,8 @@ int64_t gss_add_clauses_bulk(gss_sharer *h, const int64_t *offsets, const int *l
 void gss_set_max_clause_len(gss_sharer *h, int max_len) { h->impl.setMaxClauseLen(max_len); }
 void gss_debug_set_dense(gss_sharer *h, int dense) { h->impl.setDense(dense != 0); }
 double gss_debug_time_check(gss_sharer *h, int iters, int dense) { return h->impl.timeCheck(iters, dense != 0); }
-int gss_debug_last_run_times(gss_sharer *h, double out_us[3]) { return h->impl.lastRunTimes(out_us); }
+int gss_debug_last_run_times(gss_sharer *h, double out_us[4]) { return h->impl.lastRunTimes(out_us); }
+double gss_debug_lop3_peak(gss_sharer *h) { return h->impl.lop3Peak(); }
 void gss_debug_last_run_bytes(gss_sharer *h, int64_t *h2d, int64_t *d2h) { h->impl.lastRunBytes(h2d, d2h); }
 int64_t gss_debug_kernel_launches(gss_sharer *h) { return h->impl.kernelLaunches(); }
 void gss_debug_db_size(gss_sharer *h, int64_t *nclauses, int64_t *nlits) { h->impl.dbSize(nclauses, nlits); }

@@ -171,6 +171,22 @@ float ClauseDb::approxNthAct(int64_t n) const {
 }
 
 void ClauseDb::reduceDb(cudaStream_t stream) {
+    reduceHost();
+    for (int s = maxLen_; s >= 3; s--) {
+        PerLen &pl = *perLen_[s];
+        // give memory back when the arena is mostly empty (reference: CorrespArr.cu:103-113)
+        if (pl.dev.capacity() > 1024 && wordsFor(s, (int64_t)pl.meta.size()) * 3 < pl.dev.capacity()) {
+            GSS_CUDA(cudaStreamSynchronize(stream));
+            pl.dev.free();
+        }
+    }
+    int64_t dummy = 0;
+    if (!uploadDirty(stream, &dummy)) GSS_DIE("out of device memory while re-uploading the reduced clause database");
+    GSS_CUDA(cudaStreamSynchronize(stream));
+    logger_.log(2, "c Done reducing gpu clause db, clause count is " + std::to_string(stats_.clauses) + "\n");
+}
+
+void ClauseDb::reduceHost() {
     addedAtLastReduce_ = stats_.added;
     reduceDbs_++;
     float act = approxNthAct(stats_.clauses / 2);
@@ -198,16 +214,7 @@ void ClauseDb::reduceDb(cudaStream_t stream) {
         pl.lits.resize(wordsFor(s, to));
         pl.fullReupload = true;
         pl.dirtyFrom = 0;
-        // give memory back when the arena is mostly empty (reference: CorrespArr.cu:103-113)
-        if (pl.dev.capacity() > 1024 && wordsFor(s, to) * 3 < pl.dev.capacity()) {
-            GSS_CUDA(cudaStreamSynchronize(stream));
-            pl.dev.free();
-        }
     }
-    int64_t dummy = 0;
-    if (!uploadDirty(stream, &dummy)) GSS_DIE("out of device memory while re-uploading the reduced clause database");
-    GSS_CUDA(cudaStreamSynchronize(stream));
-    logger_.log(2, "c Done reducing gpu clause db, clause count is " + std::to_string(stats_.clauses) + "\n");
 }
 
 void ClauseDb::writeCnf(FILE *f, int varCount) const {

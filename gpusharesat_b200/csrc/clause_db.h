@@ -62,6 +62,7 @@ public:
 
     // reference HostClauses::reduceDb (actOnly), Clauses.cu:426-465 / 249-282
     void reduceDb(cudaStream_t stream);
+    void reduceHost(); // the host half: pick the threshold, compact the mirror (no device work)
     // reference approxNthAct, Clauses.cu:492-525
     float approxNthAct(int64_t n) const;
     void writeCnf(FILE *f, int varCount) const; // Clauses.cu:527-549

@@ -64,4 +64,7 @@ void launchCheck(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s
 // bench-only dense mode: no filter, no early exit
 void launchCheckDense(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
 
+// register-only LOP3 micro-benchmark: thread-level LOP3 per second on this device
+double measureLop3Peak(int numSMs, cudaStream_t s, int64_t *launches);
+
 } // namespace gss

@@ -70,6 +70,7 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
     GSS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     for (auto &s : slots_) {
         GSS_CUDA(cudaEventCreate(&s.evStart));
+        GSS_CUDA(cudaEventCreate(&s.evH2DDone));
         GSS_CUDA(cudaEventCreate(&s.evBeforeCheck));
         GSS_CUDA(cudaEventCreate(&s.evAfterCheck));
         GSS_CUDA(cudaEventCreate(&s.evEnd));
@@ -89,6 +90,7 @@ Sharer::~Sharer() {
     if (stream_) cudaStreamSynchronize(stream_);
     for (auto &s : slots_) {
         cudaEventDestroy(s.evStart);
+        cudaEventDestroy(s.evH2DDone);
         cudaEventDestroy(s.evBeforeCheck);
         cudaEventDestroy(s.evAfterCheck);
         cudaEventDestroy(s.evEnd);
@@ -376,6 +378,7 @@ bool Sharer::startRun(RunSlot &slot) {
         h2d += slot.nUpdates * (int64_t)sizeof(VarUpdate);
     }
     ensureResultBuffers();
+    GSS_CUDA(cudaEventRecord(slot.evH2DDone, stream_));
 
     // the previous batch collapses to its last slot first (deferred dSetAllAssigsToLast)
     if (collapseSlot_ >= 0) {
@@ -398,13 +401,15 @@ bool Sharer::startRun(RunSlot &slot) {
 
 void Sharer::finishRun(RunSlot &slot) {
     GSS_CUDA(cudaEventSynchronize(slot.evEnd));
-    float msApply = 0, msCheck = 0, msTotal = 0;
-    cudaEventElapsedTime(&msApply, slot.evStart, slot.evBeforeCheck);
+    float msCopy = 0, msApply = 0, msCheck = 0, msTotal = 0;
+    cudaEventElapsedTime(&msCopy, slot.evStart, slot.evH2DDone);
+    cudaEventElapsedTime(&msApply, slot.evH2DDone, slot.evBeforeCheck);
     cudaEventElapsedTime(&msCheck, slot.evBeforeCheck, slot.evAfterCheck);
     cudaEventElapsedTime(&msTotal, slot.evStart, slot.evEnd);
-    lastTimes_[0] = msApply * 1000.0;
-    lastTimes_[1] = msCheck * 1000.0;
-    lastTimes_[2] = msTotal * 1000.0;
+    lastTimes_[0] = msCopy * 1000.0;
+    lastTimes_[1] = msApply * 1000.0;
+    lastTimes_[2] = msCheck * 1000.0;
+    lastTimes_[3] = msTotal * 1000.0;
     haveTimes_ = true;
     if (opts_.quickProf) globalStats_[G_timeSpentTestingClauses] += (uint64_t)(msCheck * 1000.0f);
 
@@ -446,6 +451,14 @@ void Sharer::processResults(RunSlot &slot) {
     globalStats_[G_totalAssigClauseTested] += (uint64_t)clCount * (uint64_t)slot.assigCount;
     globalStats_[G_clauseTestsOnGroups] += (uint64_t)clCount;
     globalStats_[G_gpuReports] += hits_.size();
+    // The kernels append hits in scheduling order.  Sorting them makes everything downstream
+    // (activity bumps, batch order, hence which clause a solver sees first) reproducible;
+    // the reference hands them over in whatever order the atomics produced.
+    std::sort(hits_.begin(), hits_.end(), [](const HitRecord &a, const HitRecord &b) {
+        if (a.len != b.len) return a.len < b.len;
+        if (a.idx != b.idx) return a.idx < b.idx;
+        return a.solver < b.solver;
+    });
     lastHits_.resize(hits_.size());
     for (size_t i = 0; i < hits_.size(); i++) {
         const HitRecord &h = hits_[i];
@@ -488,12 +501,16 @@ double Sharer::timeCheck(int iters, bool dense) {
     return (double)ms * 1000.0 / iters;
 }
 
-int Sharer::lastRunTimes(double out[3]) {
+int Sharer::lastRunTimes(double out[4]) {
     if (!haveTimes_) return 0;
-    out[0] = lastTimes_[0];
-    out[1] = lastTimes_[1];
-    out[2] = lastTimes_[2];
+    for (int i = 0; i < 4; i++) out[i] = lastTimes_[i];
     return 1;
+}
+
+double Sharer::lop3Peak() {
+    useDevice();
+    GSS_CUDA(cudaStreamSynchronize(stream_));
+    return measureLop3Peak(numSMs_, stream_, &launches_);
 }
 
 } // namespace gss

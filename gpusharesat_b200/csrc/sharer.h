@@ -44,7 +44,8 @@ public:
     void setMaxClauseLen(int n) { db_->setMaxLen(n); }
     void setDense(bool d) { dense_ = d; }
     double timeCheck(int iters, bool dense);
-    int lastRunTimes(double out[3]);
+    int lastRunTimes(double out[4]);
+    double lop3Peak();
     void lastRunBytes(int64_t *h2d, int64_t *d2h) { *h2d = lastH2D_; *d2h = lastD2H_; }
     int64_t kernelLaunches() const { return launches_; }
     void dbSize(int64_t *ncl, int64_t *nlits) { *ncl = db_->stats().clauses; *nlits = db_->stats().lengthSum; }
@@ -62,7 +63,7 @@ private:
         int64_t nUpdates = 0;
         bool dense = false;
         bool inFlight = false;
-        cudaEvent_t evStart = nullptr, evBeforeCheck = nullptr, evAfterCheck = nullptr, evEnd = nullptr;
+        cudaEvent_t evStart = nullptr, evH2DDone = nullptr, evBeforeCheck = nullptr, evAfterCheck = nullptr, evEnd = nullptr;
         const LenDir *dirDev() const { return (const LenDir *)headDev.data(); }
         const SolverRunParams *paramsDev() const { return (const SolverRunParams *)(headDev.data() + dirBytes); }
         size_t dirBytes = 0;
@@ -115,7 +116,7 @@ private:
     bool ranOutOfMemory_ = false;
     int64_t launches_ = 0;
     int64_t lastH2D_ = 0, lastD2H_ = 0;
-    double lastTimes_[3] = {0, 0, 0};
+    double lastTimes_[4] = {0, 0, 0, 0};
     bool haveTimes_ = false;
 };
 

@@ -125,10 +125,16 @@ void gss_debug_set_dense(gss_sharer *h, int dense);
  * of the last iteration replaces the run's hits.  GPU thread only; waits for the run. */
 double gss_debug_time_check(gss_sharer *h, int iters, int dense);
 
-/* Device time in microseconds of the phases of the last gathered run: [0] upload+apply
- * (collapse of the previous batch, clause upload, delta apply), [1] check kernels, [2] total
- * from first H2D to last D2H.  Returns 0 if no run has been gathered. */
-int gss_debug_last_run_times(gss_sharer *h, double out_us[3]);
+/* Device time in microseconds of the phases of the last gathered run (CUDA events on the
+ * library's stream): [0] host->device copies (new clause tiles, run header, assignment deltas),
+ * [1] table kernels (collapse of the previous batch + delta apply), [2] check kernels,
+ * [3] total from the first copy to the end of the device->host copy of the hits.
+ * Returns 0 if no run has been gathered. */
+int gss_debug_last_run_times(gss_sharer *h, double out_us[4]);
+
+/* Register-only LOP3 micro-benchmark on the sharer's device: returns the measured peak in
+ * thread-level LOP3 operations per second (the integer-pipe roofline denominator). */
+double gss_debug_lop3_peak(gss_sharer *h);
 
 /* bytes moved by the last started run: host->device and device->host */
 void gss_debug_last_run_bytes(gss_sharer *h, int64_t *h2d, int64_t *d2h);

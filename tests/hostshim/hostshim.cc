@@ -1,0 +1,92 @@
+// hostshim.cc -- TEST-ONLY C hooks over the host classes of the product (assigs.cc, reported.cc,
+// clause_db.cc) so that `pytest -m "not gpu"` can exercise the slot state machine, the hand-over
+// rules and the reduceDb host logic without a CUDA device.  Not part of libgpushare_b200.so.
+#include "../../gpusharesat_b200/csrc/assigs.h"
+#include "../../gpusharesat_b200/csrc/clause_db.h"
+#include "../../gpusharesat_b200/csrc/reported.h"
+#include "../../gpusharesat_b200/csrc/stats.h"
+#include <cstring>
+
+using namespace gss;
+
+struct HostRig {
+    Logger logger;
+    HostAssigs assigs;
+    ClauseDb db;
+    std::vector<std::vector<uint64_t>> stats;
+    Reported reported;
+    HostBuf<VarUpdate> updates;
+    std::vector<SolverRunParams> params;
+    std::vector<AssigIds> ids;
+    HostRig(int nvars, int nsolvers, double decay) : db(decay, logger, 0), reported(db, stats) {
+        logger.verbosity = 0;
+        assigs.setVarCount(nvars);
+        assigs.growSolvers(nsolvers);
+        stats.assign(nsolvers, std::vector<uint64_t>(S_COUNT, 0));
+        reported.setSolverCount(nsolvers);
+    }
+};
+
+extern "C" {
+
+HostRig *hs_create(int nvars, int nsolvers, double decay) { return new HostRig(nvars, nsolvers, decay); }
+void hs_destroy(HostRig *r) { delete r; }
+
+// ---- slot state machine ----
+int hs_available(HostRig *r, int s) { return r->assigs.solver(s).isAssignmentAvailableLocked() ? 1 : 0; }
+void hs_set_var(HostRig *r, int s, int var, int val) { r->assigs.solver(s).setVarLocked(var, (uint8_t)val); }
+int64_t hs_send(HostRig *r, int s) {
+    int64_t id = r->assigs.solver(s).assignmentDoneLocked();
+    r->reported.assigWasSent(s, id);
+    return id;
+}
+// one run's collection for every solver; returns the number of updates
+int hs_collect(HostRig *r, int fullRebuild) {
+    int n = r->assigs.solverCount();
+    r->updates.clear();
+    r->params.assign(n, SolverRunParams{});
+    r->ids.assign(n, AssigIds{});
+    for (int s = 0; s < n; s++) r->assigs.solver(s).collectLocked(r->updates, r->params[s], r->ids[s], fullRebuild != 0);
+    return (int)r->updates.size();
+}
+void hs_get_params(HostRig *r, int s, SolverRunParams *out) { *out = r->params[s]; }
+void hs_get_updates(HostRig *r, VarUpdate *out) { memcpy(out, r->updates.data(), r->updates.size() * sizeof(VarUpdate)); }
+void hs_get_ids(HostRig *r, int s, int64_t *start, int *count) { *start = r->ids[s].start; *count = r->ids[s].count; }
+
+// ---- clause database (host half) ----
+int64_t hs_add_clause(HostRig *r, const int *lits, int n) { return r->db.addClause(lits, n); }
+void hs_drain(HostRig *r) { r->db.drainPending(); }
+int hs_count(HostRig *r, int len) { return r->db.count(len); }
+int64_t hs_clause_id(HostRig *r, int len, int idx) { return r->db.clauseId(len, idx); }
+float hs_activity(HostRig *r, int len, int idx) { return r->db.activity(len, idx); }
+void hs_bump(HostRig *r, int len, int idx) { r->db.bumpActivity(len, idx); }
+float hs_approx_nth_act(HostRig *r, int64_t n) { return r->db.approxNthAct(n); }
+void hs_reduce_host(HostRig *r) { r->db.reduceHost(); }
+int64_t hs_db_clauses(HostRig *r) { return r->db.stats().clauses; }
+int64_t hs_db_length_sum(HostRig *r) { return r->db.stats().lengthSum; }
+int hs_get_clause(HostRig *r, int len, int idx, int *out) {
+    std::vector<int> l;
+    int64_t id;
+    r->db.getClause(len, idx, l, id);
+    memcpy(out, l.data(), l.size() * sizeof(int));
+    return (int)l.size();
+}
+
+// ---- hand-over ----
+void hs_clause_was_added(HostRig *r, int s, int64_t id) { r->reported.clauseWasAdded(s, id); }
+// hits: (mask, solver, len, idx) quadruples; uses the ids of the last hs_collect
+void hs_fill(HostRig *r, const HitRecord *hits, int n) { r->reported.fill(r->ids, hits, (size_t)n); }
+int hs_pop(HostRig *r, int s, int *lits, int *count, int64_t *id) {
+    int *l;
+    int c;
+    int64_t i;
+    if (!r->reported.pop(s, l, c, i)) return 0;
+    memcpy(lits, l, c * sizeof(int));
+    *count = c;
+    *id = i;
+    return 1;
+}
+int64_t hs_last_all_reported(HostRig *r, int s) { return r->reported.lastAssigAllReported(s); }
+int64_t hs_solver_stat(HostRig *r, int s, int stat) { return (int64_t)r->stats[s][stat]; }
+
+} // extern "C"
