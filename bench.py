@@ -54,7 +54,7 @@ def parse():
     p.add_argument("--solvers", type=int, default=32)
     p.add_argument("--slots", type=int, default=32)
     p.add_argument("--max-len", type=int, default=30)
-    p.add_argument("--churn", type=float, default=0.001,
+    p.add_argument("--churn", type=float, default=0.01,
                    help="fraction of variables whose status is re-drawn between consecutive assignments of a solver")
     p.add_argument("--p-undef", type=float, default=0.01)
     p.add_argument("--p-agree", type=float, default=0.98)
@@ -62,6 +62,7 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-dense", action="store_true")
     p.add_argument("--dense-iters", type=int, default=3)
+    p.add_argument("--prod-iters", type=int, default=20)
     return p.parse_args()
 
 
@@ -270,33 +271,114 @@ def run_reference_gpu(a):
 # own arm
 # ------------------------------------------------------------------------------------------------
 
-def run_b200(a):
-    from gpusharesat_b200 import GpuClauseSharer, GpuClauseSharerOptions
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        os.environ["GPUSHARE_DEVICE"] = str(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    else:
-        os.environ.setdefault("GPUSHARE_DEVICE", "0")
+def run_b200_sharded(a):
+    """N > 1: one process per GPU (torchrun).  Every rank holds the whole clause database on the
+    host and the clause tiles t with t % N == rank on its device.  Rank 0 is the front-end: it owns
+    the solver streams and the assignment slot machines.  Per step: rank 0 collects the batch
+    (run parameters + deltas), the payload is broadcast with NCCL, every rank checks its shard,
+    the hit lists are gathered with NCCL and rank 0 hands them to the solver queues."""
+    import torch
+    import torch.distributed as dist
+    from gpusharesat_b200 import GpuClauseSharer, GpuClauseSharerOptions, mgpu
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ["GPUSHARE_DEVICE"] = str(local)
+    device = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=device)
 
     sig, offsets, lits = make_inputs(a)
     L_total, A = int(offsets[-1]), a.solvers * a.slots
-    # clause sharding: rank r owns clauses r, r+world, ... (every length is split evenly)
-    if world > 1:
-        idx = np.arange(rank, a.clauses, world)
-        lens = (offsets[1:] - offsets[:-1])[idx]
-        my_off = np.zeros(idx.size + 1, dtype=np.int64)
-        np.cumsum(lens, out=my_off[1:])
-        take = np.repeat(offsets[:-1][idx] - my_off[:-1], lens) + np.arange(my_off[-1])
-        my_lits = lits[take]
-    else:
-        my_off, my_lits = offsets, lits
+    sh = GpuClauseSharer(GpuClauseSharerOptions(minGpuLatencyMicros=0, verbosity=0))
+    sh.setShard(rank, world)
+    sh.setVarCount(a.vars)
+    sh.setCpuSolverCount(a.solvers)
+    sh.addClausesBulk(offsets, lits)
+    streams = make_streams(a, sig) if rank == 0 else None
+    pool = ThreadPoolExecutor(max_workers=a.solvers) if rank == 0 else None
+
+    def drain():
+        if rank == 0:
+            for s in range(a.solvers):
+                while sh.popReportedClause(s) is not None:
+                    pass
+
+    def step():
+        if rank == 0:
+            push_batch(sh, streams, a.slots, pool)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        collected = sh.mgpuCollect() if rank == 0 else None
+        e0.record()
+        status, params, updates, nupd = mgpu.broadcast_batch(dist, rank, device, collected)
+        e1.record()
+        torch.cuda.synchronize()
+        sh.mgpuRun(params.data_ptr(), params.numel(), updates.data_ptr(), nupd, status)
+        mine = sh.mgpuWait()
+        allhits = mgpu.gather_hits(dist, rank, world, device, mine)
+        if rank == 0:
+            sh.mgpuImport(allhits)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        ph = sh.debugLastRunTimes()
+        bcast_us = e0.elapsed_time(e1) * 1e3
+        nh = len(allhits) if rank == 0 else 0
+        drain()
+        return dt, bcast_us, ph, nh, nupd
+
+    for _ in range(a.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = sh.debugKernelLaunches()
+    wall = dev = 0.0
+    hits = upd = 0
+    bc, tk, ck = [], [], []
+    for _ in range(a.steps):
+        dt, bcast_us, ph, nh, nupd = step()
+        wall += dt
+        dev += (bcast_us + ph[1] + ph[2]) * 1e-6
+        bc.append(bcast_us); tk.append(ph[1]); ck.append(ph[2])
+        hits += nh
+        upd += nupd
+    launches = sh.debugKernelLaunches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([dev, wall], dtype=torch.float64, device=device)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ll = torch.tensor([launches], dtype=torch.int64, device=device)
+    dist.all_reduce(ll)
+    dev, wall = float(tt[0]), float(tt[1])
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": L_total * A * a.steps / dev, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * dev / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(a),
+            "e2e": {"value": L_total * A * a.steps / wall, "unit": UNIT, "ms_per_step": 1e3 * wall / a.steps,
+                    "h2d_bytes_per_step": int(upd / a.steps * 12 + a.solvers * 288),
+                    "d2h_bytes_per_step": int(hits / a.steps * 16),
+                    "timed_region": "rank 0 collect + H2D, NCCL broadcast of the batch, table + check kernels on every "
+                                    "shard, NCCL gather of the hits, host hand-over on rank 0; max over ranks"},
+            "gpu_launches": int(ll[0]), "clocks": clocks, "hits_per_step": hits / a.steps,
+            "phases_us_per_step": {"nccl_broadcast": float(np.mean(bc)), "table_kernels": float(np.mean(tk)),
+                                   "check_kernels": float(np.mean(ck))},
+            "literals": L_total, "assignments": A,
+            "note": "value = device time per step (broadcast + table kernels + check kernels), max over ranks",
+        }))
+    dist.destroy_process_group()
+
+
+def run_b200(a):
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_b200_sharded(a)
+    from gpusharesat_b200 import GpuClauseSharer, GpuClauseSharerOptions
+    rank, world, local, dist = 0, 1, 0, None
+    os.environ.setdefault("GPUSHARE_DEVICE", "0")
+
+    sig, offsets, lits = make_inputs(a)
+    L_total, A = int(offsets[-1]), a.solvers * a.slots
+    my_off, my_lits = offsets, lits
 
     sh = GpuClauseSharer(GpuClauseSharerOptions(minGpuLatencyMicros=0, verbosity=0))
     sh.setVarCount(a.vars)
@@ -387,13 +469,15 @@ def run_b200(a):
         "phases_us_per_step": {"table_kernels": float(np.mean(dev_tables) + np.mean(collapse)),
                                "check_kernels": float(np.mean(dev_check)), "h2d_to_d2h_total": float(np.mean(dev_total))},
         "literals": L_total, "assignments": A,
+        "host_us_total": {"fill_assigs": sh.getGlobalStat(10), "fill_reported": sh.getGlobalStat(11),
+                          "gpu_runs": sh.getGlobalStat(3)},
     }
 
     if rank == 0 and world == 1:
         # kernel-only timings on the last batch (tables still resident)
         push_batch(sh, streams, a.slots, pool)
         sh.gpuRun()
-        t_prod = sh.debugTimeCheck(20, dense=False)
+        t_prod = sh.debugTimeCheck(a.prod_iters, dense=False)
         n_prod = None
         lop3 = sh.debugLop3Peak()
         peaks = {}

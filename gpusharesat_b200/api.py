@@ -34,6 +34,8 @@ class gss_hit(C.Structure):
 
 HIT_DTYPE = np.dtype([("clause_id", "<i8"), ("solver_id", "<i4"), ("mask", "<u4")])
 
+RAW_HIT_DTYPE = np.dtype([("mask", "<u4"), ("solver", "<i4"), ("len", "<i4"), ("idx", "<i4")])
+
 _LOGFN = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
 
 _P = C.c_void_p
@@ -78,6 +80,11 @@ SIGNATURES = {
     "gss_debug_last_run_bytes": (None, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "gss_debug_kernel_launches": (_L, [_P]),
     "gss_debug_db_size": (None, [_P, C.POINTER(_L), C.POINTER(_L)]),
+    "gss_set_shard": (None, [_P, _I, _I]),
+    "gss_mgpu_collect": (_I, [_P, C.POINTER(C.c_void_p), C.POINTER(_L), C.POINTER(C.c_void_p), C.POINTER(_L)]),
+    "gss_mgpu_run": (None, [_P, C.c_void_p, _L, C.c_void_p, _L, _I]),
+    "gss_mgpu_wait": (_L, [_P, C.POINTER(C.c_void_p)]),
+    "gss_mgpu_import": (None, [_P, C.c_void_p, _L]),
     "gss_version": (C.c_char_p, []),
     # include/gpushare_b200_synth.h
     "gss_synth_total_lits": (_L, [_L, _I]),
@@ -330,6 +337,34 @@ class GpuClauseSharer:
 
     def debugKernelLaunches(self):
         return self._lib.gss_debug_kernel_launches(self._h)
+
+    # ---- multi-GPU (include/gpushare_b200.h) ----
+    def setShard(self, rank, world):
+        self._lib.gss_set_shard(self._h, int(rank), int(world))
+
+    def mgpuCollect(self):
+        """rank 0: returns (rebuild, params_ptr, params_bytes, updates_ptr, n_updates) or None"""
+        pp, pb, up, un = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
+        r = self._lib.gss_mgpu_collect(self._h, C.byref(pp), C.byref(pb), C.byref(up), C.byref(un))
+        if r < 0:
+            return None
+        return r, pp.value, pb.value, up.value or 0, un.value
+
+    def mgpuRun(self, params_ptr, params_bytes, updates_ptr, n_updates, rebuild):
+        self._lib.gss_mgpu_run(self._h, params_ptr, params_bytes, updates_ptr, n_updates, int(rebuild))
+
+    def mgpuWait(self):
+        """returns this rank's hits as a numpy array (mask, solver, len, idx) -- a copy"""
+        p = C.c_void_p()
+        n = self._lib.gss_mgpu_wait(self._h, C.byref(p))
+        out = np.zeros(n, dtype=RAW_HIT_DTYPE)
+        if n:
+            C.memmove(out.ctypes.data, p.value, n * RAW_HIT_DTYPE.itemsize)
+        return out
+
+    def mgpuImport(self, hits):
+        a = np.ascontiguousarray(hits, dtype=RAW_HIT_DTYPE)
+        self._lib.gss_mgpu_import(self._h, a.ctypes.data, int(a.size))
 
     def debugDbSize(self):
         a, b = C.c_int64(), C.c_int64()

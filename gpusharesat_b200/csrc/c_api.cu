@@ -86,6 +86,22 @@ double gss_debug_lop3_peak(gss_sharer *h) { return h->impl.lop3Peak(); }
 void gss_debug_last_run_bytes(gss_sharer *h, int64_t *h2d, int64_t *d2h) { h->impl.lastRunBytes(h2d, d2h); }
 int64_t gss_debug_kernel_launches(gss_sharer *h) { return h->impl.kernelLaunches(); }
 void gss_debug_db_size(gss_sharer *h, int64_t *nclauses, int64_t *nlits) { h->impl.dbSize(nclauses, nlits); }
+void gss_set_shard(gss_sharer *h, int rank, int world) { h->impl.setShard(rank, world); }
+int gss_mgpu_collect(gss_sharer *h, const void **params, int64_t *params_bytes, const void **updates, int64_t *n_updates) {
+    return h->impl.mgpuCollect(params, params_bytes, updates, n_updates);
+}
+void gss_mgpu_run(gss_sharer *h, const void *params, int64_t params_bytes, const void *updates, int64_t n_updates, int rebuild) {
+    h->impl.mgpuRun(params, params_bytes, updates, n_updates, rebuild);
+}
+int64_t gss_mgpu_wait(gss_sharer *h, const gss_raw_hit **hits) {
+    const gss::HitRecord *p = nullptr;
+    int64_t n = h->impl.mgpuWait(&p);
+    *hits = reinterpret_cast<const gss_raw_hit *>(p);
+    return n;
+}
+void gss_mgpu_import(gss_sharer *h, const gss_raw_hit *hits, int64_t n) {
+    h->impl.mgpuImport(reinterpret_cast<const gss::HitRecord *>(hits), n);
+}
 const char *gss_version(void) { return "gpushare_b200 0.1 sm_100a"; }
 
 } // extern "C"

@@ -27,7 +27,7 @@ struct LenDir {
     const int32_t *base; // device arena of this length
     int32_t len;
     int32_t count;   // clauses of this length
-    int32_t tileEnd; // cumulative tile count including this length (lengths in descending order)
+    int32_t tileEnd; // cumulative count of THIS DEVICE's tiles including this length (longest length first)
     int32_t pad;
 };
 
@@ -41,6 +41,11 @@ public:
 
     void setMaxLen(int maxLen);
     int maxLen() const { return maxLen_; }
+    // Multi-GPU: this database keeps every clause on the host but only the tiles t with
+    // t % world == rank on its device (local tile index t / world).  Before the first clause.
+    void setShard(int rank, int world);
+    int shardRank() const { return shardRank_; }
+    int shardWorld() const { return shardWorld_; }
 
     // ---- any thread (locked): reference HostClauses::addClause, Clauses.cu:349-356 ----
     int64_t addClause(const int *lits, int n);
@@ -55,9 +60,42 @@ public:
     int buildDirectory(std::vector<LenDir> &dir) const;
 
     void getClause(int len, int idx, std::vector<int> &lits, int64_t &id) const;
+    // append the literals to `out` (no temporary); returns the clause id
+    int64_t appendClause(int len, int idx, std::vector<int> &out) const {
+        const PerLen &pl = *perLen_[len];
+        size_t at = out.size();
+        out.resize(at + len);
+        const int32_t *p = pl.lits.data() + wordPos(len, idx, 0);
+        for (int i = 0; i < len; i++) out[at + i] = p[(size_t)i * kTileClauses];
+        return pl.meta[idx].id;
+    }
+    // hint the caches about a clause that is about to be read (hits arrive sorted by index)
+    void prefetchClause(int len, int idx) const {
+        const PerLen &pl = *perLen_[len];
+        __builtin_prefetch(&pl.meta[idx]);
+        __builtin_prefetch(pl.lits.data() + wordPos(len, idx, 0));
+        if (len > 1) __builtin_prefetch(pl.lits.data() + wordPos(len, idx, 1));
+    }
     int64_t clauseId(int len, int idx) const { return perLen_[len]->meta[idx].id; }
     float activity(int len, int idx) const { return perLen_[len]->meta[idx].activity; }
     void bumpActivity(int len, int idx); // Clauses.cu:231-237
+    // same bump from several threads at once (large hit lists are processed per solver in
+    // parallel); returns true when the activity passed the rescale limit -- the caller then calls
+    // rescaleIfNeeded() once the parallel section is over
+    bool bumpActivityAtomic(int len, int idx) {
+        float *p = &perLen_[len]->meta[idx].activity;
+        uint32_t *bits = reinterpret_cast<uint32_t *>(p);
+        uint32_t old = __atomic_load_n(bits, __ATOMIC_RELAXED), want;
+        float nv;
+        do {
+            float cur;
+            memcpy(&cur, &old, 4);
+            nv = cur + actIncr_;
+            memcpy(&want, &nv, 4);
+        } while (!__atomic_compare_exchange_n(bits, &old, want, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+        return nv > 1e19f;
+    }
+    void rescaleIfNeeded(bool needed) { if (needed) rescaleActivity(); }
     int count(int len) const { return len <= maxLen_ ? (int)perLen_[len]->meta.size() : 0; }
 
     // reference HostClauses::reduceDb (actOnly), Clauses.cu:426-465 / 249-282
@@ -78,6 +116,7 @@ private:
         HostBuf<int32_t> lits;    // tiled host mirror
         std::vector<ClauseMeta> meta;
         DevBuf<int32_t> dev;
+        HostBuf<int32_t> stage;   // sharded upload: this rank's dirty tiles, packed
         int64_t dirtyFrom = 0;    // first clause index not yet on the device
         bool fullReupload = false;
     };
@@ -91,7 +130,11 @@ private:
     void appendToMirror(const int *lits, int n, int64_t id);
     void rescaleActivity();
 
+    int64_t localTiles(int64_t globalTiles) const {
+        return globalTiles > shardRank_ ? (globalTiles - shardRank_ + shardWorld_ - 1) / shardWorld_ : 0;
+    }
     int maxLen_ = kDefaultMaxClauseLen;
+    int shardRank_ = 0, shardWorld_ = 1;
     std::vector<std::unique_ptr<PerLen>> perLen_;
     const Logger &logger_;
     size_t pinnedLimit_;

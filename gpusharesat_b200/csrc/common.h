@@ -41,10 +41,9 @@ struct HitRecord {
 
 // A clause that survived the aggregate filter
 struct Survivor {
-    int32_t dirIdx; // index into the run's length directory
-    int32_t idx;    // index of the clause inside its length array
+    uint64_t ptrLen; // device address of the clause's first literal (low 48 bits) | length << 48
+    int32_t idx;     // index of the clause inside its length array
     uint32_t aggBits;
-    uint32_t pad;
 };
 
 // Per-solver parameters of one run (reference DOneSolverAssigs + AggCorresp,

@@ -114,6 +114,38 @@ __global__ void __launch_bounds__(256) k_collapse(const VarUpdate *__restrict__ 
     }
 }
 
+// Per-warp staging of output records in shared memory.  A global atomicAdd whose result is needed
+// (to know where to write) is a ~0.7 us round trip; paying it per tile / per survivor put it on the
+// critical path of every warp.  Records are staged per warp and flushed with ONE atomic and one
+// coalesced burst when the stage fills up (and at the end of the kernel).
+constexpr int kStageCap = 64;   // records per warp (>= 32)
+constexpr int kMaxWarpsPerBlock = 8;
+
+template <typename T> struct WarpStage {
+    T *buf;  // this warp's kStageCap slots in shared memory
+    int n;   // staged records (warp-uniform)
+    __device__ __forceinline__ void flush(T *out, unsigned int *counter, unsigned int cap, int lane) {
+        if (n == 0) return;
+        __syncwarp();
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned int)n);
+        base = __shfl_sync(FULL, base, 0);
+        for (int i = lane; i < n; i += 32)
+            if (base + i < cap) out[base + i] = buf[i];
+        __syncwarp();
+        n = 0;
+    }
+    // every lane contributes at most one record
+    __device__ __forceinline__ void push(bool has, const T &rec, T *out, unsigned int *counter, unsigned int cap, int lane) {
+        const unsigned m = __ballot_sync(FULL, has);
+        if (!m) return;
+        const int cnt = __popc(m);
+        if (n + cnt > kStageCap) flush(out, counter, cap, lane);
+        if (has) buf[n + __popc(m & ((1u << lane) - 1))] = rec;
+        n += cnt;
+    }
+};
+
 // directory lookup: first entry whose cumulative tile count exceeds `tile`
 __device__ __forceinline__ int findDir(const int *sTileEnd, int nDir, int tile) {
     int lo = 0, hi = nDir - 1;
@@ -130,7 +162,7 @@ __device__ __forceinline__ int findDir(const int *sTileEnd, int nDir, int tile) 
 // (reference pass 1 of dFindClauses, GpuRunner.cu:148-172: one clause per thread, 4 B loads,
 // 12 B gathers with a sign select, no early exit across the warp)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_filter(CheckArgs a) {
+__global__ void __launch_bounds__(256, 6) k_filter(CheckArgs a) {
     extern __shared__ int sTileEnd[];
     for (int i = threadIdx.x; i < a.nDir; i += blockDim.x) sTileEnd[i] = a.dir[i].tileEnd;
     __syncthreads();
@@ -141,6 +173,9 @@ __global__ void __launch_bounds__(256) k_filter(CheckArgs a) {
     const int nWarps = gridDim.x * warpsPerBlock;
     const uint2 *__restrict__ a1 = a.tables.a1 + (size_t)(a.groupBase / kMaxSolversPerGroup) * 2 * (size_t)a.tables.varCap;
     const uint32_t start = a.aggStart;
+    __shared__ Survivor sStage[kMaxWarpsPerBlock][kStageCap];
+    WarpStage<Survivor> stage{sStage[threadIdx.x >> 5], 0};
+    unsigned int *survCounter = &a.counters->nSurvivors[a.groupBase / kMaxSolversPerGroup];
 
     for (int tile = warp; tile < a.totalTiles; tile += nWarps) {
         const int k = findDir(sTileEnd, a.nDir, tile);
@@ -148,7 +183,7 @@ __global__ void __launch_bounds__(256) k_filter(CheckArgs a) {
         const int tileInLen = tile - (k ? sTileEnd[k - 1] : 0);
         const int len = d.len;
         const int32_t *row = d.base + (size_t)tileInLen * kTileClauses * len + lane * 4;
-        const int c0 = tileInLen * kTileClauses + lane * 4;
+        const int c0 = (tileInLen * a.shardWorld + a.shardRank) * kTileClauses + lane * 4; // global clause index
         const int nValid = d.count - c0; // clauses of this lane that exist (may be <= 0 or >= 4)
 
         uint32_t all0 = nValid > 0 ? start : 0u, all1 = nValid > 1 ? start : 0u;
@@ -160,8 +195,13 @@ __global__ void __launch_bounds__(256) k_filter(CheckArgs a) {
         for (int i = 0; i < len; i++) {
             int4 next = lits;
             if (i + 1 < len) next = ldStream128(row + (size_t)(i + 1) * kTileClauses); // overlaps the gathers
-            uint2 g0 = ldTable(a1 + lits.x), g1 = ldTable(a1 + lits.y);
-            uint2 g2 = ldTable(a1 + lits.z), g3 = ldTable(a1 + lits.w);
+            // a dead clause stays dead: gather only for the live ones (every gather costs a 32 B
+            // L2 sector, and after the first literal ~97 % of the clauses are dead)
+            const uint2 dead = make_uint2(0u, 0u);
+            uint2 g0 = (all0 | one0) ? ldTable(a1 + lits.x) : dead;
+            uint2 g1 = (all1 | one1) ? ldTable(a1 + lits.y) : dead;
+            uint2 g2 = (all2 | one2) ? ldTable(a1 + lits.z) : dead;
+            uint2 g3 = (all3 | one3) ? ldTable(a1 + lits.w) : dead;
             step(all0, one0, g0.x, g0.y);
             step(all1, one1, g1.x, g1.y);
             step(all2, one2, g2.x, g2.y);
@@ -172,25 +212,15 @@ __global__ void __launch_bounds__(256) k_filter(CheckArgs a) {
         }
         if (!__any_sync(FULL, alive)) continue;
 
-        // warp-aggregated append of the survivors (rare)
+        // survivors go to the warp's stage (one global atomic per ~64 survivors)
+        const uint64_t rowTag = (uint64_t)(uintptr_t)row | ((uint64_t)len << 48);
         const uint32_t m0 = all0 | one0, m1 = all1 | one1, m2 = all2 | one2, m3 = all3 | one3;
-        const int cnt = (m0 != 0) + (m1 != 0) + (m2 != 0) + (m3 != 0);
-        int incl = cnt;
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) {
-            int n = __shfl_up_sync(FULL, incl, dlt);
-            if (lane >= dlt) incl += n;
-        }
-        const int total = __shfl_sync(FULL, incl, 31);
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(&a.counters->nSurvivors[a.groupBase / kMaxSolversPerGroup], (unsigned int)total);
-        base = __shfl_sync(FULL, base, 0);
-        unsigned int pos = base + (unsigned int)(incl - cnt);
-        if (m0) { if (pos < a.survCap) a.survivors[pos] = Survivor{k, c0 + 0, m0, 0u}; pos++; }
-        if (m1) { if (pos < a.survCap) a.survivors[pos] = Survivor{k, c0 + 1, m1, 0u}; pos++; }
-        if (m2) { if (pos < a.survCap) a.survivors[pos] = Survivor{k, c0 + 2, m2, 0u}; pos++; }
-        if (m3) { if (pos < a.survCap) a.survivors[pos] = Survivor{k, c0 + 3, m3, 0u}; pos++; }
+        stage.push(m0 != 0, Survivor{rowTag + 0 * sizeof(int32_t), c0 + 0, m0}, a.survivors, survCounter, a.survCap, lane);
+        stage.push(m1 != 0, Survivor{rowTag + 1 * sizeof(int32_t), c0 + 1, m1}, a.survivors, survCounter, a.survCap, lane);
+        stage.push(m2 != 0, Survivor{rowTag + 2 * sizeof(int32_t), c0 + 2, m2}, a.survivors, survCounter, a.survCap, lane);
+        stage.push(m3 != 0, Survivor{rowTag + 3 * sizeof(int32_t), c0 + 3, m3}, a.survivors, survCounter, a.survCap, lane);
     }
+    stage.flush(a.survivors, survCounter, a.survCap, lane);
 }
 
 // append one hit per lane with a non-zero mask; one atomic per warp
@@ -226,29 +256,69 @@ __global__ void __launch_bounds__(256) k_exact(CheckArgs a) {
     unsigned int n = a.counters->nSurvivors[a.groupBase / kMaxSolversPerGroup];
     if (n > a.survCap) n = a.survCap;
     unsigned long long tests = 0;
+    const uint2 ident = make_uint2(0u, 0u);
+    __shared__ HitRecord sStage[kMaxWarpsPerBlock][kStageCap];
+    WarpStage<HitRecord> stage{sStage[threadIdx.x >> 5], 0};
+
+    // Software pipeline over the survivors of this warp: while survivor i is checked, the literals
+    // of survivor i+1 and the record of survivor i+2 are already in flight (each is a dependent
+    // DRAM/L2 round trip; one warp sees ~20 survivors, so the chain would otherwise be exposed).
+    auto ldSurv = [&](unsigned int i) -> uint4 {
+        return i < n ? __ldg(reinterpret_cast<const uint4 *>(a.survivors + i)) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    auto litPtr = [](const uint4 &sv) -> const int32_t * {
+        return reinterpret_cast<const int32_t *>(((uint64_t)(sv.y & 0xFFFFu) << 32) | sv.x);
+    };
+    auto ldLits = [&](const uint4 &sv, int base) -> int {
+        const int len = (int)(sv.y >> 16);
+        return base + lane < len ? __ldg(litPtr(sv) + (size_t)(base + lane) * kTileClauses) : 0;
+    };
+    uint4 sv0 = ldSurv(warp), sv1 = ldSurv(warp + nWarps);
+    int lit0 = ldLits(sv0, 0);
     for (unsigned int sIdx = warp; sIdx < n; sIdx += nWarps) {
-        const Survivor sv = a.survivors[sIdx];
-        const LenDir d = a.dir[sv.dirIdx];
-        const int len = d.len;
-        const int32_t *lp = d.base + (size_t)(sv.idx / kTileClauses) * kTileClauses * len + (sv.idx % kTileClauses);
-        uint32_t all = (sv.aggBits & myAgg) ? myStart : 0u, one = 0;
+        const uint4 sv2 = ldSurv(sIdx + 2u * nWarps);
+        const int lit1 = ldLits(sv1, 0);
+        const int len = (int)(sv0.y >> 16), idx = (int)sv0.z;
+        uint32_t all = (sv0.w & myAgg) ? myStart : 0u, one = 0;
         tests += __popc(__ballot_sync(FULL, all != 0));
-        for (int i = 0; i < len; i++) {
-            const int lit = __ldg(lp + (size_t)i * kTileClauses);
-            const uint2 e = ldTable(t2 + (size_t)(lit >> 1) * stride);
-            const uint32_t f = e.x & ((lit & 1) ? e.y : ~e.y);
-            step(all, one, f, ~e.x);
-            if (!__any_sync(FULL, all | one)) break;
+        bool dead = false;
+        for (int base = 0; base < len && !dead; base += 32) {
+            const int nl = min(32, len - base);
+            const int myLit = base == 0 ? lit0 : ldLits(sv0, base);
+            for (int j = 0; j < nl; j += 4) {
+                // four independent row gathers per step; lanes whose solver is already dead
+                // (or was never selected by the filter) do not load at all
+                const int l0 = __shfl_sync(FULL, myLit, j), l1 = __shfl_sync(FULL, myLit, (j + 1) & 31);
+                const int l2 = __shfl_sync(FULL, myLit, (j + 2) & 31), l3 = __shfl_sync(FULL, myLit, (j + 3) & 31);
+                const bool live = (all | one) != 0;
+                const uint2 e0 = live ? ldTable(t2 + (size_t)(l0 >> 1) * stride) : ident;
+                const uint2 e1 = (live && j + 1 < nl) ? ldTable(t2 + (size_t)(l1 >> 1) * stride) : ident;
+                const uint2 e2 = (live && j + 2 < nl) ? ldTable(t2 + (size_t)(l2 >> 1) * stride) : ident;
+                const uint2 e3 = (live && j + 3 < nl) ? ldTable(t2 + (size_t)(l3 >> 1) * stride) : ident;
+                step(all, one, e0.x & ((l0 & 1) ? e0.y : ~e0.y), ~e0.x);
+                if (j + 1 < nl) step(all, one, e1.x & ((l1 & 1) ? e1.y : ~e1.y), ~e1.x);
+                if (j + 2 < nl) step(all, one, e2.x & ((l2 & 1) ? e2.y : ~e2.y), ~e2.x);
+                if (j + 3 < nl) step(all, one, e3.x & ((l3 & 1) ? e3.y : ~e3.y), ~e3.x);
+                if (!__any_sync(FULL, all | one)) { dead = true; break; }
+            }
         }
-        reportHits(a, all | one, solver, len, sv.idx, lane);
+        stage.push((all | one) != 0, HitRecord{all | one, solver, len, idx}, a.hits, &a.counters->nHits, a.hitCap, lane);
+        sv0 = sv1;
+        lit0 = lit1;
+        sv1 = sv2;
     }
+    stage.flush(a.hits, &a.counters->nHits, a.hitCap, lane);
     if (lane == 0 && tests) atomicAdd(&a.counters->exactTests, tests);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Dense mode (bench only).  One warp per quarter tile (32 clauses), lane = solver.  The 32
-// clauses are advanced together, so 32 independent T2 row gathers are in flight per warp.
+// Dense mode (bench only).  One warp per group of kDenseGroup clauses, lane = solver.  The
+// clauses of a group advance together one literal at a time: all their T2 row gathers are issued
+// back to back (kDenseGroup independent 256 B rows in flight per warp) before any result is
+// consumed -- this kernel is bound by the gather stream, so memory-level parallelism is everything.
 // ---------------------------------------------------------------------------------------------
+constexpr int kDenseGroup = 16;
+
 __global__ void __launch_bounds__(128) k_check_dense(CheckArgs a) {
     extern __shared__ int sTileEnd[];
     for (int i = threadIdx.x; i < a.nDir; i += blockDim.x) sTileEnd[i] = a.dir[i].tileEnd;
@@ -263,34 +333,42 @@ __global__ void __launch_bounds__(128) k_check_dense(CheckArgs a) {
     const uint32_t myStart = active ? a.params[solver].startVals : 0u;
     const uint2 *__restrict__ t2 = a.tables.t2 + solver;
     const size_t stride = (size_t)a.tables.solverStride;
+    constexpr int kGroupsPerTile = kTileClauses / kDenseGroup;
 
-    const long long nWork = (long long)a.totalTiles * 4;
+    const long long nWork = (long long)a.totalTiles * kGroupsPerTile;
     for (long long w = warp; w < nWork; w += nWarps) {
-        const int tile = (int)(w >> 2), q = (int)(w & 3);
+        const int tile = (int)(w / kGroupsPerTile), q = (int)(w % kGroupsPerTile);
         const int k = findDir(sTileEnd, a.nDir, tile);
         const LenDir d = a.dir[k];
         const int tileInLen = tile - (k ? sTileEnd[k - 1] : 0);
         const int len = d.len;
-        const int c0 = tileInLen * kTileClauses + q * 32;
+        const int c0 = (tileInLen * a.shardWorld + a.shardRank) * kTileClauses + q * kDenseGroup;
         const int nValid = d.count - c0;
         if (nValid <= 0) continue;
-        const int32_t *col = d.base + (size_t)tileInLen * kTileClauses * len + q * 32 + lane;
+        // lane l < kDenseGroup holds literal i of clause c0 + l
+        const int32_t *col = d.base + (size_t)tileInLen * kTileClauses * len + q * kDenseGroup + (lane & (kDenseGroup - 1));
 
-        uint32_t all[32], one[32];
+        uint32_t all[kDenseGroup], one[kDenseGroup];
 #pragma unroll
-        for (int c = 0; c < 32; c++) { all[c] = c < nValid ? myStart : 0u; one[c] = 0u; }
+        for (int c = 0; c < kDenseGroup; c++) { all[c] = c < nValid ? myStart : 0u; one[c] = 0u; }
+        int word = ldStream32(col);
         for (int i = 0; i < len; i++) {
-            const int word = ldStream32(col + (size_t)i * kTileClauses); // literal i of clause c0+lane
+            int nextWord = word;
+            if (i + 1 < len) nextWord = ldStream32(col + (size_t)(i + 1) * kTileClauses);
+            int lit[kDenseGroup];
+            uint2 e[kDenseGroup];
 #pragma unroll
-            for (int c = 0; c < 32; c++) {
-                const int lit = __shfl_sync(FULL, word, c);
-                const uint2 e = ldTable(t2 + (size_t)(lit >> 1) * stride);
-                const uint32_t f = e.x & ((lit & 1) ? e.y : ~e.y);
-                step(all[c], one[c], f, ~e.x);
+            for (int c = 0; c < kDenseGroup; c++) {
+                lit[c] = __shfl_sync(FULL, word, c);
+                e[c] = ldTable(t2 + (size_t)(lit[c] >> 1) * stride);
             }
+#pragma unroll
+            for (int c = 0; c < kDenseGroup; c++)
+                step(all[c], one[c], e[c].x & ((lit[c] & 1) ? e[c].y : ~e[c].y), ~e[c].x);
+            word = nextWord;
         }
 #pragma unroll
-        for (int c = 0; c < 32; c++) reportHits(a, all[c] | one[c], solver, len, c0 + c, lane);
+        for (int c = 0; c < kDenseGroup; c++) reportHits(a, all[c] | one[c], solver, len, c0 + c, lane);
     }
 }
 
@@ -413,7 +491,7 @@ void launchCheckDense(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStrea
     int threads = 128;
     size_t smem = (size_t)a.nDir * sizeof(int);
     int blocks = resolveBlocks((const void *)k_check_dense, threads, smem, numSMs, dims.blocks,
-                               ((long long)a.totalTiles * 4 + 3) / 4);
+                               ((long long)a.totalTiles * (kTileClauses / kDenseGroup) + 3) / 4);
     k_check_dense<<<blocks, threads, smem, s>>>(a);
     checkLaunch("k_check_dense");
     ++*launches;

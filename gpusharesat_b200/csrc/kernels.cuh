@@ -41,7 +41,8 @@ struct LaunchDims {
 struct CheckArgs {
     const LenDir *dir; // device copy of the length directory
     int nDir;
-    int totalTiles;
+    int totalTiles;               // tiles held by THIS device
+    int shardRank, shardWorld;    // device tile t of a length is global tile t * shardWorld + shardRank
     const SolverRunParams *params; // device, all solvers
     int groupBase;                 // first solver of this group
     int groupSolvers;              // solvers in this group (<= 32)

@@ -78,14 +78,45 @@ void Reported::fill(const std::vector<AssigIds> &ids, const HitRecord *hits, siz
         if (ids[s].count > 0) batchOf((int)s).ids = ids[s];
     for (size_t i = 0; i < nHits; i++) {
         const HitRecord &h = hits[i];
+        if (i + 16 < nHits) db_.prefetchClause(hits[i + 16].len, hits[i + 16].idx);
         ClauseBatch &b = batchOf(h.solver);
-        int64_t id;
-        db_.getClause(h.len, h.idx, tmpLits_, id);
-        b.entries.push_back(ClauseBatch::Entry{id, (int32_t)b.lits.size()});
-        b.lits.insert(b.lits.end(), tmpLits_.begin(), tmpLits_.end());
+        int32_t pos = (int32_t)b.lits.size();
+        int64_t id = db_.appendClause(h.len, h.idx, b.lits);
+        b.entries.push_back(ClauseBatch::Entry{id, pos});
         b.hadSomeReported |= h.mask;
     }
     for (size_t s = 0; s < queues_.size(); s++)
+        if (perSolver[s]) queues_[s]->publish();
+}
+
+void Reported::fillBuckets(const std::vector<AssigIds> &ids, const HitRecord *hits, const std::vector<size_t> &start,
+                           const std::function<void(const std::function<void(int)> &)> &forEach,
+                           const std::function<void(int, int)> &bump) {
+    size_t nSolvers = queues_.size();
+    std::vector<ClauseBatch *> perSolver(nSolvers, nullptr);
+    for (size_t s = 0; s < nSolvers; s++) {
+        bool hasIds = s < ids.size() && ids[s].count > 0;
+        bool hasHits = s + 1 < start.size() && start[s + 1] > start[s];
+        if (!hasIds && !hasHits) continue;
+        perSolver[s] = &queues_[s]->begin();
+        if (hasIds) perSolver[s]->ids = ids[s];
+    }
+    forEach([&](int s) {
+        if ((size_t)s >= nSolvers || !perSolver[s] || (size_t)s + 1 >= start.size()) return;
+        ClauseBatch &b = *perSolver[s];
+        size_t lo = start[s], hi = start[s + 1];
+        b.entries.reserve(hi - lo);
+        for (size_t i = lo; i < hi; i++) {
+            const HitRecord &h = hits[i];
+            if (i + 16 < hi) db_.prefetchClause(hits[i + 16].len, hits[i + 16].idx);
+            int32_t pos = (int32_t)b.lits.size();
+            int64_t id = db_.appendClause(h.len, h.idx, b.lits);
+            b.entries.push_back(ClauseBatch::Entry{id, pos});
+            b.hadSomeReported |= h.mask;
+            bump(h.len, h.idx);
+        }
+    });
+    for (size_t s = 0; s < nSolvers; s++)
         if (perSolver[s]) queues_[s]->publish();
 }
 

@@ -7,6 +7,7 @@
 #include "clause_db.h"
 #include "common.h"
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <queue>
@@ -74,6 +75,13 @@ public:
     void assigWasSent(int solver, int64_t id) { lastSent_[solver] = id; } // Reported.cuh:118
     // GPU thread: Reported.cu:160-204
     void fill(const std::vector<AssigIds> &ids, const HitRecord *hits, size_t nHits);
+    // Same result as fill() for hits already grouped by solver (bucket s = hits[start[s]..start[s+1]),
+    // each bucket in hand-over order); the buckets are filled concurrently through `forEach`,
+    // which must call its argument once for every solver index (any thread, any order).
+    // bump(len, idx) is invoked once per hit from the filling thread.
+    void fillBuckets(const std::vector<AssigIds> &ids, const HitRecord *hits, const std::vector<size_t> &start,
+                     const std::function<void(const std::function<void(int)> &)> &forEach,
+                     const std::function<void(int, int)> &bump);
     // solver thread: Reported.cu:105-158
     bool pop(int solver, int *&lits, int &count, int64_t &id);
     int64_t lastAssigAllReported(int solver) const { return lastAllReported_[solver]; }

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <atomic>
 #include <thread>
 
 namespace gss {
@@ -226,6 +227,7 @@ void Sharer::reduceDb() {
     // GpuClauseSharerImpl.cu:105-110: no run may be in flight, clause indices change
     wholeRun(false);
     useDevice();
+    materializeLastHits(); // clause indices are about to change
     TimeAdder t(globalStats_[G_timeSpentReduceGpuDb], true);
     db_->reduceDb(stream_);
     lastStarted_ = -1;
@@ -250,6 +252,7 @@ void Sharer::wholeRun(bool canStart) {
     if (outOfMemory) {
         // GpuRunner.cu:243-246
         logger_.log(1, "c gpushare_b200: out of GPU memory, reducing the clause database\n");
+        materializeLastHits();
         TimeAdder t(globalStats_[G_timeSpentReduceGpuDb], true);
         db_->reduceDb(stream_);
         lastStarted_ = -1;
@@ -293,6 +296,8 @@ CheckArgs Sharer::checkArgs(const RunSlot &slot, int g) const {
     a.dir = slot.dirDev();
     a.nDir = slot.nDir;
     a.totalTiles = slot.totalTiles;
+    a.shardRank = db_->shardRank();
+    a.shardWorld = db_->shardWorld();
     a.params = slot.paramsDev();
     a.groupBase = g * kMaxSolversPerGroup;
     a.groupSolvers = std::min(kMaxSolversPerGroup, slot.nSolvers - a.groupBase);
@@ -324,13 +329,12 @@ void Sharer::enqueueResultCopy(RunSlot &slot) {
     lastD2H_ = (int64_t)bytes;
 }
 
-bool Sharer::startRun(RunSlot &slot) {
-    int64_t h2d = 0;
+// tables, clause upload, length directory (everything of a run that is local to this device)
+bool Sharer::prepareRun(RunSlot &slot, bool &rebuild, int64_t &h2d) {
     GSS_CUDA(cudaEventRecord(slot.evStart, stream_));
-    bool rebuild = false;
+    rebuild = false;
     if (!ensureTables(rebuild)) return false;
     if (!db_->uploadDirty(stream_, &h2d)) return false;
-
     std::vector<LenDir> dir;
     slot.totalTiles = db_->buildDirectory(dir);
     slot.nDir = (int)dir.size();
@@ -338,34 +342,44 @@ bool Sharer::startRun(RunSlot &slot) {
     slot.dirBytes = ((size_t)slot.nDir * sizeof(LenDir) + 15) / 16 * 16;
     slot.headHost.resize(slot.dirBytes + (size_t)slot.nSolvers * sizeof(SolverRunParams));
     memcpy(slot.headHost.data(), dir.data(), dir.size() * sizeof(LenDir));
-    SolverRunParams *params = (SolverRunParams *)(slot.headHost.data() + slot.dirBytes);
+    return true;
+}
 
-    // reference HostAssigs::fillAssigsAsync, Assigs.cu:326-372
+// reference HostAssigs::fillAssigsAsync, Assigs.cu:326-372: every solver's deltas and run masks
+void Sharer::collectBatch(RunSlot &slot, bool rebuild) {
+    SolverRunParams *params = (SolverRunParams *)(slot.headHost.data() + slot.dirBytes);
     slot.updHost.clear();
     slot.ids.assign(slot.nSolvers, AssigIds{});
-    int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
-    slot.aggStart.assign(groups, 0u);
     slot.assigCount = 0;
-    slot.maxUpd = 0;
-    {
-        TimeAdder t(globalStats_[G_timeSpentFillingAssigs], opts_.quickProf != 0);
-        for (int s = 0; s < slot.nSolvers; s++) {
-            SolverAssigs &sa = assigs_->solver(s);
-            SolverRunParams &p = params[s];
-            memset(&p, 0, sizeof(p));
-            p.updStart = (int32_t)slot.updHost.size();
-            // a solver busy writing its assignment is skipped for this run (Assigs.cu:350);
-            // during a table rebuild every solver must contribute, so wait for it
-            bool locked = rebuild ? (sa.lock(), true) : sa.tryLock();
-            if (!locked) continue;
-            sa.collectLocked(slot.updHost, p, slot.ids[s], rebuild);
-            sa.unlock();
-            slot.aggStart[s / kMaxSolversPerGroup] |= p.usedAggBits;
-            slot.assigCount += slot.ids[s].count;
-            slot.maxUpd = std::max(slot.maxUpd, (int)p.updCount);
-        }
+    TimeAdder t(globalStats_[G_timeSpentFillingAssigs], opts_.quickProf != 0);
+    for (int s = 0; s < slot.nSolvers; s++) {
+        SolverAssigs &sa = assigs_->solver(s);
+        SolverRunParams &p = params[s];
+        memset(&p, 0, sizeof(p));
+        p.updStart = (int32_t)slot.updHost.size();
+        // a solver busy writing its assignment is skipped for this run (Assigs.cu:350);
+        // during a table rebuild every solver must contribute, so wait for it
+        bool locked = rebuild ? (sa.lock(), true) : sa.tryLock();
+        if (!locked) continue;
+        sa.collectLocked(slot.updHost, p, slot.ids[s], rebuild);
+        sa.unlock();
+        slot.assigCount += slot.ids[s].count;
     }
     slot.nUpdates = (int64_t)slot.updHost.size();
+}
+
+// device half of a run.  The run parameters are already in slot.headHost; `updSrc` may be a host
+// or a device pointer (multi-GPU: the broadcast payload), cudaMemcpyDefault sorts it out.
+void Sharer::launchRun(RunSlot &slot, const void *updSrc, int64_t nUpdates, int64_t &h2d) {
+    const SolverRunParams *params = (const SolverRunParams *)(slot.headHost.data() + slot.dirBytes);
+    int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
+    slot.aggStart.assign(groups, 0u);
+    slot.maxUpd = 0;
+    for (int s = 0; s < slot.nSolvers; s++) {
+        slot.aggStart[s / kMaxSolversPerGroup] |= params[s].usedAggBits;
+        slot.maxUpd = std::max(slot.maxUpd, (int)params[s].updCount);
+    }
+    slot.nUpdates = nUpdates;
     slot.dense = dense_;
 
     slot.headDev.reserve(slot.headHost.size(), 0, stream_);
@@ -373,8 +387,7 @@ bool Sharer::startRun(RunSlot &slot) {
     h2d += (int64_t)slot.headHost.size();
     if (slot.nUpdates) {
         slot.updDev.reserve((size_t)slot.nUpdates, 0, stream_);
-        GSS_CUDA(cudaMemcpyAsync(slot.updDev.data(), slot.updHost.data(), (size_t)slot.nUpdates * sizeof(VarUpdate),
-                                 cudaMemcpyHostToDevice, stream_));
+        GSS_CUDA(cudaMemcpyAsync(slot.updDev.data(), updSrc, (size_t)slot.nUpdates * sizeof(VarUpdate), cudaMemcpyDefault, stream_));
         h2d += slot.nUpdates * (int64_t)sizeof(VarUpdate);
     }
     ensureResultBuffers();
@@ -396,7 +409,82 @@ bool Sharer::startRun(RunSlot &slot) {
     if (slot.nUpdates) collapseSlot_ = (int)(&slot - slots_);
     lastStarted_ = (int)(&slot - slots_);
     lastH2D_ = h2d;
+}
+
+bool Sharer::startRun(RunSlot &slot) {
+    int64_t h2d = 0;
+    bool rebuild = false;
+    if (!prepareRun(slot, rebuild, h2d)) return false;
+    collectBatch(slot, rebuild);
+    launchRun(slot, slot.updHost.data(), (int64_t)slot.updHost.size(), h2d);
     return true;
+}
+
+// --------------------------------------------------------------------------------------------
+// multi-GPU: one front-end (rank 0: solver threads, slot machines, hand-over) and one clause
+// shard per device.  Per batch: rank 0 collects -> the payload (run parameters + deltas) is
+// broadcast -> every rank runs its shard -> hits are gathered -> rank 0 hands them over.
+// --------------------------------------------------------------------------------------------
+
+int Sharer::nextSlot() const { return cur_ >= 0 ? 1 - cur_ : (collapseSlot_ >= 0 ? 1 - collapseSlot_ : 0); }
+
+int Sharer::mgpuCollect(const void **params, int64_t *paramsBytes, const void **updates, int64_t *nUpdates) {
+    useDevice();
+    GSS_CHECK(cur_ < 0 && mgpuPending_ < 0);
+    db_->drainPending();
+    if (db_->stats().clauses == 0) return -1;
+    RunSlot &slot = slots_[nextSlot()];
+    bool rebuild = false;
+    mgpuH2D_ = 0;
+    if (!prepareRun(slot, rebuild, mgpuH2D_)) GSS_DIE("out of device memory (multi-GPU mode does not reduce the database by itself)");
+    collectBatch(slot, rebuild);
+    mgpuPending_ = (int)(&slot - slots_);
+    *params = slot.headHost.data() + slot.dirBytes;
+    *paramsBytes = (int64_t)slot.nSolvers * (int64_t)sizeof(SolverRunParams);
+    *updates = slot.updHost.data();
+    *nUpdates = slot.nUpdates;
+    return rebuild ? 1 : 0;
+}
+
+void Sharer::mgpuRun(const void *params, int64_t paramsBytes, const void *updates, int64_t nUpdates, int rebuild) {
+    useDevice();
+    GSS_CHECK(cur_ < 0);
+    int64_t h2d = 0;
+    RunSlot *slot;
+    if (mgpuPending_ >= 0) { // rank 0: the slot was prepared by mgpuCollect
+        slot = &slots_[mgpuPending_];
+        mgpuPending_ = -1;
+        h2d = mgpuH2D_;
+    } else {
+        db_->drainPending();
+        slot = &slots_[nextSlot()];
+        bool myRebuild = false;
+        if (!prepareRun(*slot, myRebuild, h2d)) GSS_DIE("out of device memory (multi-GPU mode)");
+        if (myRebuild && !rebuild) GSS_DIE("multi-GPU ranks disagree about a table rebuild (call setVarCount / setCpuSolverCount identically on every rank)");
+        slot->ids.assign(slot->nSolvers, AssigIds{});
+        slot->assigCount = 0;
+    }
+    GSS_CHECK(paramsBytes == (int64_t)slot->nSolvers * (int64_t)sizeof(SolverRunParams));
+    void *dst = slot->headHost.data() + slot->dirBytes;
+    if (params != dst) GSS_CUDA(cudaMemcpy(dst, params, (size_t)paramsBytes, cudaMemcpyDefault));
+    launchRun(*slot, updates, nUpdates, h2d);
+    cur_ = (int)(slot - slots_);
+}
+
+int64_t Sharer::mgpuWait(const HitRecord **hits) {
+    useDevice();
+    GSS_CHECK(cur_ >= 0);
+    finishRun(slots_[cur_]);
+    mgpuLast_ = cur_;
+    cur_ = -1;
+    *hits = hits_.data();
+    return (int64_t)hits_.size();
+}
+
+void Sharer::mgpuImport(const HitRecord *hits, int64_t n) {
+    GSS_CHECK(mgpuLast_ >= 0);
+    if (hits != hits_.data()) hits_.assign(hits, hits + n);
+    processResults(slots_[mgpuLast_]);
 }
 
 void Sharer::finishRun(RunSlot &slot) {
@@ -454,25 +542,65 @@ void Sharer::processResults(RunSlot &slot) {
     // The kernels append hits in scheduling order.  Sorting them makes everything downstream
     // (activity bumps, batch order, hence which clause a solver sees first) reproducible;
     // the reference hands them over in whatever order the atomics produced.
-    std::sort(hits_.begin(), hits_.end(), [](const HitRecord &a, const HitRecord &b) {
+    auto byClause = [](const HitRecord &a, const HitRecord &b) {
         if (a.len != b.len) return a.len < b.len;
         if (a.idx != b.idx) return a.idx < b.idx;
         return a.solver < b.solver;
-    });
-    lastHits_.resize(hits_.size());
-    for (size_t i = 0; i < hits_.size(); i++) {
-        const HitRecord &h = hits_[i];
-        db_->bumpActivity(h.len, h.idx);
-        lastHits_[i] = gss_hit{db_->clauseId(h.len, h.idx), h.solver, h.mask};
+    };
+    lastHitsValid_ = false; // gss_debug_last_hits converts hits_ on demand
+    if (hits_.size() < kParallelHits) {
+        std::sort(hits_.begin(), hits_.end(), byClause);
+        for (size_t i = 0; i < hits_.size(); i++) {
+            if (i + 16 < hits_.size()) db_->prefetchClause(hits_[i + 16].len, hits_[i + 16].idx);
+            db_->bumpActivity(hits_[i].len, hits_[i].idx);
+        }
+        TimeAdder t(globalStats_[G_timeSpentFillingReported], opts_.quickProf != 0);
+        reported_->fill(slot.ids, hits_.data(), hits_.size());
+        return;
     }
+    // Large hit list: the per-solver batches are independent.  Group the hits by solver (one
+    // counting pass), then sort / bump / copy literals per solver on the worker pool.  Every
+    // solver's batch ends up in the same (len, idx) order as on the serial path.
+    TimeAdder t(globalStats_[G_timeSpentFillingReported], opts_.quickProf != 0);
+    const int nSolvers = slot.nSolvers;
+    std::vector<size_t> start(nSolvers + 1, 0);
+    for (const HitRecord &h : hits_) start[h.solver + 1]++;
+    for (int s = 0; s < nSolvers; s++) start[s + 1] += start[s];
+    grouped_.resize(hits_.size());
+    {
+        std::vector<size_t> cursor(start.begin(), start.end() - 1);
+        for (const HitRecord &h : hits_) grouped_[cursor[h.solver]++] = h;
+    }
+    hits_.swap(grouped_);
+    if (!pool_) pool_ = std::make_unique<WorkerPool>(std::max(1, std::min(15, (int)std::thread::hardware_concurrency() - 1)));
+    std::atomic<bool> rescale{false};
+    reported_->fillBuckets(
+        slot.ids, hits_.data(), start,
+        [&](const std::function<void(int)> &perSolver) {
+            pool_->parallelFor(nSolvers, [&](int s) {
+                std::sort(hits_.begin() + start[s], hits_.begin() + start[s + 1], byClause);
+                perSolver(s);
+            });
+        },
+        [&](int len, int idx) {
+            if (db_->bumpActivityAtomic(len, idx)) rescale.store(true);
+        });
+    db_->rescaleIfNeeded(rescale.load());
+}
+
+void Sharer::materializeLastHits() {
+    if (lastHitsValid_) return;
+    lastHits_.resize(hits_.size());
+    for (size_t i = 0; i < hits_.size(); i++)
+        lastHits_[i] = gss_hit{db_->clauseId(hits_[i].len, hits_[i].idx), hits_[i].solver, hits_[i].mask};
     std::sort(lastHits_.begin(), lastHits_.end(), [](const gss_hit &a, const gss_hit &b) {
         return a.clause_id != b.clause_id ? a.clause_id < b.clause_id : a.solver_id < b.solver_id;
     });
-    TimeAdder t(globalStats_[G_timeSpentFillingReported], opts_.quickProf != 0);
-    reported_->fill(slot.ids, hits_.data(), hits_.size());
+    lastHitsValid_ = true;
 }
 
 int64_t Sharer::lastHits(gss_hit *out, int64_t cap) {
+    materializeLastHits();
     int64_t n = (int64_t)lastHits_.size();
     if (out && cap > 0) memcpy(out, lastHits_.data(), (size_t)std::min(n, cap) * sizeof(gss_hit));
     return n;

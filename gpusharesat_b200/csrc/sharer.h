@@ -6,6 +6,7 @@
 #include "assigs.h"
 #include "clause_db.h"
 #include "kernels.cuh"
+#include "pool.h"
 #include "reported.h"
 #include "stats.h"
 #include <memory>
@@ -48,6 +49,12 @@ public:
     double lop3Peak();
     void lastRunBytes(int64_t *h2d, int64_t *d2h) { *h2d = lastH2D_; *d2h = lastD2H_; }
     int64_t kernelLaunches() const { return launches_; }
+    // ---- multi-GPU (see include/gpushare_b200.h) ----
+    void setShard(int rank, int world) { db_->setShard(rank, world); }
+    int mgpuCollect(const void **params, int64_t *paramsBytes, const void **updates, int64_t *nUpdates);
+    void mgpuRun(const void *params, int64_t paramsBytes, const void *updates, int64_t nUpdates, int rebuild);
+    int64_t mgpuWait(const HitRecord **hits);
+    void mgpuImport(const HitRecord *hits, int64_t n);
     void dbSize(int64_t *ncl, int64_t *nlits) { *ncl = db_->stats().clauses; *nlits = db_->stats().lengthSum; }
 
 private:
@@ -72,10 +79,15 @@ private:
     void useDevice();
     void wholeRun(bool canStart);
     bool startRun(RunSlot &slot);      // false: nothing started
+    bool prepareRun(RunSlot &slot, bool &rebuild, int64_t &h2d);
+    void collectBatch(RunSlot &slot, bool rebuild);
+    void launchRun(RunSlot &slot, const void *updSrc, int64_t nUpdates, int64_t &h2d);
+    int nextSlot() const;
     void finishRun(RunSlot &slot);     // wait, re-run on overflow, pull every hit to the host
     void processResults(RunSlot &slot);
     void launchCheckKernels(RunSlot &slot, bool dense);
     void enqueueResultCopy(RunSlot &slot);
+    void materializeLastHits();
     bool ensureTables(bool &rebuild);
     void ensureResultBuffers();
     void unsetPendingLocked(int solver);
@@ -109,9 +121,16 @@ private:
     int cur_ = -1;          // slot of the run in flight
     int collapseSlot_ = -1; // slot whose updates still have to be collapsed on the device
     int lastStarted_ = -1;  // slot whose tables are still intact (for timeCheck)
+    int mgpuPending_ = -1;  // multi-GPU: slot collected but not yet launched
+    int mgpuLast_ = -1;     // multi-GPU: slot of the last finished run
+    int64_t mgpuH2D_ = 0;
 
     std::vector<HitRecord> hits_;   // hits of the run being processed
-    std::vector<gss_hit> lastHits_; // sorted, for gss_debug_last_hits
+    std::vector<HitRecord> grouped_; // scratch: hits grouped by solver
+    std::unique_ptr<WorkerPool> pool_; // created on the first large hit list
+    static constexpr size_t kParallelHits = 8192;
+    std::vector<gss_hit> lastHits_; // sorted, for gss_debug_last_hits (built on demand)
+    bool lastHitsValid_ = true;
     bool dense_ = false;
     bool ranOutOfMemory_ = false;
     int64_t launches_ = 0;

@@ -145,6 +145,32 @@ int64_t gss_debug_kernel_launches(gss_sharer *h);
 /* Sum of clause lengths / clause count currently in the database */
 void gss_debug_db_size(gss_sharer *h, int64_t *nclauses, int64_t *nlits);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU (new functionality; the reference drives device 0 only, GpuClauseSharerImpl.cu:52).
+ * One process per GPU.  Every rank creates a sharer, calls gss_set_shard(rank, world) and then
+ * the same gss_set_var_count / gss_set_cpu_solver_count / gss_add_clause sequence: the host
+ * mirror is complete everywhere, each device holds the clause tiles t with t % world == rank.
+ * Rank 0 is the front-end (solver threads, assignment slots, hand-over).  Per batch:
+ *   rank 0      gss_mgpu_collect   -> run parameters + assignment deltas (pinned host memory)
+ *   all ranks   [broadcast them, e.g. NCCL over NVLink]  gss_mgpu_run(payload: host OR device ptr)
+ *   all ranks   gss_mgpu_wait      -> this rank's hits (global clause references)
+ *   rank 0      [gather the hits]  gss_mgpu_import(union of all ranks' hits)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gss_raw_hit {
+    uint32_t mask;
+    int32_t  solver;
+    int32_t  len;  /* clause length */
+    int32_t  idx;  /* index of the clause among the clauses of that length (global) */
+} gss_raw_hit;
+
+void    gss_set_shard(gss_sharer *h, int rank, int world);
+/* returns 1 if this batch rebuilds the device tables (payload lists every variable), 0 if not,
+ * -1 if there is no clause yet (nothing to run) */
+int     gss_mgpu_collect(gss_sharer *h, const void **params, int64_t *params_bytes, const void **updates, int64_t *n_updates);
+void    gss_mgpu_run(gss_sharer *h, const void *params, int64_t params_bytes, const void *updates, int64_t n_updates, int rebuild);
+int64_t gss_mgpu_wait(gss_sharer *h, const gss_raw_hit **hits);
+void    gss_mgpu_import(gss_sharer *h, const gss_raw_hit *hits, int64_t n);
+
 /* library build info: "gpushare_b200 <version> sm_100a" */
 const char *gss_version(void);
 

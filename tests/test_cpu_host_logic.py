@@ -1,0 +1,226 @@
+"""CPU tier: the product's host logic (slot state machine, run parameters, hand-over rules,
+reduceDb thresholds) through tests/hostshim, against the reference's golden values."""
+import numpy as np
+import pytest
+
+from hostshim_lib import DeviceModel, Rig
+
+TRUE, FALSE, UNDEF = 0, 1, 2
+ALL = 0xFFFFFFFF
+
+
+def test_two_solvers_one_assignment_each():
+    # GpuSolverTest.cu:78-121 testAssigsTwoSolvers
+    r = Rig(2, 2)
+    r.set(0, 0, FALSE); r.set(0, 1, UNDEF); assert r.send(0) == 0
+    r.set(1, 0, UNDEF); r.set(1, 1, TRUE); assert r.send(1) == 0
+    upd, params = r.collect()
+    dev = DeviceModel(2, 2)
+    dev.apply(upd, params)
+    assert dev.def_[0, 0] & 1 == 1 and dev.tru[0, 0] & 1 == 0 and dev.def_[0, 1] & 1 == 0
+    assert dev.def_[1, 0] & 1 == 0 and dev.def_[1, 1] & 1 == 1 and dev.tru[1, 1] & 1 == 1
+    assert params[0].startVals == 1 and params[1].startVals == 1
+
+
+def test_two_assignments_value_inheritance():
+    # GpuSolverTest.cu:123-161 testAssigsTwoAssignments
+    r = Rig(2, 1)
+    r.set(0, 0, TRUE); r.set(0, 1, FALSE); r.send(0)
+    r.set(0, 0, UNDEF); r.send(0)
+    upd, params = r.collect()
+    dev = DeviceModel(2, 1)
+    dev.apply(upd, params)
+    assert dev.def_[0, 0] & 1 and dev.tru[0, 0] & 1 and dev.def_[0, 1] & 1 and not dev.tru[0, 1] & 1
+    assert not dev.def_[0, 0] & 2
+    assert dev.def_[0, 1] & 2 and not dev.tru[0, 1] & 2   # still false in the second slot
+    assert params[0].startVals == 3 and params[0].lastMask == 4  # in-progress slot 2 mirrors lastVarVal
+
+
+def test_32_slots_then_reuse_after_collapse():
+    # GpuSolverTest.cu:163-211 testManyAssignments
+    r = Rig(32, 1)
+    for i in range(32):
+        assert r.available(0)
+        r.set(0, i, TRUE if i % 2 == 0 else FALSE)
+        assert r.send(0) == i
+    assert not r.available(0)
+    upd, params = r.collect()
+    assert params[0].startVals == ALL and params[0].lastMask == 1 << 31
+    assert r.ids(0) == (0, 32)
+    dev = DeviceModel(32, 1)
+    dev.apply(upd, params)
+    dev.collapse(upd, params)
+    assert r.available(0)
+    r.set(0, 7, UNDEF); assert r.send(0) == 32
+    upd, params = r.collect()
+    dev.apply(upd, params)
+    assert params[0].startVals == 1 and r.ids(0) == (32, 1)
+    for i in range(32):
+        if i == 7:
+            assert dev.def_[0, i] & 1 == 0
+        else:
+            assert dev.def_[0, i] & 1 == 1 and bool(dev.tru[0, i] & 1) == (i % 2 == 0)
+
+
+def test_aggregate_words_golden():
+    # GpuSolverTest.cu:213-243 testAssigAggregates: 2 solvers x 32 slots on one variable
+    r = Rig(1, 2)
+    for s in range(2):
+        for i in range(32):
+            r.set(s, 0, (TRUE if s == 0 else FALSE) if i % 2 == 0 else UNDEF)
+            r.send(s)
+    upd, params = r.collect()
+    assert params[0].usedAggBits | params[1].usedAggBits == ALL
+    assert params[0].allAggBits == 0x0000FFFF and params[1].allAggBits == 0xFFFF0000
+    dev = DeviceModel(1, 2)
+    dev.apply(upd, params)
+    assert dev.can_true[0] == 0x0000FFFF
+    assert dev.can_false[0] == 0xFFFF0000
+    assert dev.can_undef[0] == ALL
+
+
+def test_aggregate_bit_partition_like_reference():
+    # Assigs.cu:402-426: 32 bits over n solvers, the first 32 % n get one more
+    for n in (1, 2, 3, 5, 7, 32):
+        r = Rig(1, n)
+        for s in range(n):
+            r.set(s, 0, TRUE); r.send(s)
+        _, params = r.collect()
+        sizes = [bin(p.allAggBits).count("1") for p in params]
+        assert sum(sizes) == 32 and sizes == sorted(sizes, reverse=True)
+        assert max(sizes) - min(sizes) <= 1
+        union = 0
+        for p in params:
+            assert union & p.allAggBits == 0
+            union |= p.allAggBits
+            assert p.nGroups == 1  # one frozen slot -> one aggregate bit in use
+    # more than 32 solvers: every group of 32 has its own aggregate word (the reference gives
+    # solvers 32.. no bit at all, Assigs.cu:409-425)
+    r = Rig(1, 40)
+    for s in range(40):
+        r.send(s)
+    _, params = r.collect()
+    assert all(p.allAggBits != 0 for p in params)
+    assert params[32].allAggBits & 1 and sum(bin(p.allAggBits).count("1") for p in params[32:]) == 32
+
+
+def test_slot_groups_cover_frozen_slots():
+    # Assigs.cu:263-284: k = min(bits, frozen) groups, sizes differ by at most one, ids in order
+    r = Rig(1, 3)  # solver 0 owns 11 aggregate bits
+    for i in range(25):
+        r.send(0)
+    _, params = r.collect()
+    p = params[0]
+    assert p.nGroups == 11 and p.startVals == (1 << 25) - 1
+    sizes = [bin(p.groupSlotMask[g]).count("1") for g in range(11)]
+    assert sizes == [3, 3, 3] + [2] * 8
+    u = 0
+    for g in range(11):
+        assert u & p.groupSlotMask[g] == 0
+        u |= p.groupSlotMask[g]
+    assert u == p.startVals
+
+
+def test_full_rebuild_lists_every_variable():
+    r = Rig(5, 1)
+    r.set(0, 1, TRUE); r.set(0, 3, FALSE); r.send(0)
+    r.collect()
+    r.set(0, 3, UNDEF); r.send(0)
+    upd, params = r.collect(full=True)
+    assert upd["var"].tolist() == [0, 1, 2, 3, 4]
+    # untouched variables carry their current value in every slot; variable 3 was unset after the
+    # previous batch had shipped, so the change covers all 32 slots
+    assert upd["def"].tolist() == [0, ALL, 0, 0, 0] and int(upd["tru"][1]) == ALL
+    assert params[0].startVals == 2 and params[0].updCount == 5
+
+
+def _run(r, hits):
+    r.collect()
+    r.fill(hits)
+
+
+def test_reported_counts_and_progress_marker():
+    r = Rig(3, 2)
+    ids = [r.add_clause([2 * v]) for v in range(3)]
+    assert ids == [0, 1, 2]
+    r.drain()
+    assert r.count(1) == 3 and r.db_clauses() == 3 and r.db_length_sum() == 3
+    r.send(0); r.send(0); r.send(1)
+    _run(r, [(3, 0, 1, 0), (1, 0, 1, 1), (2, 1, 1, 2)])
+    assert r.last_all_reported(0) == 0
+    assert [x[1] for x in r.pop_all(0)] == [0, 1]
+    assert r.pop_all(1) == [([4], 2)]
+    assert r.last_all_reported(0) == 2 and r.last_all_reported(1) == 1
+    assert r.stat(0, 3) == 2 and r.stat(0, 4) == 2  # reportedClauses, reportedClausesUnit
+
+
+def test_no_double_import_across_runs_and_reimport_later():
+    # GpuSolverTest.cu:540-563 and :566-603 / Reported.cu:105-158
+    r = Rig(2, 1)
+    r.add_clause([1, 2]); r.drain()
+    r.send(0)
+    _run(r, [(1, 0, 2, 0)])          # run A: assignment 0
+    r.send(0)                        # assignment 1 sent before the solver saw the report
+    assert len(r.pop_all(0)) == 1
+    _run(r, [(2, 0, 2, 0)])          # run B: assignment 1 did not know the clause -> suppressed
+    assert r.pop_all(0) == []
+    r.send(0)                        # assignment 2 knows it; if it fires again the solver deleted it
+    _run(r, [(4, 0, 2, 0)])
+    assert len(r.pop_all(0)) == 1
+    assert r.stat(0, 3) == 2 and r.stat(0, 5) == 2  # reportedClauses, reportedClausesBinary
+
+
+def test_exporter_echo_suppressed_until_known():
+    # Reported.cu:97-103 clauseWasAdded
+    r = Rig(2, 2)
+    r.send(0); r.send(1)
+    cid = r.add_clause([1, 3]); r.clause_was_added(0, cid); r.drain()
+    _run(r, [(1, 0, 2, 0), (1, 1, 2, 0)])
+    assert r.pop_all(0) == [] and len(r.pop_all(1)) == 1
+
+
+def test_duplicate_ends_batch_like_reference():
+    # Reported.cu:113-129: a re-reported clause falls through to the end-of-batch block
+    r = Rig(4, 1)
+    for v in range(3):
+        r.add_clause([2 * v])
+    r.drain()
+    r.send(0)
+    _run(r, [(1, 0, 1, 1)])              # clause 1 reported for assignment 0
+    r.send(0)
+    assert len(r.pop_all(0)) == 1
+    _run(r, [(2, 0, 1, 0), (2, 0, 1, 1), (2, 0, 1, 2)])   # batch: clause 0, then duplicate 1, then 2
+    got = r.pop_all(0)
+    assert [g[1] for g in got] == [0]    # clause 2 is abandoned with the batch, as in the reference
+
+
+def test_activity_decay_bump_and_reduce():
+    # ClauseActivityLbdTest.cu:59-275 / Clauses.cu:200-237,426-465 (activity-only policy)
+    r = Rig(10, 1, decay=0.5)
+    for i in range(8):
+        r.add_clause([2 * i, 2 * i + 2, 2 * ((i + 2) % 10)])   # length 3
+    r.add_clause([0, 2]); r.add_clause([4])
+    r.drain()
+    acts = [r.activity(3, i) for i in range(8)]
+    assert acts == [2.0 ** (i + 1) for i in range(8)]          # increment doubles per added clause
+    r.bump(3, 0)
+    assert r.activity(3, 0) == 2.0 + 2.0 ** 10
+    thr = r.approx_nth_act(5)
+    # activities: 4 8 16 32 [64] 128 256 512(len 2) 1024(len 1) 1026(bumped); the 5th smallest is 64 and
+    # the log-scale bucket is rounded UP (Clauses.cu:521), so the threshold lies just above it
+    assert 64.0 < thr <= 64.0 * 1.01
+    r.reduce_host()
+    # lengths 1 and 2 are never removed; length 3 keeps activity >= threshold
+    assert r.count(1) == 1 and r.count(2) == 1
+    kept = [r.clause_id(3, i) for i in range(r.count(3))]
+    assert kept == [0, 6, 7]
+    assert r.get_clause(3, 0) == [0, 2, 4]
+    assert r.db_clauses() == len(kept) + 2
+
+
+def test_activity_rescale():
+    r = Rig(4, 1, decay=1e-10)
+    r.add_clause([0, 2, 4]); r.add_clause([0, 2, 6]); r.add_clause([2, 4, 6])
+    r.drain()
+    # the increment passed 1e19 on the second clause and everything was rescaled (Clauses.cu:284-291)
+    assert r.activity(3, 2) < 1e19 and r.activity(3, 0) < r.activity(3, 1) < r.activity(3, 2)

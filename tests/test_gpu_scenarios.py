@@ -308,3 +308,28 @@ def test_no_run_on_empty_database():
     execute(sh)
     assert sh.trySendAssignment(0) == 32
     assert int(sh.debugLastHits()["mask"][0]) == 0xFFFFFFFF
+
+
+def test_large_hit_list_parallel_hand_over():
+    # > 8192 hits takes the per-solver parallel hand-over path: same batches, same order
+    n, nsolvers = 20000, 4
+    sh = make(n, nsolvers, gpuBlockCountGuideline=-1, gpuThreadsPerBlockGuideline=-1)
+    for i in range(n):
+        sh.addClause(-1, [mkLit(i), mkLit((i + 1) % n, True)])
+    for s in range(nsolvers):
+        # solver s: variable v false when v % (s + 2) == 0, else undefined
+        assert sh.trySetSolverValues(s, [mkLit(v, True) for v in range(0, n, s + 2)])
+        sh.trySendAssignment(s)
+    execute(sh)
+    hits = sh.debugLastHits()
+    for s in range(nsolvers):
+        m = s + 2
+        # clause i = (i, not i+1) fires iff i is false (no true literal, at most one undefined)
+        # and i+1 is not false (else its negation is true)
+        expect = [i for i in range(n) if i % m == 0 and ((i + 1) % n) % m != 0]
+        got = hits[hits["solver_id"] == s]["clause_id"].tolist()
+        assert got == expect
+        pops = popped(sh, s)
+        assert [p[1] for p in pops] == expect           # handed over in clause order
+        assert pops[0][0] == [mkLit(expect[0]), mkLit((expect[0] + 1) % n, True)]
+    assert len(hits) > 8192
