@@ -84,6 +84,10 @@ SIGNATURES = {
     "gss_mgpu_collect": (_I, [_P, C.POINTER(C.c_void_p), C.POINTER(_L), C.POINTER(C.c_void_p), C.POINTER(_L)]),
     "gss_mgpu_run": (None, [_P, C.c_void_p, _L, C.c_void_p, _L, _I]),
     "gss_mgpu_wait": (_L, [_P, C.POINTER(C.c_void_p)]),
+    "gss_mgpu_collect_to": (_L, [_P, C.c_void_p, _L]),
+    "gss_mgpu_run_payload": (_I, [_P, C.c_void_p, _L]),
+    "gss_mgpu_hits_to_device": (_L, [_P, C.c_void_p, _L]),
+    "gss_set_stream": (None, [_P, C.c_void_p]),
     "gss_mgpu_import": (None, [_P, C.c_void_p, _L]),
     "gss_version": (C.c_char_p, []),
     # include/gpushare_b200_synth.h
@@ -318,8 +322,8 @@ class GpuClauseSharer:
     def debugSetDense(self, dense):
         self._lib.gss_debug_set_dense(self._h, 1 if dense else 0)
 
-    def debugTimeCheck(self, iters, dense=False):
-        return self._lib.gss_debug_time_check(self._h, int(iters), 1 if dense else 0)
+    def debugTimeCheck(self, iters, dense=False, filter_only=False):
+        return self._lib.gss_debug_time_check(self._h, int(iters), 2 if filter_only else (1 if dense else 0))
 
     def debugLastRunTimes(self):
         t = (C.c_double * 4)()
@@ -352,6 +356,22 @@ class GpuClauseSharer:
 
     def mgpuRun(self, params_ptr, params_bytes, updates_ptr, n_updates, rebuild):
         self._lib.gss_mgpu_run(self._h, params_ptr, params_bytes, updates_ptr, n_updates, int(rebuild))
+
+    def mgpuCollectTo(self, dev_ptr, cap_bytes):
+        return self._lib.gss_mgpu_collect_to(self._h, dev_ptr, int(cap_bytes))
+
+    def mgpuRunPayload(self, dev_ptr, nbytes):
+        return self._lib.gss_mgpu_run_payload(self._h, dev_ptr, int(nbytes))
+
+    def mgpuHitsToDevice(self, dev_ptr, cap_records):
+        return self._lib.gss_mgpu_hits_to_device(self._h, dev_ptr, int(cap_records))
+
+    def mgpuWaitCount(self):
+        """wait for the run; returns this rank's hit count (hits stay on the device / in the library)"""
+        return self._lib.gss_mgpu_wait(self._h, None)
+
+    def setStream(self, cuda_stream):
+        self._lib.gss_set_stream(self._h, C.c_void_p(cuda_stream))
 
     def mgpuWait(self):
         """returns this rank's hits as a numpy array (mask, solver, len, idx) -- a copy"""

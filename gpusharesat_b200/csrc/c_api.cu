@@ -80,7 +80,10 @@ int64_t gss_debug_last_hits(gss_sharer *h, gss_hit *out, int64_t cap) { return h
 int64_t gss_add_clauses_bulk(gss_sharer *h, const int64_t *offsets, const int *lits, int64_t n) { return h->impl.addClausesBulk(offsets, lits, n); }
 void gss_set_max_clause_len(gss_sharer *h, int max_len) { h->impl.setMaxClauseLen(max_len); }
 void gss_debug_set_dense(gss_sharer *h, int dense) { h->impl.setDense(dense != 0); }
-double gss_debug_time_check(gss_sharer *h, int iters, int dense) { return h->impl.timeCheck(iters, dense != 0); }
+double gss_debug_time_check(gss_sharer *h, int iters, int dense) {
+    // dense: 0 production (k_filter + k_exact), 1 dense kernel, 2 k_filter alone
+    return h->impl.timeCheck(iters, dense == 1, dense == 2);
+}
 int gss_debug_last_run_times(gss_sharer *h, double out_us[4]) { return h->impl.lastRunTimes(out_us); }
 double gss_debug_lop3_peak(gss_sharer *h) { return h->impl.lop3Peak(); }
 void gss_debug_last_run_bytes(gss_sharer *h, int64_t *h2d, int64_t *d2h) { h->impl.lastRunBytes(h2d, d2h); }
@@ -93,7 +96,12 @@ int gss_mgpu_collect(gss_sharer *h, const void **params, int64_t *params_bytes, 
 void gss_mgpu_run(gss_sharer *h, const void *params, int64_t params_bytes, const void *updates, int64_t n_updates, int rebuild) {
     h->impl.mgpuRun(params, params_bytes, updates, n_updates, rebuild);
 }
+int64_t gss_mgpu_collect_to(gss_sharer *h, void *dev_dst, int64_t cap_bytes) { return h->impl.mgpuCollectTo(dev_dst, cap_bytes); }
+int gss_mgpu_run_payload(gss_sharer *h, const void *dev_payload, int64_t payload_bytes) { return h->impl.mgpuRunPayload(dev_payload, payload_bytes); }
+int64_t gss_mgpu_hits_to_device(gss_sharer *h, void *dev_dst, int64_t cap_records) { return h->impl.mgpuHitsToDevice(dev_dst, cap_records); }
+void gss_set_stream(gss_sharer *h, void *cuda_stream) { h->impl.setStream(cuda_stream); }
 int64_t gss_mgpu_wait(gss_sharer *h, const gss_raw_hit **hits) {
+    if (!hits) return h->impl.mgpuWait(nullptr);
     const gss::HitRecord *p = nullptr;
     int64_t n = h->impl.mgpuWait(&p);
     *hits = reinterpret_cast<const gss_raw_hit *>(p);

@@ -89,6 +89,8 @@ void ClauseDb::drainPending() {
         lens.swap(pendingLens_);
         firstId = pendingFirstId_;
     }
+    std::vector<char> wasEmpty(maxLen_ + 1, 0);
+    for (int s = 1; s <= maxLen_; s++) wasEmpty[s] = perLen_[s]->meta.empty();
     size_t pos = 0;
     for (size_t c = 0; c < lens.size(); c++) {
         // Clauses.cu:334 + Clauses.cuh:192: the increment decays once per added clause
@@ -96,6 +98,30 @@ void ClauseDb::drainPending() {
         appendToMirror(&lits[pos], lens[c], firstId + (int64_t)c);
         pos += lens[c];
     }
+    // bulk load into an empty arena: nothing refers to these clause indices yet, order them
+    for (int s = 1; s <= maxLen_; s++)
+        if (wasEmpty[s] && perLen_[s]->meta.size() >= kSortMinClauses) sortArena(s);
+}
+
+void ClauseDb::sortArena(int len) {
+    PerLen &pl = *perLen_[len];
+    const int64_t n = (int64_t)pl.meta.size();
+    if (n < 2) return;
+    // counting sort by first literal (stable: equal literals keep arrival order)
+    int32_t maxLit = 0;
+    for (int64_t i = 0; i < n; i++) maxLit = std::max(maxLit, pl.lits[wordPos(len, i, 0)]);
+    std::vector<int64_t> bucket((size_t)maxLit + 2, 0);
+    for (int64_t i = 0; i < n; i++) bucket[(size_t)pl.lits[wordPos(len, i, 0)] + 1]++;
+    for (size_t b = 1; b < bucket.size(); b++) bucket[b] += bucket[b - 1];
+    std::vector<int32_t> oldLits(pl.lits.data(), pl.lits.data() + pl.lits.size());
+    std::vector<ClauseMeta> oldMeta(pl.meta);
+    for (int64_t i = 0; i < n; i++) {
+        int64_t to = bucket[(size_t)oldLits[wordPos(len, i, 0)]]++;
+        for (int k = 0; k < len; k++) pl.lits[wordPos(len, to, k)] = oldLits[wordPos(len, i, k)];
+        pl.meta[to] = oldMeta[i];
+    }
+    pl.fullReupload = true;
+    pl.dirtyFrom = 0;
 }
 
 bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
@@ -246,6 +272,9 @@ void ClauseDb::reduceHost() {
         pl.fullReupload = true;
         pl.dirtyFrom = 0;
     }
+    // clause indices change anyway: put every arena back in first-literal order
+    for (int s = 1; s <= maxLen_; s++)
+        if ((int64_t)perLen_[s]->meta.size() >= kSortMinClauses) sortArena(s);
 }
 
 void ClauseDb::writeCnf(FILE *f, int varCount) const {

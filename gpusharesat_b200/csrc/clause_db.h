@@ -128,11 +128,18 @@ private:
                (size_t)(idx % kTileClauses);
     }
     void appendToMirror(const int *lits, int n, int64_t id);
+    // Reorder the clauses of one length by their first literal (ids and activities move along).
+    // Consecutive clauses of a tile then gather from neighbouring entries of the level-1 table, so
+    // the 128 first-literal gathers of a warp touch a handful of L2 sectors instead of 128.
+    // Changes clause indices: only when no run refers to this arena (bulk load into an empty
+    // arena, reduceDb).
+    void sortArena(int len);
     void rescaleActivity();
 
     int64_t localTiles(int64_t globalTiles) const {
         return globalTiles > shardRank_ ? (globalTiles - shardRank_ + shardWorld_ - 1) / shardWorld_ : 0;
     }
+    static constexpr int64_t kSortMinClauses = 1024;
     int maxLen_ = kDefaultMaxClauseLen;
     int shardRank_ = 0, shardWorld_ = 1;
     std::vector<std::unique_ptr<PerLen>> perLen_;

@@ -146,6 +146,14 @@ template <typename T> struct WarpStage {
     }
 };
 
+// aggregate bits in use by the solvers of this group; taken from the launch arguments, or -- when
+// the host launched without ever seeing the run parameters (multi-GPU receivers) -- from params
+__device__ __forceinline__ uint32_t groupAggStart(const CheckArgs &a, int lane) {
+    if (!a.aggStartOnDevice) return a.aggStart;
+    uint32_t v = lane < a.groupSolvers ? a.params[a.groupBase + lane].usedAggBits : 0u;
+    return __reduce_or_sync(FULL, v);
+}
+
 // directory lookup: first entry whose cumulative tile count exceeds `tile`
 __device__ __forceinline__ int findDir(const int *sTileEnd, int nDir, int tile) {
     int lo = 0, hi = nDir - 1;
@@ -172,7 +180,8 @@ __global__ void __launch_bounds__(256, 6) k_filter(CheckArgs a) {
     const int warp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
     const int nWarps = gridDim.x * warpsPerBlock;
     const uint2 *__restrict__ a1 = a.tables.a1 + (size_t)(a.groupBase / kMaxSolversPerGroup) * 2 * (size_t)a.tables.varCap;
-    const uint32_t start = a.aggStart;
+    const uint32_t start = groupAggStart(a, lane);
+    if (start == 0) return; // no frozen slot in this group
     __shared__ Survivor sStage[kMaxWarpsPerBlock][kStageCap];
     WarpStage<Survivor> stage{sStage[threadIdx.x >> 5], 0};
     unsigned int *survCounter = &a.counters->nSurvivors[a.groupBase / kMaxSolversPerGroup];
@@ -469,7 +478,7 @@ void launchCollapse(const VarUpdate *upd, const SolverRunParams *params, int nSo
     ++*launches;
 }
 
-void launchCheck(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches) {
+void launchFilterOnly(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches) {
     if (a.totalTiles == 0) return;
     int threads = dims.threads;
     size_t smem = (size_t)a.nDir * sizeof(int);
@@ -479,6 +488,12 @@ void launchCheck(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s
     k_filter<<<blocks, threads, smem, s>>>(a);
     checkLaunch("k_filter");
     ++*launches;
+}
+
+void launchCheck(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches) {
+    if (a.totalTiles == 0) return;
+    int threads = dims.threads;
+    launchFilterOnly(a, dims, numSMs, s, launches);
     // the survivor count is only known on the device: a fixed grid strides over it
     int blocks2 = resolveBlocks((const void *)k_exact, threads, 0, numSMs, dims.blocks, -1);
     k_exact<<<blocks2, threads, 0, s>>>(a);

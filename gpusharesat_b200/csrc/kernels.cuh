@@ -47,6 +47,7 @@ struct CheckArgs {
     int groupBase;                 // first solver of this group
     int groupSolvers;              // solvers in this group (<= 32)
     uint32_t aggStart;             // aggregate bits in use by this group this run
+    int aggStartOnDevice;          // != 0: the kernels derive aggStart from params (host never saw them)
     DeviceTables tables;
     Survivor *survivors;           // this group's survivor list
     unsigned int survCap;
@@ -62,6 +63,8 @@ void launchCollapse(const VarUpdate *upd, const SolverRunParams *params, int nSo
                     const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches);
 // production: aggregate filter + survivor compaction, then the exact pass on the survivors
 void launchCheck(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
+// level 1 alone (bench: per-kernel timing of the dominant production kernel)
+void launchFilterOnly(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
 // bench-only dense mode: no filter, no early exit
 void launchCheckDense(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
 

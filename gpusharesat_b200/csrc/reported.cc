@@ -1,6 +1,10 @@
 // reported.cc -- see reported.h
 #include "reported.h"
 #include "stats.h"
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 
 namespace gss {
 
@@ -120,6 +124,60 @@ void Reported::fillBuckets(const std::vector<AssigIds> &ids, const HitRecord *hi
         if (perSolver[s]) queues_[s]->publish();
 }
 
+void Reported::handOver(std::vector<HitRecord> &hits, const std::vector<AssigIds> &ids, int nSolvers) {
+    // The kernels append hits in scheduling order.  Sorting them makes everything downstream
+    // (activity bumps, batch order, hence which clause a solver sees first) reproducible;
+    // the reference hands them over in whatever order the atomics produced.
+    auto byClause = [](const HitRecord &a, const HitRecord &b) {
+        if (a.len != b.len) return a.len < b.len;
+        if (a.idx != b.idx) return a.idx < b.idx;
+        return a.solver < b.solver;
+    };
+    if (hits.size() < kParallelHits) {
+        std::sort(hits.begin(), hits.end(), byClause);
+        for (size_t i = 0; i < hits.size(); i++) {
+            if (i + 16 < hits.size()) db_.prefetchClause(hits[i + 16].len, hits[i + 16].idx);
+            db_.bumpActivity(hits[i].len, hits[i].idx);
+        }
+        fill(ids, hits.data(), hits.size());
+        return;
+    }
+    // Large hit list: the per-solver batches are independent.  Group the hits by solver (one
+    // counting pass), then sort / bump / copy literals per solver on the worker pool.  Every
+    // solver's batch ends up in the same (len, idx) order as on the serial path.
+    static const bool prof = getenv("GSS_PROFILE_HANDOVER") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    auto t0 = now();
+    std::vector<size_t> start(nSolvers + 1, 0);
+    for (const HitRecord &h : hits) start[h.solver + 1]++;
+    for (int s = 0; s < nSolvers; s++) start[s + 1] += start[s];
+    grouped_.resize(hits.size());
+    {
+        std::vector<size_t> cursor(start.begin(), start.end() - 1);
+        for (const HitRecord &h : hits) grouped_[cursor[h.solver]++] = h;
+    }
+    hits.swap(grouped_);
+    auto t1 = now();
+    if (!pool_) pool_ = std::make_unique<WorkerPool>(std::max(1, std::min(15, (int)std::thread::hardware_concurrency() - 1)));
+    std::atomic<bool> rescale{false};
+    fillBuckets(
+        ids, hits.data(), start,
+        [&](const std::function<void(int)> &perSolver) {
+            pool_->parallelFor(nSolvers, [&](int s) {
+                std::sort(hits.begin() + start[s], hits.begin() + start[s + 1], byClause);
+                perSolver(s);
+            });
+        },
+        [&](int len, int idx) {
+            if (db_.bumpActivityAtomic(len, idx)) rescale.store(true);
+        });
+    db_.rescaleIfNeeded(rescale.load());
+    if (prof) fprintf(stderr, "handOver: group %.0f us, sort+fill %.0f us (%zu hits)\n", us(t0, t1), us(t1, now()), hits.size());
+}
+
 bool Reported::pop(int s, int *&lits, int &count, int64_t &id) {
     while (true) {
         if (!current_[s]) queues_[s]->takeNext(current_[s]);
@@ -135,8 +193,12 @@ bool Reported::pop(int s, int *&lits, int &count, int64_t &id) {
                 if (count == 2) stats_[s][S_reportedClausesBinary]++;
                 return true;
             }
-            // NOTE: like the reference, a duplicate ends this batch (control reaches the
-            // end-of-batch block below); the remaining clauses of the batch are not delivered.
+            // Already handed over: skip it and look at the next clause of the batch.  In the
+            // reference control falls through to the end-of-batch block here, so one re-reported
+            // clause silently discards the REST of its batch (Reported.cu:113-129) -- with a
+            // reproducible hand-over order that would starve newly added clauses for good.
+            // GPUSHARE_REFERENCE_DUP_QUIRK=1 restores the reference behaviour (parity tests).
+            if (!referenceDupQuirk_) continue;
         }
         cur->assigWhichKnowsAboutThese = lastSent_[s] + 1;
         int64_t seenAllReportsUntil = cur->ids.start + cur->ids.count;

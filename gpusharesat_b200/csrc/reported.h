@@ -6,6 +6,7 @@
 #include "assigs.h"
 #include "clause_db.h"
 #include "common.h"
+#include "pool.h"
 #include <deque>
 #include <functional>
 #include <memory>
@@ -68,7 +69,8 @@ private:
 
 class Reported {
 public:
-    Reported(ClauseDb &db, std::vector<std::vector<uint64_t>> &oneSolverStats) : db_(db), stats_(oneSolverStats) {}
+    Reported(ClauseDb &db, std::vector<std::vector<uint64_t>> &oneSolverStats)
+        : db_(db), stats_(oneSolverStats), referenceDupQuirk_(getenv("GPUSHARE_REFERENCE_DUP_QUIRK") != nullptr) {}
     void setSolverCount(int n);
 
     void clauseWasAdded(int solver, int64_t clauseId);                 // Reported.cu:97-103
@@ -82,6 +84,12 @@ public:
     void fillBuckets(const std::vector<AssigIds> &ids, const HitRecord *hits, const std::vector<size_t> &start,
                      const std::function<void(const std::function<void(int)> &)> &forEach,
                      const std::function<void(int, int)> &bump);
+    // GPU thread: everything that happens to the hits of a finished run -- sort (reproducible
+    // hand-over order), activity bumps (Clauses.cu:231-237), batches.  Hit lists of kParallelHits or
+    // more are grouped by solver and processed per solver on a small worker pool; `hits` is
+    // reordered in place.
+    void handOver(std::vector<HitRecord> &hits, const std::vector<AssigIds> &ids, int nSolvers);
+    static constexpr size_t kParallelHits = 8192;
     // solver thread: Reported.cu:105-158
     bool pop(int solver, int *&lits, int &count, int64_t &id);
     int64_t lastAssigAllReported(int solver) const { return lastAllReported_[solver]; }
@@ -100,6 +108,9 @@ private:
     std::vector<int64_t> lastAllReported_;
     std::vector<std::queue<DontImport>> dontImport_;
     std::vector<int> tmpLits_;
+    bool referenceDupQuirk_;
+    std::vector<HitRecord> grouped_;   // scratch: hits grouped by solver
+    std::unique_ptr<WorkerPool> pool_; // created on the first large hit list
 };
 
 } // namespace gss

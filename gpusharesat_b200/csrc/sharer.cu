@@ -96,7 +96,7 @@ Sharer::~Sharer() {
         cudaEventDestroy(s.evAfterCheck);
         cudaEventDestroy(s.evEnd);
     }
-    if (stream_) cudaStreamDestroy(stream_);
+    if (stream_ && ownStream_) cudaStreamDestroy(stream_);
 }
 
 void Sharer::useDevice() { GSS_CUDA(cudaSetDevice(device_)); }
@@ -311,13 +311,14 @@ CheckArgs Sharer::checkArgs(const RunSlot &slot, int g) const {
     return a;
 }
 
-void Sharer::launchCheckKernels(RunSlot &slot, bool dense) {
+void Sharer::launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly) {
     GSS_CUDA(cudaMemsetAsync(resDev_.data(), 0, sizeof(Counters), stream_));
     int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
     for (int g = 0; g < groups; g++) {
         if (slot.aggStart[g] == 0) continue; // no frozen slot in this group
         CheckArgs a = checkArgs(slot, g);
-        if (dense) launchCheckDense(a, dims_, numSMs_, stream_, &launches_);
+        if (filterOnly) launchFilterOnly(a, dims_, numSMs_, stream_, &launches_);
+        else if (dense) launchCheckDense(a, dims_, numSMs_, stream_, &launches_);
         else launchCheck(a, dims_, numSMs_, stream_, &launches_);
     }
 }
@@ -348,7 +349,11 @@ bool Sharer::prepareRun(RunSlot &slot, bool &rebuild, int64_t &h2d) {
 // reference HostAssigs::fillAssigsAsync, Assigs.cu:326-372: every solver's deltas and run masks
 void Sharer::collectBatch(RunSlot &slot, bool rebuild) {
     SolverRunParams *params = (SolverRunParams *)(slot.headHost.data() + slot.dirBytes);
+    // the update staging starts with room for [PayloadHeader][SolverRunParams x nSolvers], so that
+    // the multi-GPU path can ship header + parameters + deltas as one contiguous payload
+    const size_t P = payloadPrefixRecords(slot.nSolvers);
     slot.updHost.clear();
+    slot.updHost.append(P);
     slot.ids.assign(slot.nSolvers, AssigIds{});
     slot.assigCount = 0;
     TimeAdder t(globalStats_[G_timeSpentFillingAssigs], opts_.quickProf != 0);
@@ -356,16 +361,17 @@ void Sharer::collectBatch(RunSlot &slot, bool rebuild) {
         SolverAssigs &sa = assigs_->solver(s);
         SolverRunParams &p = params[s];
         memset(&p, 0, sizeof(p));
-        p.updStart = (int32_t)slot.updHost.size();
+        p.updStart = (int32_t)(slot.updHost.size() - P);
         // a solver busy writing its assignment is skipped for this run (Assigs.cu:350);
         // during a table rebuild every solver must contribute, so wait for it
         bool locked = rebuild ? (sa.lock(), true) : sa.tryLock();
         if (!locked) continue;
         sa.collectLocked(slot.updHost, p, slot.ids[s], rebuild);
+        p.updStart -= (int32_t)P;
         sa.unlock();
         slot.assigCount += slot.ids[s].count;
     }
-    slot.nUpdates = (int64_t)slot.updHost.size();
+    slot.nUpdates = (int64_t)(slot.updHost.size() - P);
 }
 
 // device half of a run.  The run parameters are already in slot.headHost; `updSrc` may be a host
@@ -416,7 +422,7 @@ bool Sharer::startRun(RunSlot &slot) {
     bool rebuild = false;
     if (!prepareRun(slot, rebuild, h2d)) return false;
     collectBatch(slot, rebuild);
-    launchRun(slot, slot.updHost.data(), (int64_t)slot.updHost.size(), h2d);
+    launchRun(slot, slot.updHost.data() + payloadPrefixRecords(slot.nSolvers), slot.nUpdates, h2d);
     return true;
 }
 
@@ -439,11 +445,45 @@ int Sharer::mgpuCollect(const void **params, int64_t *paramsBytes, const void **
     if (!prepareRun(slot, rebuild, mgpuH2D_)) GSS_DIE("out of device memory (multi-GPU mode does not reduce the database by itself)");
     collectBatch(slot, rebuild);
     mgpuPending_ = (int)(&slot - slots_);
+    mgpuRebuild_ = rebuild;
     *params = slot.headHost.data() + slot.dirBytes;
     *paramsBytes = (int64_t)slot.nSolvers * (int64_t)sizeof(SolverRunParams);
-    *updates = slot.updHost.data();
+    *updates = slot.updHost.data() + payloadPrefixRecords(slot.nSolvers);
     *nUpdates = slot.nUpdates;
     return rebuild ? 1 : 0;
+}
+
+// rank 0: collect and ship the batch as ONE contiguous payload [header][params][deltas] into a
+// caller-provided device buffer (the NCCL broadcast source), H2D on the library's stream
+int64_t Sharer::mgpuCollectTo(void *devDst, int64_t capBytes) {
+    const void *params, *updates;
+    int64_t paramsBytes, nUpdates;
+    int r = mgpuCollect(&params, &paramsBytes, &updates, &nUpdates);
+    PayloadHeader hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    hdr.magic = kPayloadMagic;
+    if (r < 0) {
+        hdr.status = -1;
+        hdr.totalBytes = sizeof(hdr);
+        mgpuHdrHost_.resize(sizeof(hdr));
+        memcpy(mgpuHdrHost_.data(), &hdr, sizeof(hdr));
+        GSS_CUDA(cudaMemcpyAsync(devDst, mgpuHdrHost_.data(), sizeof(hdr), cudaMemcpyHostToDevice, stream_));
+        return (int64_t)sizeof(hdr);
+    }
+    RunSlot &slot = slots_[mgpuPending_];
+    const size_t P = payloadPrefixRecords(slot.nSolvers);
+    hdr.status = r;
+    hdr.nSolvers = slot.nSolvers;
+    hdr.prefixRecords = (int32_t)P;
+    hdr.nUpdates = nUpdates;
+    hdr.totalBytes = (int64_t)((P + (size_t)nUpdates) * sizeof(VarUpdate));
+    uint8_t *base = reinterpret_cast<uint8_t *>(slot.updHost.data());
+    memcpy(base, &hdr, sizeof(hdr));
+    memcpy(base + sizeof(hdr), params, (size_t)paramsBytes);
+    if (hdr.totalBytes > capBytes) GSS_DIE("multi-GPU payload buffer too small");
+    GSS_CUDA(cudaMemcpyAsync(devDst, base, (size_t)hdr.totalBytes, cudaMemcpyHostToDevice, stream_));
+    mgpuH2D_ += hdr.totalBytes;
+    return hdr.totalBytes;
 }
 
 void Sharer::mgpuRun(const void *params, int64_t paramsBytes, const void *updates, int64_t nUpdates, int rebuild) {
@@ -466,18 +506,59 @@ void Sharer::mgpuRun(const void *params, int64_t paramsBytes, const void *update
     }
     GSS_CHECK(paramsBytes == (int64_t)slot->nSolvers * (int64_t)sizeof(SolverRunParams));
     void *dst = slot->headHost.data() + slot->dirBytes;
-    if (params != dst) GSS_CUDA(cudaMemcpy(dst, params, (size_t)paramsBytes, cudaMemcpyDefault));
+    if (params != dst) {
+        GSS_CUDA(cudaMemcpyAsync(dst, params, (size_t)paramsBytes, cudaMemcpyDefault, stream_));
+        GSS_CUDA(cudaStreamSynchronize(stream_));
+    }
     launchRun(*slot, updates, nUpdates, h2d);
     cur_ = (int)(slot - slots_);
+}
+
+// every rank: run the batch whose packed payload sits in device memory (after the broadcast)
+int Sharer::mgpuRunPayload(const void *devPayload, int64_t payloadBytes) {
+    useDevice();
+    PayloadHeader hdr;
+    if (mgpuPending_ >= 0) { // rank 0 wrote it itself
+        memcpy(&hdr, slots_[mgpuPending_].updHost.data(), sizeof(hdr));
+    } else {
+        GSS_CUDA(cudaMemcpyAsync(&hdr, devPayload, sizeof(hdr), cudaMemcpyDeviceToHost, stream_));
+        GSS_CUDA(cudaStreamSynchronize(stream_));
+    }
+    if (hdr.magic != kPayloadMagic) GSS_DIE("multi-GPU payload header corrupt");
+    if (hdr.status < 0) return -1;
+    GSS_CHECK(hdr.totalBytes <= payloadBytes);
+    const uint8_t *base = static_cast<const uint8_t *>(devPayload);
+    mgpuRun(base + sizeof(hdr), (int64_t)hdr.nSolvers * (int64_t)sizeof(SolverRunParams),
+            base + (size_t)hdr.prefixRecords * sizeof(VarUpdate), hdr.nUpdates, hdr.status);
+    return hdr.status;
+}
+
+int64_t Sharer::mgpuHitsToDevice(void *devDst, int64_t capRecords) {
+    useDevice();
+    int64_t n = std::min<int64_t>((int64_t)hits_.size(), capRecords);
+    if (n > 0)
+        GSS_CUDA(cudaMemcpyAsync(devDst, resDev_.data() + sizeof(Counters), (size_t)n * sizeof(HitRecord),
+                                 cudaMemcpyDeviceToDevice, stream_));
+    return (int64_t)hits_.size();
+}
+
+void Sharer::setStream(void *stream) {
+    useDevice();
+    GSS_CUDA(cudaStreamSynchronize(stream_));
+    if (ownStream_) cudaStreamDestroy(stream_);
+    stream_ = static_cast<cudaStream_t>(stream);
+    ownStream_ = false;
 }
 
 int64_t Sharer::mgpuWait(const HitRecord **hits) {
     useDevice();
     GSS_CHECK(cur_ >= 0);
-    finishRun(slots_[cur_]);
+    // hits == nullptr: the caller gathers the hits from device memory (gss_mgpu_hits_to_device),
+    // only the count is needed on the host
+    finishRun(slots_[cur_], hits != nullptr);
     mgpuLast_ = cur_;
     cur_ = -1;
-    *hits = hits_.data();
+    if (hits) *hits = hits_.data();
     return (int64_t)hits_.size();
 }
 
@@ -487,7 +568,7 @@ void Sharer::mgpuImport(const HitRecord *hits, int64_t n) {
     processResults(slots_[mgpuLast_]);
 }
 
-void Sharer::finishRun(RunSlot &slot) {
+void Sharer::finishRun(RunSlot &slot, bool fetchAllHits) {
     GSS_CUDA(cudaEventSynchronize(slot.evEnd));
     float msCopy = 0, msApply = 0, msCheck = 0, msTotal = 0;
     cudaEventElapsedTime(&msCopy, slot.evStart, slot.evH2DDone);
@@ -521,7 +602,7 @@ void Sharer::finishRun(RunSlot &slot) {
     hits_.resize(c.nHits);
     size_t first = std::min((size_t)c.nHits, (slot.resHost.size() - sizeof(Counters)) / sizeof(HitRecord));
     if (first) memcpy(hits_.data(), slot.resHost.data() + sizeof(Counters), first * sizeof(HitRecord));
-    if (c.nHits > first) {
+    if (c.nHits > first && fetchAllHits) {
         size_t rest = c.nHits - first;
         GSS_CUDA(cudaMemcpyAsync(hits_.data() + first, resDev_.data() + sizeof(Counters) + first * sizeof(HitRecord),
                                  rest * sizeof(HitRecord), cudaMemcpyDeviceToHost, stream_));
@@ -539,53 +620,9 @@ void Sharer::processResults(RunSlot &slot) {
     globalStats_[G_totalAssigClauseTested] += (uint64_t)clCount * (uint64_t)slot.assigCount;
     globalStats_[G_clauseTestsOnGroups] += (uint64_t)clCount;
     globalStats_[G_gpuReports] += hits_.size();
-    // The kernels append hits in scheduling order.  Sorting them makes everything downstream
-    // (activity bumps, batch order, hence which clause a solver sees first) reproducible;
-    // the reference hands them over in whatever order the atomics produced.
-    auto byClause = [](const HitRecord &a, const HitRecord &b) {
-        if (a.len != b.len) return a.len < b.len;
-        if (a.idx != b.idx) return a.idx < b.idx;
-        return a.solver < b.solver;
-    };
     lastHitsValid_ = false; // gss_debug_last_hits converts hits_ on demand
-    if (hits_.size() < kParallelHits) {
-        std::sort(hits_.begin(), hits_.end(), byClause);
-        for (size_t i = 0; i < hits_.size(); i++) {
-            if (i + 16 < hits_.size()) db_->prefetchClause(hits_[i + 16].len, hits_[i + 16].idx);
-            db_->bumpActivity(hits_[i].len, hits_[i].idx);
-        }
-        TimeAdder t(globalStats_[G_timeSpentFillingReported], opts_.quickProf != 0);
-        reported_->fill(slot.ids, hits_.data(), hits_.size());
-        return;
-    }
-    // Large hit list: the per-solver batches are independent.  Group the hits by solver (one
-    // counting pass), then sort / bump / copy literals per solver on the worker pool.  Every
-    // solver's batch ends up in the same (len, idx) order as on the serial path.
     TimeAdder t(globalStats_[G_timeSpentFillingReported], opts_.quickProf != 0);
-    const int nSolvers = slot.nSolvers;
-    std::vector<size_t> start(nSolvers + 1, 0);
-    for (const HitRecord &h : hits_) start[h.solver + 1]++;
-    for (int s = 0; s < nSolvers; s++) start[s + 1] += start[s];
-    grouped_.resize(hits_.size());
-    {
-        std::vector<size_t> cursor(start.begin(), start.end() - 1);
-        for (const HitRecord &h : hits_) grouped_[cursor[h.solver]++] = h;
-    }
-    hits_.swap(grouped_);
-    if (!pool_) pool_ = std::make_unique<WorkerPool>(std::max(1, std::min(15, (int)std::thread::hardware_concurrency() - 1)));
-    std::atomic<bool> rescale{false};
-    reported_->fillBuckets(
-        slot.ids, hits_.data(), start,
-        [&](const std::function<void(int)> &perSolver) {
-            pool_->parallelFor(nSolvers, [&](int s) {
-                std::sort(hits_.begin() + start[s], hits_.begin() + start[s + 1], byClause);
-                perSolver(s);
-            });
-        },
-        [&](int len, int idx) {
-            if (db_->bumpActivityAtomic(len, idx)) rescale.store(true);
-        });
-    db_->rescaleIfNeeded(rescale.load());
+    reported_->handOver(hits_, slot.ids, slot.nSolvers);
 }
 
 void Sharer::materializeLastHits() {
@@ -606,7 +643,7 @@ int64_t Sharer::lastHits(gss_hit *out, int64_t cap) {
     return n;
 }
 
-double Sharer::timeCheck(int iters, bool dense) {
+double Sharer::timeCheck(int iters, bool dense, bool filterOnly) {
     useDevice();
     if (lastStarted_ < 0 || iters < 1) return -1.0;
     RunSlot &slot = slots_[lastStarted_];
@@ -614,10 +651,11 @@ double Sharer::timeCheck(int iters, bool dense) {
     cudaEvent_t e0, e1;
     GSS_CUDA(cudaEventCreate(&e0));
     GSS_CUDA(cudaEventCreate(&e1));
-    launchCheckKernels(slot, dense); // warm-up, also sizes nothing: overflow is handled by finishRun
+    launchCheckKernels(slot, dense, filterOnly); // warm-up
     GSS_CUDA(cudaEventRecord(e0, stream_));
-    for (int i = 0; i < iters; i++) launchCheckKernels(slot, dense);
+    for (int i = 0; i < iters; i++) launchCheckKernels(slot, dense, filterOnly);
     GSS_CUDA(cudaEventRecord(e1, stream_));
+    if (filterOnly) launchCheckKernels(slot, dense, false); // leave a complete result behind
     enqueueResultCopy(slot);
     GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
     GSS_CUDA(cudaEventSynchronize(e1));

@@ -6,7 +6,6 @@
 #include "assigs.h"
 #include "clause_db.h"
 #include "kernels.cuh"
-#include "pool.h"
 #include "reported.h"
 #include "stats.h"
 #include <memory>
@@ -44,7 +43,7 @@ public:
     int64_t addClausesBulk(const int64_t *offsets, const int *lits, int64_t n);
     void setMaxClauseLen(int n) { db_->setMaxLen(n); }
     void setDense(bool d) { dense_ = d; }
-    double timeCheck(int iters, bool dense);
+    double timeCheck(int iters, bool dense, bool filterOnly = false);
     int lastRunTimes(double out[4]);
     double lop3Peak();
     void lastRunBytes(int64_t *h2d, int64_t *d2h) { *h2d = lastH2D_; *d2h = lastD2H_; }
@@ -53,6 +52,10 @@ public:
     void setShard(int rank, int world) { db_->setShard(rank, world); }
     int mgpuCollect(const void **params, int64_t *paramsBytes, const void **updates, int64_t *nUpdates);
     void mgpuRun(const void *params, int64_t paramsBytes, const void *updates, int64_t nUpdates, int rebuild);
+    int64_t mgpuCollectTo(void *devDst, int64_t capBytes);
+    int mgpuRunPayload(const void *devPayload, int64_t payloadBytes);
+    int64_t mgpuHitsToDevice(void *devDst, int64_t capRecords);
+    void setStream(void *stream);
     int64_t mgpuWait(const HitRecord **hits);
     void mgpuImport(const HitRecord *hits, int64_t n);
     void dbSize(int64_t *ncl, int64_t *nlits) { *ncl = db_->stats().clauses; *nlits = db_->stats().lengthSum; }
@@ -83,9 +86,9 @@ private:
     void collectBatch(RunSlot &slot, bool rebuild);
     void launchRun(RunSlot &slot, const void *updSrc, int64_t nUpdates, int64_t &h2d);
     int nextSlot() const;
-    void finishRun(RunSlot &slot);     // wait, re-run on overflow, pull every hit to the host
+    void finishRun(RunSlot &slot, bool fetchAllHits = true);     // wait, re-run on overflow, pull every hit to the host
     void processResults(RunSlot &slot);
-    void launchCheckKernels(RunSlot &slot, bool dense);
+    void launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly = false);
     void enqueueResultCopy(RunSlot &slot);
     void materializeLastHits();
     bool ensureTables(bool &rebuild);
@@ -124,11 +127,27 @@ private:
     int mgpuPending_ = -1;  // multi-GPU: slot collected but not yet launched
     int mgpuLast_ = -1;     // multi-GPU: slot of the last finished run
     int64_t mgpuH2D_ = 0;
+    bool mgpuRebuild_ = false;
+    bool ownStream_ = true;
+    HostBuf<uint8_t> mgpuHdrHost_;
+
+    // multi-GPU payload = [PayloadHeader][SolverRunParams x nSolvers][VarUpdate x n], the first two
+    // padded to a whole number of VarUpdate records
+    struct PayloadHeader {
+        uint32_t magic;
+        int32_t status; // -1 nothing to run, 0 batch, 1 batch that rebuilds the tables
+        int32_t nSolvers;
+        int32_t prefixRecords;
+        int64_t nUpdates;
+        int64_t totalBytes;
+        int64_t pad[4];
+    };
+    static constexpr uint32_t kPayloadMagic = 0x47535331u; // "GSS1"
+    static size_t payloadPrefixRecords(int nSolvers) {
+        return (sizeof(PayloadHeader) + (size_t)nSolvers * sizeof(SolverRunParams) + sizeof(VarUpdate) - 1) / sizeof(VarUpdate);
+    }
 
     std::vector<HitRecord> hits_;   // hits of the run being processed
-    std::vector<HitRecord> grouped_; // scratch: hits grouped by solver
-    std::unique_ptr<WorkerPool> pool_; // created on the first large hit list
-    static constexpr size_t kParallelHits = 8192;
     std::vector<gss_hit> lastHits_; // sorted, for gss_debug_last_hits (built on demand)
     bool lastHitsValid_ = true;
     bool dense_ = false;

@@ -84,3 +84,105 @@ def run_batch(sh, dist, rank, world, device):
         sh.mgpuImport(allhits)
         return len(allhits)
     return len(mine)
+
+
+HEADER_BYTES = 64
+
+
+def _round_up(n, q):
+    return (n + q - 1) // q * q
+
+
+def _next_pow2(n):
+    p = 1
+    while p < n:
+        p *= 2
+    return p
+
+
+class ShardedRunner:
+    """Fast path: the library runs on torch's current stream, the batch travels as ONE packed
+    payload ([header][params][deltas], gss_mgpu_collect_to) and is broadcast with a single
+    collective whose size every rank predicts from the previous batch (a second collective only
+    when a batch outgrows the prediction); the per-rank hits are all-gathered from device memory.
+
+    Collectives per batch: one broadcast (payload) + one all_gather ([count][hits] per rank)."""
+
+    def __init__(self, sh, dist, rank, world, device, payload_cap=64 << 20, min_bcast=1 << 16):
+        self.sh, self.dist, self.rank, self.world, self.device = sh, dist, rank, world, device
+        self.payload = torch.empty(payload_cap, dtype=torch.uint8, device=device)
+        self.pred = min_bcast
+        self.min_bcast = min_bcast
+        self.hit_buf = torch.empty(1 << 16, dtype=torch.uint8, device=device)
+        self.counts = torch.zeros(world, dtype=torch.int64, device=device)
+        if device.type == "cuda":
+            sh.setStream(torch.cuda.current_stream(device).cuda_stream)
+        self.ev0 = self.ev1 = None
+        self.hit_pred = 4096
+
+    def device_us(self):
+        """device time of the last step from the start of the payload broadcast to the gathered hits"""
+        if self.ev0 is None or self.ev1 is None:
+            return 0.0
+        self.ev1.synchronize()
+        return self.ev0.elapsed_time(self.ev1) * 1e3
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def step(self):
+        """one batch; returns the total number of hits (rank 0) / local hits (others), None if nothing ran"""
+        sh, dist, rank, world = self.sh, self.dist, self.rank, self.world
+        cap = self.payload.numel()
+        cuda = self.device.type == "cuda"
+        rec = RAW_HIT_DTYPE.itemsize
+        total = sh.mgpuCollectTo(self.payload.data_ptr(), cap) if rank == 0 else 0
+        if cuda:  # device-side time of the exchange + kernels: from the broadcast to the gathered hits
+            self.ev0, self.ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.ev0.record()
+        n = min(self.pred, cap)
+        dist.broadcast(self.payload[:n], 0)
+        if rank != 0:
+            hdr = self.payload[:HEADER_BYTES].cpu().numpy()  # syncs the stream
+            total = int(hdr.view(np.int64)[3])
+        else:
+            self._sync()
+        if total > n:  # the batch outgrew the prediction: ship the rest
+            dist.broadcast(self.payload[n:min(cap, _round_up(total, 1 << 16))], 0)
+        self.pred = max(self.min_bcast, _round_up(total + total // 4, 1 << 16))
+        status = sh.mgpuRunPayload(self.payload.data_ptr(), cap)
+        if status < 0:
+            return None
+        mine = sh.mgpuWaitCount()
+        # Hit exchange with ONE collective: every rank contributes [count][hits...] padded to the
+        # size predicted from the previous batch; a second round only if some rank overflowed it.
+        slot = 16 + self.hit_pred * rec
+        if self.hit_buf.numel() < slot:
+            self.hit_buf = torch.empty(_next_pow2(slot), dtype=torch.uint8, device=self.device)
+        self.hit_buf[:16].copy_(torch.tensor([mine, 0], dtype=torch.int64).view(torch.uint8), non_blocking=True)
+        sh.mgpuHitsToDevice(self.hit_buf.data_ptr() + 16, self.hit_pred)
+        gathered = torch.empty(world * slot, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(gathered, self.hit_buf[:slot])
+        if cuda:
+            self.ev1.record()
+        host = gathered.cpu().numpy()
+        counts = [int(host[r * slot: r * slot + 8].view(np.int64)[0]) for r in range(world)]
+        m = max(counts)
+        if m > self.hit_pred:  # overflow: redo the gather with room for everything
+            self.hit_pred = _next_pow2(m)
+            slot = 16 + self.hit_pred * rec
+            if self.hit_buf.numel() < slot:
+                self.hit_buf = torch.empty(_next_pow2(slot), dtype=torch.uint8, device=self.device)
+            self.hit_buf[:16].copy_(torch.tensor([mine, 0], dtype=torch.int64).view(torch.uint8))
+            sh.mgpuHitsToDevice(self.hit_buf.data_ptr() + 16, self.hit_pred)
+            gathered = torch.empty(world * slot, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(gathered, self.hit_buf[:slot])
+            host = gathered.cpu().numpy()
+        self.hit_pred = max(1024, _round_up(m + m // 2, 1024))
+        if rank != 0:
+            return mine
+        parts = [host[r * slot + 16: r * slot + 16 + c * rec] for r, c in enumerate(counts) if c]
+        allhits = np.concatenate(parts).view(RAW_HIT_DTYPE) if parts else np.zeros(0, dtype=RAW_HIT_DTYPE)
+        sh.mgpuImport(allhits)
+        return len(allhits)

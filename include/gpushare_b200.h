@@ -122,7 +122,8 @@ void gss_debug_set_dense(gss_sharer *h, int dense);
 /* Re-launch the check kernels `iters` times on the tables of the last started run (the
  * assignment tables stay intact until the next run starts) and return the average device
  * time of one sweep in microseconds (CUDA events on the library's stream).  The hit buffer
- * of the last iteration replaces the run's hits.  GPU thread only; waits for the run. */
+ * of the last iteration replaces the run's hits.  GPU thread only; waits for the run.
+ * dense: 0 = production kernels (k_filter + k_exact), 1 = dense kernel, 2 = k_filter alone. */
 double gss_debug_time_check(gss_sharer *h, int iters, int dense);
 
 /* Device time in microseconds of the phases of the last gathered run (CUDA events on the
@@ -168,7 +169,20 @@ void    gss_set_shard(gss_sharer *h, int rank, int world);
  * -1 if there is no clause yet (nothing to run) */
 int     gss_mgpu_collect(gss_sharer *h, const void **params, int64_t *params_bytes, const void **updates, int64_t *n_updates);
 void    gss_mgpu_run(gss_sharer *h, const void *params, int64_t params_bytes, const void *updates, int64_t n_updates, int rebuild);
+/* hits == NULL: only wait and return the count (the hits are fetched with gss_mgpu_hits_to_device) */
 int64_t gss_mgpu_wait(gss_sharer *h, const gss_raw_hit **hits);
+/* Fast path used by bench.py: the batch as ONE packed payload [64 B header][params][deltas].
+ * gss_mgpu_collect_to (rank 0) collects and copies it host->device into dev_dst on the library's
+ * stream and returns its size in bytes (the header says "nothing to run" when there is no clause);
+ * after the broadcast every rank calls gss_mgpu_run_payload on its copy (returns -1 nothing ran,
+ * 0 batch, 1 batch that rebuilt the tables).  gss_mgpu_hits_to_device copies this rank's hits of
+ * the finished run device->device into dev_dst (the NCCL gather source) and returns their count. */
+int64_t gss_mgpu_collect_to(gss_sharer *h, void *dev_dst, int64_t cap_bytes);
+int     gss_mgpu_run_payload(gss_sharer *h, const void *dev_payload, int64_t payload_bytes);
+int64_t gss_mgpu_hits_to_device(gss_sharer *h, void *dev_dst, int64_t cap_records);
+/* Make the library enqueue everything on the caller's CUDA stream (e.g. torch's current stream,
+ * so that its work is ordered with the NCCL collectives without host synchronisation). */
+void    gss_set_stream(gss_sharer *h, void *cuda_stream);
 void    gss_mgpu_import(gss_sharer *h, const gss_raw_hit *hits, int64_t n);
 
 /* library build info: "gpushare_b200 <version> sm_100a" */

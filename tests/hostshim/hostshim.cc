@@ -5,6 +5,7 @@
 #include "../../gpusharesat_b200/csrc/clause_db.h"
 #include "../../gpusharesat_b200/csrc/reported.h"
 #include "../../gpusharesat_b200/csrc/stats.h"
+#include <chrono>
 #include <cstring>
 
 using namespace gss;
@@ -76,6 +77,14 @@ int hs_get_clause(HostRig *r, int len, int idx, int *out) {
 void hs_clause_was_added(HostRig *r, int s, int64_t id) { r->reported.clauseWasAdded(s, id); }
 // hits: (mask, solver, len, idx) quadruples; uses the ids of the last hs_collect
 void hs_fill(HostRig *r, const HitRecord *hits, int n) { r->reported.fill(r->ids, hits, (size_t)n); }
+// the whole post-run host path (sort, bumps, batches; parallel for large lists); returns microseconds
+double hs_hand_over(HostRig *r, const HitRecord *hits, int n) {
+    std::vector<HitRecord> v(hits, hits + n);
+    auto t0 = std::chrono::steady_clock::now();
+    r->reported.handOver(v, r->ids, r->assigs.solverCount());
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+}
+int64_t hs_add_clauses_bulk(HostRig *r, const int64_t *offsets, const int *lits, int64_t n) { return r->db.addClausesBulk(offsets, lits, n); }
 int hs_pop(HostRig *r, int s, int *lits, int *count, int64_t *id) {
     int *l;
     int c;

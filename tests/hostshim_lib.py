@@ -35,6 +35,8 @@ def load():
         "hs_approx_nth_act": (C.c_float, [P, Q]), "hs_reduce_host": (None, [P]),
         "hs_db_clauses": (Q, [P]), "hs_db_length_sum": (Q, [P]), "hs_get_clause": (I, [P, I, I, IP]),
         "hs_clause_was_added": (None, [P, I, Q]), "hs_fill": (None, [P, C.c_void_p, I]),
+        "hs_hand_over": (C.c_double, [P, C.c_void_p, I]),
+        "hs_add_clauses_bulk": (Q, [P, C.POINTER(Q), IP, Q]),
         "hs_pop": (I, [P, I, IP, IP, C.POINTER(Q)]), "hs_last_all_reported": (Q, [P, I]),
         "hs_solver_stat": (Q, [P, I, I]),
     }
@@ -101,6 +103,15 @@ class Rig:
     def fill(self, hits):
         a = np.array(hits, dtype=HIT) if len(hits) else np.zeros(0, dtype=HIT)
         self.L.hs_fill(self.h, a.ctypes.data, a.size)
+
+    def hand_over(self, hits):
+        a = np.ascontiguousarray(hits, dtype=HIT)
+        return self.L.hs_hand_over(self.h, a.ctypes.data, a.size)
+
+    def add_clauses_bulk(self, offsets, lits):
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        li = np.ascontiguousarray(lits, dtype=np.int32)
+        return self.L.hs_add_clauses_bulk(self.h, off.ctypes.data_as(C.POINTER(C.c_int64)), li.ctypes.data_as(C.POINTER(C.c_int)), off.size - 1)
 
     def pop(self, s):
         lits = (C.c_int * 1024)()

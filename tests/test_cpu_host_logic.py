@@ -179,8 +179,7 @@ def test_exporter_echo_suppressed_until_known():
     assert r.pop_all(0) == [] and len(r.pop_all(1)) == 1
 
 
-def test_duplicate_ends_batch_like_reference():
-    # Reported.cu:113-129: a re-reported clause falls through to the end-of-batch block
+def _dup_scenario():
     r = Rig(4, 1)
     for v in range(3):
         r.add_clause([2 * v])
@@ -190,8 +189,17 @@ def test_duplicate_ends_batch_like_reference():
     r.send(0)
     assert len(r.pop_all(0)) == 1
     _run(r, [(2, 0, 1, 0), (2, 0, 1, 1), (2, 0, 1, 2)])   # batch: clause 0, then duplicate 1, then 2
-    got = r.pop_all(0)
-    assert [g[1] for g in got] == [0]    # clause 2 is abandoned with the batch, as in the reference
+    return [g[1] for g in r.pop_all(0)]
+
+
+def test_duplicate_is_skipped_not_the_rest_of_the_batch(monkeypatch):
+    # Reported.cu:113-129: in the reference a re-reported clause falls through to the end-of-batch
+    # block and the rest of the batch (clause 2 here) is silently lost.  Deliberate difference:
+    # only the duplicate is skipped; GPUSHARE_REFERENCE_DUP_QUIRK=1 restores the reference behaviour.
+    monkeypatch.delenv("GPUSHARE_REFERENCE_DUP_QUIRK", raising=False)
+    assert _dup_scenario() == [0, 2]
+    monkeypatch.setenv("GPUSHARE_REFERENCE_DUP_QUIRK", "1")
+    assert _dup_scenario() == [0]
 
 
 def test_activity_decay_bump_and_reduce():

@@ -72,3 +72,109 @@ def test_payload_broadcast_and_hit_gather_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == {0: True, 1: True}
+
+
+class FakeSharer:
+    """stands in for the library in the ShardedRunner protocol test: scripted payload sizes and
+    hit counts, host memory instead of device memory"""
+
+    def __init__(self, rank, world, script):
+        import ctypes
+        self.C = ctypes
+        self.rank, self.world, self.script, self.k = rank, world, script, 0
+        self.imported = []
+        self.seen_payload = []
+
+    def setStream(self, s):
+        pass
+
+    def mgpuCollectTo(self, ptr, cap):
+        total, _ = self.script[self.k]
+        if total == 0:
+            hdr = np.zeros(8, dtype=np.int64)
+            hdr[0] = 0x47535331  # magic (the fake keeps the "nothing to run" status in its script)
+            hdr[3] = 64
+            self.C.memmove(ptr, hdr.ctypes.data, 64)
+            return 64
+        body = (np.arange(total, dtype=np.int64) * 7 + self.k) % 251
+        buf = body.astype(np.uint8)
+        hdr = np.zeros(8, dtype=np.int64)
+        hdr[0] = 0x47535331
+        hdr[3] = total
+        buf[:64] = hdr.view(np.uint8)
+        self.C.memmove(ptr, buf.ctypes.data, total)
+        return total
+
+    def mgpuRunPayload(self, ptr, cap):
+        total, _ = self.script[self.k]
+        if total == 0:
+            self.k += 1
+            return -1
+        got = np.ctypeslib.as_array((self.C.c_uint8 * total).from_address(ptr)).copy()
+        want = ((np.arange(total, dtype=np.int64) * 7 + self.k) % 251).astype(np.uint8)
+        self.seen_payload.append(bool(np.array_equal(got[64:], want[64:]) and got[:64].view(np.int64)[3] == total))
+        return 0
+
+    def _hits(self):
+        n = self.script[self.k][1] * (self.rank + 1)
+        h = np.zeros(n, dtype=RAW_HIT_DTYPE)
+        h["mask"] = np.arange(n) + 1
+        h["solver"] = self.rank
+        h["idx"] = self.k
+        return h
+
+    def mgpuWaitCount(self):
+        return len(self._hits())
+
+    def mgpuHitsToDevice(self, ptr, cap):
+        h = self._hits()
+        n = min(len(h), cap)
+        if n:
+            self.C.memmove(ptr, h.ctypes.data, n * 16)
+        return len(h)
+
+    def mgpuImport(self, hits):
+        self.imported.append(np.array(hits, copy=True))
+        self.k += 1
+
+
+def _runner_worker(rank, world, port, q):
+    from gpusharesat_b200 import mgpu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # (payload bytes, base hit count): growth beyond the prediction, shrink, nothing-to-run, hit overflow
+    script = [(70000, 10), (400000, 3), (65600, 0), (0, 0), (300000, 9000), (66000, 5)]
+    sh = FakeSharer(rank, world, script)
+    runner = mgpu.ShardedRunner(sh, dist, rank, world, torch.device("cpu"), payload_cap=1 << 20, min_bcast=1 << 16)
+    results = []
+    for k in range(len(script)):
+        sh.k = k
+        results.append(runner.step())
+    ok = all(sh.seen_payload) and len(sh.seen_payload) == 5
+    ok = ok and results[3] is None
+    if rank == 0:
+        steps = [k for k in range(len(script)) if script[k][0]]
+        ok = ok and len(sh.imported) == len(steps)
+        for imp, k in zip(sh.imported, steps):
+            base = script[k][1]
+            ok = ok and len(imp) == sum(base * (r + 1) for r in range(world))
+            for r in range(world):
+                part = imp[imp["solver"] == r]
+                ok = ok and part["mask"].tolist() == list(range(1, base * (r + 1) + 1)) and bool(np.all(part["idx"] == k))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_sharded_runner_protocol_world2_gloo():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_runner_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: True, 1: True}
