@@ -87,6 +87,10 @@ SIGNATURES = {
     "gss_mgpu_collect_to": (_L, [_P, C.c_void_p, _L]),
     "gss_mgpu_run_payload": (_I, [_P, C.c_void_p, _L]),
     "gss_mgpu_hits_to_device": (_L, [_P, C.c_void_p, _L]),
+    "gss_mgpu_enqueue_payload": (_I, [_P, C.c_void_p, _L]),
+    "gss_mgpu_redo_payload": (None, [_P, C.c_void_p, _L]),
+    "gss_mgpu_enqueue_result": (_L, [_P, C.c_void_p, _L]),
+    "gss_mgpu_finish": (_I, [_P]),
     "gss_set_stream": (None, [_P, C.c_void_p]),
     "gss_mgpu_import": (None, [_P, C.c_void_p, _L]),
     "gss_version": (C.c_char_p, []),
@@ -365,6 +369,18 @@ class GpuClauseSharer:
 
     def mgpuHitsToDevice(self, dev_ptr, cap_records):
         return self._lib.gss_mgpu_hits_to_device(self._h, dev_ptr, int(cap_records))
+
+    def mgpuEnqueuePayload(self, dev_ptr, valid_bytes):
+        return self._lib.gss_mgpu_enqueue_payload(self._h, dev_ptr, int(valid_bytes))
+
+    def mgpuRedoPayload(self, dev_ptr, total_bytes):
+        self._lib.gss_mgpu_redo_payload(self._h, dev_ptr, int(total_bytes))
+
+    def mgpuEnqueueResult(self, dev_ptr, cap_records):
+        return self._lib.gss_mgpu_enqueue_result(self._h, dev_ptr, int(cap_records))
+
+    def mgpuFinish(self):
+        return self._lib.gss_mgpu_finish(self._h)
 
     def mgpuWaitCount(self):
         """wait for the run; returns this rank's hit count (hits stay on the device / in the library)"""

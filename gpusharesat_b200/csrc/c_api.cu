@@ -99,6 +99,10 @@ void gss_mgpu_run(gss_sharer *h, const void *params, int64_t params_bytes, const
 int64_t gss_mgpu_collect_to(gss_sharer *h, void *dev_dst, int64_t cap_bytes) { return h->impl.mgpuCollectTo(dev_dst, cap_bytes); }
 int gss_mgpu_run_payload(gss_sharer *h, const void *dev_payload, int64_t payload_bytes) { return h->impl.mgpuRunPayload(dev_payload, payload_bytes); }
 int64_t gss_mgpu_hits_to_device(gss_sharer *h, void *dev_dst, int64_t cap_records) { return h->impl.mgpuHitsToDevice(dev_dst, cap_records); }
+int gss_mgpu_enqueue_payload(gss_sharer *h, const void *dev_payload, int64_t valid_bytes) { return h->impl.mgpuEnqueuePayload(dev_payload, valid_bytes); }
+void gss_mgpu_redo_payload(gss_sharer *h, const void *dev_payload, int64_t total_bytes) { h->impl.mgpuRedoPayload(dev_payload, total_bytes); }
+int64_t gss_mgpu_enqueue_result(gss_sharer *h, void *dev_dst, int64_t cap_records) { return h->impl.mgpuEnqueueResult(dev_dst, cap_records); }
+int gss_mgpu_finish(gss_sharer *h) { return h->impl.mgpuFinish(); }
 void gss_set_stream(gss_sharer *h, void *cuda_stream) { h->impl.setStream(cuda_stream); }
 int64_t gss_mgpu_wait(gss_sharer *h, const gss_raw_hit **hits) {
     if (!hits) return h->impl.mgpuWait(nullptr);

@@ -66,13 +66,16 @@ __global__ void k_fill_tables(DeviceTables t, int varFrom) {
 }
 
 // blockIdx.y = solver.  (reference dUpdateAssigs, Assigs.cu:100-116)
+// `avail` = number of update records that really are in `upd` (a multi-GPU receiver may have got
+// a truncated payload: it must never read past what arrived)
 __global__ void __launch_bounds__(256) k_apply_updates(const VarUpdate *__restrict__ upd,
-                                                       const SolverRunParams *__restrict__ params, DeviceTables t) {
+                                                       const SolverRunParams *__restrict__ params, DeviceTables t,
+                                                       long long avail) {
     __shared__ uint32_t sAgg[kSlots], sSlot[kSlots];
     const int s = blockIdx.y;
     const SolverRunParams &p = params[s];
-    const int n = p.updCount, nGroups = p.nGroups;
-    if (n == 0) return;
+    const int n = (int)max(0ll, min((long long)p.updCount, avail - (long long)p.updStart)), nGroups = p.nGroups;
+    if (n <= 0) return;
     if (threadIdx.x < kSlots) {
         sAgg[threadIdx.x] = p.groupAggBit[threadIdx.x];
         sSlot[threadIdx.x] = p.groupSlotMask[threadIdx.x];
@@ -99,10 +102,11 @@ __global__ void __launch_bounds__(256) k_apply_updates(const VarUpdate *__restri
 
 // blockIdx.y = solver.  (reference dSetAllAssigsToLast, Assigs.cu:127-141)
 __global__ void __launch_bounds__(256) k_collapse(const VarUpdate *__restrict__ upd,
-                                                  const SolverRunParams *__restrict__ params, DeviceTables t) {
+                                                  const SolverRunParams *__restrict__ params, DeviceTables t,
+                                                  long long avail) {
     const int s = blockIdx.y;
     const SolverRunParams &p = params[s];
-    const int n = p.updCount;
+    const int n = (int)max(0ll, min((long long)p.updCount, avail - (long long)p.updStart));
     const uint32_t last = p.lastMask, allAgg = p.allAggBits;
     const VarUpdate *u = upd + p.updStart;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -403,6 +407,15 @@ __global__ void __launch_bounds__(256) k_lop3_peak(uint32_t *out, int iters) {
     if (r == 0x12345678u) out[0] = r; // never true in practice; keeps the chains live
 }
 
+__global__ void k_finalize(const Counters *c, unsigned int hitCap, unsigned int survCap, int groups, long long *dst) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    bool over = c->nHits > hitCap;
+    for (int g = 0; g < groups && g < kMaxGroups; g++) over = over || c->nSurvivors[g] > survCap;
+    dst[0] = (long long)c->nHits;
+    dst[1] = over ? 1 : 0;
+    for (int i = 2; i < 8; i++) dst[i] = 0;
+}
+
 int resolveBlocks(const void *kernel, int threads, size_t smem, int numSMs, int requested, long long work) {
     int perSM = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, smem);
@@ -447,6 +460,13 @@ double measureLop3Peak(int numSMs, cudaStream_t s, int64_t *launches) {
     return best;
 }
 
+void launchFinalize(const Counters *counters, unsigned int hitCap, unsigned int survCap, int groups, long long *dstHeader,
+                    cudaStream_t s, int64_t *launches) {
+    k_finalize<<<1, 32, 0, s>>>(counters, hitCap, survCap, groups, dstHeader);
+    checkLaunch("k_finalize");
+    ++*launches;
+}
+
 void launchFillTables(const DeviceTables &t, int varFrom, cudaStream_t s, int64_t *launches) {
     if (t.varCap <= varFrom) return;
     k_fill_tables<<<592, 256, 0, s>>>(t, varFrom);
@@ -463,17 +483,17 @@ static dim3 updateGrid(int nSolvers, int maxUpdPerSolver, int numSMs) {
 }
 
 void launchApplyUpdates(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
-                        const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches) {
+                        int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches) {
     if (nSolvers == 0 || maxUpdPerSolver == 0) return;
-    k_apply_updates<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(upd, params, t);
+    k_apply_updates<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(upd, params, t, (long long)avail);
     checkLaunch("k_apply_updates");
     ++*launches;
 }
 
 void launchCollapse(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
-                    const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches) {
+                    int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches) {
     if (nSolvers == 0 || maxUpdPerSolver == 0) return;
-    k_collapse<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(upd, params, t);
+    k_collapse<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(upd, params, t, (long long)avail);
     checkLaunch("k_collapse");
     ++*launches;
 }

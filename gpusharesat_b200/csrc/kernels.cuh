@@ -58,15 +58,20 @@ struct CheckArgs {
 
 void launchFillTables(const DeviceTables &t, int varFrom, cudaStream_t s, int64_t *launches);
 void launchApplyUpdates(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
-                        const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches);
+                        int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches);
 void launchCollapse(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
-                    const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches);
+                    int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches);
 // production: aggregate filter + survivor compaction, then the exact pass on the survivors
 void launchCheck(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
 // level 1 alone (bench: per-kernel timing of the dominant production kernel)
 void launchFilterOnly(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
 // bench-only dense mode: no filter, no early exit
 void launchCheckDense(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
+
+// multi-GPU: 64-byte result header {nHits, overflow flag} written on the device, so that every rank
+// can tell from the gathered buffers whether some rank has to run again with larger buffers
+void launchFinalize(const Counters *counters, unsigned int hitCap, unsigned int survCap, int groups, long long *dstHeader,
+                    cudaStream_t s, int64_t *launches);
 
 // register-only LOP3 micro-benchmark: thread-level LOP3 per second on this device
 double measureLop3Peak(int numSMs, cudaStream_t s, int64_t *launches);

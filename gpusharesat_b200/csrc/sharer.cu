@@ -302,6 +302,7 @@ CheckArgs Sharer::checkArgs(const RunSlot &slot, int g) const {
     a.groupBase = g * kMaxSolversPerGroup;
     a.groupSolvers = std::min(kMaxSolversPerGroup, slot.nSolvers - a.groupBase);
     a.aggStart = slot.aggStart[g];
+    a.aggStartOnDevice = slot.aggOnDevice ? 1 : 0;
     a.tables = tables_;
     a.survivors = const_cast<Survivor *>(survDev_.data()) + (size_t)g * survCap_;
     a.survCap = (unsigned int)survCap_;
@@ -380,6 +381,7 @@ void Sharer::launchRun(RunSlot &slot, const void *updSrc, int64_t nUpdates, int6
     const SolverRunParams *params = (const SolverRunParams *)(slot.headHost.data() + slot.dirBytes);
     int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
     slot.aggStart.assign(groups, 0u);
+    slot.aggOnDevice = false;
     slot.maxUpd = 0;
     for (int s = 0; s < slot.nSolvers; s++) {
         slot.aggStart[s / kMaxSolversPerGroup] |= params[s].usedAggBits;
@@ -402,10 +404,10 @@ void Sharer::launchRun(RunSlot &slot, const void *updSrc, int64_t nUpdates, int6
     // the previous batch collapses to its last slot first (deferred dSetAllAssigsToLast)
     if (collapseSlot_ >= 0) {
         RunSlot &c = slots_[collapseSlot_];
-        launchCollapse(c.updDev.data(), c.paramsDev(), c.nSolvers, c.maxUpd, tables_, numSMs_, stream_, &launches_);
+        launchCollapse(c.updDev.data(), c.paramsDev(), c.nSolvers, c.maxUpd, c.nUpdates, tables_, numSMs_, stream_, &launches_);
         collapseSlot_ = -1;
     }
-    launchApplyUpdates(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, tables_, numSMs_, stream_, &launches_);
+    launchApplyUpdates(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, slot.nUpdates, tables_, numSMs_, stream_, &launches_);
     GSS_CUDA(cudaEventRecord(slot.evBeforeCheck, stream_));
     launchCheckKernels(slot, slot.dense);
     GSS_CUDA(cudaEventRecord(slot.evAfterCheck, stream_));
@@ -518,8 +520,14 @@ void Sharer::mgpuRun(const void *params, int64_t paramsBytes, const void *update
 int Sharer::mgpuRunPayload(const void *devPayload, int64_t payloadBytes) {
     useDevice();
     PayloadHeader hdr;
-    if (mgpuPending_ >= 0) { // rank 0 wrote it itself
-        memcpy(&hdr, slots_[mgpuPending_].updHost.data(), sizeof(hdr));
+    if (mgpuPending_ >= 0) { // rank 0 wrote it itself: no device round trip at all
+        RunSlot &slot = slots_[mgpuPending_];
+        memcpy(&hdr, slot.updHost.data(), sizeof(hdr));
+        if (hdr.status < 0) { mgpuPending_ = -1; return -1; }
+        const uint8_t *base = static_cast<const uint8_t *>(devPayload);
+        mgpuRun(slot.headHost.data() + slot.dirBytes, (int64_t)hdr.nSolvers * (int64_t)sizeof(SolverRunParams),
+                base + (size_t)hdr.prefixRecords * sizeof(VarUpdate), hdr.nUpdates, hdr.status);
+        return hdr.status;
     } else {
         GSS_CUDA(cudaMemcpyAsync(&hdr, devPayload, sizeof(hdr), cudaMemcpyDeviceToHost, stream_));
         GSS_CUDA(cudaStreamSynchronize(stream_));
@@ -531,6 +539,104 @@ int Sharer::mgpuRunPayload(const void *devPayload, int64_t payloadBytes) {
     mgpuRun(base + sizeof(hdr), (int64_t)hdr.nSolvers * (int64_t)sizeof(SolverRunParams),
             base + (size_t)hdr.prefixRecords * sizeof(VarUpdate), hdr.nUpdates, hdr.status);
     return hdr.status;
+}
+
+// receivers, asynchronous: enqueue the whole batch without ever looking at the payload on the host.
+// Counts and masks are read by the kernels from the device copy of the run parameters; grids are
+// sized from the upper bound the payload size gives.  Returns -1 when there is no clause yet.
+int Sharer::mgpuEnqueuePayload(const void *devPayload, int64_t validBytes) {
+    useDevice();
+    GSS_CHECK(cur_ < 0 && mgpuPending_ < 0);
+    db_->drainPending();
+    if (db_->stats().clauses == 0) return -1;
+    RunSlot &slot = slots_[nextSlot()];
+    bool rebuild = false;
+    int64_t h2d = 0;
+    if (!prepareRun(slot, rebuild, h2d)) GSS_DIE("out of device memory (multi-GPU mode)");
+    slot.ids.assign(slot.nSolvers, AssigIds{});
+    slot.assigCount = 0;
+    enqueueFromDevicePayload(slot, devPayload, validBytes, true, h2d);
+    cur_ = (int)(&slot - slots_);
+    return rebuild ? 1 : 0;
+}
+
+void Sharer::enqueueFromDevicePayload(RunSlot &slot, const void *devPayload, int64_t validBytes, bool collapsePrev, int64_t h2d) {
+    const uint8_t *base = static_cast<const uint8_t *>(devPayload);
+    const size_t P = payloadPrefixRecords(slot.nSolvers);
+    int64_t nUpper = validBytes / (int64_t)sizeof(VarUpdate) - (int64_t)P;
+    if (nUpper < 0) nUpper = 0;
+    int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
+    slot.aggStart.assign(groups, ~0u);
+    slot.aggOnDevice = true;
+    slot.maxUpd = (int)std::min<int64_t>(nUpper, 1 << 30);
+    slot.nUpdates = nUpper;
+    slot.dense = dense_;
+    slot.headDev.reserve(slot.headHost.size(), 0, stream_);
+    GSS_CUDA(cudaMemcpyAsync(slot.headDev.data(), slot.headHost.data(), slot.dirBytes, cudaMemcpyHostToDevice, stream_));
+    GSS_CUDA(cudaMemcpyAsync(slot.headDev.data() + slot.dirBytes, base + sizeof(PayloadHeader),
+                             (size_t)slot.nSolvers * sizeof(SolverRunParams), cudaMemcpyDeviceToDevice, stream_));
+    if (nUpper) {
+        slot.updDev.reserve((size_t)nUpper, 0, stream_);
+        GSS_CUDA(cudaMemcpyAsync(slot.updDev.data(), base + P * sizeof(VarUpdate), (size_t)nUpper * sizeof(VarUpdate),
+                                 cudaMemcpyDeviceToDevice, stream_));
+    }
+    ensureResultBuffers();
+    GSS_CUDA(cudaEventRecord(slot.evH2DDone, stream_));
+    if (collapsePrev && collapseSlot_ >= 0) {
+        RunSlot &c = slots_[collapseSlot_];
+        launchCollapse(c.updDev.data(), c.paramsDev(), c.nSolvers, c.maxUpd, c.nUpdates, tables_, numSMs_, stream_, &launches_);
+        collapseSlot_ = -1;
+    }
+    launchApplyUpdates(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, slot.nUpdates, tables_, numSMs_, stream_, &launches_);
+    GSS_CUDA(cudaEventRecord(slot.evBeforeCheck, stream_));
+    launchCheckKernels(slot, slot.dense);
+    GSS_CUDA(cudaEventRecord(slot.evAfterCheck, stream_));
+    enqueueResultCopy(slot);
+    GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
+    slot.inFlight = true;
+    collapseSlot_ = (int)(&slot - slots_);
+    lastStarted_ = (int)(&slot - slots_);
+    lastH2D_ = h2d;
+}
+
+// receivers: the broadcast was truncated (the batch outgrew the predicted size); run the same batch
+// again on the complete payload.  apply is idempotent and the previous batch is already collapsed.
+void Sharer::mgpuRedoPayload(const void *devPayload, int64_t totalBytes) {
+    useDevice();
+    GSS_CHECK(cur_ < 0 && mgpuLast_ >= 0);
+    RunSlot &slot = slots_[mgpuLast_];
+    GSS_CUDA(cudaEventRecord(slot.evStart, stream_));
+    collapseSlot_ = -1;
+    enqueueFromDevicePayload(slot, devPayload, totalBytes, false, 0);
+    cur_ = mgpuLast_;
+}
+
+// enqueue [64 B header {nHits, overflow}][hits x capRecords] of the run in flight into devDst
+int64_t Sharer::mgpuEnqueueResult(void *devDst, int64_t capRecords) {
+    useDevice();
+    int slotIdx = cur_ >= 0 ? cur_ : mgpuLast_;
+    GSS_CHECK(slotIdx >= 0);
+    RunSlot &slot = slots_[slotIdx];
+    int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
+    launchFinalize((const Counters *)resDev_.data(), (unsigned int)hitCap_, (unsigned int)survCap_, groups,
+                   static_cast<long long *>(devDst), stream_, &launches_);
+    int64_t n = std::min<int64_t>(capRecords, (int64_t)hitCap_);
+    if (n > 0)
+        GSS_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(devDst) + 64, resDev_.data() + sizeof(Counters),
+                                 (size_t)n * sizeof(HitRecord), cudaMemcpyDeviceToDevice, stream_));
+    return 64 + n * (int64_t)sizeof(HitRecord);
+}
+
+// after the caller has synchronised: bookkeeping of the finished run; returns 1 when this rank had
+// to run again with larger buffers (what it contributed to the gather is stale), else 0
+int Sharer::mgpuFinish() {
+    useDevice();
+    GSS_CHECK(cur_ >= 0);
+    finishReran_ = false;
+    finishRun(slots_[cur_], false);
+    mgpuLast_ = cur_;
+    cur_ = -1;
+    return finishReran_ ? 1 : 0;
 }
 
 int64_t Sharer::mgpuHitsToDevice(void *devDst, int64_t capRecords) {
@@ -589,6 +695,7 @@ void Sharer::finishRun(RunSlot &slot, bool fetchAllHits) {
         for (int g = 0; g < kMaxGroups; g++) maxSurv = std::max(maxSurv, (size_t)c.nSurvivors[g]);
         if (c.nHits <= hitCap_ && maxSurv <= survCap_) break;
         GSS_CHECK(attempt < 8);
+        finishReran_ = true;
         // Overflow: the tables of this run are still intact (collapse is deferred), so grow the
         // buffers and run the check again.  Nothing is dropped.
         if (c.nHits > hitCap_) hitCap_ = std::max(hitCap_ * 2, (size_t)c.nHits + c.nHits / 4);

@@ -54,6 +54,10 @@ public:
     void mgpuRun(const void *params, int64_t paramsBytes, const void *updates, int64_t nUpdates, int rebuild);
     int64_t mgpuCollectTo(void *devDst, int64_t capBytes);
     int mgpuRunPayload(const void *devPayload, int64_t payloadBytes);
+    int mgpuEnqueuePayload(const void *devPayload, int64_t validBytes);
+    void mgpuRedoPayload(const void *devPayload, int64_t totalBytes);
+    int64_t mgpuEnqueueResult(void *devDst, int64_t capRecords);
+    int mgpuFinish();
     int64_t mgpuHitsToDevice(void *devDst, int64_t capRecords);
     void setStream(void *stream);
     int64_t mgpuWait(const HitRecord **hits);
@@ -73,6 +77,7 @@ private:
         int64_t nUpdates = 0;
         bool dense = false;
         bool inFlight = false;
+        bool aggOnDevice = false; // multi-GPU receiver: the host never saw the run parameters
         cudaEvent_t evStart = nullptr, evH2DDone = nullptr, evBeforeCheck = nullptr, evAfterCheck = nullptr, evEnd = nullptr;
         const LenDir *dirDev() const { return (const LenDir *)headDev.data(); }
         const SolverRunParams *paramsDev() const { return (const SolverRunParams *)(headDev.data() + dirBytes); }
@@ -86,6 +91,7 @@ private:
     void collectBatch(RunSlot &slot, bool rebuild);
     void launchRun(RunSlot &slot, const void *updSrc, int64_t nUpdates, int64_t &h2d);
     int nextSlot() const;
+    void enqueueFromDevicePayload(RunSlot &slot, const void *devPayload, int64_t validBytes, bool collapsePrev, int64_t h2d);
     void finishRun(RunSlot &slot, bool fetchAllHits = true);     // wait, re-run on overflow, pull every hit to the host
     void processResults(RunSlot &slot);
     void launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly = false);
@@ -128,6 +134,7 @@ private:
     int mgpuLast_ = -1;     // multi-GPU: slot of the last finished run
     int64_t mgpuH2D_ = 0;
     bool mgpuRebuild_ = false;
+    bool finishReran_ = false;
     bool ownStream_ = true;
     HostBuf<uint8_t> mgpuHdrHost_;
 

@@ -131,8 +131,24 @@ class ShardedRunner:
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
 
+    def _gather(self, enqueue=True):
+        """all-gather of [64 B header][hits x hit_pred] from every rank; returns (host headers
+        [world, 8] int64, gathered device tensor, slot bytes)"""
+        rec = RAW_HIT_DTYPE.itemsize
+        slot = HEADER_BYTES + self.hit_pred * rec
+        if self.hit_buf.numel() < slot:
+            self.hit_buf = torch.empty(_next_pow2(slot), dtype=torch.uint8, device=self.device)
+        self.sh.mgpuEnqueueResult(self.hit_buf.data_ptr(), self.hit_pred)
+        gathered = torch.empty(self.world * slot, dtype=torch.uint8, device=self.device)
+        self.dist.all_gather_into_tensor(gathered, self.hit_buf[:slot])
+        return gathered, slot
+
     def step(self):
-        """one batch; returns the total number of hits (rank 0) / local hits (others), None if nothing ran"""
+        """One batch.  Between the payload broadcast and the gathered hits nothing synchronises with
+        the host: receivers enqueue the batch blindly (gss_mgpu_enqueue_payload), every rank
+        enqueues its result block, one all-gather, ONE synchronisation at the end.  Mis-predicted
+        sizes (payload or hit block) are detected from the headers afterwards and repaired with a
+        second round.  Returns the total number of hits (rank 0) / 0 (others), None if nothing ran."""
         sh, dist, rank, world = self.sh, self.dist, self.rank, self.world
         cap = self.payload.numel()
         cuda = self.device.type == "cuda"
@@ -143,46 +159,50 @@ class ShardedRunner:
             self.ev0.record()
         n = min(self.pred, cap)
         dist.broadcast(self.payload[:n], 0)
-        if rank != 0:
-            hdr = self.payload[:HEADER_BYTES].cpu().numpy()  # syncs the stream
-            total = int(hdr.view(np.int64)[3])
+        if rank == 0:
+            status = sh.mgpuRunPayload(self.payload.data_ptr(), cap)
         else:
+            status = sh.mgpuEnqueuePayload(self.payload.data_ptr(), n)
+        if status < 0:  # no clause anywhere yet (every rank holds the same clause stream)
             self._sync()
-        if total > n:  # the batch outgrew the prediction: ship the rest
-            dist.broadcast(self.payload[n:min(cap, _round_up(total, 1 << 16))], 0)
-        self.pred = max(self.min_bcast, _round_up(total + total // 4, 1 << 16))
-        status = sh.mgpuRunPayload(self.payload.data_ptr(), cap)
-        if status < 0:
             return None
-        mine = sh.mgpuWaitCount()
-        # Hit exchange with ONE collective: every rank contributes [count][hits...] padded to the
-        # size predicted from the previous batch; a second round only if some rank overflowed it.
-        slot = 16 + self.hit_pred * rec
-        if self.hit_buf.numel() < slot:
-            self.hit_buf = torch.empty(_next_pow2(slot), dtype=torch.uint8, device=self.device)
-        self.hit_buf[:16].copy_(torch.tensor([mine, 0], dtype=torch.int64).view(torch.uint8), non_blocking=True)
-        sh.mgpuHitsToDevice(self.hit_buf.data_ptr() + 16, self.hit_pred)
-        gathered = torch.empty(world * slot, dtype=torch.uint8, device=self.device)
-        dist.all_gather_into_tensor(gathered, self.hit_buf[:slot])
+        gathered, slot = self._gather()
         if cuda:
             self.ev1.record()
-        host = gathered.cpu().numpy()
-        counts = [int(host[r * slot: r * slot + 8].view(np.int64)[0]) for r in range(world)]
-        m = max(counts)
-        if m > self.hit_pred:  # overflow: redo the gather with room for everything
-            self.hit_pred = _next_pow2(m)
-            slot = 16 + self.hit_pred * rec
-            if self.hit_buf.numel() < slot:
-                self.hit_buf = torch.empty(_next_pow2(slot), dtype=torch.uint8, device=self.device)
-            self.hit_buf[:16].copy_(torch.tensor([mine, 0], dtype=torch.int64).view(torch.uint8))
-            sh.mgpuHitsToDevice(self.hit_buf.data_ptr() + 16, self.hit_pred)
-            gathered = torch.empty(world * slot, dtype=torch.uint8, device=self.device)
-            dist.all_gather_into_tensor(gathered, self.hit_buf[:slot])
+        # ---- the only synchronisation of the step ----
+        if rank == 0:
             host = gathered.cpu().numpy()
+            heads = host.reshape(world, slot)[:, :HEADER_BYTES].copy().view(np.int64)
+        else:
+            heads = gathered.view(world, slot)[:, :HEADER_BYTES].contiguous().cpu().numpy().view(np.int64)
+            total = int(self.payload[:HEADER_BYTES].cpu().numpy().view(np.int64)[3])
+        sh.mgpuFinish()  # a rank whose header says "overflow" grows its buffers and runs again in here
+        counts, flags = heads[:, 0].tolist(), heads[:, 1].tolist()
+        redo_in_flight = False
+        if total > n:  # the batch outgrew the predicted broadcast: ship the rest, receivers run again
+            dist.broadcast(self.payload[n:min(cap, _round_up(total, 1 << 16))], 0)
+            if rank != 0:
+                sh.mgpuRedoPayload(self.payload.data_ptr(), total)
+                redo_in_flight = True
+            need = True
+        else:
+            need = any(flags) or max(counts) > self.hit_pred
+        while need:  # second round(s): every rank re-contributes its (now complete) result block
+            self.hit_pred = max(self.hit_pred, _next_pow2(max(counts) + 1))
+            gathered, slot = self._gather()
+            host = gathered.cpu().numpy()
+            heads = host.reshape(world, slot)[:, :HEADER_BYTES].copy().view(np.int64)
+            if redo_in_flight:
+                sh.mgpuFinish()
+                redo_in_flight = False
+            counts, flags = heads[:, 0].tolist(), heads[:, 1].tolist()
+            need = any(flags) or max(counts) > self.hit_pred
+        self.pred = max(self.min_bcast, _round_up(total + total // 4, 1 << 16))
+        m = max(counts)
         self.hit_pred = max(1024, _round_up(m + m // 2, 1024))
         if rank != 0:
-            return mine
-        parts = [host[r * slot + 16: r * slot + 16 + c * rec] for r, c in enumerate(counts) if c]
+            return 0
+        parts = [host[r * slot + HEADER_BYTES: r * slot + HEADER_BYTES + c * rec] for r, c in enumerate(counts) if c]
         allhits = np.concatenate(parts).view(RAW_HIT_DTYPE) if parts else np.zeros(0, dtype=RAW_HIT_DTYPE)
         sh.mgpuImport(allhits)
         return len(allhits)

@@ -180,6 +180,19 @@ int64_t gss_mgpu_wait(gss_sharer *h, const gss_raw_hit **hits);
 int64_t gss_mgpu_collect_to(gss_sharer *h, void *dev_dst, int64_t cap_bytes);
 int     gss_mgpu_run_payload(gss_sharer *h, const void *dev_payload, int64_t payload_bytes);
 int64_t gss_mgpu_hits_to_device(gss_sharer *h, void *dev_dst, int64_t cap_records);
+/* Fully asynchronous receiver path (no host synchronisation between the broadcast and the gather):
+ * gss_mgpu_enqueue_payload (ranks != 0) enqueues the whole batch from the first valid_bytes of the
+ * broadcast payload without reading it on the host (-1: no clause yet); gss_mgpu_enqueue_result
+ * (all ranks) enqueues [64 B header {int64 nHits, int64 overflow}][hits x cap_records] into dev_dst
+ * (the all-gather source) and returns its size; after the caller has synchronised,
+ * gss_mgpu_finish (all ranks) closes the run and returns 1 if this rank had to run again with
+ * larger buffers (its header said overflow).  gss_mgpu_redo_payload (ranks != 0) runs the same batch
+ * again on the complete payload when the broadcast had been truncated (header.totalBytes, the 4th
+ * int64 of the payload, exceeded the predicted broadcast size). */
+int     gss_mgpu_enqueue_payload(gss_sharer *h, const void *dev_payload, int64_t valid_bytes);
+void    gss_mgpu_redo_payload(gss_sharer *h, const void *dev_payload, int64_t total_bytes);
+int64_t gss_mgpu_enqueue_result(gss_sharer *h, void *dev_dst, int64_t cap_records);
+int     gss_mgpu_finish(gss_sharer *h);
 /* Make the library enqueue everything on the caller's CUDA stream (e.g. torch's current stream,
  * so that its work is ordered with the NCCL collectives without host synchronisation). */
 void    gss_set_stream(gss_sharer *h, void *cuda_stream);

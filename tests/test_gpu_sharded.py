@@ -121,3 +121,80 @@ def test_packed_payload_fast_path_single_device():
         ranks[0].mgpuImport(np.concatenate(parts))
         want = model.run(); model.run()
         assert np.array_equal(ranks[0].debugLastHits(), want) and len(want) > 0
+
+
+def test_async_receiver_path_truncated_payload_and_overflowing_buffers():
+    """gss_mgpu_enqueue_payload / _enqueue_result / _finish / _redo_payload: the receiver never
+    looks at the payload on the host.  Exercises a truncated broadcast (first prediction far too
+    small) and survivor / hit buffers that start at ONE record (device overflow flags)."""
+    import torch
+    from gpusharesat_b200.api import RAW_HIT_DTYPE
+    rng = np.random.default_rng(123)
+    nvars, nsolvers, world = 120, 4, 2
+    opts = dict(minGpuLatencyMicros=0, gpuBlockCountGuideline=1, gpuThreadsPerBlockGuideline=64, initReportCountPerCategory=1)
+    ranks = [GpuClauseSharer(GpuClauseSharerOptions(**opts)) for _ in range(world)]
+    model = SharerModel(nvars, nsolvers)
+    for r, sh in enumerate(ranks):
+        sh.setShard(r, world)
+        sh.setVarCount(nvars)
+        sh.setCpuSolverCount(nsolvers)
+    dev = torch.device("cuda", 0)
+    cap = 1 << 20
+    bufs = [torch.zeros(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
+    hbs = [torch.zeros(1 << 20, dtype=torch.uint8, device=dev) for _ in range(world)]
+    pred, hit_pred = 2048, 2  # both far too small at first
+    saw_trunc = saw_flag = False
+
+    def heads_and_hits(hp):
+        out = []
+        for r, sh in enumerate(ranks):
+            nb = sh.mgpuEnqueueResult(hbs[r].data_ptr(), hp)
+            assert nb == 64 + min(hp, nb // 16) * 16 or nb <= 64 + hp * 16
+        torch.cuda.synchronize()
+        for r in range(world):
+            h = hbs[r][:64].cpu().numpy().view(np.int64)
+            out.append((int(h[0]), int(h[1]), hbs[r][64:64 + hp * 16].cpu().numpy().view(RAW_HIT_DTYPE).copy()))
+        return out
+
+    for rnd in range(5):
+        for _ in range(500):
+            k = int(rng.integers(1, 5))
+            lits = [mkLit(int(rng.integers(0, nvars)), bool(rng.integers(0, 2))) for _ in range(k)]
+            assert {sh.addClause(-1, lits) for sh in ranks} == {model.addClause(lits)}
+        for s in range(nsolvers):
+            for _ in range(4):
+                vs = rng.choice(nvars, size=70, replace=False)
+                sets = [mkLit(int(v), bool(rng.random() < 0.85)) for v in vs]
+                for sh in (ranks[0], model):
+                    assert sh.trySetSolverValues(s, sets) and sh.trySendAssignment(s) >= 0
+        total = ranks[0].mgpuCollectTo(bufs[0].data_ptr(), cap)
+        torch.cuda.synchronize()
+        n = min(pred, cap)
+        bufs[1][:n].copy_(bufs[0][:n])                       # the (possibly truncated) broadcast
+        assert ranks[0].mgpuRunPayload(bufs[0].data_ptr(), cap) >= 0
+        assert ranks[1].mgpuEnqueuePayload(bufs[1].data_ptr(), n) >= 0
+        res = heads_and_hits(hit_pred)
+        for sh in ranks:
+            sh.mgpuFinish()
+        redo = False
+        if total > n:
+            saw_trunc = True
+            bufs[1][:total].copy_(bufs[0][:total])
+            ranks[1].mgpuRedoPayload(bufs[1].data_ptr(), total)
+            redo = True
+        need = redo or any(f for _, f, _ in res) or max(c for c, _, _ in res) > hit_pred
+        saw_flag = saw_flag or any(f for _, f, _ in res)
+        while need:
+            hit_pred = max(hit_pred, 2 * max(c for c, _, _ in res) + 1)
+            res = heads_and_hits(hit_pred)
+            if redo:
+                ranks[1].mgpuFinish()
+                redo = False
+            need = any(f for _, f, _ in res) or max(c for c, _, _ in res) > hit_pred
+        pred = total + total // 4
+        union = np.concatenate([h[:c] for c, _, h in res])
+        ranks[0].mgpuImport(union)
+        want = model.run(); model.run()
+        assert np.array_equal(ranks[0].debugLastHits(), want), rnd
+        assert len(want) > 10
+    assert saw_trunc and saw_flag
