@@ -429,7 +429,7 @@ def run_b200(a):
         collapse_us.append(prev[1] if prev else 0.0)
         dev_tables.append(ph[1]); dev_check.append(ph[2]); dev_total.append(ph[3])
         hits.append(len(sh.debugLastHits()))
-        h2d.append(b1[0]); d2h.append(b1[1] + sh.debugLastRunBytes()[1])
+        h2d.append(b1[0]); d2h.append(sh.debugLastRunBytes()[1])
         drain()
     launches = sh.debugKernelLaunches() - launches0
     clocks = sampler.stop()
@@ -480,6 +480,11 @@ def run_b200(a):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["bytes_per_launch"]
+        except Exception:
+            pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         W = (A + 31) // 32
@@ -494,7 +499,7 @@ def run_b200(a):
         out["roofline_production"] = {"kernel": "k_filter", "bound": "hbm", "achieved": fb / (t_filter * 1e-6) / 1e9,
                                       "peak": hbm_peak, "unit": "GB/s", "frac": fb / (t_filter * 1e-6) / 1e9 / hbm_peak,
                                       "algorithmic_bytes": fb, "us_per_launch": t_filter,
-                                      "traffic": None, "peak_source": peak_src,
+                                      "traffic": traffic.get("k_filter"), "peak_source": peak_src,
                                       "note": "early exit skips rows: measured DRAM traffic is below the algorithmic bytes "
                                               "(profiles/r01_check_kernels.md); the kernel is bound by L1TEX/L2 sector "
                                               "throughput of the 8 B gathers, not by HBM"}
@@ -515,7 +520,7 @@ def run_b200(a):
                 "peak": lop3 / 1e12 if bound_int else hbm_peak,
                 "unit": "TLOP3/s" if bound_int else "GB/s",
                 "frac": max(t_hbm, t_int) / (t_dense * 1e-6),
-                "traffic": None,
+                "traffic": traffic.get("k_check_dense"),
                 "us_per_sweep": t_dense, "t_roof_us": max(t_hbm, t_int) * 1e6,
                 "t_hbm_us": t_hbm * 1e6, "t_int_us": t_int * 1e6,
                 "algorithmic_bytes": bytes_alg, "algorithmic_lop3": lop3_alg,

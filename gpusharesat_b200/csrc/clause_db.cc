@@ -124,7 +124,14 @@ void ClauseDb::sortArena(int len) {
     pl.dirtyFrom = 0;
 }
 
+void scaleActivitiesOnDevice(float *acts, int64_t n, float factor, cudaStream_t stream); // kernels.cu
+
 bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
+    // rescales decided while draining (Clauses.cu:284-291) reach the device copies first
+    for (; pendingDeviceRescales_ > 0; pendingDeviceRescales_--)
+        for (int s = 1; s <= maxLen_; s++)
+            if (perLen_[s]->actsOnDevice > 0)
+                scaleActivitiesOnDevice(perLen_[s]->actsDev.data(), perLen_[s]->actsOnDevice, 1.0f / kRescale, stream);
     for (int s = maxLen_; s >= 1; s--) {
         PerLen &pl = *perLen_[s];
         int64_t n = (int64_t)pl.meta.size();
@@ -159,6 +166,30 @@ bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
                 if (bytesCopied) *bytesCopied += (int64_t)((size_t)mine * tileWords * sizeof(int32_t));
             }
         }
+        // clause ids of the same dirty range
+        {
+            int64_t from = pl.fullReupload ? 0 : pl.dirtyFrom;
+            if (n > from) {
+                if (!pl.idsDev.tryReserve((size_t)n, (size_t)from, stream)) return false;
+                pl.idsStage.setPinnedLimit(pinnedLimit_);
+                pl.idsStage.clear();
+                pl.idsStage.resize((size_t)(n - from));
+                for (int64_t i = from; i < n; i++) pl.idsStage[(size_t)(i - from)] = pl.meta[(size_t)i].id;
+                GSS_CUDA(cudaMemcpyAsync(pl.idsDev.data() + from, pl.idsStage.data(), (size_t)(n - from) * sizeof(int64_t),
+                                         cudaMemcpyHostToDevice, stream));
+                if (bytesCopied) *bytesCopied += (n - from) * (int64_t)sizeof(int64_t);
+                if (deviceActs_) {
+                    if (!pl.actsDev.tryReserve((size_t)n, (size_t)from, stream)) return false;
+                    pl.actsStage.setPinnedLimit(pinnedLimit_);
+                    pl.actsStage.clear();
+                    pl.actsStage.resize((size_t)(n - from));
+                    for (int64_t i = from; i < n; i++) pl.actsStage[(size_t)(i - from)] = pl.meta[(size_t)i].activity;
+                    GSS_CUDA(cudaMemcpyAsync(pl.actsDev.data() + from, pl.actsStage.data(), (size_t)(n - from) * sizeof(float),
+                                             cudaMemcpyHostToDevice, stream));
+                    pl.actsOnDevice = n;
+                }
+            }
+        }
         pl.dirtyFrom = n;
         pl.fullReupload = false;
     }
@@ -175,7 +206,7 @@ int ClauseDb::buildDirectory(std::vector<LenDir> &dir) const {
         int64_t mine = localTiles((n + kTileClauses - 1) / kTileClauses);
         if (mine == 0) continue;
         tiles += (int)mine;
-        dir.push_back(LenDir{pl.dev.data(), s, (int32_t)n, tiles, 0});
+        dir.push_back(LenDir{pl.dev.data(), s, (int32_t)n, tiles, 0, pl.idsDev.data(), const_cast<float *>(pl.actsDev.data())});
     }
     return tiles;
 }
@@ -197,6 +228,21 @@ void ClauseDb::rescaleActivity() { // Clauses.cu:284-291
     for (int s = 0; s <= maxLen_; s++)
         for (auto &m : perLen_[s]->meta) m.activity /= kRescale;
     actIncr_ /= kRescale;
+    if (deviceActs_) pendingDeviceRescales_++;
+}
+
+void ClauseDb::downloadActivities(cudaStream_t stream) {
+    if (!deviceActs_) return;
+    std::vector<float> tmp;
+    for (int s = 1; s <= maxLen_; s++) {
+        PerLen &pl = *perLen_[s];
+        int64_t n = std::min<int64_t>(pl.actsOnDevice, (int64_t)pl.meta.size());
+        if (n <= 0) continue;
+        tmp.resize((size_t)n);
+        GSS_CUDA(cudaMemcpyAsync(tmp.data(), pl.actsDev.data(), (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        GSS_CUDA(cudaStreamSynchronize(stream));
+        for (int64_t i = 0; i < n; i++) pl.meta[(size_t)i].activity = tmp[(size_t)i];
+    }
 }
 
 float ClauseDb::approxNthAct(int64_t n) const {
@@ -228,6 +274,12 @@ float ClauseDb::approxNthAct(int64_t n) const {
 }
 
 void ClauseDb::reduceDb(cudaStream_t stream) {
+    // apply host-decided rescales to the device copies, then bring the activities home
+    for (; pendingDeviceRescales_ > 0; pendingDeviceRescales_--)
+        for (int s = 1; s <= maxLen_; s++)
+            if (perLen_[s]->actsOnDevice > 0)
+                scaleActivitiesOnDevice(perLen_[s]->actsDev.data(), perLen_[s]->actsOnDevice, 1.0f / kRescale, stream);
+    downloadActivities(stream);
     reduceHost();
     for (int s = maxLen_; s >= 3; s--) {
         PerLen &pl = *perLen_[s];
@@ -235,6 +287,8 @@ void ClauseDb::reduceDb(cudaStream_t stream) {
         if (pl.dev.capacity() > 1024 && wordsFor(s, (int64_t)pl.meta.size()) * 3 < pl.dev.capacity()) {
             GSS_CUDA(cudaStreamSynchronize(stream));
             pl.dev.free();
+            pl.idsDev.free();
+            pl.actsDev.free();
         }
     }
     int64_t dummy = 0;

@@ -29,6 +29,8 @@ struct LenDir {
     int32_t count;   // clauses of this length
     int32_t tileEnd; // cumulative count of THIS DEVICE's tiles including this length (longest length first)
     int32_t pad;
+    const int64_t *ids; // device copy of the clause ids of this length, indexed by (global) clause index
+    float *acts;        // device-resident clause activities (bumped by k_bump_activity), same indexing
 };
 
 struct DbStats {
@@ -76,6 +78,7 @@ public:
         __builtin_prefetch(pl.lits.data() + wordPos(len, idx, 0));
         if (len > 1) __builtin_prefetch(pl.lits.data() + wordPos(len, idx, 1));
     }
+    void prefetchMeta(int len, int idx) const { __builtin_prefetch(&perLen_[len]->meta[idx]); }
     int64_t clauseId(int len, int idx) const { return perLen_[len]->meta[idx].id; }
     float activity(int len, int idx) const { return perLen_[len]->meta[idx].activity; }
     void bumpActivity(int len, int idx); // Clauses.cu:231-237
@@ -101,6 +104,14 @@ public:
     // reference HostClauses::reduceDb (actOnly), Clauses.cu:426-465 / 249-282
     void reduceDb(cudaStream_t stream);
     void reduceHost(); // the host half: pick the threshold, compact the mirror (no device work)
+    // Device-resident activities (product path): hits bump them on the GPU, the host copy is only
+    // refreshed right before a reduceDb.
+    void setDeviceActivities(bool on) { deviceActs_ = on; }
+    bool deviceActivities() const { return deviceActs_; }
+    float activityIncrement() const { return actIncr_; }
+    void downloadActivities(cudaStream_t stream);
+    // a bump on the device pushed an activity past the rescale limit (Clauses.cu:231-237)
+    void rescaleAfterDeviceOverflow() { rescaleActivity(); }
     // reference approxNthAct, Clauses.cu:492-525
     float approxNthAct(int64_t n) const;
     void writeCnf(FILE *f, int varCount) const; // Clauses.cu:527-549
@@ -116,6 +127,11 @@ private:
         HostBuf<int32_t> lits;    // tiled host mirror
         std::vector<ClauseMeta> meta;
         DevBuf<int32_t> dev;
+        DevBuf<int64_t> idsDev;   // clause ids (the GPU emits them with the hits of large result lists)
+        HostBuf<int64_t> idsStage;
+        DevBuf<float> actsDev;    // clause activities live on the device between two reduceDb calls
+        HostBuf<float> actsStage;
+        int64_t actsOnDevice = 0; // clauses [0, actsOnDevice) have their authoritative activity on the device
         HostBuf<int32_t> stage;   // sharded upload: this rank's dirty tiles, packed
         int64_t dirtyFrom = 0;    // first clause index not yet on the device
         bool fullReupload = false;
@@ -157,6 +173,8 @@ private:
     float actIncr_ = 1.0f;
     float actDecay_;
     DbStats stats_;
+    bool deviceActs_ = false;
+    int pendingDeviceRescales_ = 0; // rescales decided on the host, not yet applied to the device copies
     int64_t addedAtLastReduce_ = 0;
     int64_t reduceDbs_ = 0;
     int maxVarPlusOne_ = 0;

@@ -39,6 +39,17 @@ struct HitRecord {
     int32_t idx; // index of the clause inside its length array
 };
 
+// A hit after the GPU-side post-processing of a large result list: ordered by (solver, length,
+// index), with the clause id and the position of the clause's literals in the emitted literal stream
+struct SortedHit {
+    uint32_t mask;
+    int32_t solver;
+    int32_t len;
+    int32_t idx;
+    int64_t id;
+    int64_t litPos;
+};
+
 // A clause that survived the aggregate filter
 struct Survivor {
     uint64_t ptrLen; // device address of the clause's first literal (low 48 bits) | length << 48

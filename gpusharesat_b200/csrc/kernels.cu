@@ -16,6 +16,8 @@
 //                    warp-aggregated hit append
 //   k_check_dense    bench-only: every (literal, solver word) pair, no filter, no early exit
 #include "kernels.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace gss {
 
@@ -416,6 +418,68 @@ __global__ void k_finalize(const Counters *c, unsigned int hitCap, unsigned int 
     for (int i = 2; i < 8; i++) dst[i] = 0;
 }
 
+// ---- post-processing of large hit lists ----
+__global__ void k_post_keys(const HitRecord *__restrict__ hits, unsigned int n, unsigned long long *keys, unsigned int *vals) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const HitRecord h = hits[i];
+    keys[i] = ((unsigned long long)(unsigned int)h.solver << 48) | ((unsigned long long)(unsigned int)h.len << 32) |
+              (unsigned long long)(unsigned int)h.idx;
+    vals[i] = i;
+}
+
+__global__ void k_post_lens(const HitRecord *__restrict__ hits, const unsigned int *__restrict__ order, unsigned int n,
+                            long long *lens) {
+    unsigned int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) lens[j] = hits[order[j]].len;
+    if (j == n) lens[j] = 0;
+}
+
+// one warp per hit (in sorted order): record + literals
+__global__ void __launch_bounds__(256) k_post_emit(const HitRecord *__restrict__ hits, const unsigned int *__restrict__ order,
+                                                   unsigned int n, const LenDir *__restrict__ dir, int nDir, int shardWorld,
+                                                   const long long *__restrict__ litPos, SortedHit *__restrict__ out,
+                                                   int32_t *__restrict__ lits, long long litCap) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int nWarps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += nWarps) {
+        const HitRecord h = hits[order[j]];
+        // the directory is sorted by descending length
+        int lo = 0, hi = nDir - 1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (dir[mid].len <= h.len) hi = mid; else lo = mid + 1;
+        }
+        const LenDir d = dir[lo];
+        const long long pos = litPos[j];
+        const int tile = h.idx / kTileClauses;
+        const int32_t *src = d.base + (size_t)(tile / shardWorld) * kTileClauses * h.len + (h.idx % kTileClauses);
+        for (int i = lane; i < h.len; i += 32)
+            if (pos + i < litCap) lits[pos + i] = __ldg(src + (size_t)i * kTileClauses);
+        if (lane == 0) out[j] = SortedHit{h.mask, h.solver, h.len, h.idx, d.ids[h.idx], pos};
+    }
+}
+
+__global__ void k_bump_activity(const unsigned char *__restrict__ recs, int stride, unsigned int n,
+                                const LenDir *__restrict__ dir, int nDir, float inc, int *overflow) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int len = *reinterpret_cast<const int *>(recs + (size_t)i * stride + 8);
+    const int idx = *reinterpret_cast<const int *>(recs + (size_t)i * stride + 12);
+    int lo = 0, hi = nDir - 1; // descending length
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (dir[mid].len <= len) hi = mid; else lo = mid + 1;
+    }
+    float old = atomicAdd(dir[lo].acts + idx, inc);
+    if (old + inc > 1e19f) *overflow = 1;
+}
+
+__global__ void k_scale_acts(float *acts, long long n, float factor) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acts[i] *= factor;
+}
+
 int resolveBlocks(const void *kernel, int threads, size_t smem, int numSMs, int requested, long long work) {
     int perSM = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, smem);
@@ -458,6 +522,49 @@ double measureLop3Peak(int numSMs, cudaStream_t s, int64_t *launches) {
     cudaEventDestroy(e1);
     cudaFree(d);
     return best;
+}
+
+size_t postprocessTempBytes(unsigned int n) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (unsigned int *)nullptr, (unsigned int *)nullptr, (int)n, 0, 56);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (long long *)nullptr, (long long *)nullptr, (int)n + 1);
+    return std::max(a, b) + 256;
+}
+
+void launchPostSort(const HitRecord *hits, unsigned int n, const PostBuffers &b, cudaStream_t s, int64_t *launches) {
+    const unsigned int blocks = (n + 1 + 255) / 256;
+    k_post_keys<<<blocks, 256, 0, s>>>(hits, n, b.keysIn, b.valsIn);
+    size_t tb = b.tempBytes;
+    cub::DeviceRadixSort::SortPairs(b.temp, tb, b.keysIn, b.keysOut, b.valsIn, b.valsOut, (int)n, 0, 56, s);
+    // literal positions: exclusive sum of the lengths in sorted order (litPos doubles as the input)
+    k_post_lens<<<blocks, 256, 0, s>>>(hits, b.valsOut, n, b.litPos);
+    tb = b.tempBytes;
+    cub::DeviceScan::ExclusiveSum(b.temp, tb, b.litPos, b.litPos, (int)n + 1, s);
+    checkLaunch("post sort");
+    *launches += 4;
+}
+
+void launchPostEmit(const HitRecord *hits, unsigned int n, const LenDir *dir, int nDir, int shardWorld, const PostBuffers &b,
+                    cudaStream_t s, int64_t *launches) {
+    unsigned int blocks = std::min<unsigned int>((n + 7) / 8, 148 * 8);
+    k_post_emit<<<blocks, 256, 0, s>>>(hits, b.valsOut, n, dir, nDir, shardWorld, b.litPos, b.sorted, b.lits, b.litCap);
+    checkLaunch("k_post_emit");
+    ++*launches;
+}
+
+void launchBumpActivity(const void *recs, int strideBytes, unsigned int n, const LenDir *dir, int nDir, float inc,
+                        int *overflow, cudaStream_t s, int64_t *launches) {
+    if (n == 0) return;
+    k_bump_activity<<<(n + 255) / 256, 256, 0, s>>>((const unsigned char *)recs, strideBytes, n, dir, nDir, inc, overflow);
+    checkLaunch("k_bump_activity");
+    ++*launches;
+}
+
+void scaleActivitiesOnDevice(float *acts, int64_t n, float factor, cudaStream_t stream) {
+    if (n <= 0) return;
+    k_scale_acts<<<(unsigned int)((n + 255) / 256), 256, 0, stream>>>(acts, (long long)n, factor);
+    checkLaunch("k_scale_acts");
 }
 
 void launchFinalize(const Counters *counters, unsigned int hitCap, unsigned int survCap, int groups, long long *dstHeader,

@@ -68,6 +68,33 @@ void launchFilterOnly(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStrea
 // bench-only dense mode: no filter, no early exit
 void launchCheckDense(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
 
+// Post-processing of a large hit list on the device (the host hand-over is the bottleneck of a run
+// that returns 10^5 hits): radix-sort the hits by (solver, length, index) -- the reproducible
+// hand-over order --, then emit for every hit its clause id and its literals as one contiguous
+// stream.  The host then builds each solver's batch with sequential copies only.
+struct PostBuffers {
+    unsigned long long *keysIn, *keysOut; // n
+    unsigned int *valsIn, *valsOut;       // n
+    long long *litPos;                    // n + 1 (last = total literal count)
+    SortedHit *sorted;                    // n
+    int32_t *lits;                        // litCap
+    long long litCap;
+    void *temp;
+    size_t tempBytes;
+};
+size_t postprocessTempBytes(unsigned int n);
+// phase 1: sort + literal positions (litPos[n] = total); phase 2 (after the host has made room for the
+// literals): emit records and literals
+void launchPostSort(const HitRecord *hits, unsigned int n, const PostBuffers &b, cudaStream_t s, int64_t *launches);
+void launchPostEmit(const HitRecord *hits, unsigned int n, const LenDir *dir, int nDir, int shardWorld, const PostBuffers &b,
+                    cudaStream_t s, int64_t *launches);
+
+// Activity bumps of a run's hits on the device (reference: one host-side bump per hit record,
+// Clauses.cu:231-237 / GpuRunner.cu:375-378).  `recs` are HitRecord or SortedHit records (len / idx
+// at byte offsets 8 / 12); *overflow is set when an activity passes the rescale limit.
+void launchBumpActivity(const void *recs, int strideBytes, unsigned int n, const LenDir *dir, int nDir, float inc,
+                        int *overflow, cudaStream_t s, int64_t *launches);
+
 // multi-GPU: 64-byte result header {nHits, overflow flag} written on the device, so that every rank
 // can tell from the gathered buffers whether some rank has to run again with larger buffers
 void launchFinalize(const Counters *counters, unsigned int hitCap, unsigned int survCap, int groups, long long *dstHeader,

@@ -136,6 +136,7 @@ void Reported::handOver(std::vector<HitRecord> &hits, const std::vector<AssigIds
     if (hits.size() < kParallelHits) {
         std::sort(hits.begin(), hits.end(), byClause);
         for (size_t i = 0; i < hits.size(); i++) {
+            if (!hostBumps_) break;
             if (i + 16 < hits.size()) db_.prefetchClause(hits[i + 16].len, hits[i + 16].idx);
             db_.bumpActivity(hits[i].len, hits[i].idx);
         }
@@ -172,10 +173,58 @@ void Reported::handOver(std::vector<HitRecord> &hits, const std::vector<AssigIds
             });
         },
         [&](int len, int idx) {
-            if (db_.bumpActivityAtomic(len, idx)) rescale.store(true);
+            if (hostBumps_ && db_.bumpActivityAtomic(len, idx)) rescale.store(true);
         });
     db_.rescaleIfNeeded(rescale.load());
     if (prof) fprintf(stderr, "handOver: group %.0f us, sort+fill %.0f us (%zu hits)\n", us(t0, t1), us(t1, now()), hits.size());
+}
+
+void Reported::handOverSorted(const SortedHit *recs, size_t n, const int32_t *lits, int64_t totalLits,
+                              const std::vector<AssigIds> &ids, int nSolvers) {
+    // recs are ordered by (solver, length, index): find every solver's slice
+    std::vector<size_t> start((size_t)nSolvers + 1, n);
+    {
+        size_t i = 0;
+        for (int s = 0; s < nSolvers; s++) {
+            while (i < n && recs[i].solver < s) i++;
+            start[s] = i;
+        }
+        start[nSolvers] = n;
+    }
+    size_t nQueues = queues_.size();
+    std::vector<ClauseBatch *> perSolver(nQueues, nullptr);
+    for (size_t s = 0; s < nQueues && s < (size_t)nSolvers; s++) {
+        bool hasIds = s < ids.size() && ids[s].count > 0;
+        if (!hasIds && start[s + 1] == start[s]) continue;
+        perSolver[s] = &queues_[s]->begin();
+        if (hasIds) perSolver[s]->ids = ids[s];
+    }
+    if (!pool_) pool_ = std::make_unique<WorkerPool>(std::max(1, std::min(15, (int)std::thread::hardware_concurrency() - 1)));
+    std::atomic<bool> rescale{false};
+    pool_->parallelFor(nSolvers, [&](int s) {
+        if ((size_t)s >= nQueues || !perSolver[s]) return;
+        size_t lo = start[s], hi = start[s + 1];
+        if (lo == hi) return;
+        ClauseBatch &b = *perSolver[s];
+        const int64_t base = recs[lo].litPos;
+        const int64_t end = hi < n ? recs[hi].litPos : totalLits;
+        b.lits.assign(lits + base, lits + end);
+        b.entries.resize(hi - lo);
+        uint32_t any = 0;
+        for (size_t i = lo; i < hi; i++) {
+            const SortedHit &h = recs[i];
+            b.entries[i - lo] = ClauseBatch::Entry{h.id, (int32_t)(h.litPos - base)};
+            any |= h.mask;
+            if (hostBumps_) {
+                if (i + 16 < hi) db_.prefetchMeta(recs[i + 16].len, recs[i + 16].idx);
+                if (db_.bumpActivityAtomic(h.len, h.idx)) rescale.store(true);
+            }
+        }
+        b.hadSomeReported |= any;
+    });
+    db_.rescaleIfNeeded(rescale.load());
+    for (size_t s = 0; s < nQueues; s++)
+        if (perSolver[s]) queues_[s]->publish();
 }
 
 bool Reported::pop(int s, int *&lits, int &count, int64_t &id) {

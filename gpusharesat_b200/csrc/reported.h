@@ -72,6 +72,8 @@ public:
     Reported(ClauseDb &db, std::vector<std::vector<uint64_t>> &oneSolverStats)
         : db_(db), stats_(oneSolverStats), referenceDupQuirk_(getenv("GPUSHARE_REFERENCE_DUP_QUIRK") != nullptr) {}
     void setSolverCount(int n);
+    // false: the caller bumps the activities itself (on the device); true (default): per hit on the host
+    void setHostBumps(bool on) { hostBumps_ = on; }
 
     void clauseWasAdded(int solver, int64_t clauseId);                 // Reported.cu:97-103
     void assigWasSent(int solver, int64_t id) { lastSent_[solver] = id; } // Reported.cuh:118
@@ -90,6 +92,10 @@ public:
     // reordered in place.
     void handOver(std::vector<HitRecord> &hits, const std::vector<AssigIds> &ids, int nSolvers);
     static constexpr size_t kParallelHits = 8192;
+    // Same for a hit list the GPU has already put in hand-over order and resolved (ids, literal
+    // stream): every solver's batch is one contiguous slice -- sequential copies only.
+    void handOverSorted(const SortedHit *recs, size_t n, const int32_t *lits, int64_t totalLits,
+                        const std::vector<AssigIds> &ids, int nSolvers);
     // solver thread: Reported.cu:105-158
     bool pop(int solver, int *&lits, int &count, int64_t &id);
     int64_t lastAssigAllReported(int solver) const { return lastAllReported_[solver]; }
@@ -109,6 +115,7 @@ private:
     std::vector<std::queue<DontImport>> dontImport_;
     std::vector<int> tmpLits_;
     bool referenceDupQuirk_;
+    bool hostBumps_ = true;
     std::vector<HitRecord> grouped_;   // scratch: hits grouped by solver
     std::unique_ptr<WorkerPool> pool_; // created on the first large hit list
 };

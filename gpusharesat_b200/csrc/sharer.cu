@@ -82,6 +82,8 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
     db_ = std::make_unique<ClauseDb>(opts_.clauseActivityDecay, logger_, pinnedLimit);
     assigs_ = std::make_unique<HostAssigs>();
     reported_ = std::make_unique<Reported>(*db_, oneSolverStats_);
+    db_->setDeviceActivities(true);
+    reported_->setHostBumps(false);
     setCpuSolverCount(1);
     logger_.log(1, std::string("c gpushare_b200 on ") + props.name + ", " + std::to_string(numSMs_) + " SMs\n");
 }
@@ -661,7 +663,7 @@ int64_t Sharer::mgpuWait(const HitRecord **hits) {
     GSS_CHECK(cur_ >= 0);
     // hits == nullptr: the caller gathers the hits from device memory (gss_mgpu_hits_to_device),
     // only the count is needed on the host
-    finishRun(slots_[cur_], hits != nullptr);
+    finishRun(slots_[cur_], hits != nullptr, false);
     mgpuLast_ = cur_;
     cur_ = -1;
     if (hits) *hits = hits_.data();
@@ -671,10 +673,12 @@ int64_t Sharer::mgpuWait(const HitRecord **hits) {
 void Sharer::mgpuImport(const HitRecord *hits, int64_t n) {
     GSS_CHECK(mgpuLast_ >= 0);
     if (hits != hits_.data()) hits_.assign(hits, hits + n);
+    postValid_ = false;
+    parkHitsForBump(hits_.data(), (int)sizeof(HitRecord), hits_.size()); // the union lives on the host
     processResults(slots_[mgpuLast_]);
 }
 
-void Sharer::finishRun(RunSlot &slot, bool fetchAllHits) {
+void Sharer::finishRun(RunSlot &slot, bool fetchAllHits, bool allowPostprocess) {
     GSS_CUDA(cudaEventSynchronize(slot.evEnd));
     float msCopy = 0, msApply = 0, msCheck = 0, msTotal = 0;
     cudaEventElapsedTime(&msCopy, slot.evStart, slot.evH2DDone);
@@ -706,6 +710,17 @@ void Sharer::finishRun(RunSlot &slot, bool fetchAllHits) {
         enqueueResultCopy(slot);
         GSS_CUDA(cudaStreamSynchronize(stream_));
     }
+    globalStats_[G_clauseTestsOnAssigs] += c.exactTests;
+    slot.inFlight = false;
+    postValid_ = false;
+    finishedD2H_ = (int64_t)slot.resHost.size();
+    if (fetchAllHits && allowPostprocess && c.nHits >= kPostprocessHits) {
+        // large result: sort and resolve it on the device, fetch only the finished product
+        hits_.clear();
+        postprocessOnDevice(slot, c.nHits);
+        parkHitsForBump((const uint8_t *)postDev_.data() + postSortedOffset_, (int)sizeof(SortedHit), c.nHits);
+        return;
+    }
     hits_.resize(c.nHits);
     size_t first = std::min((size_t)c.nHits, (slot.resHost.size() - sizeof(Counters)) / sizeof(HitRecord));
     if (first) memcpy(hits_.data(), slot.resHost.data() + sizeof(Counters), first * sizeof(HitRecord));
@@ -714,10 +729,90 @@ void Sharer::finishRun(RunSlot &slot, bool fetchAllHits) {
         GSS_CUDA(cudaMemcpyAsync(hits_.data() + first, resDev_.data() + sizeof(Counters) + first * sizeof(HitRecord),
                                  rest * sizeof(HitRecord), cudaMemcpyDeviceToHost, stream_));
         GSS_CUDA(cudaStreamSynchronize(stream_));
-        lastD2H_ += (int64_t)(rest * sizeof(HitRecord));
+        finishedD2H_ += (int64_t)(rest * sizeof(HitRecord));
     }
-    globalStats_[G_clauseTestsOnAssigs] += c.exactTests;
-    slot.inFlight = false;
+    if (fetchAllHits) parkHitsForBump(resDev_.data() + sizeof(Counters), (int)sizeof(HitRecord), c.nHits);
+}
+
+// The records are on the device already (result buffer or post-processing buffer); both are reused
+// by the next run, so copy them aside (device to device).
+void Sharer::parkHitsForBump(const void *devRecs, int stride, size_t n) {
+    bumpN_ = n;
+    bumpStride_ = stride;
+    if (n == 0) return;
+    bumpRecs_.reserve(n * (size_t)stride, 0, stream_);
+    GSS_CUDA(cudaMemcpyAsync(bumpRecs_.data(), devRecs, n * (size_t)stride, cudaMemcpyDefault, stream_));
+}
+
+void Sharer::bumpParkedHits() {
+    // a bump of the previous batch overflowed an activity: rescale like Clauses.cu:231-237 does
+    if (bumpFlagPending_) {
+        GSS_CUDA(cudaStreamSynchronize(stream_));
+        if (bumpFlagHost_[0]) db_->rescaleAfterDeviceOverflow();
+        bumpFlagPending_ = false;
+    }
+    if (bumpN_ == 0) return;
+    std::vector<LenDir> dir;
+    db_->buildDirectory(dir);
+    bumpDirHost_.resize(dir.size() * sizeof(LenDir));
+    memcpy(bumpDirHost_.data(), dir.data(), dir.size() * sizeof(LenDir));
+    bumpDirDev_.reserve(bumpDirHost_.size(), 0, stream_);
+    GSS_CUDA(cudaMemcpyAsync(bumpDirDev_.data(), bumpDirHost_.data(), bumpDirHost_.size(), cudaMemcpyHostToDevice, stream_));
+    bumpFlagDev_.reserve(1, 0, stream_);
+    bumpFlagHost_.resize(1);
+    GSS_CUDA(cudaMemsetAsync(bumpFlagDev_.data(), 0, sizeof(int), stream_));
+    launchBumpActivity(bumpRecs_.data(), bumpStride_, (unsigned int)bumpN_, (const LenDir *)bumpDirDev_.data(), (int)dir.size(),
+                       db_->activityIncrement(), bumpFlagDev_.data(), stream_, &launches_);
+    GSS_CUDA(cudaMemcpyAsync(bumpFlagHost_.data(), bumpFlagDev_.data(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    bumpFlagPending_ = true;
+    bumpN_ = 0;
+}
+
+void Sharer::postprocessOnDevice(RunSlot &slot, size_t n) {
+    auto align = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t tempBytes = postprocessTempBytes((unsigned int)n);
+    size_t off = 0;
+    const size_t oKeysIn = off; off += align(n * 8);
+    const size_t oKeysOut = off; off += align(n * 8);
+    const size_t oValsIn = off; off += align(n * 4);
+    const size_t oValsOut = off; off += align(n * 4);
+    const size_t oLitPos = off; off += align((n + 1) * 8);
+    const size_t oSorted = off; off += align(n * sizeof(SortedHit));
+    const size_t oTemp = off; off += align(tempBytes);
+    postDev_.reserve(off, 0, stream_);
+    uint8_t *base = postDev_.data();
+    PostBuffers b;
+    b.keysIn = (unsigned long long *)(base + oKeysIn);
+    b.keysOut = (unsigned long long *)(base + oKeysOut);
+    b.valsIn = (unsigned int *)(base + oValsIn);
+    b.valsOut = (unsigned int *)(base + oValsOut);
+    b.litPos = (long long *)(base + oLitPos);
+    b.sorted = (SortedHit *)(base + oSorted);
+    postSortedOffset_ = oSorted;
+    b.temp = base + oTemp;
+    b.tempBytes = tempBytes;
+    b.lits = nullptr;
+    b.litCap = 0;
+    const HitRecord *hitsDev = (const HitRecord *)(resDev_.data() + sizeof(Counters));
+    launchPostSort(hitsDev, (unsigned int)n, b, stream_, &launches_);
+    postTotalHost_.resize(1);
+    GSS_CUDA(cudaMemcpyAsync(postTotalHost_.data(), b.litPos + n, sizeof(long long), cudaMemcpyDeviceToHost, stream_));
+    GSS_CUDA(cudaStreamSynchronize(stream_));
+    const int64_t total = postTotalHost_[0];
+    postLitsDev_.reserve((size_t)std::max<int64_t>(total, 1), 0, stream_);
+    b.lits = postLitsDev_.data();
+    b.litCap = total;
+    launchPostEmit(hitsDev, (unsigned int)n, slot.dirDev(), slot.nDir, db_->shardWorld(), b, stream_, &launches_);
+    postSortedHost_.resize(n);
+    postLitsHost_.resize((size_t)std::max<int64_t>(total, 1));
+    GSS_CUDA(cudaMemcpyAsync(postSortedHost_.data(), b.sorted, n * sizeof(SortedHit), cudaMemcpyDeviceToHost, stream_));
+    if (total)
+        GSS_CUDA(cudaMemcpyAsync(postLitsHost_.data(), b.lits, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    GSS_CUDA(cudaStreamSynchronize(stream_));
+    finishedD2H_ += (int64_t)(n * sizeof(SortedHit) + (size_t)total * sizeof(int32_t) + sizeof(long long));
+    postValid_ = true;
+    postN_ = n;
+    postLits_ = total;
 }
 
 void Sharer::processResults(RunSlot &slot) {
@@ -726,17 +821,25 @@ void Sharer::processResults(RunSlot &slot) {
     globalStats_[G_gpuRuns]++;
     globalStats_[G_totalAssigClauseTested] += (uint64_t)clCount * (uint64_t)slot.assigCount;
     globalStats_[G_clauseTestsOnGroups] += (uint64_t)clCount;
-    globalStats_[G_gpuReports] += hits_.size();
+    globalStats_[G_gpuReports] += postValid_ ? postN_ : hits_.size();
     lastHitsValid_ = false; // gss_debug_last_hits converts hits_ on demand
+    bumpParkedHits();
     TimeAdder t(globalStats_[G_timeSpentFillingReported], opts_.quickProf != 0);
-    reported_->handOver(hits_, slot.ids, slot.nSolvers);
+    if (postValid_) reported_->handOverSorted(postSortedHost_.data(), postN_, postLitsHost_.data(), postLits_, slot.ids, slot.nSolvers);
+    else reported_->handOver(hits_, slot.ids, slot.nSolvers);
 }
 
 void Sharer::materializeLastHits() {
     if (lastHitsValid_) return;
-    lastHits_.resize(hits_.size());
-    for (size_t i = 0; i < hits_.size(); i++)
-        lastHits_[i] = gss_hit{db_->clauseId(hits_[i].len, hits_[i].idx), hits_[i].solver, hits_[i].mask};
+    if (postValid_) {
+        lastHits_.resize(postN_);
+        for (size_t i = 0; i < postN_; i++)
+            lastHits_[i] = gss_hit{postSortedHost_[i].id, postSortedHost_[i].solver, postSortedHost_[i].mask};
+    } else {
+        lastHits_.resize(hits_.size());
+        for (size_t i = 0; i < hits_.size(); i++)
+            lastHits_[i] = gss_hit{db_->clauseId(hits_[i].len, hits_[i].idx), hits_[i].solver, hits_[i].mask};
+    }
     std::sort(lastHits_.begin(), lastHits_.end(), [](const gss_hit &a, const gss_hit &b) {
         return a.clause_id != b.clause_id ? a.clause_id < b.clause_id : a.solver_id < b.solver_id;
     });

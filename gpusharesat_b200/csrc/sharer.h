@@ -46,7 +46,7 @@ public:
     double timeCheck(int iters, bool dense, bool filterOnly = false);
     int lastRunTimes(double out[4]);
     double lop3Peak();
-    void lastRunBytes(int64_t *h2d, int64_t *d2h) { *h2d = lastH2D_; *d2h = lastD2H_; }
+    void lastRunBytes(int64_t *h2d, int64_t *d2h) { *h2d = lastH2D_; *d2h = finishedD2H_; }
     int64_t kernelLaunches() const { return launches_; }
     // ---- multi-GPU (see include/gpushare_b200.h) ----
     void setShard(int rank, int world) { db_->setShard(rank, world); }
@@ -92,7 +92,7 @@ private:
     void launchRun(RunSlot &slot, const void *updSrc, int64_t nUpdates, int64_t &h2d);
     int nextSlot() const;
     void enqueueFromDevicePayload(RunSlot &slot, const void *devPayload, int64_t validBytes, bool collapsePrev, int64_t h2d);
-    void finishRun(RunSlot &slot, bool fetchAllHits = true);     // wait, re-run on overflow, pull every hit to the host
+    void finishRun(RunSlot &slot, bool fetchAllHits = true, bool allowPostprocess = true);     // wait, re-run on overflow, pull every hit to the host
     void processResults(RunSlot &slot);
     void launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly = false);
     void enqueueResultCopy(RunSlot &slot);
@@ -155,12 +155,37 @@ private:
     }
 
     std::vector<HitRecord> hits_;   // hits of the run being processed
+    // large hit lists are sorted / resolved on the device (see kernels.cuh: PostBuffers)
+    static constexpr size_t kPostprocessHits = 8192;
+    bool postValid_ = false;
+    size_t postSortedOffset_ = 0;
+    size_t postN_ = 0;
+    int64_t postLits_ = 0;
+    DevBuf<uint8_t> postDev_;            // keys, values, positions, sorted records, CUB scratch
+    DevBuf<int32_t> postLitsDev_;
+    HostBuf<SortedHit> postSortedHost_;
+    HostBuf<int32_t> postLitsHost_;
+    HostBuf<long long> postTotalHost_;
+    void postprocessOnDevice(RunSlot &slot, size_t n);
+    // activity bumps on the device: the hit records of the finished run are parked in bumpRecs_
+    // before the next run may overwrite the result buffers, and bumped once the next batch of
+    // clauses has been drained (same increment as the reference uses at that point)
+    void parkHitsForBump(const void *hostOrDevRecs, int stride, size_t n);
+    void bumpParkedHits();
+    DevBuf<uint8_t> bumpRecs_;
+    int bumpStride_ = 0;
+    size_t bumpN_ = 0;
+    HostBuf<uint8_t> bumpDirHost_;
+    DevBuf<uint8_t> bumpDirDev_;
+    DevBuf<int> bumpFlagDev_;
+    HostBuf<int> bumpFlagHost_;
+    bool bumpFlagPending_ = false;
     std::vector<gss_hit> lastHits_; // sorted, for gss_debug_last_hits (built on demand)
     bool lastHitsValid_ = true;
     bool dense_ = false;
     bool ranOutOfMemory_ = false;
     int64_t launches_ = 0;
-    int64_t lastH2D_ = 0, lastD2H_ = 0;
+    int64_t lastH2D_ = 0, lastD2H_ = 0, finishedD2H_ = 0;
     double lastTimes_[4] = {0, 0, 0, 0};
     bool haveTimes_ = false;
 };

@@ -137,7 +137,7 @@ int gss_debug_last_run_times(gss_sharer *h, double out_us[4]);
  * thread-level LOP3 operations per second (the integer-pipe roofline denominator). */
 double gss_debug_lop3_peak(gss_sharer *h);
 
-/* bytes moved by the last started run: host->device and device->host */
+/* host->device bytes of the last STARTED run and device->host bytes of the last FINISHED run */
 void gss_debug_last_run_bytes(gss_sharer *h, int64_t *h2d, int64_t *d2h);
 
 /* number of kernel launches issued by the library so far */

@@ -10,6 +10,11 @@
 
 using namespace gss;
 
+// the host-only rig never has activities on a device (kernels.cu is not linked here)
+namespace gss {
+void scaleActivitiesOnDevice(float *, int64_t, float, cudaStream_t) {}
+} // namespace gss
+
 struct HostRig {
     Logger logger;
     HostAssigs assigs;
