@@ -63,6 +63,11 @@ def parse():
     p.add_argument("--no-dense", action="store_true")
     p.add_argument("--dense-iters", type=int, default=3)
     p.add_argument("--prod-iters", type=int, default=20)
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                   help="N > 1: weak = --clauses per GPU (database grows with N), strong = --clauses in total")
+    p.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                   help="N > 1: peer memory windows over NVLink (default) or NCCL broadcast + all-gather")
+    p.add_argument("--slot-hits", type=int, default=1 << 21, help="peer exchange: hit records per rank and batch")
     return p.parse_args()
 
 
@@ -183,6 +188,9 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # same workload as the own arm at this N (weak scaling: N x --clauses clauses); the sample is a
+    # prefix of the database, so only the first --clauses clauses are generated
+    total_clauses = a.clauses * (a.gpus if a.scaling == "weak" else 1)
     sig, offsets, lits = make_inputs(a)
     d, t, start = batch_words(a, sig)
     cores = os.cpu_count() or 1
@@ -200,13 +208,17 @@ def run_reference_arm(a):
         times.append(dt)
     total = sum(times)
     value = L * A * a.steps / total
-    sample = (f"each step = first {n} of {a.clauses} clauses ({L} literals) x {A} assignments, "
+    sample = (f"each step = first {n} of {total_clauses} clauses ({L} literals) x {A} assignments, "
               f"two-level filter, {cores} threads")
+    a.clauses = total_clauses
+    cfg = workload_config(a)
+    if a.gpus > 1:
+        cfg["clauses_per_gpu"] = total_clauses // a.gpus
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": workload_config(a),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -272,11 +284,20 @@ def run_reference_gpu(a):
 # ------------------------------------------------------------------------------------------------
 
 def run_b200_sharded(a):
-    """N > 1: one process per GPU (torchrun).  Every rank holds the whole clause database on the
-    host and the clause tiles t with t % N == rank on its device.  Rank 0 is the front-end: it owns
-    the solver streams and the assignment slot machines.  Per step: rank 0 collects the batch
-    (run parameters + deltas), the payload is broadcast with NCCL, every rank checks its shard,
-    the hit lists are gathered with NCCL and rank 0 hands them to the solver queues."""
+    """N > 1: one process per GPU (torchrun).  The clause database is sharded by tiles: rank r
+    checks the tiles t with t % N == r (every rank keeps the whole arena so that rank 0 can resolve
+    any hit on its device).  Rank 0 is the front-end: it owns the solver streams, the assignment
+    slot machines and the hand-over queues.
+
+    --scaling weak (default): the database grows with N (N x --clauses clauses, i.e. --clauses per
+    GPU) and every batch of 1024 assignments is checked against all of it -- what 8 x 180 GB are
+    for.  --scaling strong: the --clauses database is split N ways (one batch is then ~100/N us of
+    work per GPU: latency-bound by construction).
+
+    --exchange peer (default): the batch and the hits travel over peer memory (CUDA IPC windows,
+    peer loads / stores over NVLink, stream memory operations; csrc/peer.cu) -- no collective on the
+    data path, NCCL only bootstraps.  --exchange nccl: one NCCL broadcast + one all-gather per batch
+    (mgpu.ShardedRunner), kept for comparison."""
     import torch
     import torch.distributed as dist
     from gpusharesat_b200 import GpuClauseSharer, GpuClauseSharerOptions, mgpu
@@ -286,6 +307,9 @@ def run_b200_sharded(a):
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
 
+    per_gpu = a.clauses
+    if a.scaling == "weak":
+        a.clauses = per_gpu * world
     sig, offsets, lits = make_inputs(a)
     L_total, A = int(offsets[-1]), a.solvers * a.slots
     sh = GpuClauseSharer(GpuClauseSharerOptions(minGpuLatencyMicros=0, verbosity=0))
@@ -293,6 +317,7 @@ def run_b200_sharded(a):
     sh.setVarCount(a.vars)
     sh.setCpuSolverCount(a.solvers)
     sh.addClausesBulk(offsets, lits)
+    del offsets, lits
     streams = make_streams(a, sig) if rank == 0 else None
     pool = ThreadPoolExecutor(max_workers=a.solvers) if rank == 0 else None
 
@@ -303,7 +328,11 @@ def run_b200_sharded(a):
                     pass
 
     # the first batch rebuilds the tables: it lists every variable of every solver
-    runner = mgpu.ShardedRunner(sh, dist, rank, world, device, payload_cap=a.solvers * a.vars * 12 + (4 << 20))
+    payload_cap = a.solvers * a.vars * 12 + (4 << 20)
+    if a.exchange == "peer":
+        runner = mgpu.PeerRunner(sh, dist, rank, world, payload_cap=payload_cap, slot_hits=a.slot_hits)
+    else:
+        runner = mgpu.ShardedRunner(sh, dist, rank, world, device, payload_cap=payload_cap)
 
     def step():
         if rank == 0:
@@ -315,10 +344,10 @@ def run_b200_sharded(a):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         ph = sh.debugLastRunTimes()
-        h2d, _ = sh.debugLastRunBytes()
+        h2d, d2h = sh.debugLastRunBytes()
         dev_us = runner.device_us()
         drain()
-        return dt, ph, (nh or 0) if rank == 0 else 0, h2d, dev_us
+        return dt, ph, (nh or 0) if rank == 0 else 0, h2d, d2h, dev_us
 
     for _ in range(a.warmup):
         step()
@@ -327,40 +356,57 @@ def run_b200_sharded(a):
         sampler.start()
     l0 = sh.debugKernelLaunches()
     wall = dev = 0.0
-    hits = upd = 0
-    bc, tk, ck = [], [], []
+    hits = upd = back = 0
+    ex, tk, ck = [], [], []
     for _ in range(a.steps):
-        dt, ph, nh, h2d, dev_us = step()
+        dt, ph, nh, h2d, d2h, dev_us = step()
         wall += dt
         dev += dev_us * 1e-6
-        bc.append(dev_us - ph[1] - ph[2]); tk.append(ph[1]); ck.append(ph[2])
+        ex.append(dev_us - ph[1] - ph[2]); tk.append(ph[1]); ck.append(ph[2])
         hits += nh
         upd += h2d
+        back += d2h
     launches = sh.debugKernelLaunches() - l0
     clocks = sampler.stop() if rank == 0 else None
     tt = torch.tensor([dev, wall], dtype=torch.float64, device=device)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ll = torch.tensor([launches], dtype=torch.int64, device=device)
     dist.all_reduce(ll)
+    mine = torch.tensor([float(np.mean(tk)), float(np.mean(ck)), float(np.mean(ex))], dtype=torch.float64, device=device)
+    allph = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allph, mine)
     dev, wall = float(tt[0]), float(tt[1])
     if rank == 0:
+        cfg = workload_config(a)
+        cfg["clauses_per_gpu"] = a.clauses // world
+        cfg["parallelism"] = (f"clause tiles sharded x{world} ({a.scaling} scaling: {a.clauses} clauses in total), "
+                              f"assignments broadcast, exchange = {a.exchange}")
+        if a.exchange == "peer":
+            region = ("rank 0: batch resident in its HBM -> mailbox signal -> every rank: table kernels (deltas read over "
+                      "NVLink from rank 0), check kernels (hits stored over NVLink into rank 0) -> rank 0 has seen every "
+                      "rank's done flag; CUDA events on rank 0's stream, max over ranks")
+            gap = "exchange_and_wait_for_slowest_rank"
+        else:
+            region = "NCCL broadcast of the batch, table + check kernels on every shard, NCCL all-gather of the hits; max over ranks"
+            gap = "nccl_broadcast_gather_and_sync_gaps"
         print(json.dumps({
             "metric": METRIC, "value": L_total * A * a.steps / dev, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 * dev / a.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(a),
+            "warmup": a.warmup, "ms_per_step": 1e3 * dev / a.steps, "higher_is_better": True, "scaling": a.scaling,
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg,
             "e2e": {"value": L_total * A * a.steps / wall, "unit": UNIT, "ms_per_step": 1e3 * wall / a.steps,
                     "h2d_bytes_per_step": int(upd / a.steps),
-                    "d2h_bytes_per_step": int(hits / a.steps * 16),
-                    "timed_region": "rank 0 collect + H2D, NCCL broadcast of the batch, table + check kernels on every "
-                                    "shard, NCCL gather of the hits, host hand-over on rank 0; max over ranks"},
+                    "d2h_bytes_per_step": int(back / a.steps),
+                    "timed_region": "rank 0 collect + H2D, exchange, table + check kernels on every shard, device-side sort / "
+                                    "resolve of the union, D2H, host hand-over on rank 0; wall clock, max over ranks"},
             "gpu_launches": int(ll[0]), "clocks": clocks, "hits_per_step": hits / a.steps,
-            "phases_us_per_step": {"nccl_broadcast_gather_and_sync_gaps": float(np.mean(bc)), "table_kernels": float(np.mean(tk)),
-                                   "check_kernels": float(np.mean(ck))},
+            "phases_us_per_step": {gap: float(np.mean(ex)), "table_kernels": float(np.mean(tk)),
+                                   "check_kernels": float(np.mean(ck)),
+                                   "per_rank_table_check_other": [[round(float(x), 1) for x in t.tolist()] for t in allph]},
             "literals": L_total, "assignments": A,
-            "note": "N > 1: value = device time from the start of the payload broadcast to the gathered hits "
-                    "(NCCL broadcast, table + check kernels on every shard, NCCL all-gather of the hits), max over "
-                    "ranks; e2e adds rank 0's collect, the payload H2D, the hit D2H and the host hand-over",
+            "note": "N > 1: value = " + region + "; e2e adds rank 0's collect, the payload H2D, the sort / resolve of the hits, "
+                    "their D2H and the host hand-over",
         }))
+    dist.barrier()
     dist.destroy_process_group()
 
 
@@ -454,7 +500,7 @@ def run_b200(a):
 
     out = {
         "metric": METRIC, "value": L_total * A * a.steps / dev_s, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(a),
         "e2e": {"value": L_total * A * a.steps / wall_s, "unit": UNIT, "ms_per_step": 1e3 * wall_s / a.steps,
                 "h2d_bytes_per_step": int(np.mean(h2d)), "d2h_bytes_per_step": int(np.mean(d2h)),

@@ -91,6 +91,11 @@ SIGNATURES = {
     "gss_mgpu_redo_payload": (None, [_P, C.c_void_p, _L]),
     "gss_mgpu_enqueue_result": (_L, [_P, C.c_void_p, _L]),
     "gss_mgpu_finish": (_I, [_P]),
+    "gss_mgpu_import_gathered": (None, [_P, C.c_void_p, _I, _L, C.POINTER(_L)]),
+    "gss_peer_init": (_L, [_P, _I, _I, _L, _L, C.c_void_p, _L]),
+    "gss_peer_connect": (None, [_P, C.c_void_p, _L]),
+    "gss_peer_enqueue": (_I, [_P]),
+    "gss_peer_finish": (_L, [_P]),
     "gss_set_stream": (None, [_P, C.c_void_p]),
     "gss_mgpu_import": (None, [_P, C.c_void_p, _L]),
     "gss_version": (C.c_char_p, []),
@@ -378,6 +383,27 @@ class GpuClauseSharer:
 
     def mgpuEnqueueResult(self, dev_ptr, cap_records):
         return self._lib.gss_mgpu_enqueue_result(self._h, dev_ptr, int(cap_records))
+
+    def mgpuImportGathered(self, dev_ptr, world, slot_bytes, counts):
+        c = np.ascontiguousarray(counts, dtype=np.int64)
+        self._lib.gss_mgpu_import_gathered(self._h, dev_ptr, int(world), int(slot_bytes), c.ctypes.data_as(C.POINTER(_L)))
+
+    def peerInit(self, rank, world, payload_cap, slot_hits):
+        buf = C.create_string_buffer(128)
+        n = self._lib.gss_peer_init(self._h, rank, world, int(payload_cap), int(slot_hits), buf, 128)
+        return buf.raw[:n]
+
+    def peerConnect(self, blobs):
+        """blobs: list of the ranks' peerInit() results, in rank order"""
+        stride = len(blobs[0])
+        raw = b"".join(blobs)
+        self._lib.gss_peer_connect(self._h, C.c_char_p(raw), stride)
+
+    def peerEnqueue(self):
+        return self._lib.gss_peer_enqueue(self._h)
+
+    def peerFinish(self):
+        return self._lib.gss_peer_finish(self._h)
 
     def mgpuFinish(self):
         return self._lib.gss_mgpu_finish(self._h)

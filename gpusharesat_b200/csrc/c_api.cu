@@ -103,6 +103,15 @@ int gss_mgpu_enqueue_payload(gss_sharer *h, const void *dev_payload, int64_t val
 void gss_mgpu_redo_payload(gss_sharer *h, const void *dev_payload, int64_t total_bytes) { h->impl.mgpuRedoPayload(dev_payload, total_bytes); }
 int64_t gss_mgpu_enqueue_result(gss_sharer *h, void *dev_dst, int64_t cap_records) { return h->impl.mgpuEnqueueResult(dev_dst, cap_records); }
 int gss_mgpu_finish(gss_sharer *h) { return h->impl.mgpuFinish(); }
+void gss_mgpu_import_gathered(gss_sharer *h, const void *dev_gathered, int world, int64_t slot_bytes, const int64_t *counts) {
+    h->impl.mgpuImportGathered(dev_gathered, world, slot_bytes, counts);
+}
+int64_t gss_peer_init(gss_sharer *h, int rank, int world, int64_t payload_cap, int64_t slot_hits, void *blob_out, int64_t blob_cap) {
+    return h->impl.peerInit(rank, world, payload_cap, slot_hits, blob_out, blob_cap);
+}
+void gss_peer_connect(gss_sharer *h, const void *blobs, int64_t blob_bytes) { h->impl.peerConnect(blobs, blob_bytes); }
+int gss_peer_enqueue(gss_sharer *h) { return h->impl.peerEnqueue(); }
+int64_t gss_peer_finish(gss_sharer *h) { return h->impl.peerFinish(); }
 void gss_set_stream(gss_sharer *h, void *cuda_stream) { h->impl.setStream(cuda_stream); }
 int64_t gss_mgpu_wait(gss_sharer *h, const gss_raw_hit **hits) {
     if (!hits) return h->impl.mgpuWait(nullptr);

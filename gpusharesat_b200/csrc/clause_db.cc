@@ -139,31 +139,16 @@ bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
         const size_t tileWords = (size_t)kTileClauses * s;
         const int64_t tiles = (n + kTileClauses - 1) / kTileClauses;
         const int64_t firstTile = pl.fullReupload ? 0 : pl.dirtyFrom / kTileClauses;
-        if (shardWorld_ == 1) {
+        {
+            // Sharding (multi-GPU) splits the WORK, not the storage: every device holds the whole
+            // arena (176 MB at 10 M clauses is nothing next to 180 GB), so any rank can resolve any
+            // hit (ids, literals) on its device; a rank only checks the tiles t with t % world == rank.
             size_t total = (size_t)tiles * tileWords, from = (size_t)firstTile * tileWords;
             if (total > 0) {
                 if (!pl.dev.tryReserve(total, pl.fullReupload ? 0 : from, stream)) return false;
                 GSS_CUDA(cudaMemcpyAsync(pl.dev.data() + from, pl.lits.data() + from, (total - from) * sizeof(int32_t),
                                          cudaMemcpyHostToDevice, stream));
                 if (bytesCopied) *bytesCopied += (int64_t)((total - from) * sizeof(int32_t));
-            }
-        } else {
-            // this rank's tiles among [firstTile, tiles): pack them, one copy
-            int64_t gt0 = firstTile + ((shardRank_ - firstTile) % shardWorld_ + shardWorld_) % shardWorld_;
-            int64_t mine = gt0 < tiles ? (tiles - gt0 + shardWorld_ - 1) / shardWorld_ : 0;
-            if (mine > 0) {
-                size_t lt0 = (size_t)(gt0 / shardWorld_);
-                if (!pl.dev.tryReserve((size_t)localTiles(tiles) * tileWords, pl.fullReupload ? 0 : lt0 * tileWords, stream))
-                    return false;
-                pl.stage.setPinnedLimit(pinnedLimit_);
-                pl.stage.clear();
-                pl.stage.resize((size_t)mine * tileWords);
-                for (int64_t k = 0; k < mine; k++)
-                    memcpy(pl.stage.data() + (size_t)k * tileWords,
-                           pl.lits.data() + (size_t)(gt0 + k * shardWorld_) * tileWords, tileWords * sizeof(int32_t));
-                GSS_CUDA(cudaMemcpyAsync(pl.dev.data() + lt0 * tileWords, pl.stage.data(), (size_t)mine * tileWords * sizeof(int32_t),
-                                         cudaMemcpyHostToDevice, stream));
-                if (bytesCopied) *bytesCopied += (int64_t)((size_t)mine * tileWords * sizeof(int32_t));
             }
         }
         // clause ids of the same dirty range
@@ -203,9 +188,9 @@ int ClauseDb::buildDirectory(std::vector<LenDir> &dir) const {
         const PerLen &pl = *perLen_[s];
         int64_t n = (int64_t)pl.meta.size();
         if (n == 0) continue;
-        int64_t mine = localTiles((n + kTileClauses - 1) / kTileClauses);
-        if (mine == 0) continue;
-        tiles += (int)mine;
+        // a length none of whose tiles is checked here still gets its entry: hits of other ranks
+        // are resolved (ids, literals, activity bumps) through this directory
+        tiles += (int)localTiles((n + kTileClauses - 1) / kTileClauses);
         dir.push_back(LenDir{pl.dev.data(), s, (int32_t)n, tiles, 0, pl.idsDev.data(), const_cast<float *>(pl.actsDev.data())});
     }
     return tiles;

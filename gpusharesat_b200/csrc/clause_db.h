@@ -43,8 +43,8 @@ public:
 
     void setMaxLen(int maxLen);
     int maxLen() const { return maxLen_; }
-    // Multi-GPU: this database keeps every clause on the host but only the tiles t with
-    // t % world == rank on its device (local tile index t / world).  Before the first clause.
+    // Multi-GPU: every rank keeps every clause (host mirror and device arenas) but checks only the
+    // tiles t with t % world == rank.  Before the first clause.
     void setShard(int rank, int world);
     int shardRank() const { return shardRank_; }
     int shardWorld() const { return shardWorld_; }
@@ -132,7 +132,6 @@ private:
         DevBuf<float> actsDev;    // clause activities live on the device between two reduceDb calls
         HostBuf<float> actsStage;
         int64_t actsOnDevice = 0; // clauses [0, actsOnDevice) have their authoritative activity on the device
-        HostBuf<int32_t> stage;   // sharded upload: this rank's dirty tiles, packed
         int64_t dirtyFrom = 0;    // first clause index not yet on the device
         bool fullReupload = false;
     };

@@ -70,9 +70,11 @@ __global__ void k_fill_tables(DeviceTables t, int varFrom) {
 // blockIdx.y = solver.  (reference dUpdateAssigs, Assigs.cu:100-116)
 // `avail` = number of update records that really are in `upd` (a multi-GPU receiver may have got
 // a truncated payload: it must never read past what arrived)
+// `keep` != nullptr: `upd` is another GPU's memory (read once over NVLink); the records are also
+// written to this device's own copy, which the deferred k_collapse of this batch reads later
 __global__ void __launch_bounds__(256) k_apply_updates(const VarUpdate *__restrict__ upd,
                                                        const SolverRunParams *__restrict__ params, DeviceTables t,
-                                                       long long avail) {
+                                                       long long avail, VarUpdate *__restrict__ keep) {
     __shared__ uint32_t sAgg[kSlots], sSlot[kSlots];
     const int s = blockIdx.y;
     const SolverRunParams &p = params[s];
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(256) k_apply_updates(const VarUpdate *__restri
     const VarUpdate *u = upd + p.updStart;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         VarUpdate vu = u[i];
+        if (keep) keep[p.updStart + i] = vu;
         t.t2[(size_t)vu.var * t.solverStride + s] = make_uint2(vu.def, vu.tru);
         if (used) {
             uint32_t bt = vu.tru & vu.def, bf = ~vu.tru & vu.def, bu = ~vu.def;
@@ -197,8 +200,10 @@ __global__ void __launch_bounds__(256, 6) k_filter(CheckArgs a) {
         const LenDir d = a.dir[k];
         const int tileInLen = tile - (k ? sTileEnd[k - 1] : 0);
         const int len = d.len;
-        const int32_t *row = d.base + (size_t)tileInLen * kTileClauses * len + lane * 4;
-        const int c0 = (tileInLen * a.shardWorld + a.shardRank) * kTileClauses + lane * 4; // global clause index
+        // every device holds the whole arena; this rank checks the tiles t with t % world == rank
+        const int gTile = tileInLen * a.shardWorld + a.shardRank;
+        const int32_t *row = d.base + (size_t)gTile * kTileClauses * len + lane * 4;
+        const int c0 = gTile * kTileClauses + lane * 4; // global clause index
         const int nValid = d.count - c0; // clauses of this lane that exist (may be <= 0 or >= 4)
 
         uint32_t all0 = nValid > 0 ? start : 0u, all1 = nValid > 1 ? start : 0u;
@@ -357,11 +362,12 @@ __global__ void __launch_bounds__(128) k_check_dense(CheckArgs a) {
         const LenDir d = a.dir[k];
         const int tileInLen = tile - (k ? sTileEnd[k - 1] : 0);
         const int len = d.len;
-        const int c0 = (tileInLen * a.shardWorld + a.shardRank) * kTileClauses + q * kDenseGroup;
+        const int gTile = tileInLen * a.shardWorld + a.shardRank;
+        const int c0 = gTile * kTileClauses + q * kDenseGroup;
         const int nValid = d.count - c0;
         if (nValid <= 0) continue;
         // lane l < kDenseGroup holds literal i of clause c0 + l
-        const int32_t *col = d.base + (size_t)tileInLen * kTileClauses * len + q * kDenseGroup + (lane & (kDenseGroup - 1));
+        const int32_t *col = d.base + (size_t)gTile * kTileClauses * len + q * kDenseGroup + (lane & (kDenseGroup - 1));
 
         uint32_t all[kDenseGroup], one[kDenseGroup];
 #pragma unroll
@@ -418,6 +424,51 @@ __global__ void k_finalize(const Counters *c, unsigned int hitCap, unsigned int 
     for (int i = 2; i < 8; i++) dst[i] = 0;
 }
 
+// ---- peer-memory exchange (multi-GPU, peer.cu) ----
+// root: tell every worker that payload `seq` is complete in the root's window (the H2D copy that
+// wrote it precedes this kernel on the stream)
+__global__ void k_peer_signal(PeerFlagList boxes, uint32_t seq) {
+    const int r = threadIdx.x;
+    if (r >= boxes.n) return;
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(boxes.p[r]) = seq;
+}
+
+// every rank, after its check kernels: result header into its slot of the root's gather window, then
+// the done flag.  The hits themselves were appended to the slot by k_exact (peer stores), which has
+// completed.  flag = 2*seq when the result is complete, 2*seq-1 when a survivor / hit buffer
+// overflowed and this rank is going to run again.
+__global__ void k_peer_finalize(const Counters *c, unsigned int hitCap, unsigned int survCap, int groups, long long *hdr,
+                                uint32_t *doneFlag, uint32_t seq) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    long long flags = c->nHits > hitCap ? 2 : 0;
+    for (int g = 0; g < groups && g < kMaxGroups; g++)
+        if (c->nSurvivors[g] > survCap) flags |= 1;
+    hdr[0] = (long long)c->nHits;
+    hdr[1] = flags;
+    hdr[2] = (long long)c->exactTests;
+    hdr[3] = (long long)seq;
+    for (int i = 4; i < 8; i++) hdr[i] = 0;
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(doneFlag) = flags ? 2u * seq - 1u : 2u * seq;
+}
+
+// fallback for drivers without stream memory operations: poll a flag in this device's memory
+// (bounded: *err is set after ~timeoutNs instead of hanging the device)
+__global__ void k_peer_wait(const uint32_t *flag, uint32_t value, unsigned long long timeoutNs, int *err) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        const uint32_t v = *reinterpret_cast<const volatile uint32_t *>(flag);
+        if ((int32_t)(v - value) >= 0) return;
+        __nanosleep(200);
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeoutNs) { *err = 1; return; }
+    }
+}
+
 // ---- post-processing of large hit lists ----
 __global__ void k_post_keys(const HitRecord *__restrict__ hits, unsigned int n, unsigned long long *keys, unsigned int *vals) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,7 +488,7 @@ __global__ void k_post_lens(const HitRecord *__restrict__ hits, const unsigned i
 
 // one warp per hit (in sorted order): record + literals
 __global__ void __launch_bounds__(256) k_post_emit(const HitRecord *__restrict__ hits, const unsigned int *__restrict__ order,
-                                                   unsigned int n, const LenDir *__restrict__ dir, int nDir, int shardWorld,
+                                                   unsigned int n, const LenDir *__restrict__ dir, int nDir,
                                                    const long long *__restrict__ litPos, SortedHit *__restrict__ out,
                                                    int32_t *__restrict__ lits, long long litCap) {
     const int lane = threadIdx.x & 31;
@@ -453,7 +504,7 @@ __global__ void __launch_bounds__(256) k_post_emit(const HitRecord *__restrict__
         const LenDir d = dir[lo];
         const long long pos = litPos[j];
         const int tile = h.idx / kTileClauses;
-        const int32_t *src = d.base + (size_t)(tile / shardWorld) * kTileClauses * h.len + (h.idx % kTileClauses);
+        const int32_t *src = d.base + (size_t)tile * kTileClauses * h.len + (h.idx % kTileClauses);
         for (int i = lane; i < h.len; i += 32)
             if (pos + i < litCap) lits[pos + i] = __ldg(src + (size_t)i * kTileClauses);
         if (lane == 0) out[j] = SortedHit{h.mask, h.solver, h.len, h.idx, d.ids[h.idx], pos};
@@ -545,10 +596,10 @@ void launchPostSort(const HitRecord *hits, unsigned int n, const PostBuffers &b,
     *launches += 4;
 }
 
-void launchPostEmit(const HitRecord *hits, unsigned int n, const LenDir *dir, int nDir, int shardWorld, const PostBuffers &b,
+void launchPostEmit(const HitRecord *hits, unsigned int n, const LenDir *dir, int nDir, const PostBuffers &b,
                     cudaStream_t s, int64_t *launches) {
     unsigned int blocks = std::min<unsigned int>((n + 7) / 8, 148 * 8);
-    k_post_emit<<<blocks, 256, 0, s>>>(hits, b.valsOut, n, dir, nDir, shardWorld, b.litPos, b.sorted, b.lits, b.litCap);
+    k_post_emit<<<blocks, 256, 0, s>>>(hits, b.valsOut, n, dir, nDir, b.litPos, b.sorted, b.lits, b.litCap);
     checkLaunch("k_post_emit");
     ++*launches;
 }
@@ -574,6 +625,27 @@ void launchFinalize(const Counters *counters, unsigned int hitCap, unsigned int 
     ++*launches;
 }
 
+void launchPeerSignal(const PeerFlagList &boxes, uint32_t seq, cudaStream_t s, int64_t *launches) {
+    if (boxes.n == 0) return;
+    k_peer_signal<<<1, 32, 0, s>>>(boxes, seq);
+    checkLaunch("k_peer_signal");
+    ++*launches;
+}
+
+void launchPeerFinalize(const Counters *counters, unsigned int hitCap, unsigned int survCap, int groups, long long *hdr,
+                        uint32_t *doneFlag, uint32_t seq, cudaStream_t s, int64_t *launches) {
+    k_peer_finalize<<<1, 32, 0, s>>>(counters, hitCap, survCap, groups, hdr, doneFlag, seq);
+    checkLaunch("k_peer_finalize");
+    ++*launches;
+}
+
+void launchPeerWait(const uint32_t *flag, uint32_t value, unsigned long long timeoutNs, int *err, cudaStream_t s,
+                    int64_t *launches) {
+    k_peer_wait<<<1, 32, 0, s>>>(flag, value, timeoutNs, err);
+    checkLaunch("k_peer_wait");
+    ++*launches;
+}
+
 void launchFillTables(const DeviceTables &t, int varFrom, cudaStream_t s, int64_t *launches) {
     if (t.varCap <= varFrom) return;
     k_fill_tables<<<592, 256, 0, s>>>(t, varFrom);
@@ -590,9 +662,9 @@ static dim3 updateGrid(int nSolvers, int maxUpdPerSolver, int numSMs) {
 }
 
 void launchApplyUpdates(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
-                        int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches) {
+                        int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches, VarUpdate *keep) {
     if (nSolvers == 0 || maxUpdPerSolver == 0) return;
-    k_apply_updates<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(upd, params, t, (long long)avail);
+    k_apply_updates<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(upd, params, t, (long long)avail, keep);
     checkLaunch("k_apply_updates");
     ++*launches;
 }

@@ -41,7 +41,7 @@ struct LaunchDims {
 struct CheckArgs {
     const LenDir *dir; // device copy of the length directory
     int nDir;
-    int totalTiles;               // tiles held by THIS device
+    int totalTiles;               // tiles checked by THIS device
     int shardRank, shardWorld;    // device tile t of a length is global tile t * shardWorld + shardRank
     const SolverRunParams *params; // device, all solvers
     int groupBase;                 // first solver of this group
@@ -58,7 +58,8 @@ struct CheckArgs {
 
 void launchFillTables(const DeviceTables &t, int varFrom, cudaStream_t s, int64_t *launches);
 void launchApplyUpdates(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
-                        int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches);
+                        int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches,
+                        VarUpdate *keep = nullptr);
 void launchCollapse(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
                     int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches);
 // production: aggregate filter + survivor compaction, then the exact pass on the survivors
@@ -86,7 +87,7 @@ size_t postprocessTempBytes(unsigned int n);
 // phase 1: sort + literal positions (litPos[n] = total); phase 2 (after the host has made room for the
 // literals): emit records and literals
 void launchPostSort(const HitRecord *hits, unsigned int n, const PostBuffers &b, cudaStream_t s, int64_t *launches);
-void launchPostEmit(const HitRecord *hits, unsigned int n, const LenDir *dir, int nDir, int shardWorld, const PostBuffers &b,
+void launchPostEmit(const HitRecord *hits, unsigned int n, const LenDir *dir, int nDir, const PostBuffers &b,
                     cudaStream_t s, int64_t *launches);
 
 // Activity bumps of a run's hits on the device (reference: one host-side bump per hit record,
@@ -99,6 +100,18 @@ void launchBumpActivity(const void *recs, int strideBytes, unsigned int n, const
 // can tell from the gathered buffers whether some rank has to run again with larger buffers
 void launchFinalize(const Counters *counters, unsigned int hitCap, unsigned int survCap, int groups, long long *dstHeader,
                     cudaStream_t s, int64_t *launches);
+
+// peer-memory exchange (peer.cu): flags live in device memory that other GPUs map through CUDA IPC
+constexpr int kMaxPeers = 16;
+struct PeerFlagList {
+    uint32_t *p[kMaxPeers];
+    int n;
+};
+void launchPeerSignal(const PeerFlagList &boxes, uint32_t seq, cudaStream_t s, int64_t *launches);
+void launchPeerFinalize(const Counters *counters, unsigned int hitCap, unsigned int survCap, int groups, long long *hdr,
+                        uint32_t *doneFlag, uint32_t seq, cudaStream_t s, int64_t *launches);
+void launchPeerWait(const uint32_t *flag, uint32_t value, unsigned long long timeoutNs, int *err, cudaStream_t s,
+                    int64_t *launches);
 
 // register-only LOP3 micro-benchmark: thread-level LOP3 per second on this device
 double measureLop3Peak(int numSMs, cudaStream_t s, int64_t *launches);

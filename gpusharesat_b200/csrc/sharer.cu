@@ -90,6 +90,7 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
 
 Sharer::~Sharer() {
     cudaSetDevice(device_);
+    peerClose();
     if (stream_) cudaStreamSynchronize(stream_);
     for (auto &s : slots_) {
         cudaEventDestroy(s.evStart);
@@ -308,8 +309,8 @@ CheckArgs Sharer::checkArgs(const RunSlot &slot, int g) const {
     a.tables = tables_;
     a.survivors = const_cast<Survivor *>(survDev_.data()) + (size_t)g * survCap_;
     a.survCap = (unsigned int)survCap_;
-    a.hits = (HitRecord *)(const_cast<uint8_t *>(resDev_.data()) + sizeof(Counters));
-    a.hitCap = (unsigned int)hitCap_;
+    a.hits = hitsOverride_ ? hitsOverride_ : (HitRecord *)(const_cast<uint8_t *>(resDev_.data()) + sizeof(Counters));
+    a.hitCap = hitsOverride_ ? hitCapOverride_ : (unsigned int)hitCap_;
     a.counters = (Counters *)const_cast<uint8_t *>(resDev_.data());
     return a;
 }
@@ -670,6 +671,42 @@ int64_t Sharer::mgpuWait(const HitRecord **hits) {
     return (int64_t)hits_.size();
 }
 
+// rank 0: the all-gathered result blocks are still on the device ([64 B header][hits] per rank).
+// Concatenate the valid parts on the device and treat the union like the hit list of a local run:
+// large unions are sorted / resolved on the device (every rank holds the whole clause arena).
+void Sharer::mgpuImportGathered(const void *devGathered, int world, int64_t slotBytes, const int64_t *counts) {
+    useDevice();
+    GSS_CHECK(mgpuLast_ >= 0);
+    RunSlot &slot = slots_[mgpuLast_];
+    size_t total = 0;
+    for (int r = 0; r < world; r++) total += (size_t)counts[r];
+    unionDev_.reserve(std::max<size_t>(total, 1) * sizeof(HitRecord), 0, stream_);
+    size_t off = 0;
+    const uint8_t *g = static_cast<const uint8_t *>(devGathered);
+    for (int r = 0; r < world; r++) {
+        if (counts[r] == 0) continue;
+        GSS_CUDA(cudaMemcpyAsync(unionDev_.data() + off * sizeof(HitRecord), g + (size_t)r * (size_t)slotBytes + 64,
+                                 (size_t)counts[r] * sizeof(HitRecord), cudaMemcpyDeviceToDevice, stream_));
+        off += (size_t)counts[r];
+    }
+    postValid_ = false;
+    finishedD2H_ = 0;
+    if (total >= kPostprocessHits) {
+        hits_.clear();
+        postprocessOnDevice(slot, total, (const HitRecord *)unionDev_.data());
+        parkHitsForBump((const uint8_t *)postDev_.data() + postSortedOffset_, (int)sizeof(SortedHit), total);
+    } else {
+        hits_.resize(total);
+        if (total) {
+            GSS_CUDA(cudaMemcpyAsync(hits_.data(), unionDev_.data(), total * sizeof(HitRecord), cudaMemcpyDeviceToHost, stream_));
+            GSS_CUDA(cudaStreamSynchronize(stream_));
+        }
+        finishedD2H_ = (int64_t)(total * sizeof(HitRecord));
+        parkHitsForBump(unionDev_.data(), (int)sizeof(HitRecord), total);
+    }
+    processResults(slot);
+}
+
 void Sharer::mgpuImport(const HitRecord *hits, int64_t n) {
     GSS_CHECK(mgpuLast_ >= 0);
     if (hits != hits_.data()) hits_.assign(hits, hits + n);
@@ -768,7 +805,7 @@ void Sharer::bumpParkedHits() {
     bumpN_ = 0;
 }
 
-void Sharer::postprocessOnDevice(RunSlot &slot, size_t n) {
+void Sharer::postprocessOnDevice(RunSlot &slot, size_t n, const HitRecord *hitsDevOverride) {
     auto align = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t tempBytes = postprocessTempBytes((unsigned int)n);
     size_t off = 0;
@@ -793,7 +830,7 @@ void Sharer::postprocessOnDevice(RunSlot &slot, size_t n) {
     b.tempBytes = tempBytes;
     b.lits = nullptr;
     b.litCap = 0;
-    const HitRecord *hitsDev = (const HitRecord *)(resDev_.data() + sizeof(Counters));
+    const HitRecord *hitsDev = hitsDevOverride ? hitsDevOverride : (const HitRecord *)(resDev_.data() + sizeof(Counters));
     launchPostSort(hitsDev, (unsigned int)n, b, stream_, &launches_);
     postTotalHost_.resize(1);
     GSS_CUDA(cudaMemcpyAsync(postTotalHost_.data(), b.litPos + n, sizeof(long long), cudaMemcpyDeviceToHost, stream_));
@@ -802,7 +839,7 @@ void Sharer::postprocessOnDevice(RunSlot &slot, size_t n) {
     postLitsDev_.reserve((size_t)std::max<int64_t>(total, 1), 0, stream_);
     b.lits = postLitsDev_.data();
     b.litCap = total;
-    launchPostEmit(hitsDev, (unsigned int)n, slot.dirDev(), slot.nDir, db_->shardWorld(), b, stream_, &launches_);
+    launchPostEmit(hitsDev, (unsigned int)n, slot.dirDev(), slot.nDir, b, stream_, &launches_);
     postSortedHost_.resize(n);
     postLitsHost_.resize((size_t)std::max<int64_t>(total, 1));
     GSS_CUDA(cudaMemcpyAsync(postSortedHost_.data(), b.sorted, n * sizeof(SortedHit), cudaMemcpyDeviceToHost, stream_));

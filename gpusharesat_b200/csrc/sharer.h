@@ -62,7 +62,14 @@ public:
     void setStream(void *stream);
     int64_t mgpuWait(const HitRecord **hits);
     void mgpuImport(const HitRecord *hits, int64_t n);
+    void mgpuImportGathered(const void *devGathered, int world, int64_t slotBytes, const int64_t *counts);
     void dbSize(int64_t *ncl, int64_t *nlits) { *ncl = db_->stats().clauses; *nlits = db_->stats().lengthSum; }
+    // ---- multi-GPU over peer memory (CUDA IPC windows, no collective on the data path: peer.cu) ----
+    int64_t peerInit(int rank, int world, int64_t payloadCap, int64_t slotHits, void *blobOut, int64_t blobCap);
+    void peerConnect(const void *blobs, int64_t blobBytes);
+    int peerEnqueue();
+    int64_t peerFinish();
+    void peerClose();
 
 private:
     struct RunSlot {
@@ -154,6 +161,14 @@ private:
         return (sizeof(PayloadHeader) + (size_t)nSolvers * sizeof(SolverRunParams) + sizeof(VarUpdate) - 1) / sizeof(VarUpdate);
     }
 
+    // ---- peer-memory exchange state (peer.cu) ----
+    struct PeerState;
+    PeerState *peer_ = nullptr;
+    HitRecord *hitsOverride_ = nullptr; // the check kernels append their hits here (peer mode: this rank's
+    unsigned int hitCapOverride_ = 0;   // slot in rank 0's gather window) instead of resDev_
+    void peerLaunchCheckAndFinalize(RunSlot &slot);
+    void peerWaitFlag(const uint32_t *flag, uint32_t value);
+
     std::vector<HitRecord> hits_;   // hits of the run being processed
     // large hit lists are sorted / resolved on the device (see kernels.cuh: PostBuffers)
     static constexpr size_t kPostprocessHits = 8192;
@@ -166,7 +181,8 @@ private:
     HostBuf<SortedHit> postSortedHost_;
     HostBuf<int32_t> postLitsHost_;
     HostBuf<long long> postTotalHost_;
-    void postprocessOnDevice(RunSlot &slot, size_t n);
+    void postprocessOnDevice(RunSlot &slot, size_t n, const HitRecord *hitsDevOverride = nullptr);
+    DevBuf<uint8_t> unionDev_; // multi-GPU rank 0: the ranks' hits, concatenated
     // activity bumps on the device: the hit records of the finished run are parked in bumpRecs_
     // before the next run may overwrite the result buffers, and bumped once the next batch of
     // clauses has been drained (same increment as the reference uses at that point)

@@ -170,11 +170,8 @@ class ShardedRunner:
         if cuda:
             self.ev1.record()
         # ---- the only synchronisation of the step ----
-        if rank == 0:
-            host = gathered.cpu().numpy()
-            heads = host.reshape(world, slot)[:, :HEADER_BYTES].copy().view(np.int64)
-        else:
-            heads = gathered.view(world, slot)[:, :HEADER_BYTES].contiguous().cpu().numpy().view(np.int64)
+        heads = gathered.view(world, slot)[:, :HEADER_BYTES].contiguous().cpu().numpy().view(np.int64)
+        if rank != 0:
             total = int(self.payload[:HEADER_BYTES].cpu().numpy().view(np.int64)[3])
         sh.mgpuFinish()  # a rank whose header says "overflow" grows its buffers and runs again in here
         counts, flags = heads[:, 0].tolist(), heads[:, 1].tolist()
@@ -190,8 +187,7 @@ class ShardedRunner:
         while need:  # second round(s): every rank re-contributes its (now complete) result block
             self.hit_pred = max(self.hit_pred, _next_pow2(max(counts) + 1))
             gathered, slot = self._gather()
-            host = gathered.cpu().numpy()
-            heads = host.reshape(world, slot)[:, :HEADER_BYTES].copy().view(np.int64)
+            heads = gathered.view(world, slot)[:, :HEADER_BYTES].contiguous().cpu().numpy().view(np.int64)
             if redo_in_flight:
                 sh.mgpuFinish()
                 redo_in_flight = False
@@ -202,7 +198,40 @@ class ShardedRunner:
         self.hit_pred = max(1024, _round_up(m + m // 2, 1024))
         if rank != 0:
             return 0
-        parts = [host[r * slot + HEADER_BYTES: r * slot + HEADER_BYTES + c * rec] for r, c in enumerate(counts) if c]
-        allhits = np.concatenate(parts).view(RAW_HIT_DTYPE) if parts else np.zeros(0, dtype=RAW_HIT_DTYPE)
-        sh.mgpuImport(allhits)
-        return len(allhits)
+        # the union stays on the device: the library concatenates, sorts and resolves it there
+        sh.mgpuImportGathered(gathered.data_ptr(), world, slot, counts)
+        return int(sum(counts))
+
+
+class PeerRunner:
+    """Data path over peer memory instead of collectives (csrc/peer.cu): every rank exports a
+    window of its device memory with CUDA IPC, workers read the batch out of rank 0's memory and
+    append their hits into rank 0's memory over NVLink, streams wait on flags.  torch.distributed
+    only carries the 128-byte window handles once, at start-up.
+
+    SPMD: every rank calls step() for every batch (like the clause stream, which every rank sees)."""
+
+    def __init__(self, sh, dist, rank, world, payload_cap=64 << 20, slot_hits=1 << 20):
+        self.sh, self.rank, self.world = sh, rank, world
+        blob = sh.peerInit(rank, world, payload_cap, slot_hits)
+        blobs = [None] * world
+        if world > 1:
+            dist.all_gather_object(blobs, blob)
+        else:
+            blobs[0] = blob
+        sh.peerConnect(blobs)
+        if world > 1:
+            dist.barrier()
+
+    def step(self):
+        """one batch; rank 0 returns the number of hits handed over, workers their own count, None
+        when there is no clause yet"""
+        if self.sh.peerEnqueue() < 0:
+            return None
+        return self.sh.peerFinish()
+
+    def device_us(self):
+        """device time of the last batch on this rank from "batch resident in rank 0's HBM" to the end
+        of the step (rank 0: every rank's hits have arrived in its memory)"""
+        t = self.sh.debugLastRunTimes()
+        return (t[3] - t[0]) if t else 0.0

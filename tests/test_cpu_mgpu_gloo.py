@@ -173,6 +173,12 @@ class FakeSharer:
     def mgpuImport(self, hits):
         self.imported.append(np.array(hits, copy=True))
 
+    def mgpuImportGathered(self, ptr, world, slot, counts):
+        raw = np.ctypeslib.as_array((self.C.c_uint8 * (world * slot)).from_address(ptr))
+        parts = [raw[r * slot + 64: r * slot + 64 + int(c) * 16] for r, c in enumerate(counts) if c]
+        hits = np.concatenate(parts).view(RAW_HIT_DTYPE) if parts else np.zeros(0, dtype=RAW_HIT_DTYPE)
+        self.imported.append(np.array(hits, copy=True))
+
 
 def _runner_worker(rank, world, port, q):
     from gpusharesat_b200 import mgpu
@@ -210,6 +216,60 @@ def test_sharded_runner_protocol_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_runner_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: True, 1: True}
+
+
+class FakePeerSharer:
+    """stands in for the library behind mgpu.PeerRunner: records what the runner hands it"""
+
+    def __init__(self, rank):
+        self.rank, self.blobs, self.steps = rank, None, 0
+
+    def peerInit(self, rank, world, payload_cap, slot_hits):
+        return bytes([rank]) * 16 + payload_cap.to_bytes(8, "little") + slot_hits.to_bytes(8, "little")
+
+    def peerConnect(self, blobs):
+        self.blobs = list(blobs)
+
+    def peerEnqueue(self):
+        self.steps += 1
+        return -1 if self.steps == 2 else 0
+
+    def peerFinish(self):
+        return 100 * self.steps + self.rank
+
+    def debugLastRunTimes(self):
+        return [5.0, 1.0, 2.0, 30.0]
+
+
+def _peer_runner_worker(rank, world, port, q):
+    from gpusharesat_b200 import mgpu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = FakePeerSharer(rank)
+    runner = mgpu.PeerRunner(sh, dist, rank, world, payload_cap=1 << 20, slot_hits=777)
+    # every rank got every rank's window handle, in rank order
+    ok = sh.blobs == [bytes([r]) * 16 + (1 << 20).to_bytes(8, "little") + (777).to_bytes(8, "little") for r in range(world)]
+    ok = ok and runner.step() == 100 + rank
+    ok = ok and runner.step() is None  # "no clause yet": nothing is finished
+    ok = ok and runner.step() == 300 + rank
+    ok = ok and runner.device_us() == 25.0
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_peer_runner_bootstrap_world2_gloo():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_runner_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=120) for _ in range(world))

@@ -198,3 +198,62 @@ def test_async_receiver_path_truncated_payload_and_overflowing_buffers():
         assert np.array_equal(ranks[0].debugLastHits(), want), rnd
         assert len(want) > 10
     assert saw_trunc and saw_flag
+
+
+@pytest.mark.parametrize("big", [False, True])
+def test_import_from_gathered_device_buffer(big):
+    """gss_mgpu_import_gathered: rank 0 hands over the union straight from the all-gathered device
+    buffer; unions of >= 8192 hits take the device sort / resolve path (every rank holds the whole
+    clause arena, so rank 0 can resolve the other ranks' hits)."""
+    import torch
+    world, nsolvers = 2, 4
+    n = 24000 if big else 600
+    opts = dict(minGpuLatencyMicros=0)
+    ranks = [GpuClauseSharer(GpuClauseSharerOptions(**opts)) for _ in range(world)]
+    single = GpuClauseSharer(GpuClauseSharerOptions(**opts))
+    for r, sh in enumerate(ranks):
+        sh.setShard(r, world)
+    for sh in ranks + [single]:
+        sh.setVarCount(n)
+        sh.setCpuSolverCount(nsolvers)
+        for i in range(n):
+            sh.addClause(-1, [mkLit(i), mkLit((i + 1) % n, True)] if i % 3 else [mkLit(i)])
+    for sh in (ranks[0], single):
+        for s in range(nsolvers):
+            assert sh.trySetSolverValues(s, [mkLit(v, True) for v in range(0, n, s + 2)])
+            sh.trySendAssignment(s)
+    dev = torch.device("cuda", 0)
+    cap = 4 << 20
+    bufs = [torch.zeros(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
+    total = ranks[0].mgpuCollectTo(bufs[0].data_ptr(), cap)
+    torch.cuda.synchronize()
+    bufs[1][:total].copy_(bufs[0][:total])
+    assert ranks[0].mgpuRunPayload(bufs[0].data_ptr(), cap) >= 0
+    assert ranks[1].mgpuEnqueuePayload(bufs[1].data_ptr(), total) >= 0
+    hit_pred = 1 << 16
+    slot = 64 + hit_pred * 16
+    gathered = torch.zeros(world * slot, dtype=torch.uint8, device=dev)
+    def contribute():
+        for r, sh in enumerate(ranks):
+            sh.mgpuEnqueueResult(gathered.data_ptr() + r * slot, hit_pred)
+        torch.cuda.synchronize()
+        return gathered.view(world, slot)[:, :64].contiguous().cpu().numpy().view(np.int64)
+    heads = contribute()
+    reran = [sh.mgpuFinish() for sh in ranks]  # a rank whose buffers overflowed runs again in here
+    assert [bool(x) for x in reran] == [bool(f) for f in heads[:, 1]]
+    if any(reran):  # second round: every rank contributes its (now complete) block again
+        heads = contribute()
+    assert not heads[:, 1].any()
+    counts = heads[:, 0].tolist()
+    ranks[0].mgpuImportGathered(gathered.data_ptr(), world, slot, counts)
+    single.gpuRun(); single.gpuRun()
+    want = single.debugLastHits()
+    assert len(want) == sum(counts) and (len(want) >= 8192) == big
+    assert np.array_equal(ranks[0].debugLastHits(), want)
+    for s in range(nsolvers):
+        a, b = [], []
+        while (x := ranks[0].popReportedClause(s)) is not None:
+            a.append(x)
+        while (x := single.popReportedClause(s)) is not None:
+            b.append(x)
+        assert a == b and len(a) > 0
