@@ -63,6 +63,7 @@ def parse():
     p.add_argument("--no-dense", action="store_true")
     p.add_argument("--dense-iters", type=int, default=3)
     p.add_argument("--prod-iters", type=int, default=20)
+    p.add_argument("--filter-sweep", action="store_true", help="time every variant of the level-1 kernel")
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                    help="N > 1: weak = --clauses per GPU (database grows with N), strong = --clauses in total")
     p.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -458,6 +459,7 @@ def run_b200(a):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = sh.debugKernelLaunches()
+    hp0 = sh.debugHostPhases()
     wall, dev_tables, dev_check, dev_total, hits, h2d, d2h = [], [], [], [], [], [], []
     collapse_us = []
     barrier()
@@ -478,6 +480,7 @@ def run_b200(a):
         h2d.append(b1[0]); d2h.append(sh.debugLastRunBytes()[1])
         drain()
     launches = sh.debugKernelLaunches() - launches0
+    hp = [(b - a0) / a.steps for a0, b in zip(hp0, sh.debugHostPhases())]
     clocks = sampler.stop()
     # the collapse of batch k runs at the start of the following run: charge it to batch k
     sh.gpuRun()
@@ -510,6 +513,9 @@ def run_b200(a):
         "phases_us_per_step": {"table_kernels": float(np.mean(dev_tables) + np.mean(collapse)),
                                "check_kernels": float(np.mean(dev_check)), "h2d_to_d2h_total": float(np.mean(dev_total))},
         "literals": L_total, "assignments": A,
+        "e2e_host_us_per_step": {"finish_previous_run": hp[0], "of_which_wait_for_gpu": hp[4],
+                                 "of_which_sort_resolve_d2h_of_hits": hp[5], "start_next_run": hp[1],
+                                 "of_which_collect_deltas": hp[3], "hand_over_to_solver_queues": hp[2]},
         "host_us_total": {"fill_assigs": sh.getGlobalStat(10), "fill_reported": sh.getGlobalStat(11),
                           "gpu_runs": sh.getGlobalStat(3)},
     }
@@ -520,6 +526,24 @@ def run_b200(a):
         sh.gpuRun()
         t_prod = sh.debugTimeCheck(a.prod_iters, dense=False)
         t_filter = sh.debugTimeCheck(a.prod_iters, filter_only=True)
+        out["kernel_us"] = {"k_filter": t_filter, "k_exact": sh.debugTimeCheck(a.prod_iters, mode=3),
+                            "k_apply_updates": sh.debugTimeCheck(a.prod_iters, mode=4),
+                            "k_collapse": sh.debugTimeCheck(a.prod_iters, mode=5),
+                            "note": "each kernel re-launched back to back on the last batch (tables resident), CUDA events"}
+        if a.filter_sweep:
+            names = sh.debugFilterVariants()
+            sweep = []
+            for v, name in enumerate(names):
+                sh.debugSetFilterVariant(v)
+                sweep.append({"variant": v, "name": name, "us": sh.debugTimeCheck(a.prod_iters, filter_only=True)})
+            sh.debugSetFilterVariant(int(os.environ.get("GSS_FILTER_VARIANT", "-1")))
+            out["filter_variants"] = sweep
+            sweep = []
+            for v, name in enumerate(sh.debugExactVariants()):
+                sh.debugSetExactVariant(v)
+                sweep.append({"variant": v, "name": name, "us": sh.debugTimeCheck(a.prod_iters, mode=3)})
+            sh.debugSetExactVariant(int(os.environ.get("GSS_EXACT_VARIANT", "-1")))
+            out["exact_variants"] = sweep
         lop3 = sh.debugLop3Peak()
         peaks = {}
         try:

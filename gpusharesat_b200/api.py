@@ -76,6 +76,13 @@ SIGNATURES = {
     "gss_debug_set_dense": (None, [_P, _I]),
     "gss_debug_time_check": (C.c_double, [_P, _I, _I]),
     "gss_debug_last_run_times": (_I, [_P, C.POINTER(C.c_double)]),
+    "gss_debug_host_phases": (None, [_P, C.POINTER(C.c_double)]),
+    "gss_debug_filter_variants": (_I, []),
+    "gss_debug_filter_variant_name": (C.c_char_p, [_I]),
+    "gss_debug_set_filter_variant": (None, [_I]),
+    "gss_debug_exact_variants": (_I, []),
+    "gss_debug_exact_variant_name": (C.c_char_p, [_I]),
+    "gss_debug_set_exact_variant": (None, [_I]),
     "gss_debug_lop3_peak": (C.c_double, [_P]),
     "gss_debug_last_run_bytes": (None, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "gss_debug_kernel_launches": (_L, [_P]),
@@ -331,8 +338,28 @@ class GpuClauseSharer:
     def debugSetDense(self, dense):
         self._lib.gss_debug_set_dense(self._h, 1 if dense else 0)
 
-    def debugTimeCheck(self, iters, dense=False, filter_only=False):
-        return self._lib.gss_debug_time_check(self._h, int(iters), 2 if filter_only else (1 if dense else 0))
+    def debugTimeCheck(self, iters=10, dense=False, filter_only=False, mode=None):
+        """mode: 0 production check, 1 dense, 2 k_filter, 3 k_exact, 4 k_apply_updates, 5 k_collapse"""
+        if mode is None:
+            mode = 2 if filter_only else (1 if dense else 0)
+        return self._lib.gss_debug_time_check(self._h, int(iters), int(mode))
+
+    def debugHostPhases(self):
+        t = (C.c_double * 6)()
+        self._lib.gss_debug_host_phases(self._h, t)
+        return list(t)
+
+    def debugFilterVariants(self):
+        return [self._lib.gss_debug_filter_variant_name(v).decode() for v in range(self._lib.gss_debug_filter_variants())]
+
+    def debugSetFilterVariant(self, v):
+        self._lib.gss_debug_set_filter_variant(int(v))
+
+    def debugExactVariants(self):
+        return [self._lib.gss_debug_exact_variant_name(v).decode() for v in range(self._lib.gss_debug_exact_variants())]
+
+    def debugSetExactVariant(self, v):
+        self._lib.gss_debug_set_exact_variant(int(v))
 
     def debugLastRunTimes(self):
         t = (C.c_double * 4)()

@@ -58,21 +58,32 @@ uint32_t SolverAssigs::maskFromTo(int64_t fromId, int64_t toId) {
 }
 
 void SolverAssigs::collectLocked(HostBuf<VarUpdate> &out, SolverRunParams &p, AssigIds &ids, bool fullRebuild) {
-    ids.start = firstIdUsed_;
-    ids.count = (int32_t)(currentId_ - firstIdUsed_);
-
-    p.updStart = (int32_t)out.size();
+    const int32_t updStart = (int32_t)out.size();
     if (fullRebuild) {
+        ids.start = firstIdUsed_;
+        ids.count = (int32_t)(currentId_ - firstIdUsed_);
         // every variable: touched ones carry their update, the others all-slots = lastVarVal
         for (int v = 0; v < (int)lastVarVal_.size(); v++) {
             int pos = varToUpdatePos_[v];
             if (pos != -1 && pos < (int)updates_.size() && updates_[pos].var == v) out.push_back(updates_[pos]);
             else out.push_back(VarUpdate{v, fill(lastVarVal_[v] != V_UNDEF), fill(lastVarVal_[v] == V_TRUE)});
         }
+        finishCollectLocked(updStart, (int32_t)out.size() - updStart, p);
     } else {
-        if (!updates_.empty()) memcpy(out.append(updates_.size()), updates_.data(), updates_.size() * sizeof(VarUpdate));
+        collectIntoLocked(out.append(updates_.size()), updStart, p, ids);
     }
-    p.updCount = (int32_t)out.size() - p.updStart;
+}
+
+void SolverAssigs::collectIntoLocked(VarUpdate *dst, int32_t updStart, SolverRunParams &p, AssigIds &ids) {
+    ids.start = firstIdUsed_;
+    ids.count = (int32_t)(currentId_ - firstIdUsed_);
+    if (!updates_.empty()) memcpy(dst, updates_.data(), updates_.size() * sizeof(VarUpdate));
+    finishCollectLocked(updStart, (int32_t)updates_.size(), p);
+}
+
+void SolverAssigs::finishCollectLocked(int32_t updStart, int32_t updCount, SolverRunParams &p) {
+    p.updStart = updStart;
+    p.updCount = updCount;
     updatesSent_ += (int64_t)updates_.size();
 
     // Assigs.cu:255-261: the slot everything collapses to after the run

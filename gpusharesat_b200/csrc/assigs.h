@@ -37,6 +37,11 @@ public:
     // Appends the updates to `updates` and fills `p` and `ids`.  When fullRebuild is set the
     // update list covers EVERY variable (the device tables are being re-created).
     void collectLocked(HostBuf<VarUpdate> &updates, SolverRunParams &p, AssigIds &ids, bool fullRebuild);
+    // the same in two steps, so that the solvers' deltas can be copied concurrently: the number of
+    // pending delta records, then the copy into `dst` (room for exactly that many) + parameters
+    size_t pendingUpdatesLocked() const { return updates_.size(); }
+    void collectIntoLocked(VarUpdate *dst, int32_t updStart, SolverRunParams &p, AssigIds &ids);
+    void finishCollectLocked(int32_t updStart, int32_t updCount, SolverRunParams &p);
 
     void setAggBits(int start, int end) { startAggBit_ = start; endAggBit_ = end; }
     int64_t updatesSent() const { return updatesSent_; }

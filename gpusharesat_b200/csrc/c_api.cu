@@ -81,9 +81,16 @@ int64_t gss_add_clauses_bulk(gss_sharer *h, const int64_t *offsets, const int *l
 void gss_set_max_clause_len(gss_sharer *h, int max_len) { h->impl.setMaxClauseLen(max_len); }
 void gss_debug_set_dense(gss_sharer *h, int dense) { h->impl.setDense(dense != 0); }
 double gss_debug_time_check(gss_sharer *h, int iters, int dense) {
-    // dense: 0 production (k_filter + k_exact), 1 dense kernel, 2 k_filter alone
-    return h->impl.timeCheck(iters, dense == 1, dense == 2);
+    // 0 production (k_filter + k_exact), 1 dense kernel, 2 k_filter, 3 k_exact, 4 k_apply_updates, 5 k_collapse
+    return h->impl.timeCheck(iters, dense);
 }
+void gss_debug_host_phases(gss_sharer *h, double out_us[6]) { h->impl.hostPhases(out_us); }
+int gss_debug_filter_variants(void) { return gss::filterVariantCount(); }
+const char *gss_debug_filter_variant_name(int v) { return gss::filterVariantName(v); }
+void gss_debug_set_filter_variant(int v) { gss::setFilterVariant(v); }
+int gss_debug_exact_variants(void) { return gss::exactVariantCount(); }
+const char *gss_debug_exact_variant_name(int v) { return gss::exactVariantName(v); }
+void gss_debug_set_exact_variant(int v) { gss::setExactVariant(v); }
 int gss_debug_last_run_times(gss_sharer *h, double out_us[4]) { return h->impl.lastRunTimes(out_us); }
 double gss_debug_lop3_peak(gss_sharer *h) { return h->impl.lop3Peak(); }
 void gss_debug_last_run_bytes(gss_sharer *h, int64_t *h2d, int64_t *d2h) { h->impl.lastRunBytes(h2d, d2h); }

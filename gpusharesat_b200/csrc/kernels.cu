@@ -27,7 +27,6 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 
 // ---- cache-hinted loads ----
 // literal rows are streamed once: evict-first so they do not push the assignment tables out of L2
-__device__ __forceinline__ int4 ldStream128(const int32_t *p) { return __ldcs(reinterpret_cast<const int4 *>(p)); }
 __device__ __forceinline__ int ldStream32(const int32_t *p) { return __ldcs(p); }
 __device__ __forceinline__ uint2 ldTable(const uint2 *p) { return __ldg(p); }
 
@@ -36,21 +35,22 @@ __device__ __forceinline__ void step(uint32_t &all, uint32_t &one, uint32_t f, u
     all &= f;                    // 1 LOP3
 }
 
-// set the bits of `mask` in *p to `bits` (bits is a subset of mask); other solvers own the other bits
-__device__ __forceinline__ void mergeBits(uint32_t *p, uint32_t mask, uint32_t bits) {
-    uint32_t clear = mask & ~bits;
-    if (clear) atomicAnd(p, ~clear);
-    if (bits) atomicOr(p, bits);
+// One {F,U} pair of the level-1 table is 8 aligned bytes: both words are merged with ONE 64-bit
+// atomicAnd and ONE atomicOr (bits is a subset of mask; other solvers own the other bits).
+__device__ __forceinline__ void mergePair(uint2 *p, uint32_t mask, uint32_t bitsX, uint32_t bitsY) {
+    const unsigned long long clear = (unsigned long long)(mask & ~bitsX) | ((unsigned long long)(mask & ~bitsY) << 32);
+    const unsigned long long set = (unsigned long long)bitsX | ((unsigned long long)bitsY << 32);
+    unsigned long long *q = reinterpret_cast<unsigned long long *>(p);
+    if (clear) atomicAnd(q, ~clear);
+    if (set) atomicOr(q, set);
 }
 
 __device__ __forceinline__ void writeAggregates(const DeviceTables &t, int solver, int var, uint32_t mask, uint32_t T,
                                                 uint32_t F, uint32_t U) {
     uint2 *a = t.a1 + (size_t)(solver / kMaxSolversPerGroup) * 2 * (size_t)t.varCap + 2 * (size_t)var;
     // positive literal (2v) is false where the variable is false; negated (2v+1) where it is true
-    mergeBits(&a[0].x, mask, F);
-    mergeBits(&a[0].y, mask, U);
-    mergeBits(&a[1].x, mask, T);
-    mergeBits(&a[1].y, mask, U);
+    mergePair(&a[0], mask, F, U);
+    mergePair(&a[1], mask, T, U);
 }
 
 __global__ void k_fill_tables(DeviceTables t, int varFrom) {
@@ -72,12 +72,20 @@ __global__ void k_fill_tables(DeviceTables t, int varFrom) {
 // a truncated payload: it must never read past what arrived)
 // `keep` != nullptr: `upd` is another GPU's memory (read once over NVLink); the records are also
 // written to this device's own copy, which the deferred k_collapse of this batch reads later
+// (then `keepParams` likewise receives this device's copy of the run parameters, which the check
+// kernels of this batch and the collapse read)
 __global__ void __launch_bounds__(256) k_apply_updates(const VarUpdate *__restrict__ upd,
                                                        const SolverRunParams *__restrict__ params, DeviceTables t,
-                                                       long long avail, VarUpdate *__restrict__ keep) {
+                                                       long long avail, VarUpdate *__restrict__ keep,
+                                                       SolverRunParams *__restrict__ keepParams) {
     __shared__ uint32_t sAgg[kSlots], sSlot[kSlots];
     const int s = blockIdx.y;
     const SolverRunParams &p = params[s];
+    if (keepParams && blockIdx.x == 0) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&p);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(keepParams + s);
+        for (int i = threadIdx.x; i < (int)(sizeof(SolverRunParams) / 4); i += blockDim.x) dst[i] = src[i];
+    }
     const int n = (int)max(0ll, min((long long)p.updCount, avail - (long long)p.updStart)), nGroups = p.nGroups;
     if (n <= 0) return;
     if (threadIdx.x < kSlots) {
@@ -179,7 +187,31 @@ __device__ __forceinline__ int findDir(const int *sTileEnd, int nDir, int tile) 
 // (reference pass 1 of dFindClauses, GpuRunner.cu:148-172: one clause per thread, 4 B loads,
 // 12 B gathers with a sign select, no early exit across the warp)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 6) k_filter(CheckArgs a) {
+// Variants of the same kernel (template parameters), so that the choices can be measured against
+// each other on the device in one run (bench.py --filter-sweep; GSS_FILTER_VARIANT selects one):
+//   PREFETCH  request rows 0 and 1 of the warp's NEXT tile before working on the current one
+//   CONTIG    0: a warp takes every nWarps-th tile; 1: a contiguous run of tiles per warp; 2: a
+//             contiguous run per block, the block's warps interleaved inside it
+//   ROWMODE   literal rows: 0 = ld.global.cs (evict-first), 1 = ld.global.L1::no_allocate
+//   GMODE     level-1 gathers: 0 = ld.global.nc (L1 + L2), 1 = ld.global.cg (L2 only)
+template <int ROWMODE> __device__ __forceinline__ int4 ldRow(const int32_t *p) {
+    if constexpr (ROWMODE == 0) {
+        return __ldcs(reinterpret_cast<const int4 *>(p));
+    } else {
+        int4 v;
+        asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(p));
+        return v;
+    }
+}
+template <int GMODE> __device__ __forceinline__ uint2 ldGather(const uint2 *p) {
+    if constexpr (GMODE == 0) return __ldg(p);
+    else return __ldcg(p);
+}
+
+template <bool PREFETCH, int CONTIG, int ROWMODE, int GMODE, int MINBLOCKS>
+__global__ void __launch_bounds__(256, MINBLOCKS) k_filter_t(CheckArgs a) {
     extern __shared__ int sTileEnd[];
     for (int i = threadIdx.x; i < a.nDir; i += blockDim.x) sTileEnd[i] = a.dir[i].tileEnd;
     __syncthreads();
@@ -195,33 +227,88 @@ __global__ void __launch_bounds__(256, 6) k_filter(CheckArgs a) {
     WarpStage<Survivor> stage{sStage[threadIdx.x >> 5], 0};
     unsigned int *survCounter = &a.counters->nSurvivors[a.groupBase / kMaxSolversPerGroup];
 
-    for (int tile = warp; tile < a.totalTiles; tile += nWarps) {
+    // where a tile lives: every device holds the whole arena, this rank checks the tiles t with
+    // t % world == rank
+    struct Tile {
+        const int32_t *row; // this lane's column of the tile's first literal row
+        int len, c0, nValid;
+        int lenEnd; // first (device-local) tile index of the next length
+    };
+    auto locate = [&](int tile) -> Tile {
         const int k = findDir(sTileEnd, a.nDir, tile);
         const LenDir d = a.dir[k];
-        const int tileInLen = tile - (k ? sTileEnd[k - 1] : 0);
-        const int len = d.len;
-        // every device holds the whole arena; this rank checks the tiles t with t % world == rank
-        const int gTile = tileInLen * a.shardWorld + a.shardRank;
-        const int32_t *row = d.base + (size_t)gTile * kTileClauses * len + lane * 4;
+        const int gTile = (tile - (k ? sTileEnd[k - 1] : 0)) * a.shardWorld + a.shardRank;
         const int c0 = gTile * kTileClauses + lane * 4; // global clause index
-        const int nValid = d.count - c0; // clauses of this lane that exist (may be <= 0 or >= 4)
+        return Tile{d.base + (size_t)gTile * kTileClauses * d.len + lane * 4, d.len, c0, d.count - c0, sTileEnd[k]};
+    };
+    // the tile after `t` (device-local index tile + 1): the same length array continues, or look it up
+    auto advance = [&](const Tile &t, int tile) -> Tile {
+        if (tile + 1 >= t.lenEnd) return locate(tile + 1);
+        const int dc = kTileClauses * a.shardWorld;
+        return Tile{t.row + (size_t)dc * t.len, t.len, t.c0 + dc, t.nValid - dc, t.lenEnd};
+    };
+
+    int first, last, stepT;
+    if constexpr (CONTIG == 1) {
+        const int per = (a.totalTiles + nWarps - 1) / nWarps;
+        first = warp * per;
+        last = min(a.totalTiles, first + per);
+        stepT = 1;
+    } else if constexpr (CONTIG == 2) {
+        // a block takes a contiguous run of tiles and its warps interleave inside it: at any moment
+        // the warps of an SM read neighbouring tiles (one DRAM page, neighbouring level-1 entries)
+        const int perBlock = ((a.totalTiles + (int)gridDim.x - 1) / (int)gridDim.x + warpsPerBlock - 1) / warpsPerBlock * warpsPerBlock;
+        const int b0 = blockIdx.x * perBlock;
+        first = b0 + (threadIdx.x >> 5);
+        last = min(a.totalTiles, b0 + perBlock);
+        stepT = warpsPerBlock;
+    } else {
+        first = warp;
+        last = a.totalTiles;
+        stepT = nWarps;
+    }
+    if (first >= last) return;
+
+    Tile cur = locate(first);
+    int4 r0 = ldRow<ROWMODE>(cur.row), r1 = r0;
+    if constexpr (PREFETCH) r1 = cur.len > 1 ? ldRow<ROWMODE>(cur.row + kTileClauses) : r0;
+    for (int tile = first; tile < last; tile += stepT) {
+        Tile nxt = cur;
+        int4 n0 = r0, n1 = r1;
+        if constexpr (PREFETCH) {
+            // rows 0 and 1 of a tile are needed almost always (a tile of 128 clauses rarely dies on
+            // its first row): request them for the NEXT tile before this one is worked on
+            if (tile + stepT < last) {
+                if constexpr (CONTIG == 1) nxt = advance(cur, tile);
+                else nxt = locate(tile + stepT);
+                n0 = ldRow<ROWMODE>(nxt.row);
+                n1 = nxt.len > 1 ? ldRow<ROWMODE>(nxt.row + kTileClauses) : n0;
+            }
+        }
+        const int len = cur.len, nValid = cur.nValid; // clauses of this lane that exist: may be <= 0 or >= 4
+        const int32_t *row = cur.row;
 
         uint32_t all0 = nValid > 0 ? start : 0u, all1 = nValid > 1 ? start : 0u;
         uint32_t all2 = nValid > 2 ? start : 0u, all3 = nValid > 3 ? start : 0u;
         uint32_t one0 = 0, one1 = 0, one2 = 0, one3 = 0;
 
-        int4 lits = ldStream128(row);
+        int4 lits = r0;
         uint32_t alive = 0;
         for (int i = 0; i < len; i++) {
             int4 next = lits;
-            if (i + 1 < len) next = ldStream128(row + (size_t)(i + 1) * kTileClauses); // overlaps the gathers
+            if constexpr (PREFETCH) {
+                next = r1;
+                if (i >= 1 && i + 1 < len) next = ldRow<ROWMODE>(row + (size_t)(i + 1) * kTileClauses);
+            } else {
+                if (i + 1 < len) next = ldRow<ROWMODE>(row + (size_t)(i + 1) * kTileClauses); // overlaps the gathers
+            }
             // a dead clause stays dead: gather only for the live ones (every gather costs a 32 B
             // L2 sector, and after the first literal ~97 % of the clauses are dead)
             const uint2 dead = make_uint2(0u, 0u);
-            uint2 g0 = (all0 | one0) ? ldTable(a1 + lits.x) : dead;
-            uint2 g1 = (all1 | one1) ? ldTable(a1 + lits.y) : dead;
-            uint2 g2 = (all2 | one2) ? ldTable(a1 + lits.z) : dead;
-            uint2 g3 = (all3 | one3) ? ldTable(a1 + lits.w) : dead;
+            uint2 g0 = (all0 | one0) ? ldGather<GMODE>(a1 + lits.x) : dead;
+            uint2 g1 = (all1 | one1) ? ldGather<GMODE>(a1 + lits.y) : dead;
+            uint2 g2 = (all2 | one2) ? ldGather<GMODE>(a1 + lits.z) : dead;
+            uint2 g3 = (all3 | one3) ? ldGather<GMODE>(a1 + lits.w) : dead;
             step(all0, one0, g0.x, g0.y);
             step(all1, one1, g1.x, g1.y);
             step(all2, one2, g2.x, g2.y);
@@ -230,18 +317,53 @@ __global__ void __launch_bounds__(256, 6) k_filter(CheckArgs a) {
             if (!__any_sync(FULL, alive)) break; // all 128 clauses are dead: skip the remaining rows
             lits = next;
         }
-        if (!__any_sync(FULL, alive)) continue;
-
-        // survivors go to the warp's stage (one global atomic per ~64 survivors)
-        const uint64_t rowTag = (uint64_t)(uintptr_t)row | ((uint64_t)len << 48);
-        const uint32_t m0 = all0 | one0, m1 = all1 | one1, m2 = all2 | one2, m3 = all3 | one3;
-        stage.push(m0 != 0, Survivor{rowTag + 0 * sizeof(int32_t), c0 + 0, m0}, a.survivors, survCounter, a.survCap, lane);
-        stage.push(m1 != 0, Survivor{rowTag + 1 * sizeof(int32_t), c0 + 1, m1}, a.survivors, survCounter, a.survCap, lane);
-        stage.push(m2 != 0, Survivor{rowTag + 2 * sizeof(int32_t), c0 + 2, m2}, a.survivors, survCounter, a.survCap, lane);
-        stage.push(m3 != 0, Survivor{rowTag + 3 * sizeof(int32_t), c0 + 3, m3}, a.survivors, survCounter, a.survCap, lane);
+        if (__any_sync(FULL, alive)) {
+            // survivors go to the warp's stage (one global atomic per ~64 survivors)
+            const uint64_t rowTag = (uint64_t)(uintptr_t)row | ((uint64_t)len << 48);
+            const int c0 = cur.c0;
+            const uint32_t m0 = all0 | one0, m1 = all1 | one1, m2 = all2 | one2, m3 = all3 | one3;
+            stage.push(m0 != 0, Survivor{rowTag + 0 * sizeof(int32_t), c0 + 0, m0}, a.survivors, survCounter, a.survCap, lane);
+            stage.push(m1 != 0, Survivor{rowTag + 1 * sizeof(int32_t), c0 + 1, m1}, a.survivors, survCounter, a.survCap, lane);
+            stage.push(m2 != 0, Survivor{rowTag + 2 * sizeof(int32_t), c0 + 2, m2}, a.survivors, survCounter, a.survCap, lane);
+            stage.push(m3 != 0, Survivor{rowTag + 3 * sizeof(int32_t), c0 + 3, m3}, a.survivors, survCounter, a.survCap, lane);
+        }
+        if constexpr (PREFETCH) {
+            cur = nxt;
+            r0 = n0;
+            r1 = n1;
+        } else {
+            if (tile + stepT < last) {
+                if constexpr (CONTIG == 1) cur = advance(cur, tile);
+                else cur = locate(tile + stepT);
+                r0 = ldRow<ROWMODE>(cur.row);
+            }
+        }
     }
     stage.flush(a.survivors, survCounter, a.survCap, lane);
 }
+
+struct FilterVariant {
+    void (*kernel)(CheckArgs);
+    int threads;
+    const char *name;
+};
+const FilterVariant kFilterVariants[] = {
+    {k_filter_t<false, 0, 0, 0, 5>, 256, "strided tiles, 5 x 256 threads/SM"},
+    {k_filter_t<false, 1, 0, 0, 5>, 256, "contiguous tiles per warp, 5 x 256"},
+    {k_filter_t<false, 2, 0, 0, 5>, 256, "contiguous tiles per block, warps interleaved, 5 x 256"},
+    {k_filter_t<false, 1, 0, 0, 4>, 256, "contiguous per warp, 4 x 256"},
+    {k_filter_t<false, 2, 0, 0, 4>, 256, "contiguous per block, 4 x 256"},
+    {k_filter_t<false, 1, 0, 0, 6>, 256, "contiguous per warp, 6 x 256 (40 registers, spills)"},
+    {k_filter_t<false, 2, 0, 0, 6>, 256, "contiguous per block, 6 x 256 (40 registers, spills)"},
+    {k_filter_t<false, 1, 1, 0, 5>, 256, "contiguous per warp, rows L1::no_allocate, 5 x 256"},
+    {k_filter_t<false, 2, 0, 0, 5>, 128, "contiguous per block, 10 x 128"},
+    {k_filter_t<true, 0, 0, 0, 5>, 256, "strided, next tile's rows 0+1 prefetched, 5 x 256"},
+    {k_filter_t<true, 1, 0, 0, 4>, 256, "contiguous per warp + prefetch, 4 x 256"},
+    {k_filter_t<false, 0, 0, 0, 6>, 256, "strided, 6 x 256 (40 registers, spills)"},
+};
+constexpr int kNumFilterVariants = (int)(sizeof(kFilterVariants) / sizeof(kFilterVariants[0]));
+int gFilterVariant = -1; // -1: not chosen yet (GSS_FILTER_VARIANT or the default)
+constexpr int kDefaultFilterVariant = 0;
 
 // append one hit per lane with a non-zero mask; one atomic per warp
 __device__ __forceinline__ void reportHits(const CheckArgs &a, uint32_t m, int solver, int len, int idx, int lane) {
@@ -261,11 +383,12 @@ __device__ __forceinline__ void reportHits(const CheckArgs &a, uint32_t m, int s
 // load and one coalesced T2 row (8 B per lane).  (reference dCheckOneClauseAllSolvers /
 // dCheckOneClauseOneSolver, GpuRunner.cu:68-131: serial per thread, one solver after the other)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_exact(CheckArgs a) {
+// G = survivors a warp checks together (their row gathers are independent)
+template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS) k_exact_t(CheckArgs a) {
     const int lane = threadIdx.x & 31;
     const int warpsPerBlock = blockDim.x >> 5;
-    const int warp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
-    const int nWarps = gridDim.x * warpsPerBlock;
+    const unsigned int warp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
+    const unsigned int nWarps = gridDim.x * warpsPerBlock;
     const bool active = lane < a.groupSolvers;
     const int solver = a.groupBase + (active ? lane : 0);
     const uint32_t myStart = active ? a.params[solver].startVals : 0u;
@@ -275,57 +398,86 @@ __global__ void __launch_bounds__(256) k_exact(CheckArgs a) {
 
     unsigned int n = a.counters->nSurvivors[a.groupBase / kMaxSolversPerGroup];
     if (n > a.survCap) n = a.survCap;
+    const unsigned int nGroups = (n + G - 1) / G;
     unsigned long long tests = 0;
     const uint2 ident = make_uint2(0u, 0u);
     __shared__ HitRecord sStage[kMaxWarpsPerBlock][kStageCap];
     WarpStage<HitRecord> stage{sStage[threadIdx.x >> 5], 0};
 
-    // Software pipeline over the survivors of this warp: while survivor i is checked, the literals
-    // of survivor i+1 and the record of survivor i+2 are already in flight (each is a dependent
-    // DRAM/L2 round trip; one warp sees ~20 survivors, so the chain would otherwise be exposed).
-    auto ldSurv = [&](unsigned int i) -> uint4 {
-        return i < n ? __ldg(reinterpret_cast<const uint4 *>(a.survivors + i)) : make_uint4(0u, 0u, 0u, 0u);
+    // A warp takes G consecutive survivors at a time; lane g (< G) holds record g of the group.  The
+    // chain per survivor is record -> literals -> T2 rows, each a dependent DRAM / L2 round trip:
+    // the records of group i+2 and the literals of group i+1 are in flight while group i is checked,
+    // and the rows of all G survivors of a group are gathered together (2 literals x G rows in flight).
+    auto ldGroup = [&](unsigned int grp) -> uint4 {
+        const unsigned int i = grp * G + lane;
+        return (grp < nGroups && lane < G && i < n) ? __ldg(reinterpret_cast<const uint4 *>(a.survivors + i))
+                                                    : make_uint4(0u, 0u, 0u, 0u);
     };
-    auto litPtr = [](const uint4 &sv) -> const int32_t * {
-        return reinterpret_cast<const int32_t *>(((uint64_t)(sv.y & 0xFFFFu) << 32) | sv.x);
+    // literal `base + lane` of survivor g of the group whose records are in sv (0 past the end)
+    auto ldLits = [&](const uint4 &sv, int g, int base) -> int {
+        const uint32_t x = __shfl_sync(FULL, sv.x, g), y = __shfl_sync(FULL, sv.y, g);
+        const int32_t *p = reinterpret_cast<const int32_t *>(((uint64_t)(y & 0xFFFFu) << 32) | x);
+        return base + lane < (int)(y >> 16) ? __ldg(p + (size_t)(base + lane) * kTileClauses) : 0;
     };
-    auto ldLits = [&](const uint4 &sv, int base) -> int {
-        const int len = (int)(sv.y >> 16);
-        return base + lane < len ? __ldg(litPtr(sv) + (size_t)(base + lane) * kTileClauses) : 0;
-    };
-    uint4 sv0 = ldSurv(warp), sv1 = ldSurv(warp + nWarps);
-    int lit0 = ldLits(sv0, 0);
-    for (unsigned int sIdx = warp; sIdx < n; sIdx += nWarps) {
-        const uint4 sv2 = ldSurv(sIdx + 2u * nWarps);
-        const int lit1 = ldLits(sv1, 0);
-        const int len = (int)(sv0.y >> 16), idx = (int)sv0.z;
-        uint32_t all = (sv0.w & myAgg) ? myStart : 0u, one = 0;
-        tests += __popc(__ballot_sync(FULL, all != 0));
+    uint4 sv0 = ldGroup(warp), sv1 = ldGroup(warp + nWarps);
+    int lit0[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) lit0[g] = ldLits(sv0, g, 0);
+    for (unsigned int grp = warp; grp < nGroups; grp += nWarps) {
+        const uint4 sv2 = ldGroup(grp + 2u * nWarps);
+        int lit1[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) lit1[g] = ldLits(sv1, g, 0);
+        uint32_t all[G], one[G];
+        int len[G], maxLen = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            len[g] = (int)(__shfl_sync(FULL, sv0.y, g) >> 16); // 0: no such survivor
+            const uint32_t agg = __shfl_sync(FULL, sv0.w, g);
+            all[g] = (len[g] > 0 && (agg & myAgg)) ? myStart : 0u;
+            one[g] = 0u;
+            tests += __popc(__ballot_sync(FULL, all[g] != 0));
+            maxLen = max(maxLen, len[g]);
+        }
         bool dead = false;
-        for (int base = 0; base < len && !dead; base += 32) {
-            const int nl = min(32, len - base);
-            const int myLit = base == 0 ? lit0 : ldLits(sv0, base);
-            for (int j = 0; j < nl; j += 4) {
-                // four independent row gathers per step; lanes whose solver is already dead
-                // (or was never selected by the filter) do not load at all
-                const int l0 = __shfl_sync(FULL, myLit, j), l1 = __shfl_sync(FULL, myLit, (j + 1) & 31);
-                const int l2 = __shfl_sync(FULL, myLit, (j + 2) & 31), l3 = __shfl_sync(FULL, myLit, (j + 3) & 31);
-                const bool live = (all | one) != 0;
-                const uint2 e0 = live ? ldTable(t2 + (size_t)(l0 >> 1) * stride) : ident;
-                const uint2 e1 = (live && j + 1 < nl) ? ldTable(t2 + (size_t)(l1 >> 1) * stride) : ident;
-                const uint2 e2 = (live && j + 2 < nl) ? ldTable(t2 + (size_t)(l2 >> 1) * stride) : ident;
-                const uint2 e3 = (live && j + 3 < nl) ? ldTable(t2 + (size_t)(l3 >> 1) * stride) : ident;
-                step(all, one, e0.x & ((l0 & 1) ? e0.y : ~e0.y), ~e0.x);
-                if (j + 1 < nl) step(all, one, e1.x & ((l1 & 1) ? e1.y : ~e1.y), ~e1.x);
-                if (j + 2 < nl) step(all, one, e2.x & ((l2 & 1) ? e2.y : ~e2.y), ~e2.x);
-                if (j + 3 < nl) step(all, one, e3.x & ((l3 & 1) ? e3.y : ~e3.y), ~e3.x);
-                if (!__any_sync(FULL, all | one)) { dead = true; break; }
+        for (int base = 0; base < maxLen && !dead; base += 32) {
+            int myLit[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) myLit[g] = base == 0 ? lit0[g] : ldLits(sv0, g, base);
+            const int nl = min(32, maxLen - base);
+            for (int j = 0; j < nl; j += 2) {
+                int l0[G], l1[G];
+                uint2 e0[G], e1[G];
+                // lanes whose solver is already dead for a survivor (or was never selected by the
+                // filter) do not load its rows at all
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    l0[g] = __shfl_sync(FULL, myLit[g], j);
+                    l1[g] = __shfl_sync(FULL, myLit[g], (j + 1) & 31);
+                    const bool live = (all[g] | one[g]) != 0;
+                    e0[g] = (live && base + j < len[g]) ? ldTable(t2 + (size_t)(l0[g] >> 1) * stride) : ident;
+                    e1[g] = (live && base + j + 1 < len[g]) ? ldTable(t2 + (size_t)(l1[g] >> 1) * stride) : ident;
+                }
+                uint32_t any = 0;
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    if (base + j < len[g]) step(all[g], one[g], e0[g].x & ((l0[g] & 1) ? e0[g].y : ~e0[g].y), ~e0[g].x);
+                    if (base + j + 1 < len[g]) step(all[g], one[g], e1[g].x & ((l1[g] & 1) ? e1[g].y : ~e1[g].y), ~e1[g].x);
+                    any |= all[g] | one[g];
+                }
+                if (!__any_sync(FULL, any)) { dead = true; break; }
             }
         }
-        stage.push((all | one) != 0, HitRecord{all | one, solver, len, idx}, a.hits, &a.counters->nHits, a.hitCap, lane);
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int idx = (int)__shfl_sync(FULL, sv0.z, g);
+            stage.push((all[g] | one[g]) != 0, HitRecord{all[g] | one[g], solver, len[g], idx}, a.hits, &a.counters->nHits,
+                       a.hitCap, lane);
+        }
         sv0 = sv1;
-        lit0 = lit1;
         sv1 = sv2;
+#pragma unroll
+        for (int g = 0; g < G; g++) lit0[g] = lit1[g];
     }
     stage.flush(a.hits, &a.counters->nHits, a.hitCap, lane);
     if (lane == 0 && tests) atomicAdd(&a.counters->exactTests, tests);
@@ -470,12 +622,15 @@ __global__ void k_peer_wait(const uint32_t *flag, uint32_t value, unsigned long 
 }
 
 // ---- post-processing of large hit lists ----
-__global__ void k_post_keys(const HitRecord *__restrict__ hits, unsigned int n, unsigned long long *keys, unsigned int *vals) {
+// key = solver | length | index packed into the fewest bits the database needs: the radix sort makes
+// one pass per 8 key bits
+__global__ void k_post_keys(const HitRecord *__restrict__ hits, unsigned int n, unsigned long long *keys, unsigned int *vals,
+                            int lenBits, int idxBits) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const HitRecord h = hits[i];
-    keys[i] = ((unsigned long long)(unsigned int)h.solver << 48) | ((unsigned long long)(unsigned int)h.len << 32) |
-              (unsigned long long)(unsigned int)h.idx;
+    keys[i] = ((unsigned long long)(unsigned int)h.solver << (lenBits + idxBits)) |
+              ((unsigned long long)(unsigned int)h.len << idxBits) | (unsigned long long)(unsigned int)h.idx;
     vals[i] = i;
 }
 
@@ -583,11 +738,13 @@ size_t postprocessTempBytes(unsigned int n) {
     return std::max(a, b) + 256;
 }
 
-void launchPostSort(const HitRecord *hits, unsigned int n, const PostBuffers &b, cudaStream_t s, int64_t *launches) {
+void launchPostSort(const HitRecord *hits, unsigned int n, const PostBuffers &b, int solverBits, int lenBits, int idxBits,
+                    cudaStream_t s, int64_t *launches) {
     const unsigned int blocks = (n + 1 + 255) / 256;
-    k_post_keys<<<blocks, 256, 0, s>>>(hits, n, b.keysIn, b.valsIn);
+    k_post_keys<<<blocks, 256, 0, s>>>(hits, n, b.keysIn, b.valsIn, lenBits, idxBits);
     size_t tb = b.tempBytes;
-    cub::DeviceRadixSort::SortPairs(b.temp, tb, b.keysIn, b.keysOut, b.valsIn, b.valsOut, (int)n, 0, 56, s);
+    cub::DeviceRadixSort::SortPairs(b.temp, tb, b.keysIn, b.keysOut, b.valsIn, b.valsOut, (int)n, 0,
+                                    std::min(64, solverBits + lenBits + idxBits), s);
     // literal positions: exclusive sum of the lengths in sorted order (litPos doubles as the input)
     k_post_lens<<<blocks, 256, 0, s>>>(hits, b.valsOut, n, b.litPos);
     tb = b.tempBytes;
@@ -662,9 +819,11 @@ static dim3 updateGrid(int nSolvers, int maxUpdPerSolver, int numSMs) {
 }
 
 void launchApplyUpdates(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
-                        int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches, VarUpdate *keep) {
+                        int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches, VarUpdate *keep,
+                        SolverRunParams *keepParams) {
     if (nSolvers == 0 || maxUpdPerSolver == 0) return;
-    k_apply_updates<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(upd, params, t, (long long)avail, keep);
+    k_apply_updates<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(upd, params, t, (long long)avail, keep,
+                                                                                 keepParams);
     checkLaunch("k_apply_updates");
     ++*launches;
 }
@@ -677,27 +836,64 @@ void launchCollapse(const VarUpdate *upd, const SolverRunParams *params, int nSo
     ++*launches;
 }
 
+int filterVariantCount() { return kNumFilterVariants; }
+const char *filterVariantName(int v) { return v >= 0 && v < kNumFilterVariants ? kFilterVariants[v].name : ""; }
+void setFilterVariant(int v) { gFilterVariant = v >= 0 && v < kNumFilterVariants ? v : kDefaultFilterVariant; }
+
 void launchFilterOnly(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches) {
     if (a.totalTiles == 0) return;
-    int threads = dims.threads;
+    if (gFilterVariant < 0) {
+        const char *e = getenv("GSS_FILTER_VARIANT");
+        setFilterVariant(e ? atoi(e) : kDefaultFilterVariant);
+    }
+    const FilterVariant &fv = kFilterVariants[gFilterVariant];
+    int threads = std::min(dims.threads, fv.threads);
     size_t smem = (size_t)a.nDir * sizeof(int);
     int warpsPerBlock = threads / 32;
-    int blocks = resolveBlocks((const void *)k_filter, threads, smem, numSMs, dims.blocks,
+    int blocks = resolveBlocks((const void *)fv.kernel, threads, smem, numSMs, dims.blocks,
                                ((long long)a.totalTiles + warpsPerBlock - 1) / warpsPerBlock);
-    k_filter<<<blocks, threads, smem, s>>>(a);
+    fv.kernel<<<blocks, threads, smem, s>>>(a);
     checkLaunch("k_filter");
+    ++*launches;
+}
+
+struct ExactVariant {
+    void (*kernel)(CheckArgs);
+    const char *name;
+};
+const ExactVariant kExactVariants[] = {
+    {k_exact_t<4, 3>, "4 survivors per warp step, 3 x 256 threads/SM"},
+    {k_exact_t<4, 4>, "4 survivors, 4 x 256"},
+    {k_exact_t<2, 5>, "2 survivors, 5 x 256"},
+    {k_exact_t<8, 2>, "8 survivors, 2 x 256"},
+    {k_exact_t<2, 4>, "2 survivors, 4 x 256"},
+    {k_exact_t<1, 6>, "1 survivor, 6 x 256"},
+};
+constexpr int kNumExactVariants = (int)(sizeof(kExactVariants) / sizeof(kExactVariants[0]));
+int gExactVariant = -1;
+constexpr int kDefaultExactVariant = 0;
+int exactVariantCount() { return kNumExactVariants; }
+const char *exactVariantName(int v) { return v >= 0 && v < kNumExactVariants ? kExactVariants[v].name : ""; }
+void setExactVariant(int v) { gExactVariant = v >= 0 && v < kNumExactVariants ? v : kDefaultExactVariant; }
+
+void launchExactOnly(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches) {
+    if (a.totalTiles == 0) return;
+    if (gExactVariant < 0) {
+        const char *e = getenv("GSS_EXACT_VARIANT");
+        setExactVariant(e ? atoi(e) : kDefaultExactVariant);
+    }
+    void (*k_exact)(CheckArgs) = kExactVariants[gExactVariant].kernel;
+    // the survivor count is only known on the device: a fixed grid strides over it
+    int blocks2 = resolveBlocks((const void *)k_exact, dims.threads, 0, numSMs, dims.blocks, -1);
+    k_exact<<<blocks2, dims.threads, 0, s>>>(a);
+    checkLaunch("k_exact");
     ++*launches;
 }
 
 void launchCheck(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches) {
     if (a.totalTiles == 0) return;
-    int threads = dims.threads;
     launchFilterOnly(a, dims, numSMs, s, launches);
-    // the survivor count is only known on the device: a fixed grid strides over it
-    int blocks2 = resolveBlocks((const void *)k_exact, threads, 0, numSMs, dims.blocks, -1);
-    k_exact<<<blocks2, threads, 0, s>>>(a);
-    checkLaunch("k_exact");
-    ++*launches;
+    launchExactOnly(a, dims, numSMs, s, launches);
 }
 
 void launchCheckDense(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches) {

@@ -59,13 +59,22 @@ struct CheckArgs {
 void launchFillTables(const DeviceTables &t, int varFrom, cudaStream_t s, int64_t *launches);
 void launchApplyUpdates(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
                         int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches,
-                        VarUpdate *keep = nullptr);
+                        VarUpdate *keep = nullptr, SolverRunParams *keepParams = nullptr);
 void launchCollapse(const VarUpdate *upd, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
                     int64_t avail, const DeviceTables &t, int numSMs, cudaStream_t s, int64_t *launches);
 // production: aggregate filter + survivor compaction, then the exact pass on the survivors
 void launchCheck(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
+// level 2 alone, on the survivor list the last level-1 launch left behind (bench)
+void launchExactOnly(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
 // level 1 alone (bench: per-kernel timing of the dominant production kernel)
 void launchFilterOnly(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
+// bench: the level-1 kernel exists in several variants (kernels.cu: kFilterVariants)
+int filterVariantCount();
+const char *filterVariantName(int v);
+void setFilterVariant(int v);
+int exactVariantCount();
+const char *exactVariantName(int v);
+void setExactVariant(int v);
 // bench-only dense mode: no filter, no early exit
 void launchCheckDense(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
 
@@ -86,7 +95,9 @@ struct PostBuffers {
 size_t postprocessTempBytes(unsigned int n);
 // phase 1: sort + literal positions (litPos[n] = total); phase 2 (after the host has made room for the
 // literals): emit records and literals
-void launchPostSort(const HitRecord *hits, unsigned int n, const PostBuffers &b, cudaStream_t s, int64_t *launches);
+// solverBits / lenBits / idxBits: bits needed for the largest solver index, clause length and clause index
+void launchPostSort(const HitRecord *hits, unsigned int n, const PostBuffers &b, int solverBits, int lenBits, int idxBits,
+                    cudaStream_t s, int64_t *launches);
 void launchPostEmit(const HitRecord *hits, unsigned int n, const LenDir *dir, int nDir, const PostBuffers &b,
                     cudaStream_t s, int64_t *launches);
 

@@ -70,6 +70,9 @@ struct Sharer::PeerState {
     HostBuf<long long> headsHost;       // rank 0: world x 8 int64
     HostBuf<int> errHost;
     double timeoutS = 120.0;
+    cudaEvent_t evC0 = nullptr, evC1 = nullptr; // around the deferred collapse of the previous batch
+    cudaEvent_t evGathered = nullptr;           // rank 0: every rank's hits are in its memory
+    bool collapsed = false;
 
     uint8_t *payload() const { return rootWindow + kCtlBytes; }
     uint8_t *slot(int r) const { return rootWindow + kCtlBytes + payloadArea + (size_t)r * slotBytes; }
@@ -152,12 +155,18 @@ void Sharer::peerConnect(const void *blobs, int64_t blobBytes) {
         P.rootWindow = open(blobOf(0));
     }
     P.errHost.resize(1);
+    GSS_CUDA(cudaEventCreate(&P.evC0));
+    GSS_CUDA(cudaEventCreate(&P.evC1));
+    GSS_CUDA(cudaEventCreate(&P.evGathered));
     P.connected = true;
 }
 
 void Sharer::peerClose() {
     if (!peer_) return;
     for (uint8_t *p : peer_->mapped) cudaIpcCloseMemHandle(p);
+    if (peer_->evC0) cudaEventDestroy(peer_->evC0);
+    if (peer_->evC1) cudaEventDestroy(peer_->evC1);
+    if (peer_->evGathered) cudaEventDestroy(peer_->evGathered);
     if (peer_->window) cudaFree(peer_->window);
     delete peer_;
     peer_ = nullptr;
@@ -196,6 +205,17 @@ int Sharer::peerEnqueue() {
     db_->drainPending();
     if (db_->stats().clauses == 0) return -1;
     RunSlot &slot = slots_[nextSlot()];
+    // The deferred dSetAllAssigsToLast of the previous batch needs nothing of the new one: it goes
+    // first (from this device's copy of that batch), ahead of the wait for the new payload, so on the
+    // workers it is off the critical path.  Its time is still charged to the step (lastTimes_).
+    P.collapsed = collapseSlot_ >= 0;
+    if (P.collapsed) {
+        RunSlot &c = slots_[collapseSlot_];
+        GSS_CUDA(cudaEventRecord(P.evC0, stream_));
+        launchCollapse(c.updDev.data(), c.paramsDev(), c.nSolvers, c.maxUpd, c.nUpdates, tables_, numSMs_, stream_, &launches_);
+        GSS_CUDA(cudaEventRecord(P.evC1, stream_));
+        collapseSlot_ = -1;
+    }
     bool rebuild = false;
     int64_t h2d = 0;
     if (!prepareRun(slot, rebuild, h2d)) GSS_DIE("out of device memory (multi-GPU mode does not reduce the database by itself)");
@@ -243,9 +263,9 @@ int Sharer::peerEnqueue() {
         slot.aggOnDevice = true; // the host never sees the run parameters: the kernels read them
         slot.maxUpd = (int)std::min<int64_t>(nUpper, 1 << 30);
         slot.nUpdates = nUpper;
+        // (the run parameters are NOT copied here: k_apply_updates reads them out of rank 0's memory
+        // and leaves this device's copy in headDev for the kernels that follow)
         GSS_CUDA(cudaMemcpyAsync(slot.headDev.data(), slot.headHost.data(), slot.dirBytes, cudaMemcpyHostToDevice, stream_));
-        GSS_CUDA(cudaMemcpyAsync(slot.headDev.data() + slot.dirBytes, payload + sizeof(PayloadHeader),
-                                 (size_t)slot.nSolvers * sizeof(SolverRunParams), cudaMemcpyDefault, stream_));
         h2d += (int64_t)slot.dirBytes;
     }
     slot.updDev.reserve((size_t)std::max<int64_t>(slot.nUpdates, 1), 0, stream_);
@@ -253,22 +273,20 @@ int Sharer::peerEnqueue() {
     GSS_CUDA(cudaEventRecord(slot.evH2DDone, stream_));
     if (root) launchPeerSignal(P.mailboxes, P.seq, stream_, &launches_);
 
-    if (collapseSlot_ >= 0) { // deferred dSetAllAssigsToLast of the previous batch (from the local copy)
-        RunSlot &c = slots_[collapseSlot_];
-        launchCollapse(c.updDev.data(), c.paramsDev(), c.nSolvers, c.maxUpd, c.nUpdates, tables_, numSMs_, stream_, &launches_);
-        collapseSlot_ = -1;
-    }
-    launchApplyUpdates(reinterpret_cast<const VarUpdate *>(payload + PR * sizeof(VarUpdate)), slot.paramsDev(), slot.nSolvers,
-                       slot.maxUpd, slot.nUpdates, tables_, numSMs_, stream_, &launches_, slot.updDev.data());
+    const SolverRunParams *paramsSrc = root ? slot.paramsDev() : reinterpret_cast<const SolverRunParams *>(payload + sizeof(PayloadHeader));
+    SolverRunParams *paramsKeep = root ? nullptr : const_cast<SolverRunParams *>(slot.paramsDev());
+    launchApplyUpdates(reinterpret_cast<const VarUpdate *>(payload + PR * sizeof(VarUpdate)), paramsSrc, slot.nSolvers,
+                       slot.maxUpd, slot.nUpdates, tables_, numSMs_, stream_, &launches_, slot.updDev.data(), paramsKeep);
     GSS_CUDA(cudaEventRecord(slot.evBeforeCheck, stream_));
     peerLaunchCheckAndFinalize(slot);
     GSS_CUDA(cudaEventRecord(slot.evAfterCheck, stream_));
     slot.resHost.resize(sizeof(Counters));
     GSS_CUDA(cudaMemcpyAsync(slot.resHost.data(), resDev_.data(), sizeof(Counters), cudaMemcpyDeviceToHost, stream_));
-    if (root) {
+    if (root)
         for (int r = 1; r < P.world; r++) peerWaitFlag(P.done(r), 2u * P.seq - 1u);
+    GSS_CUDA(cudaEventRecord(P.evGathered, stream_)); // rank 0: the hits of every rank are in its memory
+    if (root)
         GSS_CUDA(cudaMemcpy2DAsync(P.headsHost.data(), 64, P.slot(0), P.slotBytes, 64, (size_t)P.world, cudaMemcpyDeviceToHost, stream_));
-    }
     GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
     slot.inFlight = true;
     if (slot.nUpdates) collapseSlot_ = (int)(&slot - slots_);
@@ -308,11 +326,15 @@ int64_t Sharer::peerFinish() {
     cudaEventElapsedTime(&msCopy, slot.evStart, slot.evH2DDone);
     cudaEventElapsedTime(&msApply, slot.evH2DDone, slot.evBeforeCheck);
     cudaEventElapsedTime(&msCheck, slot.evBeforeCheck, slot.evAfterCheck);
-    cudaEventElapsedTime(&msTotal, slot.evStart, slot.evEnd);
+    cudaEventElapsedTime(&msTotal, slot.evStart, P.evGathered);
+    float msCollapse = 0;
+    if (P.collapsed) cudaEventElapsedTime(&msCollapse, P.evC0, P.evC1);
+    // [0] prepare + H2D, [1] table kernels (collapse of the previous batch + apply), [2] check kernels,
+    // [3] everything up to "hits gathered" including the collapse: [3] - [0] = device time of the step
     lastTimes_[0] = msCopy * 1000.0;
-    lastTimes_[1] = msApply * 1000.0;
+    lastTimes_[1] = (msApply + msCollapse) * 1000.0;
     lastTimes_[2] = msCheck * 1000.0;
-    lastTimes_[3] = msTotal * 1000.0;
+    lastTimes_[3] = (msTotal + msCollapse) * 1000.0;
     haveTimes_ = true;
     if (opts_.quickProf) globalStats_[G_timeSpentTestingClauses] += (uint64_t)(msCheck * 1000.0f);
 

@@ -5,7 +5,9 @@
 #pragma once
 #include <atomic>
 #include <condition_variable>
+#include <algorithm>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -85,6 +87,15 @@ private:
     int active_ = 0;
     uint64_t generation_ = 0;
     bool stop_ = false;
+};
+
+// created on first use (small runs never need it); shared by the collect and the hand-over side
+struct LazyPool {
+    std::unique_ptr<WorkerPool> p;
+    WorkerPool &get() {
+        if (!p) p = std::make_unique<WorkerPool>(std::max(1, std::min(15, (int)std::thread::hardware_concurrency() - 1)));
+        return *p;
+    }
 };
 
 } // namespace gss

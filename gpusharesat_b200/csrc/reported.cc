@@ -162,12 +162,11 @@ void Reported::handOver(std::vector<HitRecord> &hits, const std::vector<AssigIds
     }
     hits.swap(grouped_);
     auto t1 = now();
-    if (!pool_) pool_ = std::make_unique<WorkerPool>(std::max(1, std::min(15, (int)std::thread::hardware_concurrency() - 1)));
     std::atomic<bool> rescale{false};
     fillBuckets(
         ids, hits.data(), start,
         [&](const std::function<void(int)> &perSolver) {
-            pool_->parallelFor(nSolvers, [&](int s) {
+            pool_->get().parallelFor(nSolvers, [&](int s) {
                 std::sort(hits.begin() + start[s], hits.begin() + start[s + 1], byClause);
                 perSolver(s);
             });
@@ -183,14 +182,9 @@ void Reported::handOverSorted(const SortedHit *recs, size_t n, const int32_t *li
                               const std::vector<AssigIds> &ids, int nSolvers) {
     // recs are ordered by (solver, length, index): find every solver's slice
     std::vector<size_t> start((size_t)nSolvers + 1, n);
-    {
-        size_t i = 0;
-        for (int s = 0; s < nSolvers; s++) {
-            while (i < n && recs[i].solver < s) i++;
-            start[s] = i;
-        }
-        start[nSolvers] = n;
-    }
+    for (int s = 0; s < nSolvers; s++)
+        start[s] = (size_t)(std::lower_bound(recs, recs + n, s, [](const SortedHit &h, int v) { return h.solver < v; }) - recs);
+    start[nSolvers] = n;
     size_t nQueues = queues_.size();
     std::vector<ClauseBatch *> perSolver(nQueues, nullptr);
     for (size_t s = 0; s < nQueues && s < (size_t)nSolvers; s++) {
@@ -199,9 +193,8 @@ void Reported::handOverSorted(const SortedHit *recs, size_t n, const int32_t *li
         perSolver[s] = &queues_[s]->begin();
         if (hasIds) perSolver[s]->ids = ids[s];
     }
-    if (!pool_) pool_ = std::make_unique<WorkerPool>(std::max(1, std::min(15, (int)std::thread::hardware_concurrency() - 1)));
     std::atomic<bool> rescale{false};
-    pool_->parallelFor(nSolvers, [&](int s) {
+    pool_->get().parallelFor(nSolvers, [&](int s) {
         if ((size_t)s >= nQueues || !perSolver[s]) return;
         size_t lo = start[s], hi = start[s + 1];
         if (lo == hi) return;

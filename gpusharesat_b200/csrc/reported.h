@@ -74,6 +74,7 @@ public:
     void setSolverCount(int n);
     // false: the caller bumps the activities itself (on the device); true (default): per hit on the host
     void setHostBumps(bool on) { hostBumps_ = on; }
+    void setPool(LazyPool *p) { pool_ = p; }
 
     void clauseWasAdded(int solver, int64_t clauseId);                 // Reported.cu:97-103
     void assigWasSent(int solver, int64_t id) { lastSent_[solver] = id; } // Reported.cuh:118
@@ -117,7 +118,8 @@ private:
     bool referenceDupQuirk_;
     bool hostBumps_ = true;
     std::vector<HitRecord> grouped_;   // scratch: hits grouped by solver
-    std::unique_ptr<WorkerPool> pool_; // created on the first large hit list
+    LazyPool ownPool_;
+    LazyPool *pool_ = &ownPool_; // worker pool for large hit lists (the engine shares its own)
 };
 
 } // namespace gss

@@ -17,6 +17,13 @@ static inline int64_t nowMicros() {
     return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+struct PhaseTimer { // host-side wall time of a phase of gss_gpu_run (gss_debug_host_phases)
+    double &acc;
+    int64_t t0;
+    explicit PhaseTimer(double &a) : acc(a), t0(nowMicros()) {}
+    ~PhaseTimer() { acc += (double)(nowMicros() - t0); }
+};
+
 struct TimeAdder { // reference TimeGauge, gpuShareLib/Profiler.h:28-46
     uint64_t &acc;
     bool on;
@@ -82,6 +89,7 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
     db_ = std::make_unique<ClauseDb>(opts_.clauseActivityDecay, logger_, pinnedLimit);
     assigs_ = std::make_unique<HostAssigs>();
     reported_ = std::make_unique<Reported>(*db_, oneSolverStats_);
+    reported_->setPool(&pool_);
     db_->setDeviceActivities(true);
     reported_->setHostBumps(false);
     setCpuSolverCount(1);
@@ -92,6 +100,7 @@ Sharer::~Sharer() {
     cudaSetDevice(device_);
     peerClose();
     if (stream_) cudaStreamSynchronize(stream_);
+    if (bumpFlagEv_) cudaEventDestroy(bumpFlagEv_);
     for (auto &s : slots_) {
         cudaEventDestroy(s.evStart);
         cudaEventDestroy(s.evH2DDone);
@@ -239,18 +248,25 @@ void Sharer::reduceDb() {
 void Sharer::wholeRun(bool canStart) {
     useDevice();
     RunSlot *prev = cur_ >= 0 ? &slots_[cur_] : nullptr;
-    if (prev) finishRun(*prev); // run k is complete and every hit is on the host
+    {
+        PhaseTimer t(hostPhases_[0]);
+        if (prev) finishRun(*prev); // run k is complete and every hit is on the host
+    }
     int startedSlot = -1;
     bool outOfMemory = false;
     if (canStart) {
         int next = cur_ >= 0 ? 1 - cur_ : (collapseSlot_ >= 0 ? 1 - collapseSlot_ : 0);
+        PhaseTimer t(hostPhases_[1]);
         db_->drainPending();
         if (db_->stats().clauses > 0) { // GpuRunner.cu:284-288: nothing starts on an empty database
             if (startRun(slots_[next])) startedSlot = next;
             else outOfMemory = true;
         }
     }
-    if (prev) processResults(*prev); // overlaps with run k+1 on the GPU
+    {
+        PhaseTimer t(hostPhases_[2]);
+        if (prev) processResults(*prev); // overlaps with run k+1 on the GPU
+    }
     cur_ = startedSlot;
     if (outOfMemory) {
         // GpuRunner.cu:243-246
@@ -361,18 +377,40 @@ void Sharer::collectBatch(RunSlot &slot, bool rebuild) {
     slot.ids.assign(slot.nSolvers, AssigIds{});
     slot.assigCount = 0;
     TimeAdder t(globalStats_[G_timeSpentFillingAssigs], opts_.quickProf != 0);
+    // a solver busy writing its assignment is skipped for this run (Assigs.cu:350);
+    // during a table rebuild every solver must contribute, so wait for it
+    std::vector<char> locked(slot.nSolvers, 0);
+    std::vector<size_t> offset(slot.nSolvers + 1, 0);
+    size_t total = 0;
     for (int s = 0; s < slot.nSolvers; s++) {
         SolverAssigs &sa = assigs_->solver(s);
-        SolverRunParams &p = params[s];
-        memset(&p, 0, sizeof(p));
-        p.updStart = (int32_t)(slot.updHost.size() - P);
-        // a solver busy writing its assignment is skipped for this run (Assigs.cu:350);
-        // during a table rebuild every solver must contribute, so wait for it
-        bool locked = rebuild ? (sa.lock(), true) : sa.tryLock();
-        if (!locked) continue;
-        sa.collectLocked(slot.updHost, p, slot.ids[s], rebuild);
-        p.updStart -= (int32_t)P;
-        sa.unlock();
+        memset(&params[s], 0, sizeof(SolverRunParams));
+        locked[s] = rebuild ? (sa.lock(), 1) : (sa.tryLock() ? 1 : 0);
+        offset[s] = total;
+        if (locked[s] && !rebuild) total += sa.pendingUpdatesLocked();
+    }
+    offset[slot.nSolvers] = total;
+    if (rebuild) {
+        for (int s = 0; s < slot.nSolvers; s++) {
+            SolverRunParams &p = params[s];
+            assigs_->solver(s).collectLocked(slot.updHost, p, slot.ids[s], true);
+            p.updStart -= (int32_t)P;
+        }
+    } else {
+        // every solver's deltas go to their own range of the staging buffer: the copies are
+        // independent, large batches spread them over the worker pool
+        VarUpdate *base = slot.updHost.append(total);
+        auto one = [&](int s) {
+            SolverRunParams &p = params[s];
+            p.updStart = (int32_t)offset[s];
+            if (locked[s]) assigs_->solver(s).collectIntoLocked(base + offset[s], (int32_t)offset[s], p, slot.ids[s]);
+        };
+        if (total >= 65536 && slot.nSolvers >= 4) pool_.get().parallelFor(slot.nSolvers, one);
+        else for (int s = 0; s < slot.nSolvers; s++) one(s);
+    }
+    for (int s = 0; s < slot.nSolvers; s++) {
+        if (!locked[s]) continue;
+        assigs_->solver(s).unlock(); // by the thread that locked it
         slot.assigCount += slot.ids[s].count;
     }
     slot.nUpdates = (int64_t)(slot.updHost.size() - P);
@@ -426,7 +464,10 @@ bool Sharer::startRun(RunSlot &slot) {
     int64_t h2d = 0;
     bool rebuild = false;
     if (!prepareRun(slot, rebuild, h2d)) return false;
-    collectBatch(slot, rebuild);
+    {
+        PhaseTimer t(hostPhases_[3]);
+        collectBatch(slot, rebuild);
+    }
     launchRun(slot, slot.updHost.data() + payloadPrefixRecords(slot.nSolvers), slot.nUpdates, h2d);
     return true;
 }
@@ -716,7 +757,10 @@ void Sharer::mgpuImport(const HitRecord *hits, int64_t n) {
 }
 
 void Sharer::finishRun(RunSlot &slot, bool fetchAllHits, bool allowPostprocess) {
-    GSS_CUDA(cudaEventSynchronize(slot.evEnd));
+    {
+        PhaseTimer t(hostPhases_[4]);
+        GSS_CUDA(cudaEventSynchronize(slot.evEnd));
+    }
     float msCopy = 0, msApply = 0, msCheck = 0, msTotal = 0;
     cudaEventElapsedTime(&msCopy, slot.evStart, slot.evH2DDone);
     cudaEventElapsedTime(&msApply, slot.evH2DDone, slot.evBeforeCheck);
@@ -754,6 +798,7 @@ void Sharer::finishRun(RunSlot &slot, bool fetchAllHits, bool allowPostprocess) 
     if (fetchAllHits && allowPostprocess && c.nHits >= kPostprocessHits) {
         // large result: sort and resolve it on the device, fetch only the finished product
         hits_.clear();
+        PhaseTimer t(hostPhases_[5]);
         postprocessOnDevice(slot, c.nHits);
         parkHitsForBump((const uint8_t *)postDev_.data() + postSortedOffset_, (int)sizeof(SortedHit), c.nHits);
         return;
@@ -784,7 +829,8 @@ void Sharer::parkHitsForBump(const void *devRecs, int stride, size_t n) {
 void Sharer::bumpParkedHits() {
     // a bump of the previous batch overflowed an activity: rescale like Clauses.cu:231-237 does
     if (bumpFlagPending_) {
-        GSS_CUDA(cudaStreamSynchronize(stream_));
+        // wait for that bump's flag only -- not for whatever has been queued since (the next run)
+        GSS_CUDA(cudaEventSynchronize(bumpFlagEv_));
         if (bumpFlagHost_[0]) db_->rescaleAfterDeviceOverflow();
         bumpFlagPending_ = false;
     }
@@ -801,6 +847,8 @@ void Sharer::bumpParkedHits() {
     launchBumpActivity(bumpRecs_.data(), bumpStride_, (unsigned int)bumpN_, (const LenDir *)bumpDirDev_.data(), (int)dir.size(),
                        db_->activityIncrement(), bumpFlagDev_.data(), stream_, &launches_);
     GSS_CUDA(cudaMemcpyAsync(bumpFlagHost_.data(), bumpFlagDev_.data(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    if (!bumpFlagEv_) GSS_CUDA(cudaEventCreateWithFlags(&bumpFlagEv_, cudaEventDisableTiming));
+    GSS_CUDA(cudaEventRecord(bumpFlagEv_, stream_));
     bumpFlagPending_ = true;
     bumpN_ = 0;
 }
@@ -831,22 +879,35 @@ void Sharer::postprocessOnDevice(RunSlot &slot, size_t n, const HitRecord *hitsD
     b.lits = nullptr;
     b.litCap = 0;
     const HitRecord *hitsDev = hitsDevOverride ? hitsDevOverride : (const HitRecord *)(resDev_.data() + sizeof(Counters));
-    launchPostSort(hitsDev, (unsigned int)n, b, stream_, &launches_);
+    auto bitsFor = [](uint64_t maxValue) { int b = 1; while (b < 63 && (maxValue >> b)) b++; return b; };
+    launchPostSort(hitsDev, (unsigned int)n, b, bitsFor((uint64_t)std::max(1, slot.nSolvers - 1)), bitsFor((uint64_t)db_->maxLen()),
+                   bitsFor((uint64_t)std::max<int64_t>(1, db_->stats().clauses)), stream_, &launches_);
+    // The literal stream is emitted into a buffer sized from the previous large result (its total is
+    // only known on the device): sort, scan, emit and all three copies are queued back to back and
+    // there is ONE synchronisation.  A result that outgrew the guess is emitted again.
     postTotalHost_.resize(1);
     GSS_CUDA(cudaMemcpyAsync(postTotalHost_.data(), b.litPos + n, sizeof(long long), cudaMemcpyDeviceToHost, stream_));
-    GSS_CUDA(cudaStreamSynchronize(stream_));
-    const int64_t total = postTotalHost_[0];
-    postLitsDev_.reserve((size_t)std::max<int64_t>(total, 1), 0, stream_);
-    b.lits = postLitsDev_.data();
-    b.litCap = total;
-    launchPostEmit(hitsDev, (unsigned int)n, slot.dirDev(), slot.nDir, b, stream_, &launches_);
+    int64_t guess = std::max<int64_t>(postLitGuess_ + postLitGuess_ / 8, (int64_t)n * 3);
     postSortedHost_.resize(n);
-    postLitsHost_.resize((size_t)std::max<int64_t>(total, 1));
-    GSS_CUDA(cudaMemcpyAsync(postSortedHost_.data(), b.sorted, n * sizeof(SortedHit), cudaMemcpyDeviceToHost, stream_));
-    if (total)
-        GSS_CUDA(cudaMemcpyAsync(postLitsHost_.data(), b.lits, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
-    GSS_CUDA(cudaStreamSynchronize(stream_));
-    finishedD2H_ += (int64_t)(n * sizeof(SortedHit) + (size_t)total * sizeof(int32_t) + sizeof(long long));
+    int64_t total = 0;
+    for (int attempt = 0;; attempt++) {
+        postLitsDev_.reserve((size_t)std::max<int64_t>(guess, 1), 0, stream_);
+        b.lits = postLitsDev_.data();
+        b.litCap = guess;
+        launchPostEmit(hitsDev, (unsigned int)n, slot.dirDev(), slot.nDir, b, stream_, &launches_);
+        if (attempt == 0)
+            GSS_CUDA(cudaMemcpyAsync(postSortedHost_.data(), b.sorted, n * sizeof(SortedHit), cudaMemcpyDeviceToHost, stream_));
+        postLitsHost_.resize((size_t)std::max<int64_t>(guess, 1));
+        GSS_CUDA(cudaMemcpyAsync(postLitsHost_.data(), b.lits, (size_t)guess * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+        GSS_CUDA(cudaStreamSynchronize(stream_));
+        total = postTotalHost_[0];
+        finishedD2H_ += (int64_t)((size_t)guess * sizeof(int32_t));
+        if (total <= guess) break;
+        GSS_CHECK(attempt == 0);
+        guess = total;
+    }
+    postLitGuess_ = total;
+    finishedD2H_ += (int64_t)(n * sizeof(SortedHit) + sizeof(long long));
     postValid_ = true;
     postN_ = n;
     postLits_ = total;
@@ -890,19 +951,42 @@ int64_t Sharer::lastHits(gss_hit *out, int64_t cap) {
     return n;
 }
 
-double Sharer::timeCheck(int iters, bool dense, bool filterOnly) {
+// mode: 0 production check (k_filter + k_exact), 1 dense kernel, 2 k_filter alone, 3 k_exact alone
+// (on the survivors of the last filter), 4 k_apply_updates alone (idempotent), 5 k_collapse alone
+// (followed by one apply, which restores the tables).  Average microseconds per launch.
+double Sharer::timeCheck(int iters, int mode) {
     useDevice();
     if (lastStarted_ < 0 || iters < 1) return -1.0;
     RunSlot &slot = slots_[lastStarted_];
     GSS_CUDA(cudaStreamSynchronize(stream_));
+    const bool dense = mode == 1, filterOnly = mode == 2;
+    int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
+    auto once = [&]() {
+        if (mode <= 2) {
+            launchCheckKernels(slot, dense, filterOnly);
+        } else if (mode == 3) {
+            for (int g = 0; g < groups; g++)
+                if (slot.aggStart[g]) launchExactOnly(checkArgs(slot, g), dims_, numSMs_, stream_, &launches_);
+        } else if (mode == 4) {
+            launchApplyUpdates(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, slot.nUpdates, tables_, numSMs_,
+                               stream_, &launches_);
+        } else {
+            launchCollapse(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, slot.nUpdates, tables_, numSMs_,
+                           stream_, &launches_);
+        }
+    };
     cudaEvent_t e0, e1;
     GSS_CUDA(cudaEventCreate(&e0));
     GSS_CUDA(cudaEventCreate(&e1));
-    launchCheckKernels(slot, dense, filterOnly); // warm-up
+    if (mode == 3) launchCheckKernels(slot, false, true); // a fresh survivor list
+    once(); // warm-up
     GSS_CUDA(cudaEventRecord(e0, stream_));
-    for (int i = 0; i < iters; i++) launchCheckKernels(slot, dense, filterOnly);
+    for (int i = 0; i < iters; i++) once();
     GSS_CUDA(cudaEventRecord(e1, stream_));
-    if (filterOnly) launchCheckKernels(slot, dense, false); // leave a complete result behind
+    if (mode == 5)
+        launchApplyUpdates(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, slot.nUpdates, tables_, numSMs_,
+                           stream_, &launches_);
+    if (mode >= 2) launchCheckKernels(slot, slot.dense, false); // leave a complete result behind
     enqueueResultCopy(slot);
     GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
     GSS_CUDA(cudaEventSynchronize(e1));
@@ -910,7 +994,7 @@ double Sharer::timeCheck(int iters, bool dense, bool filterOnly) {
     GSS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    slot.dense = dense;
+    if (mode <= 1) slot.dense = dense;
     return (double)ms * 1000.0 / iters;
 }
 

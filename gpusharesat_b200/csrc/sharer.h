@@ -43,11 +43,16 @@ public:
     int64_t addClausesBulk(const int64_t *offsets, const int *lits, int64_t n);
     void setMaxClauseLen(int n) { db_->setMaxLen(n); }
     void setDense(bool d) { dense_ = d; }
-    double timeCheck(int iters, bool dense, bool filterOnly = false);
+    double timeCheck(int iters, int mode);
     int lastRunTimes(double out[4]);
     double lop3Peak();
     void lastRunBytes(int64_t *h2d, int64_t *d2h) { *h2d = lastH2D_; *d2h = finishedD2H_; }
     int64_t kernelLaunches() const { return launches_; }
+    // cumulative host wall time (us) of the phases of gss_gpu_run: [0] finish the previous run (wait +
+    // device-side sort/resolve + D2H), [1] start the next run (drain, upload, collect, enqueue),
+    // [2] hand-over, [3] collect alone (part of 1), [4] wait for the GPU alone (part of 0),
+    // [5] sort/resolve/D2H of a large hit list (part of 0)
+    void hostPhases(double out[6]) const { for (int i = 0; i < 6; i++) out[i] = hostPhases_[i]; }
     // ---- multi-GPU (see include/gpushare_b200.h) ----
     void setShard(int rank, int world) { db_->setShard(rank, world); }
     int mgpuCollect(const void **params, int64_t *paramsBytes, const void **updates, int64_t *nUpdates);
@@ -176,6 +181,7 @@ private:
     size_t postSortedOffset_ = 0;
     size_t postN_ = 0;
     int64_t postLits_ = 0;
+    int64_t postLitGuess_ = 0; // literal count of the previous large result
     DevBuf<uint8_t> postDev_;            // keys, values, positions, sorted records, CUB scratch
     DevBuf<int32_t> postLitsDev_;
     HostBuf<SortedHit> postSortedHost_;
@@ -196,6 +202,8 @@ private:
     DevBuf<int> bumpFlagDev_;
     HostBuf<int> bumpFlagHost_;
     bool bumpFlagPending_ = false;
+    cudaEvent_t bumpFlagEv_ = nullptr;
+    LazyPool pool_; // host-side worker pool (collect of large batches, hand-over of large hit lists)
     std::vector<gss_hit> lastHits_; // sorted, for gss_debug_last_hits (built on demand)
     bool lastHitsValid_ = true;
     bool dense_ = false;
@@ -203,6 +211,7 @@ private:
     int64_t launches_ = 0;
     int64_t lastH2D_ = 0, lastD2H_ = 0, finishedD2H_ = 0;
     double lastTimes_[4] = {0, 0, 0, 0};
+    double hostPhases_[6] = {0, 0, 0, 0, 0, 0};
     bool haveTimes_ = false;
 };
 

@@ -123,8 +123,24 @@ void gss_debug_set_dense(gss_sharer *h, int dense);
  * assignment tables stay intact until the next run starts) and return the average device
  * time of one sweep in microseconds (CUDA events on the library's stream).  The hit buffer
  * of the last iteration replaces the run's hits.  GPU thread only; waits for the run.
- * dense: 0 = production kernels (k_filter + k_exact), 1 = dense kernel, 2 = k_filter alone. */
+ * dense: 0 = production kernels (k_filter + k_exact), 1 = dense kernel, 2 = k_filter alone,
+ * 3 = k_exact alone, 4 = k_apply_updates alone, 5 = k_collapse alone. */
 double gss_debug_time_check(gss_sharer *h, int iters, int dense);
+/* The level-1 kernel is built in several variants (csrc/kernels.cu: kFilterVariants) so that the
+ * choices can be timed against each other on the device; GSS_FILTER_VARIANT picks one at start-up. */
+int gss_debug_filter_variants(void);
+/* Cumulative host wall time in microseconds of the phases of gss_gpu_run: [0] finishing the previous
+ * run (wait for the GPU, device-side sort / resolve of a large hit list, D2H), [1] starting the next
+ * run (drain clauses, upload, collect the solvers' deltas, enqueue), [2] hand-over to the solver
+ * queues, [3] collecting the deltas alone (part of 1), [4] waiting for the GPU alone (part of 0),
+ * [5] sort / resolve / D2H of a large hit list alone (part of 0). */
+void gss_debug_host_phases(gss_sharer *h, double out_us[6]);
+const char *gss_debug_filter_variant_name(int v);
+void gss_debug_set_filter_variant(int v);
+/* same for the level-2 kernel (kExactVariants, GSS_EXACT_VARIANT) */
+int gss_debug_exact_variants(void);
+const char *gss_debug_exact_variant_name(int v);
+void gss_debug_set_exact_variant(int v);
 
 /* Device time in microseconds of the phases of the last gathered run (CUDA events on the
  * library's stream): [0] host->device copies (new clause tiles, run header, assignment deltas),
