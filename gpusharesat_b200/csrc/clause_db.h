@@ -140,7 +140,7 @@ private:
     }
     static size_t wordPos(int len, int64_t idx, int i) {
         return (size_t)(idx / kTileClauses) * kTileClauses * (size_t)len + (size_t)i * kTileClauses +
-               (size_t)(idx % kTileClauses);
+               (size_t)tileSlot((int)(idx % kTileClauses));
     }
     void appendToMirror(const int *lits, int n, int64_t id);
     // Reorder the clauses of one length by their first literal (ids and activities move along).

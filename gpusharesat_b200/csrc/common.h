@@ -20,6 +20,12 @@ enum : uint8_t { V_TRUE = 0, V_FALSE = 1, V_UNDEF = 2 };
 
 constexpr int kSlots = 32;          // assignment slots per solver (one 32-bit word)
 constexpr int kTileClauses = 128;   // clauses per tile: one warp x int4
+// Position of clause j (0..127) of a tile inside each of the tile's literal rows.  Lane l of the warp
+// that checks the tile loads words 4l..4l+3 of a row with one 128-bit load and must find there the
+// clauses l, l+32, l+64, l+96: then each of its four level-1 gathers is issued for 32 CONSECUTIVE
+// clauses, whose first literals are neighbours in the (first-literal-sorted) arena -- a handful of
+// 32-byte sectors per gather instead of the whole tile's range four times over.
+__host__ __device__ inline int tileSlot(int j) { return ((j & 31) << 2) | (j >> 5); }
 constexpr int kDefaultMaxClauseLen = 100; // reference MAX_CL_SIZE (BaseTypes.cuh:28)
 constexpr int kMaxSolversPerGroup = 32;   // one aggregate word / one lane per solver
 

@@ -70,10 +70,9 @@ __global__ void k_fill_tables(DeviceTables t, int varFrom) {
 // blockIdx.y = solver.  (reference dUpdateAssigs, Assigs.cu:100-116)
 // `avail` = number of update records that really are in `upd` (a multi-GPU receiver may have got
 // a truncated payload: it must never read past what arrived)
-// `keep` != nullptr: `upd` is another GPU's memory (read once over NVLink); the records are also
-// written to this device's own copy, which the deferred k_collapse of this batch reads later
-// (then `keepParams` likewise receives this device's copy of the run parameters, which the check
-// kernels of this batch and the collapse read)
+// `keep` / `keepParams` != nullptr (multi-GPU workers): the records and run parameters are also
+// copied into the run slot's own buffers, which the check kernels of this batch and the deferred
+// k_collapse read later (the window the batch arrived in is overwritten by the next batch).
 __global__ void __launch_bounds__(256) k_apply_updates(const VarUpdate *__restrict__ upd,
                                                        const SolverRunParams *__restrict__ params, DeviceTables t,
                                                        long long avail, VarUpdate *__restrict__ keep,
@@ -86,18 +85,19 @@ __global__ void __launch_bounds__(256) k_apply_updates(const VarUpdate *__restri
         uint32_t *dst = reinterpret_cast<uint32_t *>(keepParams + s);
         for (int i = threadIdx.x; i < (int)(sizeof(SolverRunParams) / 4); i += blockDim.x) dst[i] = src[i];
     }
-    const int n = (int)max(0ll, min((long long)p.updCount, avail - (long long)p.updStart)), nGroups = p.nGroups;
+    const int updStart = p.updStart;
+    const int n = (int)max(0ll, min((long long)p.updCount, avail - (long long)updStart)), nGroups = p.nGroups;
     if (n <= 0) return;
     if (threadIdx.x < kSlots) {
         sAgg[threadIdx.x] = p.groupAggBit[threadIdx.x];
         sSlot[threadIdx.x] = p.groupSlotMask[threadIdx.x];
     }
-    __syncthreads();
     const uint32_t used = p.usedAggBits;
-    const VarUpdate *u = upd + p.updStart;
+    __syncthreads();
+    const VarUpdate *u = upd + updStart;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        VarUpdate vu = u[i];
-        if (keep) keep[p.updStart + i] = vu;
+        const VarUpdate vu = u[i];
+        if (keep) keep[updStart + i] = vu;
         t.t2[(size_t)vu.var * t.solverStride + s] = make_uint2(vu.def, vu.tru);
         if (used) {
             uint32_t bt = vu.tru & vu.def, bf = ~vu.tru & vu.def, bu = ~vu.def;
@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(256, MINBLOCKS) k_filter_t(CheckArgs a) {
         const int k = findDir(sTileEnd, a.nDir, tile);
         const LenDir d = a.dir[k];
         const int gTile = (tile - (k ? sTileEnd[k - 1] : 0)) * a.shardWorld + a.shardRank;
-        const int c0 = gTile * kTileClauses + lane * 4; // global clause index
+        // words 4*lane .. 4*lane+3 of a row hold the clauses lane, lane+32, lane+64, lane+96 (tileSlot)
+        const int c0 = gTile * kTileClauses + lane; // global clause index of this lane's first clause
         return Tile{d.base + (size_t)gTile * kTileClauses * d.len + lane * 4, d.len, c0, d.count - c0, sTileEnd[k]};
     };
     // the tile after `t` (device-local index tile + 1): the same length array continues, or look it up
@@ -269,27 +270,13 @@ __global__ void __launch_bounds__(256, MINBLOCKS) k_filter_t(CheckArgs a) {
     }
     if (first >= last) return;
 
-    Tile cur = locate(first);
-    int4 r0 = ldRow<ROWMODE>(cur.row), r1 = r0;
-    if constexpr (PREFETCH) r1 = cur.len > 1 ? ldRow<ROWMODE>(cur.row + kTileClauses) : r0;
-    for (int tile = first; tile < last; tile += stepT) {
-        Tile nxt = cur;
-        int4 n0 = r0, n1 = r1;
-        if constexpr (PREFETCH) {
-            // rows 0 and 1 of a tile are needed almost always (a tile of 128 clauses rarely dies on
-            // its first row): request them for the NEXT tile before this one is worked on
-            if (tile + stepT < last) {
-                if constexpr (CONTIG == 1) nxt = advance(cur, tile);
-                else nxt = locate(tile + stepT);
-                n0 = ldRow<ROWMODE>(nxt.row);
-                n1 = nxt.len > 1 ? ldRow<ROWMODE>(nxt.row + kTileClauses) : n0;
-            }
-        }
-        const int len = cur.len, nValid = cur.nValid; // clauses of this lane that exist: may be <= 0 or >= 4
+    // one tile, whose first row (and, when PREFETCH, second row) has been requested already
+    auto process = [&](const Tile &cur, const int4 &r0, const int4 &r1) {
+        const int len = cur.len, nValid = cur.nValid; // clause c0 + 32q exists iff nValid > 32q
         const int32_t *row = cur.row;
 
-        uint32_t all0 = nValid > 0 ? start : 0u, all1 = nValid > 1 ? start : 0u;
-        uint32_t all2 = nValid > 2 ? start : 0u, all3 = nValid > 3 ? start : 0u;
+        uint32_t all0 = nValid > 0 ? start : 0u, all1 = nValid > 32 ? start : 0u;
+        uint32_t all2 = nValid > 64 ? start : 0u, all3 = nValid > 96 ? start : 0u;
         uint32_t one0 = 0, one1 = 0, one2 = 0, one3 = 0;
 
         int4 lits = r0;
@@ -323,18 +310,47 @@ __global__ void __launch_bounds__(256, MINBLOCKS) k_filter_t(CheckArgs a) {
             const int c0 = cur.c0;
             const uint32_t m0 = all0 | one0, m1 = all1 | one1, m2 = all2 | one2, m3 = all3 | one3;
             stage.push(m0 != 0, Survivor{rowTag + 0 * sizeof(int32_t), c0 + 0, m0}, a.survivors, survCounter, a.survCap, lane);
-            stage.push(m1 != 0, Survivor{rowTag + 1 * sizeof(int32_t), c0 + 1, m1}, a.survivors, survCounter, a.survCap, lane);
-            stage.push(m2 != 0, Survivor{rowTag + 2 * sizeof(int32_t), c0 + 2, m2}, a.survivors, survCounter, a.survCap, lane);
-            stage.push(m3 != 0, Survivor{rowTag + 3 * sizeof(int32_t), c0 + 3, m3}, a.survivors, survCounter, a.survCap, lane);
+            stage.push(m1 != 0, Survivor{rowTag + 1 * sizeof(int32_t), c0 + 32, m1}, a.survivors, survCounter, a.survCap, lane);
+            stage.push(m2 != 0, Survivor{rowTag + 2 * sizeof(int32_t), c0 + 64, m2}, a.survivors, survCounter, a.survCap, lane);
+            stage.push(m3 != 0, Survivor{rowTag + 3 * sizeof(int32_t), c0 + 96, m3}, a.survivors, survCounter, a.survCap, lane);
         }
-        if constexpr (PREFETCH) {
-            cur = nxt;
-            r0 = n0;
-            r1 = n1;
-        } else {
+    };
+    auto following = [&](const Tile &t, int tile) -> Tile { // the tile this warp takes after `tile`
+        if constexpr (CONTIG == 1) return advance(t, tile);
+        else return locate(tile + stepT);
+    };
+
+    if constexpr (PREFETCH) {
+        // Software pipeline ACROSS tiles, two register sets in ping-pong (no copies between them, a
+        // copy would wait for the load): while tile A is worked on, rows 0 and 1 of tile B -- needed
+        // almost always, a tile of 128 clauses rarely dies on its first row -- are in flight, and
+        // vice versa.  A warp never waits for a DRAM round trip with nothing else to do.
+        Tile tA = locate(first), tB = tA;
+        int4 a0 = ldRow<ROWMODE>(tA.row), a1v = tA.len > 1 ? ldRow<ROWMODE>(tA.row + kTileClauses) : a0;
+        int4 b0 = a0, b1 = a0;
+        for (int tile = first; tile < last; tile += 2 * stepT) {
+            const bool hasB = tile + stepT < last;
+            if (hasB) {
+                tB = following(tA, tile);
+                b0 = ldRow<ROWMODE>(tB.row);
+                b1 = tB.len > 1 ? ldRow<ROWMODE>(tB.row + kTileClauses) : b0;
+            }
+            process(tA, a0, a1v);
+            if (!hasB) break;
+            if (tile + 2 * stepT < last) {
+                tA = following(tB, tile + stepT);
+                a0 = ldRow<ROWMODE>(tA.row);
+                a1v = tA.len > 1 ? ldRow<ROWMODE>(tA.row + kTileClauses) : a0;
+            }
+            process(tB, b0, b1);
+        }
+    } else {
+        Tile cur = locate(first);
+        int4 r0 = ldRow<ROWMODE>(cur.row);
+        for (int tile = first; tile < last; tile += stepT) {
+            process(cur, r0, r0);
             if (tile + stepT < last) {
-                if constexpr (CONTIG == 1) cur = advance(cur, tile);
-                else cur = locate(tile + stepT);
+                cur = following(cur, tile);
                 r0 = ldRow<ROWMODE>(cur.row);
             }
         }
@@ -357,13 +373,16 @@ const FilterVariant kFilterVariants[] = {
     {k_filter_t<false, 2, 0, 0, 6>, 256, "contiguous per block, 6 x 256 (40 registers, spills)"},
     {k_filter_t<false, 1, 1, 0, 5>, 256, "contiguous per warp, rows L1::no_allocate, 5 x 256"},
     {k_filter_t<false, 2, 0, 0, 5>, 128, "contiguous per block, 10 x 128"},
-    {k_filter_t<true, 0, 0, 0, 5>, 256, "strided, next tile's rows 0+1 prefetched, 5 x 256"},
-    {k_filter_t<true, 1, 0, 0, 4>, 256, "contiguous per warp + prefetch, 4 x 256"},
+    {k_filter_t<true, 0, 0, 0, 5>, 256, "strided, next tile's rows 0+1 in flight (ping-pong), 5 x 256"},
+    {k_filter_t<true, 1, 0, 0, 4>, 256, "contiguous per warp + ping-pong prefetch, 4 x 256"},
+    {k_filter_t<true, 1, 0, 0, 5>, 256, "contiguous per warp + ping-pong prefetch, 5 x 256"},
+    {k_filter_t<true, 1, 0, 0, 3>, 256, "contiguous per warp + ping-pong prefetch, 3 x 256"},
+    {k_filter_t<true, 1, 1, 0, 4>, 256, "contiguous per warp + ping-pong prefetch, rows no_allocate, 4 x 256"},
     {k_filter_t<false, 0, 0, 0, 6>, 256, "strided, 6 x 256 (40 registers, spills)"},
 };
 constexpr int kNumFilterVariants = (int)(sizeof(kFilterVariants) / sizeof(kFilterVariants[0]));
 int gFilterVariant = -1; // -1: not chosen yet (GSS_FILTER_VARIANT or the default)
-constexpr int kDefaultFilterVariant = 0;
+constexpr int kDefaultFilterVariant = 1;
 
 // append one hit per lane with a non-zero mask; one atomic per warp
 __device__ __forceinline__ void reportHits(const CheckArgs &a, uint32_t m, int solver, int len, int idx, int lane) {
@@ -481,6 +500,34 @@ template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS
     }
     stage.flush(a.hits, &a.counters->nHits, a.hitCap, lane);
     if (lane == 0 && tests) atomicAdd(&a.counters->exactTests, tests);
+    if (a.peerDone) {
+        // Multi-GPU: the hits went straight into this rank's slot of rank 0's gather window (peer
+        // stores).  The block that finishes last publishes the result: slot header, then the done
+        // flag (2*seq: complete; 2*seq-1: a buffer overflowed, this rank is going to run again).
+        // (barrier, then ONE fence by the thread that takes the ticket: the fence is cumulative over
+        // what the barrier ordered before it -- the pattern of a grid-wide barrier)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system(); // this block's hits and counter updates are visible system-wide
+            const unsigned int ticket = atomicAdd(a.peerTicket, 1u);
+            if (ticket == gridDim.x - 1) {
+                *a.peerTicket = 0u;
+                __threadfence();
+                const volatile Counters *c = a.counters;
+                const unsigned int nHits = c->nHits;
+                long long flags = nHits > a.hitCap ? 2 : 0;
+                for (int g = 0; g < a.peerGroups && g < kMaxGroups; g++)
+                    if (c->nSurvivors[g] > a.survCap) flags |= 1;
+                a.peerHdr[0] = (long long)nHits;
+                a.peerHdr[1] = flags;
+                a.peerHdr[2] = (long long)c->exactTests;
+                a.peerHdr[3] = (long long)a.peerSeq;
+                for (int i = 4; i < 8; i++) a.peerHdr[i] = 0;
+                __threadfence_system();
+                *reinterpret_cast<volatile uint32_t *>(a.peerDone) = flags ? 2u * a.peerSeq - 1u : 2u * a.peerSeq;
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -519,7 +566,7 @@ __global__ void __launch_bounds__(128) k_check_dense(CheckArgs a) {
         const int nValid = d.count - c0;
         if (nValid <= 0) continue;
         // lane l < kDenseGroup holds literal i of clause c0 + l
-        const int32_t *col = d.base + (size_t)gTile * kTileClauses * len + q * kDenseGroup + (lane & (kDenseGroup - 1));
+        const int32_t *col = d.base + (size_t)gTile * kTileClauses * len + tileSlot(q * kDenseGroup + (lane & (kDenseGroup - 1)));
 
         uint32_t all[kDenseGroup], one[kDenseGroup];
 #pragma unroll
@@ -586,7 +633,29 @@ __global__ void k_peer_signal(PeerFlagList boxes, uint32_t seq) {
     *reinterpret_cast<volatile uint32_t *>(boxes.p[r]) = seq;
 }
 
-// every rank, after its check kernels: result header into its slot of the root's gather window, then
+// root: push the batch into every worker's window with plain (posted) peer stores and then store the
+// sequence number into every mailbox -- one launch; the block that finishes last signals.  (A copy-
+// engine transfer costs ~17 us of fixed latency per peer for these 2 MB payloads; SM stores do not.)
+__global__ void __launch_bounds__(256) k_peer_push(const uint4 *__restrict__ src, long long bytes, PeerPushList L, uint32_t seq,
+                                                   unsigned int *ticket) {
+    const long long n16 = (bytes + 15) / 16;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = src[i];
+        for (int r = 0; r < L.n; r++) L.dst[r][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system(); // this block's stores have been performed at the peers (cumulative over the barrier)
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *ticket = 0u;
+            __threadfence_system();
+            for (int r = 0; r < L.n; r++) *reinterpret_cast<volatile uint32_t *>(L.mailbox[r]) = seq;
+        }
+    }
+}
+
+// every rank, when no k_exact launch could publish the result itself (see k_exact): result header into its slot of the root's gather window, then
 // the done flag.  The hits themselves were appended to the slot by k_exact (peer stores), which has
 // completed.  flag = 2*seq when the result is complete, 2*seq-1 when a survivor / hit buffer
 // overflowed and this rank is going to run again.
@@ -659,7 +728,7 @@ __global__ void __launch_bounds__(256) k_post_emit(const HitRecord *__restrict__
         const LenDir d = dir[lo];
         const long long pos = litPos[j];
         const int tile = h.idx / kTileClauses;
-        const int32_t *src = d.base + (size_t)tile * kTileClauses * h.len + (h.idx % kTileClauses);
+        const int32_t *src = d.base + (size_t)tile * kTileClauses * h.len + tileSlot(h.idx % kTileClauses);
         for (int i = lane; i < h.len; i += 32)
             if (pos + i < litCap) lits[pos + i] = __ldg(src + (size_t)i * kTileClauses);
         if (lane == 0) out[j] = SortedHit{h.mask, h.solver, h.len, h.idx, d.ids[h.idx], pos};
@@ -786,6 +855,14 @@ void launchPeerSignal(const PeerFlagList &boxes, uint32_t seq, cudaStream_t s, i
     if (boxes.n == 0) return;
     k_peer_signal<<<1, 32, 0, s>>>(boxes, seq);
     checkLaunch("k_peer_signal");
+    ++*launches;
+}
+
+void launchPeerPush(const void *src, long long bytes, const PeerPushList &L, uint32_t seq, unsigned int *ticket, int numSMs,
+                    cudaStream_t s, int64_t *launches) {
+    if (L.n == 0) return;
+    k_peer_push<<<numSMs * 2, 256, 0, s>>>(static_cast<const uint4 *>(src), bytes, L, seq, ticket);
+    checkLaunch("k_peer_push");
     ++*launches;
 }
 

@@ -54,6 +54,13 @@ struct CheckArgs {
     HitRecord *hits;
     unsigned int hitCap;
     Counters *counters;
+    // multi-GPU over peer memory: the LAST k_exact launch of a batch also publishes the result (the
+    // block that finishes last writes the slot header and the done flag: no extra kernel launch)
+    long long *peerHdr = nullptr;     // this rank's 64-byte slot header in rank 0's gather window
+    uint32_t *peerDone = nullptr;     // this rank's done flag in rank 0's window
+    unsigned int *peerTicket = nullptr; // this device: blocks that have finished
+    uint32_t peerSeq = 0;
+    int peerGroups = 0;               // solver groups whose survivor counters count for the overflow flag
 };
 
 void launchFillTables(const DeviceTables &t, int varFrom, cudaStream_t s, int64_t *launches);
@@ -119,6 +126,14 @@ struct PeerFlagList {
     int n;
 };
 void launchPeerSignal(const PeerFlagList &boxes, uint32_t seq, cudaStream_t s, int64_t *launches);
+struct PeerPushList {
+    uint4 *dst[kMaxPeers];        // every worker's payload area
+    uint32_t *mailbox[kMaxPeers]; // every worker's mailbox
+    int n;
+};
+// copy `bytes` of the batch to every worker and then store seq into every mailbox (one launch)
+void launchPeerPush(const void *src, long long bytes, const PeerPushList &L, uint32_t seq, unsigned int *ticket, int numSMs,
+                    cudaStream_t s, int64_t *launches);
 void launchPeerFinalize(const Counters *counters, unsigned int hitCap, unsigned int survCap, int groups, long long *hdr,
                         uint32_t *doneFlag, uint32_t seq, cudaStream_t s, int64_t *launches);
 void launchPeerWait(const uint32_t *flag, uint32_t value, unsigned long long timeoutNs, int *err, cudaStream_t s,

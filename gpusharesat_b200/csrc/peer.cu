@@ -6,16 +6,22 @@
 //
 //   rank 0 window   [control: done flag of every rank][payload: header, run parameters, deltas]
 //                   [gather: one slot per rank = 64 B header + hit records]
-//   worker window   [control: mailbox]
+//   worker window   [control: mailbox][payload]
 //
+// Data is always PUSHED (posted writes run at link speed; reading a peer's memory is latency-bound:
+// measured 2.3 MB in ~30 us when the workers pulled the batch, whichever way the loads were shaped).
 // Per batch (sequence number seq):
-//   rank 0   collect the batch, ONE H2D copy into its payload area, k_peer_signal stores seq into
-//            every worker's mailbox, then checks its own share of the clause tiles
+//   rank 0   collect the batch, ONE H2D copy into its payload area; then k_peer_push stores the
+//            payload into every worker's window and, from the block that finishes last, seq into
+//            every mailbox; then its own apply / check.  (Measured alternatives, profiles/: copy-engine
+//            transfers and a second stream both deliver the batch ~25 us later.)
 //   worker   stream waits for mailbox >= seq (cuStreamWaitValue32: nothing spins on an SM), then
-//            k_apply_updates reads the deltas straight out of rank 0's memory (peer loads, and keeps a
-//            local copy for the deferred collapse), k_filter / k_exact check this rank's tiles and
-//            append the hits straight into this rank's slot of rank 0's gather area (peer stores),
-//            k_peer_finalize writes the slot header and the done flag
+//            k_apply_updates (counts come from the payload itself, the host never reads it; it keeps
+//            a copy for the deferred collapse), k_filter / k_exact on this rank's tiles, which append
+//            the hits straight into this rank's slot of rank 0's gather area (peer stores); the block
+//            of k_exact that finishes last writes the slot header and the done flag.
+//   all      as soon as a batch cannot be run again (no overflow), peerFinish enqueues its collapse
+//            (dSetAllAssigsToLast): off the critical path of the next batch, on a warm GPU
 //   rank 0   stream waits for every done flag, reads the headers (one small D2H), and sorts /
 //            resolves / hands over the union of the hits on its device (every rank holds the whole
 //            clause arena, so rank 0 can resolve any hit)
@@ -39,7 +45,9 @@ constexpr size_t kFlagStride = 128;          // one flag per 128 B line
 constexpr size_t kMailboxOff = 0;
 constexpr size_t kDoneOff = 128;             // done flag of rank r at kDoneOff + r * kFlagStride
 constexpr size_t kErrOff = kCtlBytes - 64;   // error word of the polling fallback
-static_assert(kDoneOff + kMaxPeers * kFlagStride <= kErrOff, "control block too small");
+constexpr size_t kTicketOff = kCtlBytes - 256; // this device: finished-block counter of the publishing k_exact
+constexpr size_t kPushTicketOff = kCtlBytes - 192; // rank 0: finished-block counter of k_peer_push
+static_assert(kDoneOff + kMaxPeers * kFlagStride <= kTicketOff, "control block too small");
 
 struct PeerBlob {
     uint32_t magic;
@@ -64,21 +72,27 @@ struct Sharer::PeerState {
     uint8_t *rootWindow = nullptr;      // rank 0's window (mapped on the workers)
     std::vector<uint8_t *> mapped;      // windows opened through IPC (to be closed)
     PeerFlagList mailboxes{};           // rank 0: every worker's mailbox
+    PeerPushList push{};                // rank 0: every worker's payload area and mailbox
+    cudaEvent_t evPushed = nullptr;     // rank 0: the batch has been stored into every worker's window
     uint32_t seq = 0;
     WaitValue32Fn waitFn = nullptr;
     bool connected = false;
     HostBuf<long long> headsHost;       // rank 0: world x 8 int64
     HostBuf<int> errHost;
     double timeoutS = 120.0;
-    cudaEvent_t evC0 = nullptr, evC1 = nullptr; // around the deferred collapse of the previous batch
+    cudaEvent_t evC0 = nullptr, evC1 = nullptr; // around the collapse of this batch (end of peerFinish)
     cudaEvent_t evGathered = nullptr;           // rank 0: every rank's hits are in its memory
-    bool collapsed = false;
+    bool collapsed = false, collapsePending = false;
+    cudaEvent_t evWait = nullptr;               // workers: the mailbox wait has been satisfied
+    bool trace = false;                         // GSS_PEER_TRACE: per-batch phase times on stderr
 
-    uint8_t *payload() const { return rootWindow + kCtlBytes; }
+    uint8_t *payload() const { return (rank == 0 ? rootWindow : window) + kCtlBytes; } // this rank's copy of the batch
     uint8_t *slot(int r) const { return rootWindow + kCtlBytes + payloadArea + (size_t)r * slotBytes; }
     uint32_t *done(int r) const { return reinterpret_cast<uint32_t *>(rootWindow + kDoneOff + (size_t)r * kFlagStride); }
     uint32_t *mailbox() const { return reinterpret_cast<uint32_t *>(window + kMailboxOff); }
     int *err() const { return reinterpret_cast<int *>(window + kErrOff); }
+    unsigned int *ticket() const { return reinterpret_cast<unsigned int *>(window + kTicketOff); }
+    unsigned int *pushTicket() const { return reinterpret_cast<unsigned int *>(window + kPushTicketOff); }
 };
 
 int64_t Sharer::peerInit(int rank, int world, int64_t payloadCap, int64_t slotHits, void *blobOut, int64_t blobCap) {
@@ -94,7 +108,7 @@ int64_t Sharer::peerInit(int rank, int world, int64_t payloadCap, int64_t slotHi
     P.slotHits = slotHits;
     P.payloadArea = alignUp((size_t)payloadCap, 256);
     P.slotBytes = alignUp(64 + (size_t)slotHits * sizeof(HitRecord), 256);
-    P.windowBytes = rank == 0 ? kCtlBytes + P.payloadArea + (size_t)world * P.slotBytes : kCtlBytes;
+    P.windowBytes = kCtlBytes + P.payloadArea + (rank == 0 ? (size_t)world * P.slotBytes : 0);
     GSS_CUDA(cudaMalloc(reinterpret_cast<void **>(&P.window), P.windowBytes));
     GSS_CUDA(cudaMemset(P.window, 0, kCtlBytes));
     GSS_CUDA(cudaDeviceSynchronize());
@@ -148,8 +162,14 @@ void Sharer::peerConnect(const void *blobs, int64_t blobBytes) {
     };
     if (P.rank == 0) {
         P.mailboxes.n = 0;
-        for (int r = 1; r < P.world; r++)
-            P.mailboxes.p[P.mailboxes.n++] = reinterpret_cast<uint32_t *>(open(blobOf(r)) + kMailboxOff);
+        for (int r = 1; r < P.world; r++) {
+            uint8_t *w = open(blobOf(r));
+            P.mailboxes.p[P.mailboxes.n++] = reinterpret_cast<uint32_t *>(w + kMailboxOff);
+            P.push.dst[P.push.n] = reinterpret_cast<uint4 *>(w + kCtlBytes);
+            P.push.mailbox[P.push.n] = reinterpret_cast<uint32_t *>(w + kMailboxOff);
+            P.push.n++;
+        }
+        GSS_CUDA(cudaEventCreate(&P.evPushed));
         P.headsHost.resize((size_t)P.world * 8);
     } else {
         P.rootWindow = open(blobOf(0));
@@ -158,6 +178,8 @@ void Sharer::peerConnect(const void *blobs, int64_t blobBytes) {
     GSS_CUDA(cudaEventCreate(&P.evC0));
     GSS_CUDA(cudaEventCreate(&P.evC1));
     GSS_CUDA(cudaEventCreate(&P.evGathered));
+    GSS_CUDA(cudaEventCreate(&P.evWait));
+    P.trace = getenv("GSS_PEER_TRACE") != nullptr;
     P.connected = true;
 }
 
@@ -167,6 +189,8 @@ void Sharer::peerClose() {
     if (peer_->evC0) cudaEventDestroy(peer_->evC0);
     if (peer_->evC1) cudaEventDestroy(peer_->evC1);
     if (peer_->evGathered) cudaEventDestroy(peer_->evGathered);
+    if (peer_->evWait) cudaEventDestroy(peer_->evWait);
+    if (peer_->evPushed) cudaEventDestroy(peer_->evPushed);
     if (peer_->window) cudaFree(peer_->window);
     delete peer_;
     peer_ = nullptr;
@@ -177,8 +201,15 @@ void Sharer::peerLaunchCheckAndFinalize(RunSlot &slot) {
     uint8_t *mySlot = P.slot(P.rank);
     hitsOverride_ = reinterpret_cast<HitRecord *>(mySlot + 64);
     hitCapOverride_ = (unsigned int)P.slotHits;
-    launchCheckKernels(slot, slot.dense);
+    fusedPublish_.peerHdr = reinterpret_cast<long long *>(mySlot);
+    fusedPublish_.peerDone = P.done(P.rank);
+    fusedPublish_.peerTicket = P.ticket();
+    fusedPublish_.peerSeq = P.seq;
+    const bool published = launchCheckKernels(slot, slot.dense);
     hitsOverride_ = nullptr;
+    fusedPublish_.peerDone = nullptr;
+    if (published) return; // the last k_exact wrote the slot header and the done flag itself
+    // nothing was launched that could publish (no tile on this rank, no frozen slot, dense mode)
     int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
     launchPeerFinalize((const Counters *)resDev_.data(), (unsigned int)P.slotHits, (unsigned int)survCap_, groups,
                        reinterpret_cast<long long *>(mySlot), P.done(P.rank), P.seq, stream_, &launches_);
@@ -205,15 +236,11 @@ int Sharer::peerEnqueue() {
     db_->drainPending();
     if (db_->stats().clauses == 0) return -1;
     RunSlot &slot = slots_[nextSlot()];
-    // The deferred dSetAllAssigsToLast of the previous batch needs nothing of the new one: it goes
-    // first (from this device's copy of that batch), ahead of the wait for the new payload, so on the
-    // workers it is off the critical path.  Its time is still charged to the step (lastTimes_).
-    P.collapsed = collapseSlot_ >= 0;
-    if (P.collapsed) {
+    // (the collapse of the previous batch -- dSetAllAssigsToLast -- was enqueued by peerFinish as soon
+    // as that batch could no longer be run again; a batch left over from before peer mode goes here)
+    if (collapseSlot_ >= 0) {
         RunSlot &c = slots_[collapseSlot_];
-        GSS_CUDA(cudaEventRecord(P.evC0, stream_));
         launchCollapse(c.updDev.data(), c.paramsDev(), c.nSolvers, c.maxUpd, c.nUpdates, tables_, numSMs_, stream_, &launches_);
-        GSS_CUDA(cudaEventRecord(P.evC1, stream_));
         collapseSlot_ = -1;
     }
     bool rebuild = false;
@@ -222,7 +249,7 @@ int Sharer::peerEnqueue() {
     P.seq++;
     const size_t PR = payloadPrefixRecords(slot.nSolvers);
     GSS_CHECK((int64_t)(PR * sizeof(VarUpdate)) <= P.payloadCap);
-    uint8_t *payload = P.payload();
+    uint8_t *payload = P.payload(); // this device's copy of the batch (rank 0 pushes it into the workers' windows)
     const int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
     slot.dense = dense_;
     slot.headDev.reserve(slot.headHost.size(), 0, stream_);
@@ -244,6 +271,7 @@ int Sharer::peerEnqueue() {
         memcpy(base + sizeof(hdr), params, (size_t)slot.nSolvers * sizeof(SolverRunParams));
         GSS_CUDA(cudaMemcpyAsync(payload, base, (size_t)hdr.totalBytes, cudaMemcpyHostToDevice, stream_));
         h2d += hdr.totalBytes;
+        peerPayloadBytes_ = hdr.totalBytes;
         slot.aggStart.assign(groups, 0u);
         slot.aggOnDevice = false;
         slot.maxUpd = 0;
@@ -256,22 +284,33 @@ int Sharer::peerEnqueue() {
     } else {
         slot.ids.assign(slot.nSolvers, AssigIds{});
         slot.assigCount = 0;
-        // the payload of this batch is complete in rank 0's memory once the mailbox says so
-        peerWaitFlag(P.mailbox(), P.seq);
         int64_t nUpper = P.payloadCap / (int64_t)sizeof(VarUpdate) - (int64_t)PR;
         slot.aggStart.assign(groups, ~0u);
         slot.aggOnDevice = true; // the host never sees the run parameters: the kernels read them
         slot.maxUpd = (int)std::min<int64_t>(nUpper, 1 << 30);
         slot.nUpdates = nUpper;
-        // (the run parameters are NOT copied here: k_apply_updates reads them out of rank 0's memory
-        // and leaves this device's copy in headDev for the kernels that follow)
+        // everything that does not need the batch goes ahead of the wait: the length directory,
+        // buffer growth (the run parameters are not copied here at all: k_apply_updates reads them
+        // from the pulled payload and leaves a copy in headDev for the kernels that follow)
         GSS_CUDA(cudaMemcpyAsync(slot.headDev.data(), slot.headHost.data(), slot.dirBytes, cudaMemcpyHostToDevice, stream_));
         h2d += (int64_t)slot.dirBytes;
+        slot.updDev.reserve((size_t)std::max<int64_t>(slot.nUpdates, 1), 0, stream_);
+        ensureResultBuffers();
+        // rank 0 has pushed this batch into this rank's window once the mailbox says so
+        peerWaitFlag(P.mailbox(), P.seq);
+        GSS_CUDA(cudaEventRecord(P.evWait, stream_));
     }
     slot.updDev.reserve((size_t)std::max<int64_t>(slot.nUpdates, 1), 0, stream_);
     ensureResultBuffers();
     GSS_CUDA(cudaEventRecord(slot.evH2DDone, stream_));
-    if (root) launchPeerSignal(P.mailboxes, P.seq, stream_, &launches_);
+    if (root && P.push.n) {
+        // push the batch into every worker's window and signal: one kernel, FIRST on rank 0's stream
+        // (on a second stream it reached the workers ~25 us later: it competed with rank 0's own table
+        // kernels).  The workers start ~12 us after rank 0 and have no push to do: the ranks finish
+        // within a few microseconds of each other.
+        launchPeerPush(payload, peerPayloadBytes_, P.push, P.seq, P.pushTicket(), numSMs_, stream_, &launches_);
+        GSS_CUDA(cudaEventRecord(P.evPushed, stream_));
+    }
 
     const SolverRunParams *paramsSrc = root ? slot.paramsDev() : reinterpret_cast<const SolverRunParams *>(payload + sizeof(PayloadHeader));
     SolverRunParams *paramsKeep = root ? nullptr : const_cast<SolverRunParams *>(slot.paramsDev());
@@ -280,16 +319,17 @@ int Sharer::peerEnqueue() {
     GSS_CUDA(cudaEventRecord(slot.evBeforeCheck, stream_));
     peerLaunchCheckAndFinalize(slot);
     GSS_CUDA(cudaEventRecord(slot.evAfterCheck, stream_));
-    slot.resHost.resize(sizeof(Counters));
-    GSS_CUDA(cudaMemcpyAsync(slot.resHost.data(), resDev_.data(), sizeof(Counters), cudaMemcpyDeviceToHost, stream_));
     if (root)
         for (int r = 1; r < P.world; r++) peerWaitFlag(P.done(r), 2u * P.seq - 1u);
     GSS_CUDA(cudaEventRecord(P.evGathered, stream_)); // rank 0: the hits of every rank are in its memory
+    // (small copies cost ~10 us of latency each: they go after the point the batch is complete)
+    slot.resHost.resize(sizeof(Counters));
+    GSS_CUDA(cudaMemcpyAsync(slot.resHost.data(), resDev_.data(), sizeof(Counters), cudaMemcpyDeviceToHost, stream_));
     if (root)
         GSS_CUDA(cudaMemcpy2DAsync(P.headsHost.data(), 64, P.slot(0), P.slotBytes, 64, (size_t)P.world, cudaMemcpyDeviceToHost, stream_));
     GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
     slot.inFlight = true;
-    if (slot.nUpdates) collapseSlot_ = (int)(&slot - slots_);
+    P.collapsePending = slot.nUpdates != 0;
     lastStarted_ = (int)(&slot - slots_);
     lastH2D_ = h2d;
     cur_ = (int)(&slot - slots_);
@@ -322,21 +362,6 @@ int64_t Sharer::peerFinish() {
         }
     };
     waitEnd();
-    float msCopy = 0, msApply = 0, msCheck = 0, msTotal = 0;
-    cudaEventElapsedTime(&msCopy, slot.evStart, slot.evH2DDone);
-    cudaEventElapsedTime(&msApply, slot.evH2DDone, slot.evBeforeCheck);
-    cudaEventElapsedTime(&msCheck, slot.evBeforeCheck, slot.evAfterCheck);
-    cudaEventElapsedTime(&msTotal, slot.evStart, P.evGathered);
-    float msCollapse = 0;
-    if (P.collapsed) cudaEventElapsedTime(&msCollapse, P.evC0, P.evC1);
-    // [0] prepare + H2D, [1] table kernels (collapse of the previous batch + apply), [2] check kernels,
-    // [3] everything up to "hits gathered" including the collapse: [3] - [0] = device time of the step
-    lastTimes_[0] = msCopy * 1000.0;
-    lastTimes_[1] = (msApply + msCollapse) * 1000.0;
-    lastTimes_[2] = msCheck * 1000.0;
-    lastTimes_[3] = (msTotal + msCollapse) * 1000.0;
-    haveTimes_ = true;
-    if (opts_.quickProf) globalStats_[G_timeSpentTestingClauses] += (uint64_t)(msCheck * 1000.0f);
 
     // this rank's own overflow: grow and run again (the tables are intact: collapse is deferred)
     auto repairOwn = [&]() -> bool {
@@ -355,6 +380,53 @@ int64_t Sharer::peerFinish() {
         return true;
     };
 
+    // Once the batch cannot be run again, its tables are no longer needed: collapse every slot to the
+    // solver's last one right away (dSetAllAssigsToLast) -- the GPU is warm and otherwise idle while
+    // the host hands the hits over / rank 0 prepares the next batch.  Its time is charged to this batch.
+    float msFirst[5] = {0, 0, 0, 0, 0}; // first attempt: copy, apply, check, total, tail
+    cudaEventElapsedTime(&msFirst[0], slot.evStart, slot.evH2DDone);
+    cudaEventElapsedTime(&msFirst[1], slot.evH2DDone, slot.evBeforeCheck);
+    cudaEventElapsedTime(&msFirst[2], slot.evBeforeCheck, slot.evAfterCheck);
+    cudaEventElapsedTime(&msFirst[3], slot.evStart, P.evGathered);
+    cudaEventElapsedTime(&msFirst[4], slot.evAfterCheck, P.evGathered);
+    auto collapseNow = [&]() {
+        P.collapsed = P.collapsePending;
+        if (!P.collapsed) return;
+        GSS_CUDA(cudaEventRecord(P.evC0, stream_));
+        launchCollapse(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, slot.nUpdates, tables_, numSMs_, stream_, &launches_);
+        GSS_CUDA(cudaEventRecord(P.evC1, stream_));
+        P.collapsePending = false;
+        collapseSlot_ = -1;
+        lastStarted_ = -1; // the tables of this batch are gone
+    };
+    auto recordTimes = [&]() {
+        float msCollapse = 0;
+        if (P.collapsed) {
+            GSS_CUDA(cudaEventSynchronize(P.evC1));
+            cudaEventElapsedTime(&msCollapse, P.evC0, P.evC1);
+        }
+        // [0] prepare + H2D (+ wait for the batch on a worker), [1] table kernels (push on rank 0, apply,
+        // collapse), [2] check kernels, [3] everything from the start to "hits gathered" plus the
+        // collapse: [3] - [0] = device time of the batch on this rank
+        lastTimes_[0] = msFirst[0] * 1000.0;
+        lastTimes_[1] = (msFirst[1] + msCollapse) * 1000.0;
+        lastTimes_[2] = msFirst[2] * 1000.0;
+        lastTimes_[3] = (msFirst[3] + msCollapse) * 1000.0;
+        haveTimes_ = true;
+        if (opts_.quickProf) globalStats_[G_timeSpentTestingClauses] += (uint64_t)(msFirst[2] * 1000.0f);
+        if (P.trace) {
+            float msWait = 0, msAfterWait = 0, msPush = 0;
+            if (!root) {
+                cudaEventElapsedTime(&msWait, slot.evStart, P.evWait);
+                cudaEventElapsedTime(&msAfterWait, P.evWait, slot.evH2DDone);
+            } else if (P.push.n) {
+                cudaEventElapsedTime(&msPush, slot.evH2DDone, P.evPushed);
+            }
+            fprintf(stderr, "peer trace rank %d batch %u: start->batch-arrived %.1f | ->ready %.1f | push %.1f | push+apply %.1f | check %.1f | tail %.1f | collapse %.1f us\n",
+                    P.rank, P.seq, msWait * 1e3, msAfterWait * 1e3, msPush * 1e3, msFirst[1] * 1e3, msFirst[2] * 1e3, msFirst[4] * 1e3, msCollapse * 1e3);
+        }
+    };
+
     int64_t total = 0;
     if (!root) {
         for (int attempt = 0; repairOwn(); attempt++) {
@@ -362,6 +434,7 @@ int64_t Sharer::peerFinish() {
             GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
             waitEnd();
         }
+        collapseNow();
         Counters c;
         memcpy(&c, slot.resHost.data(), sizeof(c));
         globalStats_[G_clauseTestsOnAssigs] += c.exactTests;
@@ -369,6 +442,7 @@ int64_t Sharer::peerFinish() {
         slot.inFlight = false;
         mgpuLast_ = cur_;
         cur_ = -1;
+        recordTimes();
         return total;
     }
 
@@ -395,11 +469,13 @@ int64_t Sharer::peerFinish() {
         total += counts[r];
         globalStats_[G_clauseTestsOnAssigs] += (uint64_t)P.headsHost[(size_t)r * 8 + 2];
     }
+    collapseNow();
     slot.inFlight = false;
     mgpuLast_ = cur_;
     cur_ = -1;
     finishedD2H_ = (int64_t)((size_t)P.world * 64 + sizeof(Counters));
     mgpuImportGathered(P.slot(0), P.world, (int64_t)P.slotBytes, counts.data());
+    recordTimes();
     return total;
 }
 

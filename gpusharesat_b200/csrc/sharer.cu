@@ -331,16 +331,31 @@ CheckArgs Sharer::checkArgs(const RunSlot &slot, int g) const {
     return a;
 }
 
-void Sharer::launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly) {
+bool Sharer::launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly) {
     GSS_CUDA(cudaMemsetAsync(resDev_.data(), 0, sizeof(Counters), stream_));
     int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
+    int lastGroup = -1;
+    for (int g = 0; g < groups; g++)
+        if (slot.aggStart[g] != 0) lastGroup = g;
+    bool published = false;
     for (int g = 0; g < groups; g++) {
         if (slot.aggStart[g] == 0) continue; // no frozen slot in this group
         CheckArgs a = checkArgs(slot, g);
         if (filterOnly) launchFilterOnly(a, dims_, numSMs_, stream_, &launches_);
         else if (dense) launchCheckDense(a, dims_, numSMs_, stream_, &launches_);
-        else launchCheck(a, dims_, numSMs_, stream_, &launches_);
+        else {
+            if (fusedPublish_.peerDone && g == lastGroup && a.totalTiles > 0) {
+                a.peerHdr = fusedPublish_.peerHdr;
+                a.peerDone = fusedPublish_.peerDone;
+                a.peerTicket = fusedPublish_.peerTicket;
+                a.peerSeq = fusedPublish_.peerSeq;
+                a.peerGroups = groups;
+                published = true;
+            }
+            launchCheck(a, dims_, numSMs_, stream_, &launches_);
+        }
     }
+    return published;
 }
 
 void Sharer::enqueueResultCopy(RunSlot &slot) {

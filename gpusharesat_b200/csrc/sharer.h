@@ -106,7 +106,8 @@ private:
     void enqueueFromDevicePayload(RunSlot &slot, const void *devPayload, int64_t validBytes, bool collapsePrev, int64_t h2d);
     void finishRun(RunSlot &slot, bool fetchAllHits = true, bool allowPostprocess = true);     // wait, re-run on overflow, pull every hit to the host
     void processResults(RunSlot &slot);
-    void launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly = false);
+    // returns true when the last k_exact launch also published the peer result (fusedPublish_ set)
+    bool launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly = false);
     void enqueueResultCopy(RunSlot &slot);
     void materializeLastHits();
     bool ensureTables(bool &rebuild);
@@ -169,8 +170,10 @@ private:
     // ---- peer-memory exchange state (peer.cu) ----
     struct PeerState;
     PeerState *peer_ = nullptr;
+    int64_t peerPayloadBytes_ = 0;
     HitRecord *hitsOverride_ = nullptr; // the check kernels append their hits here (peer mode: this rank's
     unsigned int hitCapOverride_ = 0;   // slot in rank 0's gather window) instead of resDev_
+    CheckArgs fusedPublish_;            // peer mode: peerHdr / peerDone / peerTicket / peerSeq for the last k_exact
     void peerLaunchCheckAndFinalize(RunSlot &slot);
     void peerWaitFlag(const uint32_t *flag, uint32_t value);
 
