@@ -5,16 +5,22 @@
 //
 // Kernel inventory
 //   k_fill_tables    initial table contents (everything undefined)
-//   k_apply_updates  per-run assignment deltas -> T2 rows + the solver's aggregate bits in A1
+//   k_apply_updates  per-run assignment deltas -> T2 rows + the solver's aggregate bits in A1 (one
+//                    64-bit atomicAnd + one atomicOr per {F,U} pair)
 //   k_collapse       after a run: every slot := the solver's last slot (reference
-//                    dSetAllAssigsToLast, Assigs.cu:127-141), run at the START of the next run so
-//                    that a run whose hit buffer overflowed can simply be re-launched
-//   k_filter         level 1: one warp per 128-clause tile, lane = 4 clauses (LDG.128 literal
+//                    dSetAllAssigsToLast, Assigs.cu:127-141), deferred until the run is known not
+//                    to need a repeat, so a run whose buffers overflowed can simply be re-launched
+//   k_filter_t<>     level 1: one warp per 128-clause tile, lane = 4 clauses (LDG.128 literal
 //                    rows, LDG.64 gathers from the L2-resident A1), ballot early exit per row,
-//                    warp-aggregated survivor append
-//   k_exact          level 2: one warp per survivor, lane = solver (coalesced 256 B T2 rows),
-//                    warp-aggregated hit append
+//                    warp-aggregated survivor append; template over scheduling / cache policy
+//                    (kFilterVariants, timed against each other by bench.py --filter-sweep)
+//   k_exact_t<>      level 2: lane = solver (coalesced 256 B T2 rows), G survivors per warp step,
+//                    software-pipelined, warp-aggregated hit append; multi-GPU: its last block
+//                    publishes the rank's result (slot header + done flag in rank 0's memory)
 //   k_check_dense    bench-only: every (literal, solver word) pair, no filter, no early exit
+//   k_peer_*         multi-GPU exchange over peer memory (push of the batch + mailbox store, polling
+//                    fallbacks / wait-for-all, stand-alone publish): see peer.cu
+//   k_post_*         large hit lists: sort keys, literal positions, id + literal emission
 #include "kernels.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -368,17 +374,12 @@ const FilterVariant kFilterVariants[] = {
     {k_filter_t<false, 1, 0, 0, 5>, 256, "contiguous tiles per warp, 5 x 256"},
     {k_filter_t<false, 2, 0, 0, 5>, 256, "contiguous tiles per block, warps interleaved, 5 x 256"},
     {k_filter_t<false, 1, 0, 0, 4>, 256, "contiguous per warp, 4 x 256"},
-    {k_filter_t<false, 2, 0, 0, 4>, 256, "contiguous per block, 4 x 256"},
     {k_filter_t<false, 1, 0, 0, 6>, 256, "contiguous per warp, 6 x 256 (40 registers, spills)"},
-    {k_filter_t<false, 2, 0, 0, 6>, 256, "contiguous per block, 6 x 256 (40 registers, spills)"},
     {k_filter_t<false, 1, 1, 0, 5>, 256, "contiguous per warp, rows L1::no_allocate, 5 x 256"},
+    {k_filter_t<false, 1, 0, 1, 5>, 256, "contiguous per warp, gathers ld.cg (L2 only), 5 x 256"},
     {k_filter_t<false, 2, 0, 0, 5>, 128, "contiguous per block, 10 x 128"},
-    {k_filter_t<true, 0, 0, 0, 5>, 256, "strided, next tile's rows 0+1 in flight (ping-pong), 5 x 256"},
     {k_filter_t<true, 1, 0, 0, 4>, 256, "contiguous per warp + ping-pong prefetch, 4 x 256"},
     {k_filter_t<true, 1, 0, 0, 5>, 256, "contiguous per warp + ping-pong prefetch, 5 x 256"},
-    {k_filter_t<true, 1, 0, 0, 3>, 256, "contiguous per warp + ping-pong prefetch, 3 x 256"},
-    {k_filter_t<true, 1, 1, 0, 4>, 256, "contiguous per warp + ping-pong prefetch, rows no_allocate, 4 x 256"},
-    {k_filter_t<false, 0, 0, 0, 6>, 256, "strided, 6 x 256 (40 registers, spills)"},
 };
 constexpr int kNumFilterVariants = (int)(sizeof(kFilterVariants) / sizeof(kFilterVariants[0]));
 int gFilterVariant = -1; // -1: not chosen yet (GSS_FILTER_VARIANT or the default)
@@ -690,6 +691,23 @@ __global__ void k_peer_wait(const uint32_t *flag, uint32_t value, unsigned long 
     }
 }
 
+// rank 0: wait for the done flags of ALL workers with one launch (thread r polls flag r).  Seven
+// stream memory operations in a row cost ~2.5 us each even when the flags are already set.
+__global__ void k_peer_wait_all(PeerFlagList flags, uint32_t value, unsigned long long timeoutNs, int *err) {
+    const int r = threadIdx.x;
+    if (r >= flags.n) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        const uint32_t v = *reinterpret_cast<const volatile uint32_t *>(flags.p[r]);
+        if ((int32_t)(v - value) >= 0) return;
+        __nanosleep(100);
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeoutNs) { *err = 1; return; }
+    }
+}
+
 // ---- post-processing of large hit lists ----
 // key = solver | length | index packed into the fewest bits the database needs: the radix sort makes
 // one pass per 8 key bits
@@ -870,6 +888,14 @@ void launchPeerFinalize(const Counters *counters, unsigned int hitCap, unsigned 
                         uint32_t *doneFlag, uint32_t seq, cudaStream_t s, int64_t *launches) {
     k_peer_finalize<<<1, 32, 0, s>>>(counters, hitCap, survCap, groups, hdr, doneFlag, seq);
     checkLaunch("k_peer_finalize");
+    ++*launches;
+}
+
+void launchPeerWaitAll(const PeerFlagList &flags, uint32_t value, unsigned long long timeoutNs, int *err, cudaStream_t s,
+                       int64_t *launches) {
+    if (flags.n == 0) return;
+    k_peer_wait_all<<<1, 32, 0, s>>>(flags, value, timeoutNs, err);
+    checkLaunch("k_peer_wait_all");
     ++*launches;
 }
 

@@ -136,6 +136,8 @@ void launchPeerPush(const void *src, long long bytes, const PeerPushList &L, uin
                     cudaStream_t s, int64_t *launches);
 void launchPeerFinalize(const Counters *counters, unsigned int hitCap, unsigned int survCap, int groups, long long *hdr,
                         uint32_t *doneFlag, uint32_t seq, cudaStream_t s, int64_t *launches);
+void launchPeerWaitAll(const PeerFlagList &flags, uint32_t value, unsigned long long timeoutNs, int *err, cudaStream_t s,
+                       int64_t *launches);
 void launchPeerWait(const uint32_t *flag, uint32_t value, unsigned long long timeoutNs, int *err, cudaStream_t s,
                     int64_t *launches);
 

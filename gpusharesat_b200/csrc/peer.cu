@@ -319,8 +319,15 @@ int Sharer::peerEnqueue() {
     GSS_CUDA(cudaEventRecord(slot.evBeforeCheck, stream_));
     peerLaunchCheckAndFinalize(slot);
     GSS_CUDA(cudaEventRecord(slot.evAfterCheck, stream_));
-    if (root)
-        for (int r = 1; r < P.world; r++) peerWaitFlag(P.done(r), 2u * P.seq - 1u);
+    if (root) {
+        if (P.world > 2) { // all workers' flags with one launch
+            PeerFlagList all{};
+            for (int r = 1; r < P.world; r++) all.p[all.n++] = P.done(r);
+            launchPeerWaitAll(all, 2u * P.seq - 1u, (unsigned long long)(P.timeoutS * 1e9), P.err(), stream_, &launches_);
+        } else if (P.world == 2) {
+            peerWaitFlag(P.done(1), 2u * P.seq - 1u);
+        }
+    }
     GSS_CUDA(cudaEventRecord(P.evGathered, stream_)); // rank 0: the hits of every rank are in its memory
     // (small copies cost ~10 us of latency each: they go after the point the batch is complete)
     slot.resHost.resize(sizeof(Counters));
@@ -355,7 +362,7 @@ int64_t Sharer::peerFinish() {
                 GSS_DIE("peer exchange timed out (rank " + std::to_string(P.rank) + ", batch " + std::to_string(P.seq) + ")");
             std::this_thread::yield();
         }
-        if (!P.waitFn) {
+        if (!P.waitFn || (root && P.world > 2)) {
             GSS_CUDA(cudaMemcpyAsync(P.errHost.data(), P.err(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
             GSS_CUDA(cudaStreamSynchronize(stream_));
             if (P.errHost[0]) GSS_DIE("peer exchange timed out on the device (rank " + std::to_string(P.rank) + ")");
