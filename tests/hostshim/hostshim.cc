@@ -5,6 +5,7 @@
 #include "../../gpusharesat_b200/csrc/clause_db.h"
 #include "../../gpusharesat_b200/csrc/reported.h"
 #include "../../gpusharesat_b200/csrc/stats.h"
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 
@@ -55,6 +56,26 @@ int hs_collect(HostRig *r, int fullRebuild) {
     for (int s = 0; s < n; s++) r->assigs.solver(s).collectLocked(r->updates, r->params[s], r->ids[s], fullRebuild != 0);
     return (int)r->updates.size();
 }
+// the same collection the way the engine does it for large batches (Sharer::collectBatch): one pass
+// for the sizes, then every solver copies into its own range -- here on a worker pool
+int hs_collect_split(HostRig *r) {
+    int n = r->assigs.solverCount();
+    r->updates.clear();
+    r->params.assign(n, SolverRunParams{});
+    r->ids.assign(n, AssigIds{});
+    std::vector<size_t> offset(n + 1, 0);
+    size_t total = 0;
+    for (int s = 0; s < n; s++) {
+        offset[s] = total;
+        total += r->assigs.solver(s).pendingUpdatesLocked();
+    }
+    VarUpdate *base = r->updates.append(total);
+    LazyPool pool;
+    pool.get().parallelFor(n, [&](int s) {
+        r->assigs.solver(s).collectIntoLocked(base + offset[s], (int32_t)offset[s], r->params[s], r->ids[s]);
+    });
+    return (int)total;
+}
 void hs_get_params(HostRig *r, int s, SolverRunParams *out) { *out = r->params[s]; }
 void hs_get_updates(HostRig *r, VarUpdate *out) { memcpy(out, r->updates.data(), r->updates.size() * sizeof(VarUpdate)); }
 void hs_get_ids(HostRig *r, int s, int64_t *start, int *count) { *start = r->ids[s].start; *count = r->ids[s].count; }
@@ -87,6 +108,26 @@ double hs_hand_over(HostRig *r, const HitRecord *hits, int n) {
     std::vector<HitRecord> v(hits, hits + n);
     auto t0 = std::chrono::steady_clock::now();
     r->reported.handOver(v, r->ids, r->assigs.solverCount());
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+}
+// the hand-over of a hit list the GPU has already sorted and resolved (Reported::handOverSorted): the
+// records, ids and the literal stream are built here from the host mirror, in (solver, len, idx) order
+double hs_hand_over_sorted(HostRig *r, const HitRecord *hits, int n) {
+    std::vector<HitRecord> v(hits, hits + n);
+    std::sort(v.begin(), v.end(), [](const HitRecord &a, const HitRecord &b) {
+        if (a.solver != b.solver) return a.solver < b.solver;
+        if (a.len != b.len) return a.len < b.len;
+        return a.idx < b.idx;
+    });
+    std::vector<SortedHit> recs(v.size());
+    std::vector<int> lits;
+    for (size_t i = 0; i < v.size(); i++) {
+        const int64_t pos = (int64_t)lits.size();
+        const int64_t id = r->db.appendClause(v[i].len, v[i].idx, lits);
+        recs[i] = SortedHit{v[i].mask, v[i].solver, v[i].len, v[i].idx, id, pos};
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    r->reported.handOverSorted(recs.data(), recs.size(), lits.data(), (int64_t)lits.size(), r->ids, r->assigs.solverCount());
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
 }
 int64_t hs_add_clauses_bulk(HostRig *r, const int64_t *offsets, const int *lits, int64_t n) { return r->db.addClausesBulk(offsets, lits, n); }

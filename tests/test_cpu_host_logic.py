@@ -3,7 +3,7 @@ reduceDb thresholds) through tests/hostshim, against the reference's golden valu
 import numpy as np
 import pytest
 
-from hostshim_lib import DeviceModel, Rig
+from hostshim_lib import HIT, DeviceModel, Rig
 
 TRUE, FALSE, UNDEF = 0, 1, 2
 ALL = 0xFFFFFFFF
@@ -232,3 +232,96 @@ def test_activity_rescale():
     r.drain()
     # the increment passed 1e19 on the second clause and everything was rescaled (Clauses.cu:284-291)
     assert r.activity(3, 2) < 1e19 and r.activity(3, 0) < r.activity(3, 1) < r.activity(3, 2)
+
+
+def _params_tuple(p):
+    return (p.startVals, p.lastMask, p.allAggBits, p.usedAggBits, p.updStart, p.updCount, p.nGroups,
+            tuple(p.groupAggBit[: p.nGroups]), tuple(p.groupSlotMask[: p.nGroups]))
+
+
+def test_split_collect_equals_single_pass_collect():
+    """Sharer::collectBatch collects large batches in two steps (sizes, then concurrent copies into
+    disjoint ranges): same deltas, same run parameters, same assignment ids as the one-pass collect"""
+    rng = np.random.default_rng(5)
+    nvars, nsolvers = 500, 7
+    a, b = Rig(nvars, nsolvers), Rig(nvars, nsolvers)
+    for rnd in range(4):
+        for s in range(nsolvers):
+            for _ in range(int(rng.integers(0, 9))):
+                for v in rng.choice(nvars, size=int(rng.integers(0, 60)), replace=False):
+                    val = int(rng.integers(0, 3))
+                    a.set(s, int(v), val)
+                    b.set(s, int(v), val)
+                assert a.send(s) == b.send(s)
+        ua, pa = a.collect()
+        ub, pb = b.collect_split()
+        assert np.array_equal(ua, ub)
+        assert [_params_tuple(p) for p in pa] == [_params_tuple(p) for p in pb]
+        assert [a.ids(s) for s in range(nsolvers)] == [b.ids(s) for s in range(nsolvers)]
+
+
+def test_sorted_hand_over_equals_host_hand_over():
+    """a hit list sorted and resolved 'by the GPU' (ids + literal stream, Reported::handOverSorted: every
+    solver's batch is one slice found by binary search) hands over exactly what the host path does"""
+    rng = np.random.default_rng(6)
+    nvars, nsolvers = 300, 6
+    a, b = Rig(nvars, nsolvers), Rig(nvars, nsolvers)
+    counts = {}
+    for i in range(8000):  # several 128-clause tiles per length
+        n = int(rng.integers(1, 7))
+        lits = [2 * int(v) + int(rng.integers(0, 2)) for v in rng.choice(nvars, size=n, replace=False)]
+        assert a.add_clause(lits) == b.add_clause(lits)
+        counts[n] = counts.get(n, 0) + 1
+    a.drain(); b.drain()
+    for rnd in range(3):
+        for r in (a, b):
+            for s in range(nsolvers):
+                if s != 3:  # one solver without any assignment
+                    r.set(s, rnd, 0)
+                    r.send(s)
+            r.collect()
+        hits = []
+        for s in (0, 1, 2, 4, 5):  # solver 3 has no hit; solver 5 few
+            for _ in range(5 if s == 5 else 4000):
+                n = int(rng.integers(1, 7))
+                hits.append((int(rng.integers(1, 1 << 31)), s, n, int(rng.integers(0, counts[n]))))
+        hits = np.array(sorted(set((s, n, i) for _, s, n, i in hits)), dtype=np.int64)
+        rec = np.zeros(len(hits), dtype=HIT)
+        rec["solver"], rec["len"], rec["idx"] = hits[:, 0], hits[:, 1], hits[:, 2]
+        rec["mask"] = rng.integers(1, 1 << 31, size=len(hits))
+        assert len(rec) >= 8192  # the parallel host path
+        a.hand_over(rec[rng.permutation(len(rec))])
+        b.hand_over_sorted(rec[rng.permutation(len(rec))])
+        for s in range(nsolvers):
+            pa, pb = a.pop_all(s), b.pop_all(s)
+            assert pa == pb
+            assert (len(pa) > 0) == (s != 3)
+            assert a.last_all_reported(s) == b.last_all_reported(s)
+
+
+def test_clause_mirror_round_trip_across_tiles():
+    """the tiled, lane-interleaved host mirror (clause_db.h wordPos / common.h tileSlot) gives every
+    clause back, before and after the first-literal sort of a bulk load"""
+    rng = np.random.default_rng(8)
+    r = Rig(400, 1)
+    want = {}
+    offsets, flat = [0], []
+    for i in range(9000):  # > 1024 clauses per length: the bulk load is sorted by first literal
+        n = int(rng.integers(1, 6))
+        lits = [2 * int(v) + int(rng.integers(0, 2)) for v in rng.choice(400, size=n, replace=False)]
+        flat += lits
+        offsets.append(len(flat))
+    first = r.add_clauses_bulk(offsets, flat)
+    r.drain()
+    for i in range(9000):
+        want[first + i] = flat[offsets[i]:offsets[i + 1]]
+    seen = 0
+    for n in range(1, 6):
+        prev_first = -1
+        for i in range(r.count(n)):
+            lits = r.get_clause(n, i)
+            assert lits == want[r.clause_id(n, i)]
+            assert lits[0] >= prev_first  # bulk loads are ordered by first literal
+            prev_first = lits[0]
+            seen += 1
+    assert seen == 9000
