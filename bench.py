@@ -236,7 +236,8 @@ def workload_config(a):
                       f"{(1 - a.p_agree) * (1 - a.p_undef):.4f}/{a.p_undef}",
             "churn_per_assignment": a.churn,
             "l2_policy": "inputs larger than L2 (clause arenas + assignment tables > 126 MB)",
-            "parallelism": f"clause-sharded x{a.gpus}" if a.gpus > 1 else "single GPU"}
+            "parallelism": (f"clause tiles sharded x{a.gpus} ({a.scaling} scaling: {a.clauses} clauses in total), "
+                            f"assignments broadcast, exchange = {a.exchange}") if a.gpus > 1 else "single GPU"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -288,7 +289,7 @@ def run_reference_gpu(a):
 
 def run_b200_sharded(a):
     """N > 1: one process per GPU (torchrun).  The clause database is sharded by tiles: rank r
-    checks the tiles t with t % N == r (every rank keeps the whole arena so that rank 0 can resolve
+    checks its contiguous 1/N of the tiles of every length (every rank keeps the whole arena so that rank 0 can resolve
     any hit on its device).  Rank 0 is the front-end: it owns the solver streams, the assignment
     slot machines and the hand-over queues.
 
@@ -310,6 +311,7 @@ def run_b200_sharded(a):
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
 
+    a.gpus = world
     per_gpu = a.clauses
     if a.scaling == "weak":
         a.clauses = per_gpu * world
@@ -382,8 +384,6 @@ def run_b200_sharded(a):
     if rank == 0:
         cfg = workload_config(a)
         cfg["clauses_per_gpu"] = a.clauses // world
-        cfg["parallelism"] = (f"clause tiles sharded x{world} ({a.scaling} scaling: {a.clauses} clauses in total), "
-                              f"assignments broadcast, exchange = {a.exchange}")
         if a.exchange == "peer":
             region = ("rank 0: batch resident in its HBM -> mailbox signal -> every rank: table kernels (deltas read over "
                       "NVLink from rank 0), check kernels (hits stored over NVLink into rank 0) -> rank 0 has seen every "

@@ -142,7 +142,7 @@ bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
         {
             // Sharding (multi-GPU) splits the WORK, not the storage: every device holds the whole
             // arena (176 MB at 10 M clauses is nothing next to 180 GB), so any rank can resolve any
-            // hit (ids, literals) on its device; a rank only checks the tiles t with t % world == rank.
+            // hit (ids, literals) on its device; a rank only checks its share of the tiles.
             size_t total = (size_t)tiles * tileWords, from = (size_t)firstTile * tileWords;
             if (total > 0) {
                 if (!pl.dev.tryReserve(total, pl.fullReupload ? 0 : from, stream)) return false;
@@ -190,8 +190,10 @@ int ClauseDb::buildDirectory(std::vector<LenDir> &dir) const {
         if (n == 0) continue;
         // a length none of whose tiles is checked here still gets its entry: hits of other ranks
         // are resolved (ids, literals, activity bumps) through this directory
-        tiles += (int)localTiles((n + kTileClauses - 1) / kTileClauses);
-        dir.push_back(LenDir{pl.dev.data(), s, (int32_t)n, tiles, 0, pl.idsDev.data(), const_cast<float *>(pl.actsDev.data())});
+        const int64_t allTiles = (n + kTileClauses - 1) / kTileClauses;
+        tiles += (int)localTiles(allTiles);
+        dir.push_back(LenDir{pl.dev.data(), s, (int32_t)n, tiles, (int32_t)shardFirstTile(allTiles), pl.idsDev.data(),
+                             const_cast<float *>(pl.actsDev.data())});
     }
     return tiles;
 }

@@ -28,7 +28,7 @@ struct LenDir {
     int32_t len;
     int32_t count;   // clauses of this length
     int32_t tileEnd; // cumulative count of THIS DEVICE's tiles including this length (longest length first)
-    int32_t pad;
+    int32_t firstTile; // first tile of this length that THIS DEVICE checks (multi-GPU: its contiguous share)
     const int64_t *ids; // device copy of the clause ids of this length, indexed by (global) clause index
     float *acts;        // device-resident clause activities (bumped by k_bump_activity), same indexing
 };
@@ -43,8 +43,8 @@ public:
 
     void setMaxLen(int maxLen);
     int maxLen() const { return maxLen_; }
-    // Multi-GPU: every rank keeps every clause (host mirror and device arenas) but checks only the
-    // tiles t with t % world == rank.  Before the first clause.
+    // Multi-GPU: every rank keeps every clause (host mirror and device arenas) but checks only its
+    // contiguous share of the tiles of every length (shardFirstTile / localTiles).  Before the first clause.
     void setShard(int rank, int world);
     int shardRank() const { return shardRank_; }
     int shardWorld() const { return shardWorld_; }
@@ -151,8 +151,13 @@ private:
     void sortArena(int len);
     void rescaleActivity();
 
+    // Multi-GPU: rank r checks the contiguous share [tiles*r/world, tiles*(r+1)/world) of every length
+    // array.  Every rank holds the whole arena, so the shares simply move as the arrays grow -- no data
+    // does; contiguous shares keep a rank's reads sequential (with the first version's interleaved
+    // split -- every world-th tile -- rank 0's sweep took 84 us at 8 ranks against 70 us on one GPU).
+    int64_t shardFirstTile(int64_t globalTiles) const { return globalTiles * shardRank_ / shardWorld_; }
     int64_t localTiles(int64_t globalTiles) const {
-        return globalTiles > shardRank_ ? (globalTiles - shardRank_ + shardWorld_ - 1) / shardWorld_ : 0;
+        return globalTiles * (shardRank_ + 1) / shardWorld_ - globalTiles * shardRank_ / shardWorld_;
     }
     static constexpr int64_t kSortMinClauses = 1024;
     int maxLen_ = kDefaultMaxClauseLen;

@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(256, MINBLOCKS) k_filter_t(CheckArgs a) {
     WarpStage<Survivor> stage{sStage[threadIdx.x >> 5], 0};
     unsigned int *survCounter = &a.counters->nSurvivors[a.groupBase / kMaxSolversPerGroup];
 
-    // where a tile lives: every device holds the whole arena, this rank checks the tiles t with
-    // t % world == rank
+    // where a tile lives: every device holds the whole arena, this rank checks a contiguous share of
+    // every length's tiles, starting at LenDir::firstTile
     struct Tile {
         const int32_t *row; // this lane's column of the tile's first literal row
         int len, c0, nValid;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256, MINBLOCKS) k_filter_t(CheckArgs a) {
     auto locate = [&](int tile) -> Tile {
         const int k = findDir(sTileEnd, a.nDir, tile);
         const LenDir d = a.dir[k];
-        const int gTile = (tile - (k ? sTileEnd[k - 1] : 0)) * a.shardWorld + a.shardRank;
+        const int gTile = (tile - (k ? sTileEnd[k - 1] : 0)) + d.firstTile;
         // words 4*lane .. 4*lane+3 of a row hold the clauses lane, lane+32, lane+64, lane+96 (tileSlot)
         const int c0 = gTile * kTileClauses + lane; // global clause index of this lane's first clause
         return Tile{d.base + (size_t)gTile * kTileClauses * d.len + lane * 4, d.len, c0, d.count - c0, sTileEnd[k]};
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256, MINBLOCKS) k_filter_t(CheckArgs a) {
     // the tile after `t` (device-local index tile + 1): the same length array continues, or look it up
     auto advance = [&](const Tile &t, int tile) -> Tile {
         if (tile + 1 >= t.lenEnd) return locate(tile + 1);
-        const int dc = kTileClauses * a.shardWorld;
+        const int dc = kTileClauses;
         return Tile{t.row + (size_t)dc * t.len, t.len, t.c0 + dc, t.nValid - dc, t.lenEnd};
     };
 
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(128) k_check_dense(CheckArgs a) {
         const LenDir d = a.dir[k];
         const int tileInLen = tile - (k ? sTileEnd[k - 1] : 0);
         const int len = d.len;
-        const int gTile = tileInLen * a.shardWorld + a.shardRank;
+        const int gTile = tileInLen + d.firstTile;
         const int c0 = gTile * kTileClauses + q * kDenseGroup;
         const int nValid = d.count - c0;
         if (nValid <= 0) continue;
@@ -625,15 +625,6 @@ __global__ void k_finalize(const Counters *c, unsigned int hitCap, unsigned int 
 }
 
 // ---- peer-memory exchange (multi-GPU, peer.cu) ----
-// root: tell every worker that payload `seq` is complete in the root's window (the H2D copy that
-// wrote it precedes this kernel on the stream)
-__global__ void k_peer_signal(PeerFlagList boxes, uint32_t seq) {
-    const int r = threadIdx.x;
-    if (r >= boxes.n) return;
-    __threadfence_system();
-    *reinterpret_cast<volatile uint32_t *>(boxes.p[r]) = seq;
-}
-
 // root: push the batch into every worker's window with plain (posted) peer stores and then store the
 // sequence number into every mailbox -- one launch; the block that finishes last signals.  (A copy-
 // engine transfer costs ~17 us of fixed latency per peer for these 2 MB payloads; SM stores do not.)
@@ -866,13 +857,6 @@ void launchFinalize(const Counters *counters, unsigned int hitCap, unsigned int 
                     cudaStream_t s, int64_t *launches) {
     k_finalize<<<1, 32, 0, s>>>(counters, hitCap, survCap, groups, dstHeader);
     checkLaunch("k_finalize");
-    ++*launches;
-}
-
-void launchPeerSignal(const PeerFlagList &boxes, uint32_t seq, cudaStream_t s, int64_t *launches) {
-    if (boxes.n == 0) return;
-    k_peer_signal<<<1, 32, 0, s>>>(boxes, seq);
-    checkLaunch("k_peer_signal");
     ++*launches;
 }
 

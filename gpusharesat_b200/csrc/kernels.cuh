@@ -42,7 +42,7 @@ struct CheckArgs {
     const LenDir *dir; // device copy of the length directory
     int nDir;
     int totalTiles;               // tiles checked by THIS device
-    int shardRank, shardWorld;    // device tile t of a length is global tile t * shardWorld + shardRank
+    int shardRank, shardWorld;    // (informational: the share of this device is in LenDir::firstTile / tileEnd)
     const SolverRunParams *params; // device, all solvers
     int groupBase;                 // first solver of this group
     int groupSolvers;              // solvers in this group (<= 32)
@@ -125,7 +125,6 @@ struct PeerFlagList {
     uint32_t *p[kMaxPeers];
     int n;
 };
-void launchPeerSignal(const PeerFlagList &boxes, uint32_t seq, cudaStream_t s, int64_t *launches);
 struct PeerPushList {
     uint4 *dst[kMaxPeers];        // every worker's payload area
     uint32_t *mailbox[kMaxPeers]; // every worker's mailbox

@@ -71,7 +71,6 @@ struct Sharer::PeerState {
     uint8_t *window = nullptr;          // this rank's window
     uint8_t *rootWindow = nullptr;      // rank 0's window (mapped on the workers)
     std::vector<uint8_t *> mapped;      // windows opened through IPC (to be closed)
-    PeerFlagList mailboxes{};           // rank 0: every worker's mailbox
     PeerPushList push{};                // rank 0: every worker's payload area and mailbox
     cudaEvent_t evPushed = nullptr;     // rank 0: the batch has been stored into every worker's window
     uint32_t seq = 0;
@@ -161,10 +160,8 @@ void Sharer::peerConnect(const void *blobs, int64_t blobBytes) {
         return static_cast<uint8_t *>(p);
     };
     if (P.rank == 0) {
-        P.mailboxes.n = 0;
         for (int r = 1; r < P.world; r++) {
             uint8_t *w = open(blobOf(r));
-            P.mailboxes.p[P.mailboxes.n++] = reinterpret_cast<uint32_t *>(w + kMailboxOff);
             P.push.dst[P.push.n] = reinterpret_cast<uint4 *>(w + kCtlBytes);
             P.push.mailbox[P.push.n] = reinterpret_cast<uint32_t *>(w + kMailboxOff);
             P.push.n++;

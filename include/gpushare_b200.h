@@ -166,7 +166,8 @@ void gss_debug_db_size(gss_sharer *h, int64_t *nclauses, int64_t *nlits);
  * Multi-GPU (new functionality; the reference drives device 0 only, GpuClauseSharerImpl.cu:52).
  * One process per GPU.  Every rank creates a sharer, calls gss_set_shard(rank, world) and then
  * the same gss_set_var_count / gss_set_cpu_solver_count / gss_add_clause sequence: the host
- * mirror is complete everywhere, each device holds the clause tiles t with t % world == rank.
+ * mirror and the device arenas are complete everywhere; rank r CHECKS its contiguous share of the
+ * clause tiles of every length ([tiles*r/world, tiles*(r+1)/world)).
  * Rank 0 is the front-end (solver threads, assignment slots, hand-over).  Per batch:
  *   rank 0      gss_mgpu_collect   -> run parameters + assignment deltas (pinned host memory)
  *   all ranks   [broadcast them, e.g. NCCL over NVLink]  gss_mgpu_run(payload: host OR device ptr)
