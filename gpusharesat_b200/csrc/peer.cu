@@ -20,8 +20,10 @@
 //            a copy for the deferred collapse), k_filter / k_exact on this rank's tiles, which append
 //            the hits straight into this rank's slot of rank 0's gather area (peer stores); the block
 //            of k_exact that finishes last writes the slot header and the done flag.
-//   all      as soon as a batch cannot be run again (no overflow), peerFinish enqueues its collapse
-//            (dSetAllAssigsToLast): off the critical path of the next batch, on a warm GPU
+//   workers  as soon as a batch cannot be run again (no overflow), peerFinish enqueues its collapse
+//            (dSetAllAssigsToLast): off the critical path of the next batch, on a warm GPU.  Rank 0
+//            collapses right after the next push instead: it does not have to wait for the batch
+//            to arrive, so its collapse hides behind the workers' later start.
 //   rank 0   stream waits for every done flag, reads the headers (one small D2H), and sorts /
 //            resolves / hands over the union of the hits on its device (every rank holds the whole
 //            clause arena, so rank 0 can resolve any hit)
@@ -233,9 +235,11 @@ int Sharer::peerEnqueue() {
     db_->drainPending();
     if (db_->stats().clauses == 0) return -1;
     RunSlot &slot = slots_[nextSlot()];
-    // (the collapse of the previous batch -- dSetAllAssigsToLast -- was enqueued by peerFinish as soon
-    // as that batch could no longer be run again; a batch left over from before peer mode goes here)
-    if (collapseSlot_ >= 0) {
+    // The collapse of the previous batch (dSetAllAssigsToLast).  A worker did it in peerFinish, as soon
+    // as that batch could no longer be run again (only a batch left over from before peer mode goes
+    // here).  Rank 0 does it below, right after the push: it is the one rank that does not wait for the
+    // batch to arrive, so there the collapse hides behind the workers' later start.
+    if (!root && collapseSlot_ >= 0) {
         RunSlot &c = slots_[collapseSlot_];
         launchCollapse(c.updDev.data(), c.paramsDev(), c.nSolvers, c.maxUpd, c.nUpdates, tables_, numSMs_, stream_, &launches_);
         collapseSlot_ = -1;
@@ -307,6 +311,11 @@ int Sharer::peerEnqueue() {
         // within a few microseconds of each other.
         launchPeerPush(payload, peerPayloadBytes_, P.push, P.seq, P.pushTicket(), numSMs_, stream_, &launches_);
         GSS_CUDA(cudaEventRecord(P.evPushed, stream_));
+    }
+    if (root && collapseSlot_ >= 0) {
+        RunSlot &c = slots_[collapseSlot_];
+        launchCollapse(c.updDev.data(), c.paramsDev(), c.nSolvers, c.maxUpd, c.nUpdates, tables_, numSMs_, stream_, &launches_);
+        collapseSlot_ = -1;
     }
 
     const SolverRunParams *paramsSrc = root ? slot.paramsDev() : reinterpret_cast<const SolverRunParams *>(payload + sizeof(PayloadHeader));
@@ -394,6 +403,12 @@ int64_t Sharer::peerFinish() {
     cudaEventElapsedTime(&msFirst[3], slot.evStart, P.evGathered);
     cudaEventElapsedTime(&msFirst[4], slot.evAfterCheck, P.evGathered);
     auto collapseNow = [&]() {
+        if (root) { // rank 0: at the start of the next batch, behind the push (see peerEnqueue)
+            P.collapsed = false;
+            collapseSlot_ = P.collapsePending ? cur_ : -1;
+            P.collapsePending = false;
+            return;
+        }
         P.collapsed = P.collapsePending;
         if (!P.collapsed) return;
         GSS_CUDA(cudaEventRecord(P.evC0, stream_));
