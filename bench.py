@@ -613,6 +613,9 @@ def run_b200(a):
                                         "structure; this L2->SM stream, not LOP3 issue, bounds dense mode"},
                 "dense_hits": n_dense,
                 "production_speedup_over_dense": t_dense / t_prod,
+                # the production kernels do the same NOMINAL checks in t_prod: relative to the dense roofline
+                # time they are > 1 because the two-level filter never evaluates provably dead pairs
+                "production_us_per_sweep": t_prod, "t_roof_over_production": max(t_hbm, t_int) * 1e6 / t_prod,
             }
         else:
             sh.gpuRun()
