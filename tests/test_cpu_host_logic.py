@@ -325,3 +325,106 @@ def test_clause_mirror_round_trip_across_tiles():
             prev_first = lits[0]
             seen += 1
     assert seen == 9000
+
+
+class _Front:
+    """the thin facade logic of Sharer (trySet all-or-nothing, buffered unsets: sharer.cu:148-193) over
+    the host rig, so that the rig can be fed the same API traffic as the snapshot model"""
+
+    def __init__(self, rig, nsolvers):
+        self.r, self.to_unset = rig, [[] for _ in range(nsolvers)]
+
+    def _flush(self, s):
+        for l in self.to_unset[s]:
+            self.r.set(s, l >> 1, UNDEF)
+        self.to_unset[s] = []
+
+    def trySetSolverValues(self, s, lits):
+        if not self.r.available(s):
+            return False
+        self._flush(s)
+        for l in lits:
+            self.r.set(s, l >> 1, FALSE if l & 1 else TRUE)
+        return True
+
+    def unsetSolverValues(self, s, lits):
+        if self.r.available(s):
+            self._flush(s)
+            for l in lits:
+                self.r.set(s, l >> 1, UNDEF)
+        else:
+            self.to_unset[s].extend(lits)
+
+    def trySendAssignment(self, s):
+        return self.r.send(s) if self.r.available(s) else -1
+
+
+def _two_level_check(dev, params, clauses):
+    """numpy statement of what k_filter + k_exact compute FROM THE TABLES (aggregate filter, then the
+    exact recurrence on the surviving solvers) -- not the oracle's algorithm"""
+    M = 0xFFFFFFFF
+    agg_start = 0
+    for p in params:
+        agg_start |= p.usedAggBits
+    out = []
+    for cid, lits in clauses:
+        a, o = agg_start, 0
+        for l in lits:
+            v = l >> 1
+            f = int(dev.can_true[v]) if l & 1 else int(dev.can_false[v])
+            u = int(dev.can_undef[v])
+            o = (a & u) | (o & f)
+            a &= f
+        surv = a | o
+        for s, p in enumerate(params):
+            if not (surv & p.allAggBits) or p.startVals == 0:
+                continue
+            a, o = p.startVals, 0
+            for l in lits:
+                v = l >> 1
+                d, t = int(dev.def_[s, v]), int(dev.tru[s, v])
+                f = d & (t if l & 1 else ~t) & M
+                u = ~d & M
+                o = (a & u) | (o & f)
+                a &= f
+            if a | o:
+                out.append((cid, s, a | o))
+    return sorted(out)
+
+
+@pytest.mark.parametrize("nsolvers", [1, 3, 7, 32])
+def test_host_logic_plus_table_semantics_match_snapshot_model(nsolvers):
+    """CPU-only end to end: random API traffic -> the product's slot machine (C++) -> per-run deltas and
+    run parameters -> numpy tables (apply, deferred collapse) -> two-level check from the tables, against
+    the snapshot model (every frozen slot is a full assignment, checked by the oracle)"""
+    from oracle_lib import SharerModel
+    rng = np.random.default_rng(70 + nsolvers)
+    nvars = 40
+    rig = Rig(nvars, nsolvers)
+    front, model, dev = _Front(rig, nsolvers), SharerModel(nvars, nsolvers), DeviceModel(nvars, nsolvers)
+    clauses, prev = [], None
+    total = 0
+    for rnd in range(8):
+        for _ in range(int(rng.integers(5, 40))):
+            n = int(rng.integers(1, 5))
+            lits = [2 * int(rng.integers(0, nvars)) + int(rng.integers(0, 2)) for _ in range(n)]  # duplicates allowed
+            clauses.append((model.addClause(lits), lits))
+        for s in range(nsolvers):
+            for _ in range(int(rng.integers(0, 40 if rnd == 3 else 6))):  # round 3 runs out of slots
+                vs = rng.choice(nvars, size=int(rng.integers(0, 20)), replace=False)
+                x = rng.random(len(vs))
+                unset = [2 * int(v) for v, xx in zip(vs, x) if xx < 0.25]
+                sets = [2 * int(v) + int(xx < 0.7) for v, xx in zip(vs, x) if xx >= 0.25]
+                front.unsetSolverValues(s, unset); model.unsetSolverValues(s, unset)
+                assert front.trySetSolverValues(s, sets) == model.trySetSolverValues(s, sets)
+                assert front.trySendAssignment(s) == model.trySendAssignment(s)
+        upd, params = rig.collect()
+        if prev is not None:
+            dev.collapse(*prev)  # the collapse of the previous batch is deferred to the next run
+        dev.apply(upd, params)
+        prev = (upd, params)
+        want = model.run()
+        got = _two_level_check(dev, params, clauses)
+        assert got == [(int(h["clause_id"]), int(h["solver_id"]), int(h["mask"])) for h in want]
+        total += len(got)
+    assert total > 0
