@@ -428,3 +428,55 @@ def test_host_logic_plus_table_semantics_match_snapshot_model(nsolvers):
         assert got == [(int(h["clause_id"]), int(h["solver_id"]), int(h["mask"])) for h in want]
         total += len(got)
     assert total > 0
+
+
+def _rig_with_acts(acts, decay=1.0, length=3):
+    """one clause of `length` literals per entry of acts, bumped to that activity (decay 1: every clause
+    starts at 1) -- the fixture of the reference's ClauseActivityLbdTest.cu:109-131"""
+    r = Rig(4 * len(acts) + 8, 1, decay=decay)
+    lit = 0
+    for k, a in enumerate(acts):
+        r.add_clause([2 * (lit + j) for j in range(length)])
+        lit += length
+        r.drain()
+        for _ in range(a - 1):
+            r.bump(length, k)
+    return r
+
+
+@pytest.mark.parametrize("acts,n,lo,hi", [
+    ([1, 2, 3], 2, 2.0, 2.1), ([1, 2, 3], 0, -0.1, 0.1), ([1, 2, 3], 3, 3.0, 3.1),  # testApproxNthLargestAct :164-172
+    ([1, 1, 1, 3, 3, 100], 3, 1.0, 1.1),                                            # ...OneBig :174-183
+    ([1, 1, 1, 1, 10], 2, 1.0, 1.1),                                                # ...OneVal :185-193
+])
+def test_approx_nth_activity_like_reference(acts, n, lo, hi):
+    """the reference's own expectations for approxNthAct (Clauses.cu:492-525): the n-th smallest activity,
+    rounded up to its log-scale bucket"""
+    r = _rig_with_acts(acts)
+    assert [r.activity(3, k) for k in range(len(acts))] == [float(a) for a in acts]
+    assert lo < r.approx_nth_act(n) <= hi
+
+
+def test_activity_only_threshold_with_huge_differences():
+    """ClauseActivityLbdTest.cu:231-254 testActOnlyHugeDifferences: two early clauses (activities 2 and 4
+    at decay 0.5), ~56 decays, one late clause -- the removal threshold still separates the two early
+    ones (the log-scale buckets cope with 17 orders of magnitude)"""
+    import math
+    decay = 0.5
+    r = Rig(4000, 1, decay=decay)
+    r.add_clause([0, 2, 4]); r.drain()                    # activity 2
+    r.add_clause([6, 8, 10]); r.drain(); r.bump(3, 1)     # starts at the increment (4), bumped once: 8
+    a0, a1 = r.activity(3, 0), r.activity(3, 1)
+    assert a0 == 2.0 and a1 == 8.0
+    c = int(math.log(1e19 / 100) / math.log(1 / decay))
+    for i in range(c):                                    # every added clause decays once (Clauses.cu:334)
+        r.add_clause([2 * (20 + i)])                      # unit clauses: never removed, not in the way
+    r.add_clause([12, 14, 16]); r.drain()
+    big = r.activity(3, 2)
+    assert big > 1e15 and r.activity(3, 0) == 2.0         # no rescale happened
+    thr = r.approx_nth_act(3 // 2 + c // 2)               # the unit clauses rank above the two early ones
+    assert thr > a1
+    thr = r.approx_nth_act(1)
+    assert a0 < thr <= a0 * 1.1
+    thr = r.approx_nth_act(2)
+    assert a1 < thr <= a1 * 1.1
