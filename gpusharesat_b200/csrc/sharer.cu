@@ -98,8 +98,8 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
 
 Sharer::~Sharer() {
     cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_); // nothing may still be using the buffers (or a peer's window)
     peerClose();
-    if (stream_) cudaStreamSynchronize(stream_);
     if (bumpFlagEv_) cudaEventDestroy(bumpFlagEv_);
     for (auto &s : slots_) {
         cudaEventDestroy(s.evStart);
