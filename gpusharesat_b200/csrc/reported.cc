@@ -180,6 +180,12 @@ void Reported::handOver(std::vector<HitRecord> &hits, const std::vector<AssigIds
 
 void Reported::handOverSorted(const SortedHit *recs, size_t n, const int32_t *lits, int64_t totalLits,
                               const std::vector<AssigIds> &ids, int nSolvers) {
+    static const bool prof = getenv("GSS_PROFILE_HANDOVER") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    const auto t0 = now();
     // recs are ordered by (solver, length, index): find every solver's slice
     std::vector<size_t> start((size_t)nSolvers + 1, n);
     for (int s = 0; s < nSolvers; s++)
@@ -194,6 +200,7 @@ void Reported::handOverSorted(const SortedHit *recs, size_t n, const int32_t *li
         if (hasIds) perSolver[s]->ids = ids[s];
     }
     std::atomic<bool> rescale{false};
+    const auto t1 = now();
     pool_->get().parallelFor(nSolvers, [&](int s) {
         if ((size_t)s >= nQueues || !perSolver[s]) return;
         size_t lo = start[s], hi = start[s + 1];
@@ -216,8 +223,10 @@ void Reported::handOverSorted(const SortedHit *recs, size_t n, const int32_t *li
         b.hadSomeReported |= any;
     });
     db_.rescaleIfNeeded(rescale.load());
+    const auto t2 = now();
     for (size_t s = 0; s < nQueues; s++)
         if (perSolver[s]) queues_[s]->publish();
+    if (prof) fprintf(stderr, "handOverSorted: slices + begin %.0f us, fill %.0f us, publish %.0f us (%zu hits)\n", us(t0, t1), us(t1, t2), us(t2, now()), n);
 }
 
 bool Reported::pop(int s, int *&lits, int &count, int64_t &id) {

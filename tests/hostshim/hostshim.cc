@@ -39,6 +39,8 @@ extern "C" {
 HostRig *hs_create(int nvars, int nsolvers, double decay) { return new HostRig(nvars, nsolvers, decay); }
 void hs_destroy(HostRig *r) { delete r; }
 
+void hs_set_host_bumps(HostRig *r, int on) { r->reported.setHostBumps(on != 0); }
+
 // ---- slot state machine ----
 int hs_available(HostRig *r, int s) { return r->assigs.solver(s).isAssignmentAvailableLocked() ? 1 : 0; }
 void hs_set_var(HostRig *r, int s, int var, int val) { r->assigs.solver(s).setVarLocked(var, (uint8_t)val); }

@@ -28,7 +28,7 @@ def load():
     sig = {
         "hs_create": (P, [I, I, C.c_double]), "hs_destroy": (None, [P]),
         "hs_available": (I, [P, I]), "hs_set_var": (None, [P, I, I, I]), "hs_send": (Q, [P, I]),
-        "hs_collect": (I, [P, I]), "hs_collect_split": (I, [P]), "hs_hand_over_sorted": (C.c_double, [P, C.c_void_p, I]), "hs_get_params": (None, [P, I, C.POINTER(SolverRunParams)]),
+        "hs_set_host_bumps": (None, [P, I]), "hs_collect": (I, [P, I]), "hs_collect_split": (I, [P]), "hs_hand_over_sorted": (C.c_double, [P, C.c_void_p, I]), "hs_get_params": (None, [P, I, C.POINTER(SolverRunParams)]),
         "hs_get_updates": (None, [P, C.c_void_p]), "hs_get_ids": (None, [P, I, C.POINTER(Q), IP]),
         "hs_add_clause": (Q, [P, IP, I]), "hs_drain": (None, [P]), "hs_count": (I, [P, I]),
         "hs_clause_id": (Q, [P, I, I]), "hs_activity": (C.c_float, [P, I, I]), "hs_bump": (None, [P, I, I]),
@@ -58,6 +58,7 @@ class Rig:
         except Exception:
             pass
 
+    def set_host_bumps(self, on): self.L.hs_set_host_bumps(self.h, 1 if on else 0)
     def set(self, s, var, val): self.L.hs_set_var(self.h, s, var, val)
     def send(self, s): return self.L.hs_send(self.h, s)
     def available(self, s): return bool(self.L.hs_available(self.h, s))
