@@ -102,3 +102,38 @@ def test_sharer_model_reference_fixture():
     m.trySetSolverValues(0, [lit(1)]); m.trySendAssignment(0)
     hits = m.run()
     assert [int(np.sum(hits["solver_id"] == s)) for s in range(3)] == [1, 0, 0]
+
+
+def _mask32(lits, d, t, start=0xFFFFFFFF):
+    a = np.ascontiguousarray(lits, dtype=np.int32)
+    dd, tt = np.ascontiguousarray(d, dtype=np.uint32), np.ascontiguousarray(t, dtype=np.uint32)
+    return int(oracle().gss_oracle_clause_mask32(a.ctypes.data, len(a), dd.ctypes.data, tt.ctypes.data, start))
+
+
+def test_mask_properties_hold_for_random_clauses_and_tables():
+    """size-independent properties of the hit semantics (any implementation must have them): literal order
+    is irrelevant; an all-false literal never changes the mask; a literal true in a slot clears that slot;
+    one more occurrence of a literal undefined in a slot clears a unit hit there (multiplicity); the start
+    mask only restricts"""
+    rng = np.random.default_rng(17)
+    nv = 24
+    for _ in range(300):
+        d = rng.integers(0, 1 << 32, size=nv, dtype=np.uint64).astype(np.uint32)
+        t = rng.integers(0, 1 << 32, size=nv, dtype=np.uint64).astype(np.uint32)
+        d[:4] = 0xFFFFFFFF  # variables 0..3: defined everywhere
+        t[0], t[1] = 0, 0xFFFFFFFF  # 0 false everywhere, 1 true everywhere
+        n = int(rng.integers(1, 7))
+        lits = [2 * int(rng.integers(4, nv)) + int(rng.integers(0, 2)) for _ in range(n)]
+        m = _mask32(lits, d, t)
+        perm = list(rng.permutation(lits))
+        assert _mask32(perm, d, t) == m
+        assert _mask32(lits + [2 * 0], d, t) == m          # positive literal of an all-false variable
+        assert _mask32(lits + [2 * 1 + 1], d, t) == m      # negated literal of an all-true variable
+        assert _mask32(lits + [2 * 1], d, t) == 0          # a literal true in every slot
+        v = int(rng.integers(4, nv))
+        true_slots = int(d[v]) & int(t[v])
+        assert _mask32(lits + [2 * v], d, t) & true_slots == 0
+        undef_slots = ~int(d[v]) & 0xFFFFFFFF
+        assert _mask32(lits + [2 * v, 2 * v], d, t) & undef_slots == 0   # two undefined occurrences: never a hit
+        start = int(rng.integers(0, 1 << 32))
+        assert _mask32(lits, d, t, start) == m & start
