@@ -2,6 +2,7 @@
 #include "../../include/gpushare_b200_synth.h"
 #include <cmath>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -67,26 +68,50 @@ void gss_synth_sigma(int nvars, uint64_t seed, uint8_t *sigma) {
 
 void gss_synth_clauses(int64_t nclauses, int nvars, int max_len, const uint8_t *sigma, double p_agree,
                        uint64_t seed, int64_t *offsets, int32_t *lits) {
-    SplitMix64 r(seed);
+    // Every literal consumes exactly two draws of ONE SplitMix64 stream (variable, then agreement / sign)
+    // and SplitMix64 jumps ahead in O(1) (its state is seed + k * gamma): clause ranges are generated
+    // concurrently and the output is bit-identical to the sequential stream, whatever the thread count
+    // (GSS_SYNTH_THREADS overrides it; tests compare 1 thread against many).
     int64_t pos = 0;
     for (int64_t c = 0; c < nclauses; c++) {
         offsets[c] = pos;
-        int len = clauseLen(c, max_len);
-        for (int i = 0; i < len; i++) {
-            int v = (int)r.below((uint32_t)nvars);
-            int sign;
-            if (sigma) {
-                bool agree = r.unit() < p_agree;
-                // literal true under sigma: positive when sigma says true (0), negated otherwise
-                int trueSign = sigma[v] == 0 ? 0 : 1;
-                sign = agree ? trueSign : 1 - trueSign;
-            } else {
-                sign = (int)(r.next() & 1);
-            }
-            lits[pos++] = 2 * v + sign;
-        }
+        pos += clauseLen(c, max_len);
     }
     offsets[nclauses] = pos;
+    int nThreads = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("GSS_SYNTH_THREADS")) nThreads = atoi(e);
+    if (nThreads < 1) nThreads = 1;
+    if (nclauses < 100000) nThreads = 1;
+    auto range = [&](int64_t c0, int64_t c1) {
+        SplitMix64 r(seed + 2ull * (uint64_t)offsets[c0] * 0x9E3779B97F4A7C15ull);
+        for (int64_t c = c0; c < c1; c++) {
+            int32_t *out = lits + offsets[c];
+            const int len = (int)(offsets[c + 1] - offsets[c]);
+            for (int i = 0; i < len; i++) {
+                int v = (int)r.below((uint32_t)nvars);
+                int sign;
+                if (sigma) {
+                    bool agree = r.unit() < p_agree;
+                    // literal true under sigma: positive when sigma says true (0), negated otherwise
+                    int trueSign = sigma[v] == 0 ? 0 : 1;
+                    sign = agree ? trueSign : 1 - trueSign;
+                } else {
+                    sign = (int)(r.next() & 1);
+                }
+                out[i] = 2 * v + sign;
+            }
+        }
+    };
+    if (nThreads == 1) {
+        range(0, nclauses);
+        return;
+    }
+    std::vector<std::thread> threads;
+    for (int t = 0; t < nThreads; t++) {
+        const int64_t c0 = nclauses * t / nThreads, c1 = nclauses * (t + 1) / nThreads;
+        if (c1 > c0) threads.emplace_back(range, c0, c1);
+    }
+    for (auto &th : threads) th.join();
 }
 
 gss_synth_stream *gss_synth_stream_create(int nvars, const uint8_t *sigma, double p_undef, double churn, uint64_t seed) {

@@ -44,3 +44,19 @@ def test_no_cpu_fallback_in_product():
             if f.endswith((".cc", ".cu", ".cuh", ".h", ".py")):
                 text = open(os.path.join(dp, f)).read()
                 assert "gss_oracle" not in text and "oracle_lib" not in text, f
+
+
+def test_synthetic_clause_generator_is_thread_count_invariant(monkeypatch):
+    """include/gpushare_b200_synth.h: the clause generator jumps ahead in its one SplitMix64 stream, so
+    the database bench.py builds is the same whatever the number of host threads"""
+    import numpy as np
+    import synth
+    sig = synth.sigma(5000, 3)
+    out = []
+    for threads in ("1", "7"):
+        monkeypatch.setenv("GSS_SYNTH_THREADS", threads)
+        out.append(synth.clauses(120_000, 5000, 30, sig, 0.9, 5))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    off, lits = out[0]
+    assert off[-1] == len(lits) and lits.min() >= 0 and lits.max() < 10000
+    assert set(np.diff(off)[:64]) <= {2, 3, 5, 9, 17, 30}  # the Luby-like length mix
