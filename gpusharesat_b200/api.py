@@ -106,14 +106,6 @@ SIGNATURES = {
     "gss_set_stream": (None, [_P, C.c_void_p]),
     "gss_mgpu_import": (None, [_P, C.c_void_p, _L]),
     "gss_version": (C.c_char_p, []),
-    # include/gpushare_b200_synth.h
-    "gss_synth_total_lits": (_L, [_L, _I]),
-    "gss_synth_sigma": (None, [_I, C.c_uint64, C.POINTER(C.c_uint8)]),
-    "gss_synth_clauses": (None, [_L, _I, _I, C.POINTER(C.c_uint8), C.c_double, C.c_uint64, C.POINTER(_L), _IP]),
-    "gss_synth_stream_create": (_P, [_I, C.POINTER(C.c_uint8), C.c_double, C.c_double, C.c_uint64]),
-    "gss_synth_stream_destroy": (None, [_P]),
-    "gss_synth_stream_values": (C.POINTER(C.c_uint8), [_P]),
-    "gss_synth_stream_next": (None, [_P, _IP, _IP, _IP, _IP]),
 }
 
 

@@ -157,17 +157,102 @@ static uint32_t *build_aggregates(int nsolvers, int64_t nvars, const uint32_t *d
     return agg;
 }
 
+/* bench.py's CPU arm only: the same aggregates, built by `nthreads` threads (each owns a range of
+ * variables).  In the reference the aggregates are maintained incrementally on the device
+ * (dUpdateAssigs, Assigs.cu:100-116), so a serial rebuild per sweep would handicap the CPU arm. */
+typedef struct {
+    int nsolvers; int64_t nvars, v0, v1;
+    const uint32_t *def, *tru, *start;
+    uint32_t *agg;
+} agg_job_t;
+
+static void *run_agg_job(void *arg) {
+    agg_job_t *j = (agg_job_t *)arg;
+    int low = 32 / j->nsolvers, missing = 32 - low * j->nsolvers, bit = 0;
+    for (int s = 0; s < j->nsolvers; s++) {
+        int nbits = low + (s < missing ? 1 : 0);
+        int live = __builtin_popcount(j->start[s]);
+        int used = nbits < live ? nbits : live;
+        if (used > 0) {
+            uint32_t group_mask[32];
+            int per = live / used, extra = live - per * used, pos = 0;
+            for (int g = 0; g < used; g++) {
+                int want = per + (g < extra ? 1 : 0);
+                uint32_t m = 0;
+                while (want > 0) {
+                    if (j->start[s] & (1u << pos)) { m |= 1u << pos; want--; }
+                    pos++;
+                }
+                group_mask[g] = m;
+            }
+            const uint32_t *d = j->def + (int64_t)s * j->nvars, *t = j->tru + (int64_t)s * j->nvars;
+            for (int64_t v = j->v0; v < j->v1; v++) {
+                uint32_t bt = t[v] & d[v], bf = ~t[v] & d[v], bu = ~d[v];
+                uint32_t *a = j->agg + 3 * v;
+                for (int g = 0; g < used; g++) {
+                    uint32_t gb = 1u << (bit + g);
+                    if (bt & group_mask[g]) a[0] |= gb;
+                    if (bf & group_mask[g]) a[1] |= gb;
+                    if (bu & group_mask[g]) a[2] |= gb;
+                }
+            }
+        }
+        bit += nbits;
+    }
+    return NULL;
+}
+
+static uint32_t *build_aggregates_mt(int nsolvers, int64_t nvars, const uint32_t *def, const uint32_t *tru,
+                                     const uint32_t *start, uint32_t *agg_start, uint32_t *solver_bits, int nthreads) {
+    /* masks and bit ownership: the serial routine on zero variables */
+    free(build_aggregates(nsolvers, 0, def, tru, start, agg_start, solver_bits));
+    uint32_t *agg = (uint32_t *)calloc((size_t)nvars * 3 + 1, sizeof(uint32_t));
+    if (nthreads > nvars) nthreads = nvars > 0 ? (int)nvars : 1;
+    agg_job_t *jobs = (agg_job_t *)calloc((size_t)nthreads, sizeof(agg_job_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));
+    for (int t = 0; t < nthreads; t++) {
+        agg_job_t *j = &jobs[t];
+        j->nsolvers = nsolvers; j->nvars = nvars;
+        j->v0 = nvars * t / nthreads; j->v1 = nvars * (t + 1) / nthreads;
+        j->def = def; j->tru = tru; j->start = start; j->agg = agg;
+        pthread_create(&th[t], NULL, run_agg_job, j);
+    }
+    for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th); free(jobs);
+    return agg;
+}
+
+static int64_t check_db_impl(const int64_t *offsets, const int32_t *lits, int64_t nclauses,
+                             int nsolvers, int64_t nvars, const uint32_t *def, const uint32_t *tru,
+                             const uint32_t *start, gss_oracle_hit *out, int64_t cap,
+                             int use_filter, int nthreads, int parallel_aggregates);
+
 int64_t gss_oracle_check_db(const int64_t *offsets, const int32_t *lits, int64_t nclauses,
                             int nsolvers, int64_t nvars, const uint32_t *def, const uint32_t *tru,
                             const uint32_t *start, gss_oracle_hit *out, int64_t cap,
                             int use_filter, int nthreads) {
+    return check_db_impl(offsets, lits, nclauses, nsolvers, nvars, def, tru, start, out, cap, use_filter, nthreads, 0);
+}
+
+int64_t gss_oracle_check_db_bench(const int64_t *offsets, const int32_t *lits, int64_t nclauses,
+                                  int nsolvers, int64_t nvars, const uint32_t *def, const uint32_t *tru,
+                                  const uint32_t *start, gss_oracle_hit *out, int64_t cap, int nthreads) {
+    return check_db_impl(offsets, lits, nclauses, nsolvers, nvars, def, tru, start, out, cap, 1, nthreads, 1);
+}
+
+static int64_t check_db_impl(const int64_t *offsets, const int32_t *lits, int64_t nclauses,
+                             int nsolvers, int64_t nvars, const uint32_t *def, const uint32_t *tru,
+                             const uint32_t *start, gss_oracle_hit *out, int64_t cap,
+                             int use_filter, int nthreads, int parallel_aggregates) {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
-    if (nclauses < nthreads) nthreads = nclauses > 0 ? (int)nclauses : 1;
     uint32_t agg_start = 0, solver_bits[32];
     uint32_t *agg = NULL;
     if (use_filter && nsolvers >= 1 && nsolvers <= 32)
-        agg = build_aggregates(nsolvers, nvars, def, tru, start, &agg_start, solver_bits);
+        agg = parallel_aggregates && nthreads > 1
+                  ? build_aggregates_mt(nsolvers, nvars, def, tru, start, &agg_start, solver_bits, nthreads)
+                  : build_aggregates(nsolvers, nvars, def, tru, start, &agg_start, solver_bits);
+    if (nclauses < nthreads) nthreads = nclauses > 0 ? (int)nclauses : 1;
 
     job_t *jobs = (job_t *)calloc((size_t)nthreads, sizeof(job_t));
     pthread_t *th = (pthread_t *)calloc((size_t)nthreads, sizeof(pthread_t));

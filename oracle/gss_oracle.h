@@ -58,6 +58,11 @@ int64_t gss_oracle_check_db(const int64_t *offsets, const int32_t *lits, int64_t
                             int nsolvers, int64_t nvars, const uint32_t *def, const uint32_t *tru,
                             const uint32_t *start, gss_oracle_hit *out, int64_t cap,
                             int use_filter, int nthreads);
+/* bench.py's CPU arm: the same check with the two-level structure on, the per-variable aggregates
+ * built by all `nthreads` threads instead of serially (identical hits). */
+int64_t gss_oracle_check_db_bench(const int64_t *offsets, const int32_t *lits, int64_t nclauses,
+                                  int nsolvers, int64_t nvars, const uint32_t *def, const uint32_t *tru,
+                                  const uint32_t *start, gss_oracle_hit *out, int64_t cap, int nthreads);
 
 /* ---- the reference's perf-test known-answer inputs (perftest/perfTest.cu:70-107) ---- */
 /* clauses: seed 0.4; size = irand(seed,minLen,maxLen); per literal sign drawn BEFORE var

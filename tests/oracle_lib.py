@@ -37,11 +37,13 @@ def oracle():
         L.gss_oracle_check_db.restype = C.c_int64
         L.gss_oracle_check_db.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int]
+        L.gss_oracle_check_db_bench.restype = C.c_int64
+        L.gss_oracle_check_db_bench.argtypes = L.gss_oracle_check_db.argtypes[:10] + [C.c_int]
         _LIB = L
     return _LIB
 
 
-def check_db(offsets, lits, def_, tru, start, use_filter=0, nthreads=1, cap=None):
+def check_db(offsets, lits, def_, tru, start, use_filter=0, nthreads=1, cap=None, bench=False):
     """def_/tru: uint32 [nsolvers, nvars]; returns sorted hit array (clause index as clause_id)"""
     L = oracle()
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -55,8 +57,12 @@ def check_db(offsets, lits, def_, tru, start, use_filter=0, nthreads=1, cap=None
         cap = 1 << 16
     while True:
         out = np.zeros(cap, dtype=HIT_DTYPE)
-        n = L.gss_oracle_check_db(offsets.ctypes.data, lits.ctypes.data, ncl, nsolvers, nvars, def_.ctypes.data,
-                                  tru.ctypes.data, start.ctypes.data, out.ctypes.data, cap, use_filter, nthreads)
+        if bench:  # bench.py's CPU arm: two-level filter, aggregates built by all threads
+            n = L.gss_oracle_check_db_bench(offsets.ctypes.data, lits.ctypes.data, ncl, nsolvers, nvars, def_.ctypes.data,
+                                            tru.ctypes.data, start.ctypes.data, out.ctypes.data, cap, nthreads)
+        else:
+            n = L.gss_oracle_check_db(offsets.ctypes.data, lits.ctypes.data, ncl, nsolvers, nvars, def_.ctypes.data,
+                                      tru.ctypes.data, start.ctypes.data, out.ctypes.data, cap, use_filter, nthreads)
         if n <= cap:
             out = out[:n]
             break

@@ -1,13 +1,40 @@
-"""Synthetic inputs of the BASELINE.json shapes via the generators exported by
-libgpushare_b200.so (include/gpushare_b200_synth.h).  Input generation only."""
+"""Synthetic inputs of the BASELINE.json shapes via tests/synthlib/libgss_synth.so (gss_synth.h): a
+host-only library of its own, so generating inputs (e.g. for bench.py --impl reference) never loads
+the product library.  Input generation only."""
 import ctypes as C
+import os
+import subprocess
 
 import numpy as np
 
-from gpusharesat_b200 import load_library
-
 _IP = C.POINTER(C.c_int)
 _U8 = C.POINTER(C.c_uint8)
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "synthlib")
+_LIB = None
+
+
+def load_library():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_DIR, "libgss_synth.so")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_DIR, "synth.cc")):
+            subprocess.check_call(["make", "-C", _DIR], stdout=subprocess.DEVNULL)
+        L = C.CDLL(so)
+        _L, _I, _P = C.c_int64, C.c_int, C.c_void_p
+        sig = {
+            "gss_synth_total_lits": (_L, [_L, _I]),
+            "gss_synth_sigma": (None, [_I, C.c_uint64, _U8]),
+            "gss_synth_clauses": (None, [_L, _I, _I, _U8, C.c_double, C.c_uint64, C.POINTER(_L), _IP]),
+            "gss_synth_stream_create": (_P, [_I, _U8, C.c_double, C.c_double, C.c_uint64]),
+            "gss_synth_stream_destroy": (None, [_P]),
+            "gss_synth_stream_values": (_U8, [_P]),
+            "gss_synth_stream_next": (None, [_P, _IP, _IP, _IP, _IP]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _LIB = L
+    return _LIB
 
 
 def sigma(nvars, seed):

@@ -1,7 +1,7 @@
 /*
- * gpushare_b200_synth.h -- deterministic synthetic inputs of the shapes BASELINE.json names
- * (SURVEY.md 8d).  Exported by libgpushare_b200.so for tests and bench.py; not part of the
- * GpuClauseSharer.h surface.  RNG: SplitMix64 with the seeds given by the caller.
+ * gss_synth.h -- deterministic synthetic inputs of the shapes BASELINE.json names.
+ * Exported by tests/synthlib/libgss_synth.so (host only, plain g++) for tests and bench.py; not part
+ * of the product library nor of the GpuClauseSharer.h surface.  RNG: SplitMix64 with the seeds given by the caller.
  */
 #ifndef GPUSHARE_B200_SYNTH_H
 #define GPUSHARE_B200_SYNTH_H

@@ -1,5 +1,6 @@
-// synth.cc -- deterministic synthetic inputs (see include/gpushare_b200_synth.h)
-#include "../../include/gpushare_b200_synth.h"
+// synth.cc -- deterministic synthetic inputs (see gss_synth.h).  TEST / BENCH INFRASTRUCTURE: its own
+// host-only library (libgss_synth.so), so that input generation never loads the product library.
+#include "gss_synth.h"
 #include <cmath>
 #include <cstdlib>
 #include <thread>

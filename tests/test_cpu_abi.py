@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = set()
-    for h in ("gpushare_b200.h", "gpushare_b200_synth.h"):
+    for h in ("gpushare_b200.h",):
         text = open(os.path.join(ROOT, "include", h)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         names |= set(re.findall(r"\b(gss_[a-z0-9_]+)\s*\(", text))
@@ -47,7 +47,7 @@ def test_no_cpu_fallback_in_product():
 
 
 def test_synthetic_clause_generator_is_thread_count_invariant(monkeypatch):
-    """include/gpushare_b200_synth.h: the clause generator jumps ahead in its one SplitMix64 stream, so
+    """tests/synthlib/gss_synth.h: the clause generator jumps ahead in its one SplitMix64 stream, so
     the database bench.py builds is the same whatever the number of host threads"""
     import numpy as np
     import synth

@@ -76,6 +76,8 @@ def test_bitparallel_equals_scalar_and_filter_is_transparent():
     plain = check_db(offsets, lits, d, t, start, use_filter=0, nthreads=1)
     filt = check_db(offsets, lits, d, t, start, use_filter=1, nthreads=4)
     assert np.array_equal(plain, filt) and len(plain) > 50
+    # bench.py's CPU arm (aggregates built by all threads): same hits
+    assert np.array_equal(plain, check_db(offsets, lits, d, t, start, nthreads=3, bench=True))
     want = []
     for c in range(ncl):
         cl = lits[offsets[c]:offsets[c + 1]]
