@@ -63,6 +63,8 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-dense", action="store_true")
+    p.add_argument("--no-ref-gpu", action="store_true", help="skip the reference GPU library leg (reference_gpu object)")
+    p.add_argument("--ref-gpu-steps", type=int, default=5)
     p.add_argument("--dense-iters", type=int, default=3)
     p.add_argument("--prod-iters", type=int, default=20)
     p.add_argument("--filter-sweep", action="store_true", help="time every variant of the level-1 kernel")
@@ -70,6 +72,8 @@ def parse():
                    help="N > 1: weak = --clauses per GPU (database grows with N), strong = --clauses in total")
     p.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                    help="N > 1: peer memory windows over NVLink (default) or NCCL broadcast + all-gather")
+    p.add_argument("--no-other-scaling", action="store_true", help="N > 1: skip the second pass with the other scaling mode")
+    p.add_argument("--parity-clauses", type=int, default=400_000, help="N > 1: clauses of the CPU parity sample")
     p.add_argument("--slot-hits", type=int, default=1 << 21, help="peer exchange: hit records per rank and batch")
     return p.parse_args()
 
@@ -244,15 +248,14 @@ def workload_config(a):
 # reference GPU library arm (context only)
 # ------------------------------------------------------------------------------------------------
 
-def run_reference_gpu(a):
+def reference_gpu_numbers(a, sig, offsets, lits, steps, warmup):
+    """the reference's own GPU library (oracle/_ref: gpuShareLib recompiled for sm_100a, unmodified) on
+    the same inputs through the same call sequence: the kernel to beat"""
     import ref_lib
     if not ref_lib.available():
-        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref/libgpushare_ref.so not built"}))
-        return
+        return {"unavailable": "oracle/_ref/libgpushare_ref.so not built"}
     if a.solvers > 32:
-        print(json.dumps({"impl": "reference-gpu", "unavailable": "the reference never checks solvers >= 32"}))
-        return
-    sig, offsets, lits = make_inputs(a)
+        return {"unavailable": "the reference never checks solvers >= 32"}
     streams = make_streams(a, sig)
     sh = ref_lib.RefSharer(report=4000)
     sh.setVarCount(a.vars)
@@ -262,25 +265,35 @@ def run_reference_gpu(a):
     L, A = int(offsets[-1]), a.solvers * a.slots
     pool = ThreadPoolExecutor(max_workers=a.solvers)
     times, kern = [], []
-    for it in range(a.warmup + a.steps):
+    for it in range(warmup + steps):
         push_batch(sh, streams, a.slots, pool)
         k0 = sh.getGlobalStat(9)  # timeSpentTestingClauses (us, its own CUDA events)
         t0 = time.perf_counter()
         sh.gpuRun(); sh.gpuRun()
         dt = time.perf_counter() - t0
-        if it >= a.warmup:
+        if it >= warmup:
             times.append(dt)
             kern.append(sh.getGlobalStat(9) - k0)
         for s in range(a.solvers):
             while sh.popReportedClause(s) is not None:
                 pass
+    sh.close()
     e2e = L * A * len(times) / sum(times)
-    print(json.dumps({"impl": "reference-gpu", "metric": METRIC, "unit": UNIT, "e2e": {"value": e2e, "unit": UNIT},
-                      "ms_per_step": 1e3 * sum(times) / len(times),
-                      "dFindClauses_us_per_step": float(np.mean(kern)),
-                      "value": L * A / (np.mean(kern) * 1e-6) if np.mean(kern) > 0 else None,
-                      "note": "reference gpuShareLib recompiled for sm_100a, its own default grid (2 x SMs x 512)",
-                      "config": workload_config(a)}))
+    return {"e2e": {"value": e2e, "unit": UNIT, "ms_per_step": 1e3 * sum(times) / len(times)},
+            "dFindClauses_us_per_step": float(np.mean(kern)),
+            "value": L * A / (np.mean(kern) * 1e-6) if np.mean(kern) > 0 else None, "unit": UNIT,
+            "steps": steps, "warmup": warmup,
+            "note": "reference gpuShareLib recompiled for sm_100a (oracle/_ref), its own default grid (2 x SMs x 512), "
+                    "same inputs, same gss_gpu_run x 2 call pattern; value = its own CUDA-event time of dFindClauses"}
+
+
+def run_reference_gpu(a):
+    sig, offsets, lits = make_inputs(a)
+    r = reference_gpu_numbers(a, sig, offsets, lits, a.steps, a.warmup)
+    r.update({"impl": "reference-gpu", "metric": METRIC, "config": workload_config(a)})
+    if "e2e" in r:
+        r["ms_per_step"] = r["e2e"]["ms_per_step"]
+    print(json.dumps(r))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -302,16 +315,34 @@ def run_b200_sharded(a):
     peer loads / stores over NVLink, stream memory operations; csrc/peer.cu) -- no collective on the
     data path, NCCL only bootstraps.  --exchange nccl: one NCCL broadcast + one all-gather per batch
     (mgpu.ShardedRunner), kept for comparison."""
+    import copy
     import torch
     import torch.distributed as dist
-    from gpusharesat_b200 import GpuClauseSharer, GpuClauseSharerOptions, mgpu
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     os.environ["GPUSHARE_DEVICE"] = str(local)
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
-
     a.gpus = world
+    # the line the driver reads is the --scaling one (default weak: per-GPU work fixed); the other
+    # mode rides along as a sub-object measured in the same job, so SCALE carries both curves
+    main = sharded_pass(copy.copy(a), a.scaling, a.steps, a.warmup, dist, torch, rank, world, local, device)
+    other = "strong" if a.scaling == "weak" else "weak"
+    if not a.no_other_scaling:
+        sub = sharded_pass(copy.copy(a), other, max(3, a.steps // 2), a.warmup, dist, torch, rank, world, local, device)
+        if rank == 0:
+            main[other + "_scaling"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "scaling", "steps", "e2e", "hits_per_step",
+                                                            "phases_us_per_step", "parity_sample", "literals") if k in sub}
+            main[other + "_scaling"]["clauses"] = sub["config"]["clauses"]
+    if rank == 0:
+        print(json.dumps(main))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def sharded_pass(a, scaling, steps, warmup, dist, torch, rank, world, local, device):
+    from gpusharesat_b200 import GpuClauseSharer, GpuClauseSharerOptions, mgpu
+    a.scaling, a.steps, a.warmup = scaling, steps, warmup
     per_gpu = a.clauses
     if a.scaling == "weak":
         a.clauses = per_gpu * world
@@ -322,6 +353,11 @@ def run_b200_sharded(a):
     sh.setVarCount(a.vars)
     sh.setCpuSolverCount(a.solvers)
     sh.addClausesBulk(offsets, lits)
+    # rank 0 keeps a prefix of the clause stream for the parity sample (ids = positions in the stream; the
+    # arenas are sorted by first literal, so any id range is spread over every rank's share of the tiles)
+    n_sample = min(a.clauses, a.parity_clauses)
+    s_off = offsets[: n_sample + 1].copy() if rank == 0 else None
+    s_lits = lits[: int(offsets[n_sample])].copy() if rank == 0 else None
     del offsets, lits
     streams = make_streams(a, sig) if rank == 0 else None
     pool = ThreadPoolExecutor(max_workers=a.solvers) if rank == 0 else None
@@ -351,11 +387,14 @@ def run_b200_sharded(a):
         ph = sh.debugLastRunTimes()
         h2d, d2h = sh.debugLastRunBytes()
         dev_us = runner.device_us()
-        drain()
+        drain()  # (gss_debug_last_hits stays valid: it reads the run's records, not the solver queues)
         return dt, ph, (nh or 0) if rank == 0 else 0, h2d, d2h, dev_us
 
-    for _ in range(a.warmup):
-        step()
+    first_hits = None
+    for w in range(a.warmup):
+        step_out = step()
+        if w == 0 and rank == 0:
+            first_hits = sh.debugLastHits().copy()  # the union of every rank's hits of the first batch
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -381,7 +420,18 @@ def run_b200_sharded(a):
     allph = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(allph, mine)
     dev, wall = float(tt[0]), float(tt[1])
+    out = None
     if rank == 0:
+        parity = None
+        if first_hits is not None and not a.no_cpu:
+            from oracle_lib import check_db
+            d, t, start = batch_words(a, sig)
+            cpu_hits = check_db(s_off, s_lits, d, t, start, use_filter=1, nthreads=os.cpu_count() or 1, cap=1 << 22)
+            g = first_hits[first_hits["clause_id"] < n_sample]
+            parity = {"clauses": int(n_sample), "gpu_hits": int(len(g)), "cpu_hits": int(len(cpu_hits)),
+                      "identical": bool(np.array_equal(g, cpu_hits)),
+                      "note": "first batch: union of all ranks' hits restricted to the first clauses of the stream (spread over "
+                              "every rank's tiles by the first-literal sort) == the CPU oracle on those clauses"}
         cfg = workload_config(a)
         cfg["clauses_per_gpu"] = a.clauses // world
         if a.exchange == "peer":
@@ -392,7 +442,7 @@ def run_b200_sharded(a):
         else:
             region = "NCCL broadcast of the batch, table + check kernels on every shard, NCCL all-gather of the hits; max over ranks"
             gap = "nccl_broadcast_gather_and_sync_gaps"
-        print(json.dumps({
+        out = ({
             "metric": METRIC, "value": L_total * A * a.steps / dev, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * dev / a.steps, "higher_is_better": True, "scaling": a.scaling,
             "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": cfg,
@@ -405,12 +455,15 @@ def run_b200_sharded(a):
             "phases_us_per_step": {gap: float(np.mean(ex)), "table_kernels": float(np.mean(tk)),
                                    "check_kernels": float(np.mean(ck)),
                                    "per_rank_table_check_other": [[round(float(x), 1) for x in t.tolist()] for t in allph]},
-            "literals": L_total, "assignments": A,
+            "literals": L_total, "assignments": A, "parity_sample": parity,
             "note": "N > 1: value = " + region + "; e2e adds rank 0's collect, the payload H2D, the sort / resolve of the hits, "
                     "their D2H and the host hand-over",
-        }))
+        })
     dist.barrier()
-    dist.destroy_process_group()
+    del runner
+    sh.close()
+    dist.barrier()
+    return out
 
 
 def run_b200(a):
@@ -514,6 +567,9 @@ def run_b200(a):
         "hits_per_step": total_hits / a.steps,
         "phases_us_per_step": {"table_kernels": float(np.mean(dev_tables) + np.mean(collapse)),
                                "check_kernels": float(np.mean(dev_check)), "h2d_to_d2h_total": float(np.mean(dev_total))},
+        # everything the device does for one batch, first H2D byte to last D2H byte (CUDA events)
+        "device_step_complete": {"us": float(np.mean(dev_total) + np.mean(collapse)),
+                                 "value": L_total * A / ((float(np.mean(dev_total)) + float(np.mean(collapse))) * 1e-6), "unit": UNIT},
         "literals": L_total, "assignments": A,
         "e2e_host_us_per_step": {"finish_previous_run": hp[0], "of_which_wait_for_gpu": hp[4],
                                  "of_which_sort_resolve_d2h_of_hits": hp[5], "start_next_run": hp[1],
@@ -552,36 +608,35 @@ def run_b200(a):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        traffic = {}
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["bytes_per_launch"]
-        except Exception:
-            pass
+        # DRAM traffic per launch: ncu cannot run inside a timed bench, so the numbers come from the
+        # capture profiles/capture_traffic.py makes of THIS command (regenerated whenever a kernel changes)
+        traffic, traffic_src = {}, None
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+                traffic, traffic_src = tj["bytes_per_launch"], f"profiles/{name}: " + tj.get("source", "")
+                break
+            except Exception:
+                pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         W = (A + 31) // 32
         out["kernel_production"] = {"us_per_sweep": t_prod, "checks_per_s": L_total * A / (t_prod * 1e-6),
                                     "kernels": "k_filter + k_exact", "k_filter_us": t_filter}
-        # ---- roofline of the dominant kernel of the timed region: k_filter (level 1) ----
-        # It streams the clause arenas once and gathers from the level-1 table: algorithmic bytes per
-        # launch = 4 B x every literal + the level-1 table once (16 B per variable).  Duration: CUDA
-        # events around back-to-back launches on the library's stream, in this run.  The kernel
-        # legitimately moves LESS than that through DRAM (`traffic`, ncu): whole tiles die early and
-        # their remaining rows are skipped.
+        # ---- k_filter (level 1), the dominant kernel of the production step, against measured HBM ----
+        # nominal bytes = 4 B x every literal + the level-1 table once (16 B per variable); the kernel
+        # legitimately moves LESS through DRAM (`traffic`, ncu): whole tiles die early and their remaining
+        # rows are skipped -- both fractions are reported.
         fb = 4.0 * L_total + 16.0 * a.vars
         step_us = 1e6 * dev_s / a.steps
-        out["roofline"] = {"kernel": "k_filter", "bound": "hbm", "achieved": fb / (t_filter * 1e-6) / 1e9,
-                           "peak": hbm_peak, "unit": "GB/s", "frac": fb / (t_filter * 1e-6) / 1e9 / hbm_peak,
-                           "traffic": traffic.get("k_filter"),
-                           "algorithmic_bytes": fb, "us_per_launch": t_filter,
-                           "share_of_step": t_filter / step_us,
-                           "peak_source": peak_src,
-                           "note": "algorithmic bytes = 4 B x literals + 16 B x variables (DESIGN.md 4); early exit skips "
-                                   "rows, so the measured DRAM traffic is below them; what limits the kernel is the "
-                                   "latency of the dependent gathers at 40 resident warps per SM (profiles/)",
-                           "whole_step": {"algorithmic_bytes": fb + 2 * float(np.mean(h2d)) + 16.0 * float(np.mean(hits)),
-                                          "us": step_us,
-                                          "frac": (fb + 2 * float(np.mean(h2d)) + 16.0 * float(np.mean(hits))) / (step_us * 1e-6) / 1e9 / hbm_peak}}
+        moved = traffic.get("k_filter")
+        out["roofline_k_filter"] = {
+            "kernel": "k_filter", "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "us_per_launch": t_filter,
+            "nominal_bytes": fb, "nominal_gbs": fb / (t_filter * 1e-6) / 1e9, "frac_nominal": fb / (t_filter * 1e-6) / 1e9 / hbm_peak,
+            "moved_bytes": moved, "frac_moved": (moved / (t_filter * 1e-6) / 1e9 / hbm_peak) if moved else None,
+            "share_of_step": t_filter / step_us, "peak_source": peak_src, "traffic_source": traffic_src,
+            "whole_step": {"algorithmic_bytes": fb + 2 * float(np.mean(h2d)) + 16.0 * float(np.mean(hits)), "us": step_us,
+                           "frac": (fb + 2 * float(np.mean(h2d)) + 16.0 * float(np.mean(hits))) / (step_us * 1e-6) / 1e9 / hbm_peak}}
         if not a.no_dense:
             t_dense = sh.debugTimeCheck(a.dense_iters, dense=True)
             sh.gpuRun()
@@ -594,14 +649,14 @@ def run_b200(a):
             bound_int = t_int >= t_hbm
             # BASELINE.json's own definition: roofline = slower of HBM bytes and LOP3 issue with EVERY
             # (literal, 32-slot word) pair evaluated -- a bench-only mode (no filter, no early exit)
-            out["roofline_dense"] = {
-                "kernel": "k_check_dense", "mode": "dense (no filter, no early exit)",
+            out["roofline"] = {
+                "kernel": "k_check_dense", "mode": "dense (no filter, no early exit): the contract's roofline (SURVEY 8d)",
                 "bound": "int_lop3" if bound_int else "hbm",
                 "achieved": (lop3_alg / (t_dense * 1e-6)) / 1e12 if bound_int else bytes_alg / (t_dense * 1e-6) / 1e9,
                 "peak": lop3 / 1e12 if bound_int else hbm_peak,
                 "unit": "TLOP3/s" if bound_int else "GB/s",
                 "frac": max(t_hbm, t_int) / (t_dense * 1e-6),
-                "traffic": traffic.get("k_check_dense"),
+                "traffic": traffic.get("k_check_dense"), "traffic_source": traffic_src,
                 "us_per_sweep": t_dense, "t_roof_us": max(t_hbm, t_int) * 1e6,
                 "t_hbm_us": t_hbm * 1e6, "t_int_us": t_int * 1e6,
                 "algorithmic_bytes": bytes_alg, "algorithmic_lop3": lop3_alg,
@@ -620,6 +675,13 @@ def run_b200(a):
         else:
             sh.gpuRun()
             drain()
+        if not a.no_ref_gpu:
+            sh.close()  # free the device before the reference library loads its own copy of the database
+            out["reference_gpu"] = reference_gpu_numbers(a, sig, offsets, lits, a.ref_gpu_steps, 2)
+            if "e2e" in out["reference_gpu"]:
+                out["reference_gpu"]["ours_over_reference"] = {
+                    "e2e": out["e2e"]["value"] / out["reference_gpu"]["e2e"]["value"],
+                    "check_kernels": out["reference_gpu"]["dFindClauses_us_per_step"] / float(np.mean(dev_check))}
         if not a.no_cpu:
             d, t, start = batch_words(a, sig)
             cb, cpu_hits, n_sample = cpu_baseline(a, offsets, lits, d, t, start, a.cpu_seconds)

@@ -16,7 +16,9 @@ ClauseDb::ClauseDb(double activityDecay, const Logger &logger, size_t pinnedLimi
 
 void ClauseDb::setMaxLen(int maxLen) {
     if (frozenMaxLen_) GSS_DIE("gss_set_max_clause_len must be called before the first clause is added");
-    GSS_CHECK(maxLen >= 1);
+    // the level-1 survivor record packs the clause length into 16 bits (Survivor::ptrLen)
+    if (maxLen < 1 || maxLen > kMaxSupportedClauseLen)
+        GSS_DIE("maximum clause length must be in [1, " + std::to_string(kMaxSupportedClauseLen) + "]");
     maxLen_ = maxLen;
     perLen_.clear();
     perLen_.resize(maxLen_ + 1);
@@ -126,12 +128,16 @@ void ClauseDb::sortArena(int len) {
 
 void scaleActivitiesOnDevice(float *acts, int64_t n, float factor, cudaStream_t stream); // kernels.cu
 
-bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
-    // rescales decided while draining (Clauses.cu:284-291) reach the device copies first
+void ClauseDb::applyPendingDeviceRescales(cudaStream_t stream) {
     for (; pendingDeviceRescales_ > 0; pendingDeviceRescales_--)
         for (int s = 1; s <= maxLen_; s++)
             if (perLen_[s]->actsOnDevice > 0)
                 scaleActivitiesOnDevice(perLen_[s]->actsDev.data(), perLen_[s]->actsOnDevice, 1.0f / kRescale, stream);
+}
+
+bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
+    // rescales decided while draining (Clauses.cu:284-291) reach the device copies first
+    applyPendingDeviceRescales(stream);
     for (int s = maxLen_; s >= 1; s--) {
         PerLen &pl = *perLen_[s];
         int64_t n = (int64_t)pl.meta.size();
@@ -262,10 +268,7 @@ float ClauseDb::approxNthAct(int64_t n) const {
 
 void ClauseDb::reduceDb(cudaStream_t stream) {
     // apply host-decided rescales to the device copies, then bring the activities home
-    for (; pendingDeviceRescales_ > 0; pendingDeviceRescales_--)
-        for (int s = 1; s <= maxLen_; s++)
-            if (perLen_[s]->actsOnDevice > 0)
-                scaleActivitiesOnDevice(perLen_[s]->actsDev.data(), perLen_[s]->actsOnDevice, 1.0f / kRescale, stream);
+    applyPendingDeviceRescales(stream);
     downloadActivities(stream);
     reduceHost();
     for (int s = maxLen_; s >= 3; s--) {

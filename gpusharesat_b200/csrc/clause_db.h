@@ -112,6 +112,8 @@ public:
     void downloadActivities(cudaStream_t stream);
     // a bump on the device pushed an activity past the rescale limit (Clauses.cu:231-237)
     void rescaleAfterDeviceOverflow() { rescaleActivity(); }
+    // rescales decided on the host (drain, device overflow) that the device copies have not seen yet
+    void applyPendingDeviceRescales(cudaStream_t stream);
     // reference approxNthAct, Clauses.cu:492-525
     float approxNthAct(int64_t n) const;
     void writeCnf(FILE *f, int varCount) const; // Clauses.cu:527-549

@@ -27,6 +27,7 @@ constexpr int kTileClauses = 128;   // clauses per tile: one warp x int4
 // 32-byte sectors per gather instead of the whole tile's range four times over.
 __host__ __device__ inline int tileSlot(int j) { return ((j & 31) << 2) | (j >> 5); }
 constexpr int kDefaultMaxClauseLen = 100; // reference MAX_CL_SIZE (BaseTypes.cuh:28)
+constexpr int kMaxSupportedClauseLen = 65535; // Survivor::ptrLen keeps the length in 16 bits
 constexpr int kMaxSolversPerGroup = 32;   // one aggregate word / one lane per solver
 
 // One delta record: the 32 slots of one variable of one solver (reference VarUpdate,

@@ -87,6 +87,9 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
         s.resHost.setPinnedLimit(pinnedLimit);
     }
     db_ = std::make_unique<ClauseDb>(opts_.clauseActivityDecay, logger_, pinnedLimit);
+    // the reference hard-codes MAX_CL_SIZE 100 (BaseTypes.cuh:28); the knob is an environment variable
+    // so that it is reachable through the unmodified GpuClauseSharer.h
+    if (const char *e = getenv("GPUSHARE_MAX_CLAUSE_LEN")) db_->setMaxLen(atoi(e));
     assigs_ = std::make_unique<HostAssigs>();
     reported_ = std::make_unique<Reported>(*db_, oneSolverStats_);
     reported_->setPool(&pool_);
@@ -369,7 +372,11 @@ void Sharer::enqueueResultCopy(RunSlot &slot) {
 bool Sharer::prepareRun(RunSlot &slot, bool &rebuild, int64_t &h2d) {
     GSS_CUDA(cudaEventRecord(slot.evStart, stream_));
     rebuild = false;
-    if (!ensureTables(rebuild)) return false;
+    // Removing clauses cannot make room for the assignment tables (V x S words): fail loudly instead
+    // of reducing the database run after run.  Clause arenas that do not fit take the reduceDb path.
+    if (!ensureTables(rebuild))
+        GSS_DIE("out of device memory for the assignment tables (" + std::to_string(varCount_) + " variables x " +
+                std::to_string(assigs_->solverCount()) + " solvers)");
     if (!db_->uploadDirty(stream_, &h2d)) return false;
     std::vector<LenDir> dir;
     slot.totalTiles = db_->buildDirectory(dir);
@@ -846,7 +853,12 @@ void Sharer::bumpParkedHits() {
     if (bumpFlagPending_) {
         // wait for that bump's flag only -- not for whatever has been queued since (the next run)
         GSS_CUDA(cudaEventSynchronize(bumpFlagEv_));
-        if (bumpFlagHost_[0]) db_->rescaleAfterDeviceOverflow();
+        if (bumpFlagHost_[0]) {
+            // Clauses.cu:231-237 rescales activities and increment together: the device copies must be
+            // scaled down BEFORE the next bump uses the scaled-down increment
+            db_->rescaleAfterDeviceOverflow();
+            db_->applyPendingDeviceRescales(stream_);
+        }
         bumpFlagPending_ = false;
     }
     if (bumpN_ == 0) return;

@@ -111,7 +111,9 @@ int64_t gss_debug_last_hits(gss_sharer *h, gss_hit *out, int64_t cap);
 int64_t gss_add_clauses_bulk(gss_sharer *h, const int64_t *offsets, const int *lits, int64_t nclauses);
 
 /* Maximum clause length accepted by gss_add_clause (default 100 = the reference's
- * MAX_CL_SIZE, BaseTypes.cuh:28).  Must be called before the first clause is added. */
+ * MAX_CL_SIZE, BaseTypes.cuh:28; at most 65535).  Must be called before the first clause is
+ * added.  The environment variable GPUSHARE_MAX_CLAUSE_LEN sets it at gss_create, so that the
+ * limit can be lifted through the unmodified GpuClauseSharer.h (BASELINE config 5). */
 void gss_set_max_clause_len(gss_sharer *h, int max_len);
 
 /* kernel mode for the NEXT runs: 0 production (two-level filter + early exit, default),

@@ -28,8 +28,9 @@ def random_3sat(path, n, m, seed):
             f.write(" ".join(str(int(v * s)) for v, s in zip(vs, sg)) + " 0\n")
 
 
-def solve(exe, cnf, threads=3):
-    r = subprocess.run([exe, f"-thread-count={threads}", "-verb=0", cnf], capture_output=True, text=True, timeout=300)
+def solve(exe, cnf, threads=3, env=None, extra=()):
+    r = subprocess.run([exe, f"-thread-count={threads}", "-verb=0", *extra, cnf], capture_output=True, text=True, timeout=300,
+                       env=env)
     m = re.search(r"^s (SATISFIABLE|UNSATISFIABLE|INDETERMINATE)", r.stdout, re.M)
     assert m, r.stdout[-2000:] + r.stderr[-2000:]
     # MiniSat convention (satUtils/InitHelper.h:63-65): 10 SAT, 20 UNSAT
