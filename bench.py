@@ -562,7 +562,9 @@ def run_b200(a):
         "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(a),
         "e2e": {"value": L_total * A * a.steps / wall_s, "unit": UNIT, "ms_per_step": 1e3 * wall_s / a.steps,
                 "h2d_bytes_per_step": int(np.mean(h2d)), "d2h_bytes_per_step": int(np.mean(d2h)),
-                "timed_region": "gss_gpu_run() x 2 per batch: delta H2D, table + check kernels, hit D2H, host hand-over"},
+                "timed_region": "gss_gpu_run() x 2 per batch: collect (buffer swap), header H2D, k_apply_direct reading the deltas "
+                                "from page-locked host memory, check kernels, k_emit writing ids + literals into page-locked "
+                                "host memory, zero-copy hand-over to the solver queues"},
         "gpu_launches": int(launches), "clocks": clocks,
         "hits_per_step": total_hits / a.steps,
         "phases_us_per_step": {"table_kernels": float(np.mean(dev_tables) + np.mean(collapse)),
@@ -587,6 +589,7 @@ def run_b200(a):
         out["kernel_us"] = {"k_filter": t_filter, "k_exact": sh.debugTimeCheck(a.prod_iters, mode=3),
                             "k_apply_updates": sh.debugTimeCheck(a.prod_iters, mode=4),
                             "k_collapse": sh.debugTimeCheck(a.prod_iters, mode=5),
+                            "k_emit": sh.debugTimeCheck(a.prod_iters, mode=6),
                             "note": "each kernel re-launched back to back on the last batch (tables resident), CUDA events"}
         if a.filter_sweep:
             names = sh.debugFilterVariants()

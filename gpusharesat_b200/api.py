@@ -331,7 +331,7 @@ class GpuClauseSharer:
         self._lib.gss_debug_set_dense(self._h, 1 if dense else 0)
 
     def debugTimeCheck(self, iters=10, dense=False, filter_only=False, mode=None):
-        """mode: 0 production check, 1 dense, 2 k_filter, 3 k_exact, 4 k_apply_updates, 5 k_collapse"""
+        """mode: 0 production check, 1 dense, 2 k_filter, 3 k_exact, 4 k_apply_updates, 5 k_collapse, 6 k_emit"""
         if mode is None:
             mode = 2 if filter_only else (1 if dense else 0)
         return self._lib.gss_debug_time_check(self._h, int(iters), int(mode))

@@ -23,12 +23,15 @@ void SolverAssigs::setVarLocked(int var, uint8_t val) {
     bool isSet = val != V_UNDEF, isTrue = val == V_TRUE;
     int pos = varToUpdatePos_[var];
     uint32_t m = notCompletedMask_;
+    HostBuf<VarUpdate> &updates_ = updates();
     if (pos == -1 || (int)updates_.size() <= pos || updates_[pos].var != var) {
         VarUpdate vu;
         vu.var = var;
         vu.def = (~m & fill(lastVarVal_[var] != V_UNDEF)) | (m & fill(isSet));
         vu.tru = (~m & fill(lastVarVal_[var] == V_TRUE)) | (m & fill(isTrue));
         varToUpdatePos_[var] = (int)updates_.size();
+        if (updates_.size() == updates_.capacity() && allocDevice_ >= 0 && cudaSetDevice(allocDevice_) != cudaSuccess)
+            cudaGetLastError(); // (growth page-locks memory: do it in the sharer's context, not in device 0's)
         updates_.push_back(vu);
     } else {
         VarUpdate &vu = updates_[pos];
@@ -58,6 +61,7 @@ uint32_t SolverAssigs::maskFromTo(int64_t fromId, int64_t toId) {
 }
 
 void SolverAssigs::collectLocked(HostBuf<VarUpdate> &out, SolverRunParams &p, AssigIds &ids, bool fullRebuild) {
+    HostBuf<VarUpdate> &updates_ = updates();
     const int32_t updStart = (int32_t)out.size();
     if (fullRebuild) {
         ids.start = firstIdUsed_;
@@ -74,7 +78,21 @@ void SolverAssigs::collectLocked(HostBuf<VarUpdate> &out, SolverRunParams &p, As
     }
 }
 
+void SolverAssigs::takeUpdatesLocked(const VarUpdate *&ptr, int32_t updStart, SolverRunParams &p, AssigIds &ids, bool *pinned) {
+    ids.start = firstIdUsed_;
+    ids.count = (int32_t)(currentId_ - firstIdUsed_);
+    HostBuf<VarUpdate> &taken = updates();
+    ptr = taken.data();
+    *pinned = taken.pinned() || taken.empty();
+    finishCollectLocked(updStart, (int32_t)taken.size(), p); // resets the size of `taken`; its records stay where they are
+    curUpd_ ^= 1;
+    // grow the other buffer to the same capacity now, so that the solver thread rarely allocates
+    updates().reserve(taken.capacity());
+    updates().clear();
+}
+
 void SolverAssigs::collectIntoLocked(VarUpdate *dst, int32_t updStart, SolverRunParams &p, AssigIds &ids) {
+    HostBuf<VarUpdate> &updates_ = updates();
     ids.start = firstIdUsed_;
     ids.count = (int32_t)(currentId_ - firstIdUsed_);
     if (!updates_.empty()) memcpy(dst, updates_.data(), updates_.size() * sizeof(VarUpdate));
@@ -84,7 +102,7 @@ void SolverAssigs::collectIntoLocked(VarUpdate *dst, int32_t updStart, SolverRun
 void SolverAssigs::finishCollectLocked(int32_t updStart, int32_t updCount, SolverRunParams &p) {
     p.updStart = updStart;
     p.updCount = updCount;
-    updatesSent_ += (int64_t)updates_.size();
+    updatesSent_ += (int64_t)updates().size();
 
     // Assigs.cu:255-261: the slot everything collapses to after the run
     int64_t lastIdCopied;
@@ -118,7 +136,7 @@ void SolverAssigs::finishCollectLocked(int32_t updStart, int32_t updCount, Solve
     for (int b = startAggBit_; b < endAggBit_; b++) p.allAggBits |= 1u << b;
     p.pad = 0;
 
-    updates_.clear();
+    updates().clear();
     firstIdUsed_ = currentId_;
     notCompletedMask_ = ~0u;
 }

@@ -39,11 +39,19 @@ public:
     void collectLocked(HostBuf<VarUpdate> &updates, SolverRunParams &p, AssigIds &ids, bool fullRebuild);
     // the same in two steps, so that the solvers' deltas can be copied concurrently: the number of
     // pending delta records, then the copy into `dst` (room for exactly that many) + parameters
-    size_t pendingUpdatesLocked() const { return updates_.size(); }
+    size_t pendingUpdatesLocked() const { return updates().size(); }
     void collectIntoLocked(VarUpdate *dst, int32_t updStart, SolverRunParams &p, AssigIds &ids);
     void finishCollectLocked(int32_t updStart, int32_t updCount, SolverRunParams &p);
+    // Zero-copy collect: hands out the delta buffer itself (page-locked when a device is present, so
+    // the kernel that applies the deltas reads it in place over PCIe) and continues in the other one.
+    // The caller guarantees that the run that read the other buffer has finished (runs of a sharer
+    // finish in order and a run is finished before the next one is collected).  *pinned = false: the
+    // buffer is ordinary memory (budget exhausted / no device) and must be copied by the caller.
+    void takeUpdatesLocked(const VarUpdate *&ptr, int32_t updStart, SolverRunParams &p, AssigIds &ids, bool *pinned);
 
     void setAggBits(int start, int end) { startAggBit_ = start; endAggBit_ = end; }
+    // device whose context page-locks a delta buffer that has to grow on a solver thread
+    void setAllocDevice(int device) { allocDevice_ = device; }
     int64_t updatesSent() const { return updatesSent_; }
     int varCount() const { return (int)lastVarVal_.size(); }
 
@@ -54,11 +62,15 @@ private:
     uint32_t notCompletedMask_ = ~0u; // slots that are free or still being written
     int64_t updatesSent_ = 0;
     std::vector<uint8_t> lastVarVal_; // the solver's current value of every variable
-    std::vector<VarUpdate> updates_;  // one per variable touched in the batch being built
+    HostBuf<VarUpdate> upd_[2];       // one per variable touched in the batch being built (two in rotation)
+    int curUpd_ = 0;
+    HostBuf<VarUpdate> &updates() { return upd_[curUpd_]; }
+    const HostBuf<VarUpdate> &updates() const { return upd_[curUpd_]; }
     std::vector<int32_t> varToUpdatePos_;
     int64_t firstIdUsed_ = 0; // first assignment id not yet shipped to the GPU
     int64_t currentId_ = 0;   // id of the assignment being written
     int startAggBit_ = 0, endAggBit_ = 0;
+    int allocDevice_ = -1;
 };
 
 class HostAssigs {

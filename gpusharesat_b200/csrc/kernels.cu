@@ -488,11 +488,34 @@ template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS
                 if (!__any_sync(FULL, any)) { dead = true; break; }
             }
         }
+        if (a.recKeys) {
+            // direct pipeline: lane = solver appends to ITS OWN record list; one 64-bit atomic per lane
+            // reserves the slots of all its hits of this step and adds their literal count
+            unsigned int cnt = 0, lits = 0;
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            const int idx = (int)__shfl_sync(FULL, sv0.z, g);
-            stage.push((all[g] | one[g]) != 0, HitRecord{all[g] | one[g], solver, len[g], idx}, a.hits, &a.counters->nHits,
-                       a.hitCap, lane);
+            for (int g = 0; g < G; g++)
+                if (all[g] | one[g]) { cnt++; lits += (unsigned int)len[g]; }
+            unsigned int slot = 0;
+            if (cnt) slot = (unsigned int)atomicAdd(a.solverCtr + solver, (unsigned long long)cnt | ((unsigned long long)lits << 32));
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int idx = (int)__shfl_sync(FULL, sv0.z, g);
+                const uint32_t m = all[g] | one[g];
+                if (m) {
+                    if (slot < a.recCap) {
+                        a.recKeys[(size_t)solver * a.recCap + slot] = ((unsigned long long)(unsigned int)len[g] << 32) | (unsigned int)idx;
+                        a.recMasks[(size_t)solver * a.recCap + slot] = m;
+                    }
+                    slot++;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int idx = (int)__shfl_sync(FULL, sv0.z, g);
+                stage.push((all[g] | one[g]) != 0, HitRecord{all[g] | one[g], solver, len[g], idx}, a.hits, &a.counters->nHits,
+                           a.hitCap, lane);
+            }
         }
         sv0 = sv1;
         sv1 = sv2;
@@ -590,6 +613,263 @@ __global__ void __launch_bounds__(128) k_check_dense(CheckArgs a) {
         }
 #pragma unroll
         for (int c = 0; c < kDenseGroup; c++) reportHits(a, all[c] | one[c], solver, len, c0 + c, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Direct pipeline.  k_apply_direct = k_apply_updates with the deltas of solver s read from src[s]:
+// the solver thread's own delta buffer in mapped pinned host memory (no staging copy on the host, no
+// separate H2D: the transfer IS the kernel's load stream) or device memory.  Records are 12 bytes:
+// a block pulls 256 of them as 768 coalesced words through shared memory, so PCIe sees full lines.
+// A copy of every record goes to `keep` (the deferred collapse and re-timed launches read it).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_apply_direct(const VarUpdate *const *__restrict__ src,
+                                                      const SolverRunParams *__restrict__ params, DeviceTables t,
+                                                      VarUpdate *__restrict__ keep) {
+    __shared__ uint32_t sAgg[kSlots], sSlot[kSlots];
+    __shared__ uint32_t sWords[3 * 256];
+    const int s = blockIdx.y;
+    const SolverRunParams &p = params[s];
+    const int n = p.updCount, nGroups = p.nGroups, updStart = p.updStart;
+    if (n <= 0) return;
+    if (threadIdx.x < kSlots) {
+        sAgg[threadIdx.x] = p.groupAggBit[threadIdx.x];
+        sSlot[threadIdx.x] = p.groupSlotMask[threadIdx.x];
+    }
+    const uint32_t used = p.usedAggBits;
+    const uint32_t *__restrict__ w = reinterpret_cast<const uint32_t *>(src[s]);
+    uint32_t *__restrict__ kw = reinterpret_cast<uint32_t *>(keep + updStart);
+    for (int c0 = blockIdx.x * 256; c0 < n; c0 += gridDim.x * 256) {
+        const int cnt = min(256, n - c0), nw = 3 * cnt;
+        __syncthreads();
+        for (int k = threadIdx.x; k < nw; k += 256) {
+            const uint32_t v = w[(size_t)3 * c0 + k];
+            sWords[k] = v;
+            kw[(size_t)3 * c0 + k] = v;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) {
+            VarUpdate vu;
+            vu.var = (int32_t)sWords[3 * threadIdx.x];
+            vu.def = sWords[3 * threadIdx.x + 1];
+            vu.tru = sWords[3 * threadIdx.x + 2];
+            t.t2[(size_t)vu.var * t.solverStride + s] = make_uint2(vu.def, vu.tru);
+            if (used) {
+                uint32_t bt = vu.tru & vu.def, bf = ~vu.tru & vu.def, bu = ~vu.def;
+                uint32_t T = 0, F = 0, U = 0;
+                for (int g = 0; g < nGroups; g++) {
+                    uint32_t m = sSlot[g], bit = sAgg[g];
+                    if (bt & m) T |= bit;
+                    if (bf & m) F |= bit;
+                    if (bu & m) U |= bit;
+                }
+                writeAggregates(t, s, vu.var, used, T, F, U);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_emit: one block per solver.  Sorts the solver's hit records by (length, index) -- the
+// reproducible hand-over order -- with a bitonic network (shared memory; lists that do not fit are
+// sorted in place in global memory by the same code), turns the lengths into literal positions, and
+// writes the FINISHED result of that solver -- clause ids, positions, literal stream -- straight into
+// the run's result buffer in mapped pinned host memory, coalesced.  The host builds the solver's
+// ClauseBatch as a view over that memory: no device-side global sort, no D2H copy of unknown size,
+// no host-side literal copies (reference: Reporter.cuh:103-126 + Reported.cu:160-204).
+// The block that finishes last writes the header and, after a system fence, the run's sequence number.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEmitThreads = 1024;
+constexpr int kEmitSmemRecs = 8192; // records per solver sorted in shared memory (16 B each)
+
+__device__ __forceinline__ int dirOfLen(const int *sLen, int nDir, int len) { // directory: descending length
+    int lo = 0, hi = nDir - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (sLen[mid] <= len) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs a) {
+    extern __shared__ unsigned long long sDyn[];
+    __shared__ int sLen[128];
+    __shared__ long long sPart[kEmitThreads / 32];
+    __shared__ long long sBase[2];
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nDir = min(a.nDir, 128);
+    for (int i = tid; i < nDir; i += kEmitThreads) sLen[i] = a.dir[i].len;
+
+    // this solver's list, and where its streams start (sum over the solvers before it)
+    const unsigned long long c = a.solverCtr[s];
+    const unsigned int nRaw = (unsigned int)c;
+    const unsigned int n = min(nRaw, a.recCap);
+    const long long nLits = (long long)(c >> 32);
+    if (wid == 0) {
+        long long e = 0, l = 0;
+        for (int t = lane; t < s; t += 32) {
+            const unsigned long long ct = a.solverCtr[t];
+            e += min((unsigned int)ct, a.recCap);
+            l += (long long)(ct >> 32);
+        }
+        for (int o = 16; o; o >>= 1) {
+            e += __shfl_xor_sync(FULL, e, o);
+            l += __shfl_xor_sync(FULL, l, o);
+        }
+        if (lane == 0) { sBase[0] = e; sBase[1] = l; }
+    }
+    __syncthreads();
+    const long long entryBase = sBase[0], litBase = sBase[1];
+    const bool fits = nRaw <= a.recCap && entryBase + n <= a.entryCap && litBase + nLits <= a.litCap;
+
+    unsigned int P = 1;
+    while (P < n) P <<= 1;
+    unsigned long long *K;
+    uint32_t *M;
+    int32_t *pos;
+    if (P <= (unsigned int)kEmitSmemRecs) {
+        K = sDyn;
+        M = reinterpret_cast<uint32_t *>(sDyn + kEmitSmemRecs);
+        pos = reinterpret_cast<int32_t *>(M + kEmitSmemRecs);
+        for (unsigned int i = tid; i < P; i += kEmitThreads) {
+            K[i] = i < n ? a.recKeys[(size_t)s * a.recCap + i] : ~0ull;
+            M[i] = i < n ? a.recMasks[(size_t)s * a.recCap + i] : 0u;
+        }
+    } else { // P <= recCap (a power of two)
+        K = a.recKeys + (size_t)s * a.recCap;
+        M = a.recMasks + (size_t)s * a.recCap;
+        pos = a.recPos + (size_t)s * (a.recCap + 1);
+        for (unsigned int i = n + tid; i < P; i += kEmitThreads) { K[i] = ~0ull; M[i] = 0u; }
+    }
+    __syncthreads();
+    for (unsigned int k = 2; k <= P; k <<= 1)
+        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned int i = tid; i < P; i += kEmitThreads) {
+                const unsigned int x = i ^ j;
+                if (x > i) {
+                    const unsigned long long ki = K[i], kx = K[x];
+                    if ((ki > kx) == ((i & k) == 0)) {
+                        K[i] = kx; K[x] = ki;
+                        const uint32_t mi = M[i]; M[i] = M[x]; M[x] = mi;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    // literal positions: exclusive sum of the lengths in sorted order (pos[n] = this solver's literal count)
+    const unsigned int per = (n + kEmitThreads - 1) / kEmitThreads;
+    const unsigned int i0 = min(n, tid * per), i1 = min(n, i0 + per);
+    long long mine = 0;
+    for (unsigned int i = i0; i < i1; i++) mine += (long long)(K[i] >> 32);
+    long long incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) sPart[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        long long v = sPart[lane], inc2 = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long u = __shfl_up_sync(FULL, inc2, o);
+            if (lane >= o) inc2 += u;
+        }
+        sPart[lane] = inc2 - v;
+    }
+    __syncthreads();
+    long long run = sPart[wid] + incl - mine;
+    for (unsigned int i = i0; i < i1; i++) {
+        pos[i] = (int32_t)run;
+        run += (long long)(K[i] >> 32);
+    }
+    if (tid == 0) pos[n] = (int32_t)nLits;
+    __syncthreads();
+
+    if (fits) {
+        for (unsigned int i = tid; i < n; i += kEmitThreads) {
+            const unsigned long long key = K[i];
+            const int len = (int)(key >> 32), idx = (int)(unsigned int)key;
+            a.ids[entryBase + i] = a.dir[dirOfLen(sLen, nDir, len)].ids[idx];
+        }
+        for (unsigned int i = tid; i <= n; i += kEmitThreads) a.pos[entryBase + s + i] = pos[i];
+        // literal stream: thread per literal (consecutive threads -> consecutive host addresses)
+        for (long long q = tid; q < nLits; q += kEmitThreads) {
+            unsigned int lo = 0, hi = n; // last i with pos[i] <= q
+            while (hi - lo > 1) {
+                const unsigned int mid = (lo + hi) >> 1;
+                if ((long long)pos[mid] <= q) lo = mid; else hi = mid;
+            }
+            const unsigned long long key = K[lo];
+            const int len = (int)(key >> 32), idx = (int)(unsigned int)key, j = (int)(q - pos[lo]);
+            const int32_t *src = a.dir[dirOfLen(sLen, nDir, len)].base + (size_t)(idx / kTileClauses) * kTileClauses * len +
+                                 tileSlot(idx % kTileClauses);
+            a.lits[litBase + q] = __ldg(src + (size_t)j * kTileClauses);
+        }
+    }
+    if (P <= (unsigned int)kEmitSmemRecs) // the sorted list stays on the device: activity bumps, parity hooks
+        for (unsigned int i = tid; i < n; i += kEmitThreads) {
+            a.recKeys[(size_t)s * a.recCap + i] = K[i];
+            a.recMasks[(size_t)s * a.recCap + i] = M[i];
+        }
+    if (tid == 0) {
+        a.hdr->solver[s].entryBase = entryBase;
+        a.hdr->solver[s].litBase = litBase;
+        a.hdr->solver[s].n = (int32_t)n;
+        a.hdr->solver[s].nLits = (int32_t)nLits;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int fl = 0;
+        if (nRaw > a.recCap) fl |= 2u;
+        else if (!fits) fl |= 4u;
+        if (fl) atomicOr(a.ticket + 1, fl);
+        atomicMax(a.ticket + 2, nRaw);
+        __threadfence_system(); // this block's stores have been performed in host memory (cumulative over the barrier)
+        const unsigned int ticket = atomicAdd(a.ticket, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            const volatile Counters *cn = a.counters;
+            unsigned int flags = *reinterpret_cast<volatile unsigned int *>(a.ticket + 1);
+            for (int g = 0; g < a.groups && g < kMaxGroups; g++) {
+                a.hdr->nSurvivors[g] = cn->nSurvivors[g];
+                if (cn->nSurvivors[g] > a.survCap) flags |= 1u;
+            }
+            long long tot = 0, lt = 0;
+            for (int t = 0; t < a.nSolvers; t++) {
+                const unsigned long long ct = a.solverCtr[t];
+                tot += min((unsigned int)ct, a.recCap);
+                lt += (long long)(ct >> 32);
+            }
+            a.hdr->nTotal = tot;
+            a.hdr->litTotal = lt;
+            a.hdr->exactTests = cn->exactTests;
+            a.hdr->maxRec = *reinterpret_cast<volatile unsigned int *>(a.ticket + 2);
+            a.hdr->flags = flags;
+            a.ticket[0] = 0u;
+            a.ticket[1] = 0u;
+            a.ticket[2] = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(&a.hdr->seq) = a.seq;
+        }
+    }
+}
+
+// activity bumps straight from the sorted per-solver record lists (blockIdx.y = solver)
+__global__ void k_bump_recs(const unsigned long long *__restrict__ recKeys, unsigned int recCap,
+                            const unsigned long long *__restrict__ solverCtr, const LenDir *__restrict__ dir, int nDir, float inc,
+                            int *overflow) {
+    const int s = blockIdx.y;
+    const unsigned int n = min((unsigned int)solverCtr[s], recCap);
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = recKeys[(size_t)s * recCap + i];
+        const int len = (int)(key >> 32), idx = (int)(unsigned int)key;
+        int lo = 0, hi = nDir - 1; // descending length
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (dir[mid].len <= len) hi = mid; else lo = mid + 1;
+        }
+        float old = atomicAdd(dir[lo].acts + idx, inc);
+        if (old + inc > 1e19f) *overflow = 1;
     }
 }
 
@@ -920,6 +1200,39 @@ void launchCollapse(const VarUpdate *upd, const SolverRunParams *params, int nSo
     if (nSolvers == 0 || maxUpdPerSolver == 0) return;
     k_collapse<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(upd, params, t, (long long)avail);
     checkLaunch("k_collapse");
+    ++*launches;
+}
+
+void launchApplyDirect(const VarUpdate *const *src, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
+                       const DeviceTables &t, VarUpdate *keep, int numSMs, cudaStream_t s, int64_t *launches) {
+    if (nSolvers == 0 || maxUpdPerSolver == 0) return;
+    k_apply_direct<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(src, params, t, keep);
+    checkLaunch("k_apply_direct");
+    ++*launches;
+}
+
+void launchEmit(const EmitArgs &a, cudaStream_t s, int64_t *launches) {
+    if (a.nSolvers <= 0) return;
+    static const size_t smem = (size_t)kEmitSmemRecs * (sizeof(unsigned long long) + sizeof(uint32_t)) + (size_t)(kEmitSmemRecs + 1) * sizeof(int32_t);
+    static bool configured[64] = {}; // per device: the attribute belongs to the function in that device's context
+    int dev = 0;
+    GSS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        GSS_CUDA(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    k_emit<<<a.nSolvers, kEmitThreads, smem, s>>>(a);
+    checkLaunch("k_emit");
+    ++*launches;
+}
+
+void launchBumpFromRecs(const unsigned long long *recKeys, unsigned int recCap, const unsigned long long *solverCtr, int nSolvers,
+                        unsigned int maxCount, const LenDir *dir, int nDir, float inc, int *overflow, cudaStream_t s,
+                        int64_t *launches) {
+    if (nSolvers <= 0 || maxCount == 0) return;
+    dim3 grid(std::max(1u, std::min((maxCount + 255u) / 256u, 64u)), nSolvers, 1);
+    k_bump_recs<<<grid, 256, 0, s>>>(recKeys, recCap, solverCtr, dir, nDir, inc, overflow);
+    checkLaunch("k_bump_recs");
     ++*launches;
 }
 

@@ -61,6 +61,13 @@ struct CheckArgs {
     unsigned int *peerTicket = nullptr; // this device: blocks that have finished
     uint32_t peerSeq = 0;
     int peerGroups = 0;               // solver groups whose survivor counters count for the overflow flag
+    // direct pipeline: k_exact appends its hits to PER-SOLVER record lists instead of one global hit
+    // buffer (lane = solver: one 64-bit atomicAdd per lane and warp step reserves the slots and adds up
+    // the literal count of that solver's result stream).  recKeys == nullptr: global hit buffer.
+    unsigned long long *solverCtr = nullptr; // [solver] records (low 32 bits) | literals (high 32 bits)
+    unsigned long long *recKeys = nullptr;   // [solver][recCap]  clause length << 32 | clause index
+    uint32_t *recMasks = nullptr;            // [solver][recCap]  slot mask of the hit
+    unsigned int recCap = 0;
 };
 
 void launchFillTables(const DeviceTables &t, int varFrom, cudaStream_t s, int64_t *launches);
@@ -139,6 +146,56 @@ void launchPeerWaitAll(const PeerFlagList &flags, uint32_t value, unsigned long 
                        int64_t *launches);
 void launchPeerWait(const uint32_t *flag, uint32_t value, unsigned long long timeoutNs, int *err, cudaStream_t s,
                     int64_t *launches);
+
+// ---- direct pipeline (pipeline.cu): deltas read from, results written to, mapped pinned host memory ----
+constexpr int kMaxSolvers = kMaxGroups * kMaxSolversPerGroup;
+// Header of a result buffer in pinned host memory, written by k_emit (seq last, after a system fence).
+struct RunHdr {
+    uint32_t seq;     // the run this header belongs to (written last)
+    uint32_t flags;   // 1 survivor list overflowed, 2 a solver's record list overflowed, 4 this buffer is too small
+    int64_t nTotal;   // hit records of all solvers
+    int64_t litTotal; // literals of all solvers
+    uint64_t exactTests;
+    uint32_t maxRec;  // largest per-solver record count (before clipping)
+    uint32_t pad;
+    uint32_t nSurvivors[kMaxGroups];
+    struct PerSolver {
+        int64_t entryBase; // first entry of this solver in ids[]; its positions start at pos[entryBase + solver]
+        int64_t litBase;   // first literal of this solver in lits[]
+        int32_t n;         // entries
+        int32_t nLits;
+    } solver[kMaxSolvers];
+};
+struct EmitArgs {
+    const LenDir *dir;
+    int nDir;
+    int nSolvers;
+    unsigned long long *solverCtr;
+    unsigned long long *recKeys; // sorted in place
+    uint32_t *recMasks;
+    int32_t *recPos;             // [solver][recCap + 1] scratch for lists too large for shared memory
+    unsigned int recCap;         // power of two
+    Counters *counters;
+    unsigned int survCap;
+    int groups;
+    unsigned int *ticket;        // finished-block counter + flag word (2 x uint32)
+    uint32_t seq;
+    // result buffer in mapped pinned host memory
+    RunHdr *hdr;
+    int64_t *ids;   // entryCap
+    int32_t *pos;   // entryCap + nSolvers (one more position than entries per solver)
+    int32_t *lits;  // litCap
+    long long entryCap, litCap;
+};
+// per-solver sort by (length, index) = the reproducible hand-over order, clause ids, literal positions and
+// the literal stream of every solver, written straight into the result buffer in host memory
+void launchEmit(const EmitArgs &a, cudaStream_t s, int64_t *launches);
+// deltas of every solver read from src[s] (mapped pinned host memory or device memory), a copy kept in `keep`
+void launchApplyDirect(const VarUpdate *const *src, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
+                       const DeviceTables &t, VarUpdate *keep, int numSMs, cudaStream_t s, int64_t *launches);
+// activity bumps from the sorted per-solver record lists of a finished run
+void launchBumpFromRecs(const unsigned long long *recKeys, unsigned int recCap, const unsigned long long *solverCounts, int nSolvers,
+                        unsigned int maxCount, const LenDir *dir, int nDir, float inc, int *overflow, cudaStream_t s, int64_t *launches);
 
 // register-only LOP3 micro-benchmark: thread-level LOP3 per second on this device
 double measureLop3Peak(int numSMs, cudaStream_t s, int64_t *launches);

@@ -44,6 +44,8 @@ public:
     const T *data() const { return p_; }
     size_t size() const { return size_; }
     size_t capacity() const { return cap_; }
+    bool empty() const { return size_ == 0; }
+    bool pinned() const { return pinned_; } // page-locked: a kernel can read / write it in place
     T &operator[](size_t i) { return p_[i]; }
     const T &operator[](size_t i) const { return p_[i]; }
     void clear() { size_ = 0; }

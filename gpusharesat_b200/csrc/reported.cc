@@ -46,6 +46,7 @@ bool BatchQueue::oldest(ClauseBatch *&b) {
 void BatchQueue::retireOldest() {
     std::lock_guard<std::mutex> g(lock_);
     GSS_CHECK(taken_ > 0);
+    live_.front()->views.clear(); // give the result buffers back now, not when the batch object is reused
     spare_.push_back(std::move(live_.front()));
     live_.pop_front();
     taken_--;
@@ -229,6 +230,23 @@ void Reported::handOverSorted(const SortedHit *recs, size_t n, const int32_t *li
     if (prof) fprintf(stderr, "handOverSorted: slices + begin %.0f us, fill %.0f us, publish %.0f us (%zu hits)\n", us(t0, t1), us(t1, t2), us(t2, now()), n);
 }
 
+void Reported::handOverViews(std::vector<std::vector<ResultView>> &views, const std::vector<AssigIds> &ids, int nSolvers) {
+    const size_t nQueues = queues_.size();
+    for (size_t s = 0; s < nQueues && s < (size_t)nSolvers; s++) {
+        const bool hasIds = s < ids.size() && ids[s].count > 0;
+        bool hasHits = false;
+        if (s < views.size())
+            for (const ResultView &v : views[s]) hasHits = hasHits || v.n > 0;
+        if (!hasIds && !hasHits) continue;
+        ClauseBatch &b = queues_[s]->begin();
+        if (hasIds) b.ids = ids[s];
+        if (hasHits)
+            for (ResultView &v : views[s])
+                if (v.n > 0) b.views.push_back(std::move(v));
+        queues_[s]->publish();
+    }
+}
+
 bool Reported::pop(int s, int *&lits, int &count, int64_t &id) {
     while (true) {
         if (!current_[s]) queues_[s]->takeNext(current_[s]);
@@ -257,7 +275,7 @@ bool Reported::pop(int s, int *&lits, int &count, int64_t &id) {
         // reported, those clauses may be reported again (the solver may have deleted them)
         ClauseBatch *old;
         while (queues_[s]->oldest(old) && old->assigWhichKnowsAboutThese <= seenAllReportsUntil) {
-            for (const auto &e : old->entries) notAgain_[s].erase(e.id);
+            old->forEachId([&](int64_t oldId) { notAgain_[s].erase(oldId); });
             queues_[s]->retireOldest();
         }
         auto &q = dontImport_[s];

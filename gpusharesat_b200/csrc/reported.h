@@ -17,6 +17,17 @@
 
 namespace gss {
 
+// One solver's share of a run's result exactly as the GPU wrote it into a result buffer in pinned
+// host memory (k_emit): n clause ids, n + 1 literal positions, the literal stream.  A ClauseBatch
+// built from views copies nothing; `owner` keeps the buffer alive until the batch is recycled.
+struct ResultView {
+    const int64_t *ids = nullptr;
+    const int32_t *pos = nullptr; // n + 1 entries, relative to lits
+    int32_t *lits = nullptr;      // writable: callers permute the literals they are handed in place
+    int32_t n = 0;
+    std::shared_ptr<void> owner;
+};
+
 // The clauses reported to one solver by one GPU run.
 struct ClauseBatch {
     struct Entry {
@@ -25,7 +36,10 @@ struct ClauseBatch {
     };
     std::vector<int> lits;
     std::vector<Entry> entries;
+    std::vector<ResultView> views; // zero-copy part (one view per device that contributed), after `entries`
     size_t next = 0;
+    size_t viewAt = 0;
+    int32_t viewNext = 0;
     AssigIds ids;
     uint32_t hadSomeReported = 0;
     int64_t assigWhichKnowsAboutThese = 0;
@@ -33,18 +47,40 @@ struct ClauseBatch {
     void clear() {
         lits.clear();
         entries.clear();
+        views.clear(); // drops the references to the result buffers
         next = 0;
+        viewAt = 0;
+        viewNext = 0;
         hadSomeReported = 0;
     }
     bool pop(int *&outLits, int &count, int64_t &id) {
-        if (next >= entries.size()) return false;
-        const Entry &e = entries[next];
-        int end = next + 1 < entries.size() ? entries[next + 1].pos : (int)lits.size();
-        outLits = lits.data() + e.pos;
-        count = end - e.pos;
-        id = e.id;
-        next++;
-        return true;
+        if (next < entries.size()) {
+            const Entry &e = entries[next];
+            int end = next + 1 < entries.size() ? entries[next + 1].pos : (int)lits.size();
+            outLits = lits.data() + e.pos;
+            count = end - e.pos;
+            id = e.id;
+            next++;
+            return true;
+        }
+        while (viewAt < views.size()) {
+            const ResultView &v = views[viewAt];
+            if (viewNext < v.n) {
+                outLits = v.lits + v.pos[viewNext];
+                count = v.pos[viewNext + 1] - v.pos[viewNext];
+                id = v.ids[viewNext];
+                viewNext++;
+                return true;
+            }
+            viewAt++;
+            viewNext = 0;
+        }
+        return false;
+    }
+    template <typename F> void forEachId(F f) const {
+        for (const auto &e : entries) f(e.id);
+        for (const auto &v : views)
+            for (int32_t i = 0; i < v.n; i++) f(v.ids[i]);
     }
 };
 
@@ -97,6 +133,10 @@ public:
     // stream): every solver's batch is one contiguous slice -- sequential copies only.
     void handOverSorted(const SortedHit *recs, size_t n, const int32_t *lits, int64_t totalLits,
                         const std::vector<AssigIds> &ids, int nSolvers);
+    // Zero-copy hand-over of a run whose per-solver results the GPU(s) wrote into result buffers in
+    // pinned host memory: views[s] = solver s's slices (one per device, possibly empty).  Every solver
+    // with assignments in the run gets a batch, hits or not (progress marker, Reported.cu:166-174).
+    void handOverViews(std::vector<std::vector<ResultView>> &views, const std::vector<AssigIds> &ids, int nSolvers);
     // solver thread: Reported.cu:105-158
     bool pop(int solver, int *&lits, int &count, int64_t &id);
     int64_t lastAssigAllReported(int solver) const { return lastAllReported_[solver]; }

@@ -13,24 +13,7 @@
 
 namespace gss {
 
-static inline int64_t nowMicros() {
-    return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-
-struct PhaseTimer { // host-side wall time of a phase of gss_gpu_run (gss_debug_host_phases)
-    double &acc;
-    int64_t t0;
-    explicit PhaseTimer(double &a) : acc(a), t0(nowMicros()) {}
-    ~PhaseTimer() { acc += (double)(nowMicros() - t0); }
-};
-
-struct TimeAdder { // reference TimeGauge, gpuShareLib/Profiler.h:28-46
-    uint64_t &acc;
-    bool on;
-    int64_t t0;
-    TimeAdder(uint64_t &a, bool enabled) : acc(a), on(enabled), t0(enabled ? nowMicros() : 0) {}
-    ~TimeAdder() { if (on) acc += (uint64_t)(nowMicros() - t0); }
-};
+std::shared_ptr<Sharer::RunBufPool> makeRunBufPool(); // pipeline.cu
 
 Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
     logger_.verbosity = o.verbosity;
@@ -96,6 +79,8 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
     db_->setDeviceActivities(true);
     reported_->setHostBumps(false);
     setCpuSolverCount(1);
+    runBufs_ = makeRunBufPool();
+    directEnabled_ = getenv("GPUSHARE_LEGACY_PIPELINE") == nullptr;
     logger_.log(1, std::string("c gpushare_b200 on ") + props.name + ", " + std::to_string(numSMs_) + " SMs\n");
 }
 
@@ -130,6 +115,7 @@ void Sharer::setCpuSolverCount(int n) {
     // GpuClauseSharerImpl.cu:96-103
     if (n > kMaxGroups * kMaxSolversPerGroup) GSS_DIE("too many cpu solvers (max 256)");
     assigs_->growSolvers(n);
+    for (int s = 0; s < assigs_->solverCount(); s++) assigs_->solver(s).setAllocDevice(device_);
     reported_->setSolverCount(n);
     if ((int)toUnset_.size() < n) toUnset_.resize(n);
     size_t c = oneSolverStats_.size();
@@ -253,7 +239,10 @@ void Sharer::wholeRun(bool canStart) {
     RunSlot *prev = cur_ >= 0 ? &slots_[cur_] : nullptr;
     {
         PhaseTimer t(hostPhases_[0]);
-        if (prev) finishRun(*prev); // run k is complete and every hit is on the host
+        if (prev) { // run k is complete and every hit is on the host
+            if (prev->direct) finishRunDirect(*prev);
+            else finishRun(*prev);
+        }
     }
     int startedSlot = -1;
     bool outOfMemory = false;
@@ -268,7 +257,10 @@ void Sharer::wholeRun(bool canStart) {
     }
     {
         PhaseTimer t(hostPhases_[2]);
-        if (prev) processResults(*prev); // overlaps with run k+1 on the GPU
+        if (prev) { // overlaps with run k+1 on the GPU
+            if (prev->direct) processResultsDirect(*prev);
+            else processResults(*prev);
+        }
     }
     cur_ = startedSlot;
     if (outOfMemory) {
@@ -313,8 +305,14 @@ void Sharer::ensureResultBuffers() {
     survDev_.reserve((size_t)groups * survCap_, 0, stream_);
 }
 
-CheckArgs Sharer::checkArgs(const RunSlot &slot, int g) const {
+CheckArgs Sharer::checkArgs(const RunSlot &slot, int g, bool recs) const {
     CheckArgs a;
+    if (recs) {
+        a.solverCtr = const_cast<unsigned long long *>(slot.ctrDev.data());
+        a.recKeys = const_cast<unsigned long long *>(slot.recKeys.data());
+        a.recMasks = const_cast<uint32_t *>(slot.recMasks.data());
+        a.recCap = slot.recCap;
+    }
     a.dir = slot.dirDev();
     a.nDir = slot.nDir;
     a.totalTiles = slot.totalTiles;
@@ -335,7 +333,11 @@ CheckArgs Sharer::checkArgs(const RunSlot &slot, int g) const {
 }
 
 bool Sharer::launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly) {
+    // direct pipeline: k_exact appends to per-solver record lists (dense mode always uses the global hit buffer)
+    const bool recs = slot.direct && !dense;
+    if (slot.direct && !recs) ensureResultBuffers();
     GSS_CUDA(cudaMemsetAsync(resDev_.data(), 0, sizeof(Counters), stream_));
+    if (recs) GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)kMaxSolvers * sizeof(unsigned long long), stream_));
     int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
     int lastGroup = -1;
     for (int g = 0; g < groups; g++)
@@ -343,7 +345,7 @@ bool Sharer::launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly) {
     bool published = false;
     for (int g = 0; g < groups; g++) {
         if (slot.aggStart[g] == 0) continue; // no frozen slot in this group
-        CheckArgs a = checkArgs(slot, g);
+        CheckArgs a = checkArgs(slot, g, recs);
         if (filterOnly) launchFilterOnly(a, dims_, numSMs_, stream_, &launches_);
         else if (dense) launchCheckDense(a, dims_, numSMs_, stream_, &launches_);
         else {
@@ -483,6 +485,8 @@ void Sharer::launchRun(RunSlot &slot, const void *updSrc, int64_t nUpdates, int6
 }
 
 bool Sharer::startRun(RunSlot &slot) {
+    if (directEnabled_ && !dense_ && !peer_) return startRunDirect(slot);
+    slot.direct = false;
     int64_t h2d = 0;
     bool rebuild = false;
     if (!prepareRun(slot, rebuild, h2d)) return false;
@@ -948,6 +952,7 @@ void Sharer::processResults(RunSlot &slot) {
     globalStats_[G_clauseTestsOnGroups] += (uint64_t)clCount;
     globalStats_[G_gpuReports] += postValid_ ? postN_ : hits_.size();
     lastHitsValid_ = false; // gss_debug_last_hits converts hits_ on demand
+    lastDirect_ = nullptr;
     bumpParkedHits();
     TimeAdder t(globalStats_[G_timeSpentFillingReported], opts_.quickProf != 0);
     if (postValid_) reported_->handOverSorted(postSortedHost_.data(), postN_, postLitsHost_.data(), postLits_, slot.ids, slot.nSolvers);
@@ -956,7 +961,27 @@ void Sharer::processResults(RunSlot &slot) {
 
 void Sharer::materializeLastHits() {
     if (lastHitsValid_) return;
-    if (postValid_) {
+    if (lastDirect_) {
+        // direct pipeline: ids are in the result buffer (host), the masks of the sorted record lists on the device
+        RunSlot &slot = *lastDirect_;
+        lastHits_.clear();
+        if (slot.checked && slot.runBuf) {
+            useDevice();
+            const RunHdr *h = slot.runBuf->hdr();
+            lastHits_.resize((size_t)h->nTotal);
+            std::vector<uint32_t> masks;
+            for (int s = 0; s < slot.nSolvers; s++) {
+                const RunHdr::PerSolver &ps = h->solver[s];
+                if (ps.n <= 0) continue;
+                masks.resize((size_t)ps.n);
+                GSS_CUDA(cudaMemcpyAsync(masks.data(), slot.recMasks.data() + (size_t)s * slot.recCap, (size_t)ps.n * sizeof(uint32_t),
+                                         cudaMemcpyDeviceToHost, stream_));
+                GSS_CUDA(cudaStreamSynchronize(stream_));
+                const int64_t *ids = slot.runBuf->ids() + ps.entryBase;
+                for (int32_t i = 0; i < ps.n; i++) lastHits_[(size_t)ps.entryBase + i] = gss_hit{ids[i], s, masks[(size_t)i]};
+            }
+        }
+    } else if (postValid_) {
         lastHits_.resize(postN_);
         for (size_t i = 0; i < postN_; i++)
             lastHits_[i] = gss_hit{postSortedHost_[i].id, postSortedHost_[i].solver, postSortedHost_[i].mask};
@@ -992,8 +1017,11 @@ double Sharer::timeCheck(int iters, int mode) {
         if (mode <= 2) {
             launchCheckKernels(slot, dense, filterOnly);
         } else if (mode == 3) {
+            if (slot.direct) GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)kMaxSolvers * sizeof(unsigned long long), stream_));
             for (int g = 0; g < groups; g++)
-                if (slot.aggStart[g]) launchExactOnly(checkArgs(slot, g), dims_, numSMs_, stream_, &launches_);
+                if (slot.aggStart[g]) launchExactOnly(checkArgs(slot, g, slot.direct), dims_, numSMs_, stream_, &launches_);
+        } else if (mode == 6) {
+            launchEmitFor(slot);
         } else if (mode == 4) {
             launchApplyUpdates(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, slot.nUpdates, tables_, numSMs_,
                                stream_, &launches_);
@@ -1005,7 +1033,13 @@ double Sharer::timeCheck(int iters, int mode) {
     cudaEvent_t e0, e1;
     GSS_CUDA(cudaEventCreate(&e0));
     GSS_CUDA(cudaEventCreate(&e1));
+    if (mode == 6 && !(slot.direct && slot.checked)) return -1.0;
+    if (mode == 1 && slot.direct) { // the dense kernel reports into the global hit buffer: this run finishes on the staged path
+        slot.direct = false;
+        if (lastDirect_ == &slot) lastDirect_ = nullptr;
+    }
     if (mode == 3) launchCheckKernels(slot, false, true); // a fresh survivor list
+    if (mode == 6) launchCheckKernels(slot, false, false); // fresh record lists
     once(); // warm-up
     GSS_CUDA(cudaEventRecord(e0, stream_));
     for (int i = 0; i < iters; i++) once();
@@ -1013,8 +1047,12 @@ double Sharer::timeCheck(int iters, int mode) {
     if (mode == 5)
         launchApplyUpdates(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, slot.nUpdates, tables_, numSMs_,
                            stream_, &launches_);
-    if (mode >= 2) launchCheckKernels(slot, slot.dense, false); // leave a complete result behind
-    enqueueResultCopy(slot);
+    if (slot.direct) {
+        launchDirectCheck(slot); // leave a complete result behind
+    } else {
+        if (mode >= 2) launchCheckKernels(slot, slot.dense, false);
+        enqueueResultCopy(slot);
+    }
     GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
     GSS_CUDA(cudaEventSynchronize(e1));
     float ms = 0;

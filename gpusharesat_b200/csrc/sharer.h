@@ -8,10 +8,28 @@
 #include "kernels.cuh"
 #include "reported.h"
 #include "stats.h"
+#include <chrono>
 #include <memory>
 #include <vector>
 
 namespace gss {
+
+inline int64_t nowMicros() {
+    return std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+struct PhaseTimer { // host-side wall time of a phase of gss_gpu_run (gss_debug_host_phases)
+    double &acc;
+    int64_t t0;
+    explicit PhaseTimer(double &a) : acc(a), t0(nowMicros()) {}
+    ~PhaseTimer() { acc += (double)(nowMicros() - t0); }
+};
+struct TimeAdder { // reference TimeGauge, gpuShareLib/Profiler.h:28-46
+    uint64_t &acc;
+    bool on;
+    int64_t t0;
+    TimeAdder(uint64_t &a, bool enabled) : acc(a), on(enabled), t0(enabled ? nowMicros() : 0) {}
+    ~TimeAdder() { if (on) acc += (uint64_t)(nowMicros() - t0); }
+};
 
 class Sharer {
 public:
@@ -76,6 +94,21 @@ public:
     int64_t peerFinish();
     void peerClose();
 
+    struct RunBuf { // one run's result buffer in page-locked host memory, written by k_emit (pipeline.cu)
+        uint8_t *base = nullptr;
+        size_t bytes = 0;
+        int64_t entryCap = 0, litCap = 0;
+        RunHdr *hdr() const { return reinterpret_cast<RunHdr *>(base); }
+        int64_t *ids() const { return reinterpret_cast<int64_t *>(base + hdrBytes()); }
+        int32_t *pos() const { return reinterpret_cast<int32_t *>(base + hdrBytes() + (size_t)entryCap * 8); }
+        int32_t *lits() const { return pos() + (size_t)entryCap + kMaxSolvers; }
+        static size_t hdrBytes() { return (sizeof(RunHdr) + 255) / 256 * 256; }
+        static size_t bytesFor(int64_t entryCap, int64_t litCap) {
+            return hdrBytes() + (size_t)entryCap * 8 + ((size_t)entryCap + kMaxSolvers) * 4 + (size_t)litCap * 4;
+        }
+    };
+    class RunBufPool;
+
 private:
     struct RunSlot {
         HostBuf<uint8_t> headHost; // [LenDir x nDir][SolverRunParams x nSolvers]
@@ -91,10 +124,40 @@ private:
         bool inFlight = false;
         bool aggOnDevice = false; // multi-GPU receiver: the host never saw the run parameters
         cudaEvent_t evStart = nullptr, evH2DDone = nullptr, evBeforeCheck = nullptr, evAfterCheck = nullptr, evEnd = nullptr;
+        // ---- direct pipeline (pipeline.cu) ----
+        bool direct = false;        // this run used the direct pipeline (per-solver records, k_emit into host memory)
+        bool checked = false;       // check kernels + k_emit were launched (some solver had a frozen slot)
+        uint32_t seq = 0;           // what k_emit writes into the header last
+        std::shared_ptr<RunBuf> runBuf;
+        DevBuf<unsigned long long> ctrDev;  // [kMaxSolvers] records | literals << 32
+        DevBuf<unsigned long long> recKeys; // [nSolvers][recCap]
+        DevBuf<uint32_t> recMasks;
+        DevBuf<int32_t> recPos;             // [nSolvers][recCap + 1]
+        DevBuf<unsigned int> ticketDev;     // 4 words
+        unsigned int recCap = 0;
+        size_t srcOff = 0;          // offset of the per-solver delta pointers in headHost / headDev
         const LenDir *dirDev() const { return (const LenDir *)headDev.data(); }
         const SolverRunParams *paramsDev() const { return (const SolverRunParams *)(headDev.data() + dirBytes); }
         size_t dirBytes = 0;
     };
+
+    // ---- direct pipeline (pipeline.cu): deltas are read by the GPU from the solver threads' own
+    // page-locked buffers, results are written by the GPU into page-locked result buffers that the
+    // solvers' ClauseBatches view in place ----
+    bool startRunDirect(RunSlot &slot);
+    void launchDirectCheck(RunSlot &slot);
+    void launchEmitFor(RunSlot &slot);
+    void finishRunDirect(RunSlot &slot);
+    void processResultsDirect(RunSlot &slot);
+    void ensureDirectBuffers(RunSlot &slot);
+    void bumpDirect(RunSlot &slot, unsigned int maxRec);
+    bool waitBumpFlag();
+    std::shared_ptr<RunBufPool> runBufs_;
+    bool directEnabled_ = true;
+    size_t recCap_ = 1024;       // per-solver record capacity (power of two)
+    int64_t entryGuess_ = 4096, litGuess_ = 16384; // result buffer sizing (from previous runs)
+    uint32_t directSeq_ = 0;
+    RunSlot *lastDirect_ = nullptr; // finished direct run whose records are still on the device (parity hook)
 
     void useDevice();
     void wholeRun(bool canStart);
@@ -113,7 +176,7 @@ private:
     bool ensureTables(bool &rebuild);
     void ensureResultBuffers();
     void unsetPendingLocked(int solver);
-    CheckArgs checkArgs(const RunSlot &slot, int group) const;
+    CheckArgs checkArgs(const RunSlot &slot, int group, bool recs = false) const;
     size_t resultChunk() const { return hitCap_ < 4096 ? hitCap_ : 4096; }
 
     gss_options opts_;

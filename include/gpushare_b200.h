@@ -126,7 +126,8 @@ void gss_debug_set_dense(gss_sharer *h, int dense);
  * time of one sweep in microseconds (CUDA events on the library's stream).  The hit buffer
  * of the last iteration replaces the run's hits.  GPU thread only; waits for the run.
  * dense: 0 = production kernels (k_filter + k_exact), 1 = dense kernel, 2 = k_filter alone,
- * 3 = k_exact alone, 4 = k_apply_updates alone, 5 = k_collapse alone. */
+ * 3 = k_exact alone, 4 = k_apply_updates alone, 5 = k_collapse alone, 6 = k_emit alone (-1 when
+ * the last run did not go through the direct pipeline). */
 double gss_debug_time_check(gss_sharer *h, int iters, int dense);
 /* The level-1 kernel is built in several variants (csrc/kernels.cu: kFilterVariants) so that the
  * choices can be timed against each other on the device; GSS_FILTER_VARIANT picks one at start-up. */

@@ -36,6 +36,7 @@ def main():
         if len(r) <= cols["Metric Value"]:
             continue
         name = r[cols["Kernel Name"]].split("(")[0].split("::")[-1].split("<")[0]
+        name = name[:-2] if name.endswith("_t") else name  # k_filter_t<...> -> k_filter
         lid = r[cols["ID"]]
         unit, val = r[cols["Metric Unit"]], float(r[cols["Metric Value"]].replace(",", ""))
         scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "us": 1e3, "ms": 1e6, "ns": 1.0, "s": 1e9}.get(unit, 1.0)

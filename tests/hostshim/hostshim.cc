@@ -78,6 +78,25 @@ int hs_collect_split(HostRig *r) {
     });
     return (int)total;
 }
+// the direct pipeline's collection (Sharer::startRunDirect): every solver's delta buffer is swapped out
+// (SolverAssigs::takeUpdatesLocked) and read where it lies; here the taken buffers are concatenated so
+// that the result can be compared with hs_collect
+int hs_collect_take(HostRig *r) {
+    int n = r->assigs.solverCount();
+    r->updates.clear();
+    r->params.assign(n, SolverRunParams{});
+    r->ids.assign(n, AssigIds{});
+    int64_t total = 0;
+    for (int s = 0; s < n; s++) {
+        const VarUpdate *ptr = nullptr;
+        bool pinned = false;
+        r->assigs.solver(s).takeUpdatesLocked(ptr, (int32_t)total, r->params[s], r->ids[s], &pinned);
+        int cnt = r->params[s].updCount;
+        if (cnt) memcpy(r->updates.append((size_t)cnt), ptr, (size_t)cnt * sizeof(VarUpdate));
+        total += cnt;
+    }
+    return (int)total;
+}
 void hs_get_params(HostRig *r, int s, SolverRunParams *out) { *out = r->params[s]; }
 void hs_get_updates(HostRig *r, VarUpdate *out) { memcpy(out, r->updates.data(), r->updates.size() * sizeof(VarUpdate)); }
 void hs_get_ids(HostRig *r, int s, int64_t *start, int *count) { *start = r->ids[s].start; *count = r->ids[s].count; }
@@ -130,6 +149,51 @@ double hs_hand_over_sorted(HostRig *r, const HitRecord *hits, int n) {
     }
     auto t0 = std::chrono::steady_clock::now();
     r->reported.handOverSorted(recs.data(), recs.size(), lits.data(), (int64_t)lits.size(), r->ids, r->assigs.solverCount());
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+}
+// the direct pipeline's hand-over (Reported::handOverViews): per solver the result exactly as k_emit
+// lays it out in a result buffer -- ids, n + 1 positions, literal stream -- split in `parts` slices
+// (one per device in a multi-GPU run); the batches view the buffer, which lives until they let go
+double hs_hand_over_views(HostRig *r, const HitRecord *hits, int n, int parts) {
+    std::vector<HitRecord> v(hits, hits + n);
+    std::sort(v.begin(), v.end(), [](const HitRecord &a, const HitRecord &b) {
+        if (a.solver != b.solver) return a.solver < b.solver;
+        if (a.len != b.len) return a.len < b.len;
+        return a.idx < b.idx;
+    });
+    struct Buf {
+        std::vector<int64_t> ids;
+        std::vector<int32_t> pos, lits;
+    };
+    const int S = r->assigs.solverCount();
+    std::vector<std::vector<ResultView>> views((size_t)S);
+    size_t i = 0;
+    for (int s = 0; s < S; s++) {
+        size_t lo = i;
+        while (i < v.size() && v[i].solver == s) i++;
+        const size_t cnt = i - lo;
+        for (int part = 0; part < parts; part++) {
+            const size_t a = lo + cnt * part / parts, b = lo + cnt * (part + 1) / parts;
+            auto buf = std::make_shared<Buf>();
+            std::vector<int> tmp;
+            for (size_t k = a; k < b; k++) {
+                buf->pos.push_back((int32_t)buf->lits.size());
+                tmp.clear();
+                buf->ids.push_back(r->db.appendClause(v[k].len, v[k].idx, tmp));
+                buf->lits.insert(buf->lits.end(), tmp.begin(), tmp.end());
+            }
+            buf->pos.push_back((int32_t)buf->lits.size());
+            ResultView rv;
+            rv.ids = buf->ids.data();
+            rv.pos = buf->pos.data();
+            rv.lits = buf->lits.data();
+            rv.n = (int32_t)(b - a);
+            rv.owner = buf;
+            views[s].push_back(std::move(rv));
+        }
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    r->reported.handOverViews(views, r->ids, S);
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
 }
 int64_t hs_add_clauses_bulk(HostRig *r, const int64_t *offsets, const int *lits, int64_t n) { return r->db.addClausesBulk(offsets, lits, n); }

@@ -28,7 +28,7 @@ def load():
     sig = {
         "hs_create": (P, [I, I, C.c_double]), "hs_destroy": (None, [P]),
         "hs_available": (I, [P, I]), "hs_set_var": (None, [P, I, I, I]), "hs_send": (Q, [P, I]),
-        "hs_set_host_bumps": (None, [P, I]), "hs_collect": (I, [P, I]), "hs_collect_split": (I, [P]), "hs_hand_over_sorted": (C.c_double, [P, C.c_void_p, I]), "hs_get_params": (None, [P, I, C.POINTER(SolverRunParams)]),
+        "hs_set_host_bumps": (None, [P, I]), "hs_collect": (I, [P, I]), "hs_collect_split": (I, [P]), "hs_collect_take": (I, [P]), "hs_hand_over_views": (C.c_double, [P, C.c_void_p, I, I]), "hs_hand_over_sorted": (C.c_double, [P, C.c_void_p, I]), "hs_get_params": (None, [P, I, C.POINTER(SolverRunParams)]),
         "hs_get_updates": (None, [P, C.c_void_p]), "hs_get_ids": (None, [P, I, C.POINTER(Q), IP]),
         "hs_add_clause": (Q, [P, IP, I]), "hs_drain": (None, [P]), "hs_count": (I, [P, I]),
         "hs_clause_id": (Q, [P, I, I]), "hs_activity": (C.c_float, [P, I, I]), "hs_bump": (None, [P, I, I]),
@@ -87,6 +87,23 @@ class Rig:
             self.L.hs_get_params(self.h, s, C.byref(p))
             params.append(p)
         return upd, params
+
+    def collect_take(self):
+        """same result as collect(), produced the way the direct pipeline collects (buffer swap)"""
+        n = self.L.hs_collect_take(self.h)
+        upd = np.zeros(n, dtype=VARUPDATE)
+        if n:
+            self.L.hs_get_updates(self.h, upd.ctypes.data)
+        params = []
+        for s in range(self.nsolvers):
+            p = SolverRunParams()
+            self.L.hs_get_params(self.h, s, C.byref(p))
+            params.append(p)
+        return upd, params
+
+    def hand_over_views(self, hits, parts=1):
+        a = np.ascontiguousarray(hits, dtype=HIT)
+        return self.L.hs_hand_over_views(self.h, a.ctypes.data, a.size, parts)
 
     def hand_over_sorted(self, hits):
         a = np.ascontiguousarray(hits, dtype=HIT)

@@ -260,6 +260,68 @@ def test_split_collect_equals_single_pass_collect():
         assert [a.ids(s) for s in range(nsolvers)] == [b.ids(s) for s in range(nsolvers)]
 
 
+def test_take_collect_equals_single_pass_collect():
+    """the direct pipeline swaps every solver's delta buffer out (SolverAssigs::takeUpdatesLocked, two
+    buffers in rotation) instead of copying it: same deltas, run parameters and assignment ids as the
+    one-pass collect, run after run (the rotation re-uses a buffer every second run)"""
+    rng = np.random.default_rng(15)
+    nvars, nsolvers = 400, 5
+    a, b = Rig(nvars, nsolvers), Rig(nvars, nsolvers)
+    for rnd in range(7):
+        for s in range(nsolvers):
+            for _ in range(int(rng.integers(0, 9))):
+                for v in rng.choice(nvars, size=int(rng.integers(0, 80)), replace=False):
+                    val = int(rng.integers(0, 3))
+                    a.set(s, int(v), val)
+                    b.set(s, int(v), val)
+                assert a.send(s) == b.send(s)
+        ua, pa = a.collect()
+        ub, pb = b.collect_take()
+        assert np.array_equal(ua, ub)
+        assert [_params_tuple(p) for p in pa] == [_params_tuple(p) for p in pb]
+        assert [a.ids(s) for s in range(nsolvers)] == [b.ids(s) for s in range(nsolvers)]
+
+
+@pytest.mark.parametrize("parts", [1, 3])
+def test_view_hand_over_equals_host_hand_over(parts):
+    """the direct pipeline's zero-copy hand-over (Reported::handOverViews: every solver's batch views the
+    ids / positions / literal stream the GPU wrote, one slice per device) hands over exactly what the
+    host path does, including the re-report rules across runs and the empty progress-marker batches"""
+    rng = np.random.default_rng(16)
+    nvars, nsolvers = 300, 6
+    a, b = Rig(nvars, nsolvers), Rig(nvars, nsolvers)
+    counts = {}
+    for i in range(3000):
+        n = int(rng.integers(1, 7))
+        lits = [2 * int(v) + int(rng.integers(0, 2)) for v in rng.choice(nvars, size=n, replace=False)]
+        assert a.add_clause(lits) == b.add_clause(lits)
+        counts[n] = counts.get(n, 0) + 1
+    a.drain(); b.drain()
+    for rnd in range(4):
+        for r in (a, b):
+            for s in range(nsolvers):
+                if s != 3:  # one solver without any assignment
+                    r.set(s, rnd, 0)
+                    r.send(s)
+            r.collect()
+        hits = set()
+        for s in (0, 1, 2, 4, 5):  # solver 3 has no hit; solver 5 few
+            for _ in range(3 if s == 5 else 300):
+                n = int(rng.integers(1, 7))
+                hits.add((s, n, int(rng.integers(0, min(counts[n], 40)))))  # small range: re-reports across runs
+        hits = np.array(sorted(hits), dtype=np.int64)
+        rec = np.zeros(len(hits), dtype=HIT)
+        rec["solver"], rec["len"], rec["idx"] = hits[:, 0], hits[:, 1], hits[:, 2]
+        rec["mask"] = rng.integers(1, 1 << 31, size=len(hits))
+        a.hand_over(rec[rng.permutation(len(rec))])
+        b.hand_over_views(rec[rng.permutation(len(rec))], parts)
+        for s in range(nsolvers):
+            pa, pb = a.pop_all(s), b.pop_all(s)
+            assert pa == pb
+            assert a.last_all_reported(s) == b.last_all_reported(s)
+            assert [a.solver_stat(s, k) for k in range(3)] == [b.solver_stat(s, k) for k in range(3)] if hasattr(a, "solver_stat") else True
+
+
 def test_sorted_hand_over_equals_host_hand_over():
     """a hit list sorted and resolved 'by the GPU' (ids + literal stream, Reported::handOverSorted: every
     solver's batch is one slice found by binary search) hands over exactly what the host path does"""
