@@ -495,16 +495,22 @@ template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS
 #pragma unroll
             for (int g = 0; g < G; g++)
                 if (all[g] | one[g]) { cnt++; lits += (unsigned int)len[g]; }
+            // (a solver's list is split in kRecShards sub-lists, picked by warp: 145 k appends on 32
+            // counters took k_exact from 19 to 55 us)
+            const unsigned int shard = warp & (kRecShards - 1), shardCap = a.recCap / kRecShards;
             unsigned int slot = 0;
-            if (cnt) slot = (unsigned int)atomicAdd(a.solverCtr + solver, (unsigned long long)cnt | ((unsigned long long)lits << 32));
+            if (cnt)
+                slot = (unsigned int)atomicAdd(a.solverCtr + solver * kRecShards + shard,
+                                               (unsigned long long)cnt | ((unsigned long long)lits << 32));
+            const size_t base = (size_t)solver * a.recCap + (size_t)shard * shardCap;
 #pragma unroll
             for (int g = 0; g < G; g++) {
                 const int idx = (int)__shfl_sync(FULL, sv0.z, g);
                 const uint32_t m = all[g] | one[g];
                 if (m) {
-                    if (slot < a.recCap) {
-                        a.recKeys[(size_t)solver * a.recCap + slot] = ((unsigned long long)(unsigned int)len[g] << 32) | (unsigned int)idx;
-                        a.recMasks[(size_t)solver * a.recCap + slot] = m;
+                    if (slot < shardCap) {
+                        a.recKeys[base + slot] = ((unsigned long long)(unsigned int)len[g] << 32) | (unsigned int)idx;
+                        a.recMasks[base + slot] = m;
                     }
                     slot++;
                 }
@@ -670,17 +676,21 @@ __global__ void __launch_bounds__(256) k_apply_direct(const VarUpdate *const *__
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_emit: one block per solver.  Sorts the solver's hit records by (length, index) -- the
-// reproducible hand-over order -- with a bitonic network (shared memory; lists that do not fit are
-// sorted in place in global memory by the same code), turns the lengths into literal positions, and
-// writes the FINISHED result of that solver -- clause ids, positions, literal stream -- straight into
-// the run's result buffer in mapped pinned host memory, coalesced.  The host builds the solver's
-// ClauseBatch as a view over that memory: no device-side global sort, no D2H copy of unknown size,
-// no host-side literal copies (reference: Reporter.cuh:103-126 + Reported.cu:160-204).
-// The block that finishes last writes the header and, after a system fence, the run's sequence number.
+// k_emit_sort + k_emit_write.  k_exact appended every solver's hits to kRecShards sub-lists (so that
+// a solver's appends are spread over several counters).  k_emit_sort, one block per solver: pulls the
+// sub-lists together, sorts the records by (length, index) -- the reproducible hand-over order -- with
+// a bitonic network (shared memory; lists that do not fit are compacted and sorted in place in global
+// memory by the same code), turns the lengths into literal positions and leaves the sorted list on
+// the device.  k_emit_write, many blocks per solver (PCIe needs many SMs writing): clause ids,
+// positions and the literal stream of every solver go straight into the run's result buffer in
+// mapped page-locked host memory, coalesced.  The host builds the solver's ClauseBatch as a view
+// over that memory: no device-side global sort, no D2H copy of unknown size, no host-side literal
+// copies (reference: Reporter.cuh:103-126 + Reported.cu:160-204).  The block that finishes last
+// writes the header and, after a system fence, the run's sequence number.
 // ---------------------------------------------------------------------------------------------
 constexpr int kEmitThreads = 1024;
-constexpr int kEmitSmemRecs = 8192; // records per solver sorted in shared memory (16 B each)
+constexpr int kEmitSmemRecs = 8192; // records per solver sorted in shared memory
+constexpr int kWriteChunk = 256;    // entries per block step of k_emit_write
 
 __device__ __forceinline__ int dirOfLen(const int *sLen, int nDir, int len) { // directory: descending length
     int lo = 0, hi = nDir - 1;
@@ -691,25 +701,20 @@ __device__ __forceinline__ int dirOfLen(const int *sLen, int nDir, int len) { //
     return lo;
 }
 
-__global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs a) {
+__global__ void __launch_bounds__(kEmitThreads) k_emit_sort(EmitArgs a) {
     extern __shared__ unsigned long long sDyn[];
-    __shared__ int sLen[128];
     __shared__ long long sPart[kEmitThreads / 32];
     __shared__ long long sBase[2];
+    __shared__ unsigned int sShardOff[kRecShards + 1];
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int nDir = min(a.nDir, 128);
-    for (int i = tid; i < nDir; i += kEmitThreads) sLen[i] = a.dir[i].len;
+    const unsigned int shardCap = a.recCap / kRecShards;
 
-    // this solver's list, and where its streams start (sum over the solvers before it)
-    const unsigned long long c = a.solverCtr[s];
-    const unsigned int nRaw = (unsigned int)c;
-    const unsigned int n = min(nRaw, a.recCap);
-    const long long nLits = (long long)(c >> 32);
+    // this solver's sub-lists, and where its streams start (sum over the solvers before it)
     if (wid == 0) {
         long long e = 0, l = 0;
-        for (int t = lane; t < s; t += 32) {
+        for (int t = lane; t < s * kRecShards; t += 32) {
             const unsigned long long ct = a.solverCtr[t];
-            e += min((unsigned int)ct, a.recCap);
+            e += min((unsigned int)ct, shardCap);
             l += (long long)(ct >> 32);
         }
         for (int o = 16; o; o >>= 1) {
@@ -718,27 +723,60 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs a) {
         }
         if (lane == 0) { sBase[0] = e; sBase[1] = l; }
     }
+    if (tid == 0) {
+        unsigned int off = 0;
+        for (int k = 0; k < kRecShards; k++) {
+            sShardOff[k] = off;
+            off += min((unsigned int)a.solverCtr[s * kRecShards + k], shardCap);
+        }
+        sShardOff[kRecShards] = off;
+    }
     __syncthreads();
     const long long entryBase = sBase[0], litBase = sBase[1];
-    const bool fits = nRaw <= a.recCap && entryBase + n <= a.entryCap && litBase + nLits <= a.litCap;
+    const unsigned int n = sShardOff[kRecShards];
+    long long nLits = 0;
+    bool shardOverflow = false;
+    for (int k = 0; k < kRecShards; k++) {
+        const unsigned long long ct = a.solverCtr[s * kRecShards + k];
+        nLits += (long long)(ct >> 32);
+        shardOverflow = shardOverflow || (unsigned int)ct > shardCap;
+    }
+    const bool fits = !shardOverflow && entryBase + n <= a.entryCap && litBase + nLits <= a.litCap;
 
     unsigned int P = 1;
     while (P < n) P <<= 1;
+    unsigned long long *const gK = a.recKeys + (size_t)s * a.recCap;
+    uint32_t *const gM = a.recMasks + (size_t)s * a.recCap;
+    int32_t *const gPos = a.recPos + (size_t)s * (a.recCap + 1);
     unsigned long long *K;
     uint32_t *M;
-    int32_t *pos;
-    if (P <= (unsigned int)kEmitSmemRecs) {
+    const bool inSmem = P <= (unsigned int)kEmitSmemRecs;
+    if (inSmem) {
         K = sDyn;
         M = reinterpret_cast<uint32_t *>(sDyn + kEmitSmemRecs);
-        pos = reinterpret_cast<int32_t *>(M + kEmitSmemRecs);
-        for (unsigned int i = tid; i < P; i += kEmitThreads) {
-            K[i] = i < n ? a.recKeys[(size_t)s * a.recCap + i] : ~0ull;
-            M[i] = i < n ? a.recMasks[(size_t)s * a.recCap + i] : 0u;
+        for (int k = 0; k < kRecShards; k++) {
+            const unsigned int o = sShardOff[k], c = sShardOff[k + 1] - o;
+            for (unsigned int i = tid; i < c; i += kEmitThreads) {
+                K[o + i] = gK[(size_t)k * shardCap + i];
+                M[o + i] = gM[(size_t)k * shardCap + i];
+            }
         }
-    } else { // P <= recCap (a power of two)
-        K = a.recKeys + (size_t)s * a.recCap;
-        M = a.recMasks + (size_t)s * a.recCap;
-        pos = a.recPos + (size_t)s * (a.recCap + 1);
+        for (unsigned int i = n + tid; i < P; i += kEmitThreads) { K[i] = ~0ull; M[i] = 0u; }
+    } else { // compact the sub-lists towards the front (destination <= source, one sub-list after the other), P <= recCap
+        K = gK;
+        M = gM;
+        for (int k = 1; k < kRecShards; k++) {
+            const unsigned int o = sShardOff[k], c = sShardOff[k + 1] - o;
+            for (unsigned int i0 = 0; i0 < c; i0 += kEmitThreads) { // chunk by chunk: a chunk's reads finish before its writes start
+                const unsigned int i = i0 + tid;
+                unsigned long long kv = 0;
+                uint32_t mv = 0;
+                if (i < c) { kv = gK[(size_t)k * shardCap + i]; mv = gM[(size_t)k * shardCap + i]; }
+                __syncthreads();
+                if (i < c) { gK[o + i] = kv; gM[o + i] = mv; }
+                __syncthreads();
+            }
+        }
         for (unsigned int i = n + tid; i < P; i += kEmitThreads) { K[i] = ~0ull; M[i] = 0u; }
     }
     __syncthreads();
@@ -779,54 +817,77 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs a) {
     __syncthreads();
     long long run = sPart[wid] + incl - mine;
     for (unsigned int i = i0; i < i1; i++) {
-        pos[i] = (int32_t)run;
+        gPos[i] = (int32_t)run;
         run += (long long)(K[i] >> 32);
     }
-    if (tid == 0) pos[n] = (int32_t)nLits;
-    __syncthreads();
-
-    if (fits) {
-        for (unsigned int i = tid; i < n; i += kEmitThreads) {
-            const unsigned long long key = K[i];
-            const int len = (int)(key >> 32), idx = (int)(unsigned int)key;
-            a.ids[entryBase + i] = a.dir[dirOfLen(sLen, nDir, len)].ids[idx];
-        }
-        for (unsigned int i = tid; i <= n; i += kEmitThreads) a.pos[entryBase + s + i] = pos[i];
-        // literal stream: thread per literal (consecutive threads -> consecutive host addresses)
-        for (long long q = tid; q < nLits; q += kEmitThreads) {
-            unsigned int lo = 0, hi = n; // last i with pos[i] <= q
-            while (hi - lo > 1) {
-                const unsigned int mid = (lo + hi) >> 1;
-                if ((long long)pos[mid] <= q) lo = mid; else hi = mid;
-            }
-            const unsigned long long key = K[lo];
-            const int len = (int)(key >> 32), idx = (int)(unsigned int)key, j = (int)(q - pos[lo]);
-            const int32_t *src = a.dir[dirOfLen(sLen, nDir, len)].base + (size_t)(idx / kTileClauses) * kTileClauses * len +
-                                 tileSlot(idx % kTileClauses);
-            a.lits[litBase + q] = __ldg(src + (size_t)j * kTileClauses);
-        }
-    }
-    if (P <= (unsigned int)kEmitSmemRecs) // the sorted list stays on the device: activity bumps, parity hooks
-        for (unsigned int i = tid; i < n; i += kEmitThreads) {
-            a.recKeys[(size_t)s * a.recCap + i] = K[i];
-            a.recMasks[(size_t)s * a.recCap + i] = M[i];
-        }
+    if (tid == 0) gPos[n] = (int32_t)nLits;
+    if (inSmem) // the sorted list stays on the device: k_emit_write, activity bumps, parity hooks
+        for (unsigned int i = tid; i < n; i += kEmitThreads) { gK[i] = K[i]; gM[i] = M[i]; }
     if (tid == 0) {
-        a.hdr->solver[s].entryBase = entryBase;
-        a.hdr->solver[s].litBase = litBase;
-        a.hdr->solver[s].n = (int32_t)n;
-        a.hdr->solver[s].nLits = (int32_t)nLits;
-    }
-    __syncthreads();
-    if (tid == 0) {
+        EmitSolver &es = a.solverInfo[s];
+        es.entryBase = entryBase;
+        es.litBase = litBase;
+        es.n = fits ? (int32_t)n : -1; // -1: nothing of this solver is written (the run is repeated)
+        es.nLits = (int32_t)nLits;
+        es.nSorted = n;
         unsigned int fl = 0;
-        if (nRaw > a.recCap) fl |= 2u;
+        if (shardOverflow) fl |= 2u;
         else if (!fits) fl |= 4u;
         if (fl) atomicOr(a.ticket + 1, fl);
-        atomicMax(a.ticket + 2, nRaw);
+        unsigned int worst = 0; // what recCap would have had to be
+        for (int k = 0; k < kRecShards; k++) worst = max(worst, (unsigned int)a.solverCtr[s * kRecShards + k]);
+        atomicMax(a.ticket + 2, worst * kRecShards);
+    }
+}
+
+// blockIdx.y = solver; the blocks of a solver take chunks of kWriteChunk entries in turn
+__global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
+    __shared__ int sLen[128];
+    __shared__ int32_t sPos[kWriteChunk + 1];
+    const int s = blockIdx.y, tid = threadIdx.x;
+    const int nDir = min(a.nDir, 128);
+    for (int i = tid; i < nDir; i += blockDim.x) sLen[i] = a.dir[i].len;
+    const EmitSolver es = a.solverInfo[s];
+    const unsigned long long *__restrict__ K = a.recKeys + (size_t)s * a.recCap;
+    const int32_t *__restrict__ gPos = a.recPos + (size_t)s * (a.recCap + 1);
+    const int n = es.n; // -1: this solver does not fit
+    for (int c0 = blockIdx.x * kWriteChunk; c0 < n; c0 += gridDim.x * kWriteChunk) {
+        const int cnt = min(kWriteChunk, n - c0);
+        __syncthreads();
+        for (int i = tid; i <= cnt; i += blockDim.x) sPos[i] = gPos[c0 + i];
+        __syncthreads();
+        if (tid < cnt) {
+            const unsigned long long key = K[c0 + tid];
+            a.ids[es.entryBase + c0 + tid] = a.dir[dirOfLen(sLen, nDir, (int)(key >> 32))].ids[(unsigned int)key];
+        }
+        for (int i = tid; i < cnt + (c0 + cnt == n ? 1 : 0); i += blockDim.x) a.pos[es.entryBase + s + c0 + i] = sPos[i];
+        // literal stream of these entries: thread per literal (consecutive threads -> consecutive host addresses)
+        const int q0 = sPos[0], q1 = sPos[cnt];
+        for (int q = q0 + tid; q < q1; q += blockDim.x) {
+            int lo = 0, hi = cnt; // last i with sPos[i] <= q
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (sPos[mid] <= q) lo = mid; else hi = mid;
+            }
+            const unsigned long long key = K[c0 + lo];
+            const int len = (int)(key >> 32), idx = (int)(unsigned int)key, j = q - sPos[lo];
+            const int32_t *src = a.dir[dirOfLen(sLen, nDir, len)].base + (size_t)(idx / kTileClauses) * kTileClauses * len +
+                                 tileSlot(idx % kTileClauses);
+            a.lits[es.litBase + q] = __ldg(src + (size_t)j * kTileClauses);
+        }
+    }
+    if (n == 0 && blockIdx.x == 0 && tid == 0) a.pos[es.entryBase + s] = 0;
+    if (blockIdx.x == 0 && tid == 0) {
+        a.hdr->solver[s].entryBase = es.entryBase;
+        a.hdr->solver[s].litBase = es.litBase;
+        a.hdr->solver[s].n = max(es.n, 0);
+        a.hdr->solver[s].nLits = es.nLits;
+    }
+    __syncthreads();
+    if (tid == 0) {
         __threadfence_system(); // this block's stores have been performed in host memory (cumulative over the barrier)
         const unsigned int ticket = atomicAdd(a.ticket, 1u);
-        if (ticket == gridDim.x - 1) {
+        if (ticket == gridDim.x * gridDim.y - 1) {
             __threadfence();
             const volatile Counters *cn = a.counters;
             unsigned int flags = *reinterpret_cast<volatile unsigned int *>(a.ticket + 1);
@@ -836,9 +897,8 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs a) {
             }
             long long tot = 0, lt = 0;
             for (int t = 0; t < a.nSolvers; t++) {
-                const unsigned long long ct = a.solverCtr[t];
-                tot += min((unsigned int)ct, a.recCap);
-                lt += (long long)(ct >> 32);
+                tot += a.solverInfo[t].nSorted;
+                lt += a.solverInfo[t].nLits;
             }
             a.hdr->nTotal = tot;
             a.hdr->litTotal = lt;
@@ -856,10 +916,10 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(EmitArgs a) {
 
 // activity bumps straight from the sorted per-solver record lists (blockIdx.y = solver)
 __global__ void k_bump_recs(const unsigned long long *__restrict__ recKeys, unsigned int recCap,
-                            const unsigned long long *__restrict__ solverCtr, const LenDir *__restrict__ dir, int nDir, float inc,
+                            const EmitSolver *__restrict__ solverInfo, const LenDir *__restrict__ dir, int nDir, float inc,
                             int *overflow) {
     const int s = blockIdx.y;
-    const unsigned int n = min((unsigned int)solverCtr[s], recCap);
+    const unsigned int n = solverInfo[s].nSorted;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned long long key = recKeys[(size_t)s * recCap + i];
         const int len = (int)(key >> 32), idx = (int)(unsigned int)key;
@@ -1213,25 +1273,28 @@ void launchApplyDirect(const VarUpdate *const *src, const SolverRunParams *param
 
 void launchEmit(const EmitArgs &a, cudaStream_t s, int64_t *launches) {
     if (a.nSolvers <= 0) return;
-    static const size_t smem = (size_t)kEmitSmemRecs * (sizeof(unsigned long long) + sizeof(uint32_t)) + (size_t)(kEmitSmemRecs + 1) * sizeof(int32_t);
+    static const size_t smem = (size_t)kEmitSmemRecs * (sizeof(unsigned long long) + sizeof(uint32_t));
     static bool configured[64] = {}; // per device: the attribute belongs to the function in that device's context
     int dev = 0;
     GSS_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        GSS_CUDA(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSS_CUDA(cudaFuncSetAttribute(k_emit_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    k_emit<<<a.nSolvers, kEmitThreads, smem, s>>>(a);
+    k_emit_sort<<<a.nSolvers, kEmitThreads, smem, s>>>(a);
+    // enough writers for PCIe: the blocks of a solver take chunks of its entries in turn
+    const unsigned int perSolver = std::max(1u, std::min(64u, 1184u / (unsigned int)a.nSolvers));
+    k_emit_write<<<dim3(perSolver, a.nSolvers, 1), 256, 0, s>>>(a);
     checkLaunch("k_emit");
-    ++*launches;
+    *launches += 2;
 }
 
-void launchBumpFromRecs(const unsigned long long *recKeys, unsigned int recCap, const unsigned long long *solverCtr, int nSolvers,
+void launchBumpFromRecs(const unsigned long long *recKeys, unsigned int recCap, const EmitSolver *solverInfo, int nSolvers,
                         unsigned int maxCount, const LenDir *dir, int nDir, float inc, int *overflow, cudaStream_t s,
                         int64_t *launches) {
     if (nSolvers <= 0 || maxCount == 0) return;
     dim3 grid(std::max(1u, std::min((maxCount + 255u) / 256u, 64u)), nSolvers, 1);
-    k_bump_recs<<<grid, 256, 0, s>>>(recKeys, recCap, solverCtr, dir, nDir, inc, overflow);
+    k_bump_recs<<<grid, 256, 0, s>>>(recKeys, recCap, solverInfo, dir, nDir, inc, overflow);
     checkLaunch("k_bump_recs");
     ++*launches;
 }

@@ -24,6 +24,7 @@ struct DeviceTables {
 };
 
 constexpr int kMaxGroups = 8; // solver groups of 32 (256 solver threads)
+constexpr int kRecShards = 8; // sub-lists of a solver's hit record list (direct pipeline)
 
 // device-side counters of one run
 struct Counters {
@@ -64,10 +65,11 @@ struct CheckArgs {
     // direct pipeline: k_exact appends its hits to PER-SOLVER record lists instead of one global hit
     // buffer (lane = solver: one 64-bit atomicAdd per lane and warp step reserves the slots and adds up
     // the literal count of that solver's result stream).  recKeys == nullptr: global hit buffer.
-    unsigned long long *solverCtr = nullptr; // [solver] records (low 32 bits) | literals (high 32 bits)
-    unsigned long long *recKeys = nullptr;   // [solver][recCap]  clause length << 32 | clause index
-    uint32_t *recMasks = nullptr;            // [solver][recCap]  slot mask of the hit
-    unsigned int recCap = 0;
+    // A solver's list is split in kRecShards sub-lists (shard = warp % kRecShards) of recCap / kRecShards.
+    unsigned long long *solverCtr = nullptr; // [solver][shard] records (low 32 bits) | literals (high 32 bits)
+    unsigned long long *recKeys = nullptr;   // [solver][shard][recCap / kRecShards]  clause length << 32 | clause index
+    uint32_t *recMasks = nullptr;            // same shape: slot mask of the hit
+    unsigned int recCap = 0;                 // per solver, a power of two >= kRecShards
 };
 
 void launchFillTables(const DeviceTables &t, int varFrom, cudaStream_t s, int64_t *launches);
@@ -166,14 +168,22 @@ struct RunHdr {
         int32_t nLits;
     } solver[kMaxSolvers];
 };
+struct EmitSolver { // what k_emit_sort leaves for k_emit_write, the activity bumps and the parity hook
+    long long entryBase, litBase;
+    int32_t n;       // entries to write (-1: the solver's result does not fit, nothing is written)
+    int32_t nLits;
+    uint32_t nSorted; // records in the solver's sorted list
+    uint32_t pad;
+};
 struct EmitArgs {
     const LenDir *dir;
     int nDir;
     int nSolvers;
-    unsigned long long *solverCtr;
-    unsigned long long *recKeys; // sorted in place
+    unsigned long long *solverCtr; // [solver][kRecShards]
+    unsigned long long *recKeys; // [solver][recCap]: sub-lists in, one sorted list out
     uint32_t *recMasks;
-    int32_t *recPos;             // [solver][recCap + 1] scratch for lists too large for shared memory
+    int32_t *recPos;             // [solver][recCap + 1] literal positions of the sorted list
+    EmitSolver *solverInfo;      // [solver]
     unsigned int recCap;         // power of two
     Counters *counters;
     unsigned int survCap;
@@ -194,7 +204,7 @@ void launchEmit(const EmitArgs &a, cudaStream_t s, int64_t *launches);
 void launchApplyDirect(const VarUpdate *const *src, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
                        const DeviceTables &t, VarUpdate *keep, int numSMs, cudaStream_t s, int64_t *launches);
 // activity bumps from the sorted per-solver record lists of a finished run
-void launchBumpFromRecs(const unsigned long long *recKeys, unsigned int recCap, const unsigned long long *solverCounts, int nSolvers,
+void launchBumpFromRecs(const unsigned long long *recKeys, unsigned int recCap, const EmitSolver *solverInfo, int nSolvers,
                         unsigned int maxCount, const LenDir *dir, int nDir, float inc, int *overflow, cudaStream_t s, int64_t *launches);
 
 // register-only LOP3 micro-benchmark: thread-level LOP3 per second on this device

@@ -94,10 +94,12 @@ static size_t pow2AtLeast(size_t x) {
 
 void Sharer::ensureDirectBuffers(RunSlot &slot) {
     const size_t S = (size_t)std::max(1, slot.nSolvers);
-    if (slot.ctrDev.capacity() < (size_t)kMaxSolvers) {
-        slot.ctrDev.reserve(kMaxSolvers, 0, stream_);
+    if (slot.ctrDev.capacity() < (size_t)kMaxSolvers * kRecShards) {
+        slot.ctrDev.reserve((size_t)kMaxSolvers * kRecShards, 0, stream_);
+        slot.solverInfo.reserve(kMaxSolvers, 0, stream_);
         slot.ticketDev.reserve(4, 0, stream_);
-        GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, kMaxSolvers * sizeof(unsigned long long), stream_));
+        GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)kMaxSolvers * kRecShards * sizeof(unsigned long long), stream_));
+        GSS_CUDA(cudaMemsetAsync(slot.solverInfo.data(), 0, (size_t)kMaxSolvers * sizeof(EmitSolver), stream_));
         GSS_CUDA(cudaMemsetAsync(slot.ticketDev.data(), 0, 4 * sizeof(unsigned int), stream_));
     }
     slot.recCap = (unsigned int)recCap_;
@@ -108,66 +110,74 @@ void Sharer::ensureDirectBuffers(RunSlot &slot) {
     resDev_.reserve(sizeof(Counters) + hitCap_ * sizeof(HitRecord), 0, stream_);
 }
 
-// Collect + launch.  Falls back to the staged path for the one run that rebuilds the device tables
-// (its update list names every variable of every solver and is built by the GPU thread itself).
-bool Sharer::startRunDirect(RunSlot &slot) {
-    int64_t h2d = 0;
-    bool rebuild = false;
-    if (!prepareRun(slot, rebuild, h2d)) return false;
-    if (rebuild) {
-        slot.direct = false;
-        {
-            PhaseTimer t(hostPhases_[3]);
-            collectBatch(slot, true);
-        }
-        launchRun(slot, slot.updHost.data() + payloadPrefixRecords(slot.nSolvers), slot.nUpdates, h2d);
-        return true;
-    }
-    slot.direct = true;
+// Collect: every solver's delta buffer is swapped out and read where it lies.  The one run that
+// rebuilds the device tables lists every variable of every solver instead; that list is built by
+// the GPU thread in the slot's (page-locked) staging buffer and read from there the same way.
+// Fills slot.headHost = [directory][run parameters][per-solver delta pointers] and the slot's counts.
+void Sharer::collectDirect(RunSlot &slot, bool rebuild) {
     const int S = slot.nSolvers;
     const int groups = (S + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
-    // header = [directory][run parameters][per-solver delta pointers]
     slot.srcOff = (slot.dirBytes + (size_t)S * sizeof(SolverRunParams) + 15) / 16 * 16;
     slot.headHost.resize(slot.srcOff + (size_t)S * sizeof(void *));
+    slot.aggStart.assign(groups, 0u);
+    slot.aggOnDevice = false;
+    slot.maxUpd = 0;
+    slot.staged.clear();
+    PhaseTimer t(hostPhases_[3]);
+    if (rebuild) {
+        collectBatch(slot, true); // full update lists in slot.updHost, behind the payload prefix
+        SolverRunParams *params = (SolverRunParams *)(slot.headHost.data() + slot.dirBytes);
+        const VarUpdate **src = (const VarUpdate **)(slot.headHost.data() + slot.srcOff);
+        const VarUpdate *base = slot.updHost.data() + payloadPrefixRecords(S);
+        for (int s = 0; s < S; s++) {
+            src[s] = base + params[s].updStart;
+            if (!slot.updHost.pinned() && params[s].updCount > 0) slot.staged.push_back({s, (size_t)(src[s] - slot.updHost.data())});
+            slot.aggStart[s / kMaxSolversPerGroup] |= params[s].usedAggBits;
+            slot.maxUpd = std::max(slot.maxUpd, (int)params[s].updCount);
+        }
+        return;
+    }
     SolverRunParams *params = (SolverRunParams *)(slot.headHost.data() + slot.dirBytes);
     const VarUpdate **src = (const VarUpdate **)(slot.headHost.data() + slot.srcOff);
     slot.ids.assign(S, AssigIds{});
     slot.assigCount = 0;
-    slot.aggStart.assign(groups, 0u);
-    slot.aggOnDevice = false;
-    slot.maxUpd = 0;
     slot.updHost.clear();
-    std::vector<std::pair<int, size_t>> staged; // solvers whose buffer is not page-locked: {solver, offset in updHost}
     int64_t total = 0;
-    {
-        PhaseTimer t(hostPhases_[3]);
-        TimeAdder ta(globalStats_[G_timeSpentFillingAssigs], opts_.quickProf != 0);
-        // one solver at a time, its lock held only for the O(1) swap (reference: locks, copies and
-        // unlocks one solver after the other, Assigs.cu:346-352; a busy solver is skipped for this run)
-        for (int s = 0; s < S; s++) {
-            SolverAssigs &sa = assigs_->solver(s);
-            memset(&params[s], 0, sizeof(SolverRunParams));
-            params[s].updStart = (int32_t)total;
-            src[s] = nullptr;
-            if (!sa.tryLock()) continue;
-            bool pinned = true;
-            sa.takeUpdatesLocked(src[s], (int32_t)total, params[s], slot.ids[s], &pinned);
-            sa.unlock();
-            const int n = params[s].updCount;
-            if (!pinned && n > 0) { // ordinary memory: stage it like the reference does
-                staged.push_back({s, slot.updHost.size()});
-                memcpy(slot.updHost.append((size_t)n), src[s], (size_t)n * sizeof(VarUpdate));
-            }
-            total += n;
-            slot.assigCount += slot.ids[s].count;
-            slot.aggStart[s / kMaxSolversPerGroup] |= params[s].usedAggBits;
-            slot.maxUpd = std::max(slot.maxUpd, n);
+    TimeAdder ta(globalStats_[G_timeSpentFillingAssigs], opts_.quickProf != 0);
+    // one solver at a time, its lock held only for the O(1) swap (reference: locks, copies and unlocks
+    // one solver after the other, Assigs.cu:346-352; a busy solver is skipped for this run)
+    for (int s = 0; s < S; s++) {
+        SolverAssigs &sa = assigs_->solver(s);
+        memset(&params[s], 0, sizeof(SolverRunParams));
+        params[s].updStart = (int32_t)total;
+        src[s] = nullptr;
+        if (!sa.tryLock()) continue;
+        bool pinned = true;
+        sa.takeUpdatesLocked(src[s], (int32_t)total, params[s], slot.ids[s], &pinned);
+        sa.unlock();
+        const int n = params[s].updCount;
+        if (!pinned && n > 0) { // ordinary memory (page-locked budget exhausted): stage it like the reference does
+            slot.staged.push_back({s, slot.updHost.size()});
+            memcpy(slot.updHost.append((size_t)n), src[s], (size_t)n * sizeof(VarUpdate));
         }
+        total += n;
+        slot.assigCount += slot.ids[s].count;
+        slot.aggStart[s / kMaxSolversPerGroup] |= params[s].usedAggBits;
+        slot.maxUpd = std::max(slot.maxUpd, n);
     }
     slot.nUpdates = total;
+}
+
+// Launch the run described by slot.headHost on this device: header H2D, deferred collapse of the
+// previous batch, k_apply_direct (the deltas cross PCIe inside it), check kernels, k_emit.
+void Sharer::launchDirect(RunSlot &slot, int64_t h2d) {
+    const int S = slot.nSolvers;
+    SolverRunParams *params = (SolverRunParams *)(slot.headHost.data() + slot.dirBytes);
+    const VarUpdate **src = (const VarUpdate **)(slot.headHost.data() + slot.srcOff);
+    slot.direct = true;
     slot.dense = false;
-    slot.updDev.reserve((size_t)std::max<int64_t>(total, 1), 0, stream_);
-    for (auto &st : staged) {
+    slot.updDev.reserve((size_t)std::max<int64_t>(slot.nUpdates, 1), 0, stream_);
+    for (auto &st : slot.staged) { // deltas that are not in page-locked memory go up as ordinary copies
         const int s = st.first;
         VarUpdate *dst = slot.updDev.data() + params[s].updStart;
         GSS_CUDA(cudaMemcpyAsync(dst, slot.updHost.data() + st.second, (size_t)params[s].updCount * sizeof(VarUpdate),
@@ -176,7 +186,7 @@ bool Sharer::startRunDirect(RunSlot &slot) {
     }
     slot.headDev.reserve(slot.headHost.size(), 0, stream_);
     GSS_CUDA(cudaMemcpyAsync(slot.headDev.data(), slot.headHost.data(), slot.headHost.size(), cudaMemcpyHostToDevice, stream_));
-    h2d += (int64_t)slot.headHost.size() + total * (int64_t)sizeof(VarUpdate); // the deltas cross PCIe inside k_apply_direct
+    h2d += (int64_t)slot.headHost.size() + slot.nUpdates * (int64_t)sizeof(VarUpdate);
     ensureDirectBuffers(slot);
     GSS_CUDA(cudaEventRecord(slot.evH2DDone, stream_));
 
@@ -196,6 +206,14 @@ bool Sharer::startRunDirect(RunSlot &slot) {
     if (slot.nUpdates) collapseSlot_ = (int)(&slot - slots_);
     lastStarted_ = (int)(&slot - slots_);
     lastH2D_ = h2d;
+}
+
+bool Sharer::startRunDirect(RunSlot &slot) {
+    int64_t h2d = 0;
+    bool rebuild = false;
+    if (!prepareRun(slot, rebuild, h2d)) return false;
+    collectDirect(slot, rebuild);
+    launchDirect(slot, h2d);
     return true;
 }
 
@@ -209,7 +227,8 @@ void Sharer::launchDirectCheck(RunSlot &slot) {
     ensureDirectBuffers(slot);
     if (lastDirect_ == &slot) lastDirect_ = nullptr; // its record lists are about to be overwritten
     slot.seq = ++directSeq_;
-    slot.runBuf = runBufs_->acquire(entryGuess_, litGuess_);
+    // capacities in powers of two: a released buffer fits the next run although the guesses drift
+    slot.runBuf = runBufs_->acquire((int64_t)pow2AtLeast((size_t)entryGuess_), (int64_t)pow2AtLeast((size_t)litGuess_));
     launchCheckKernels(slot, false);
     launchEmitFor(slot);
 }
@@ -225,6 +244,7 @@ void Sharer::launchEmitFor(RunSlot &slot) {
     e.recKeys = slot.recKeys.data();
     e.recMasks = slot.recMasks.data();
     e.recPos = slot.recPos.data();
+    e.solverInfo = slot.solverInfo.data();
     e.recCap = slot.recCap;
     e.counters = (Counters *)resDev_.data();
     e.survCap = (unsigned int)survCap_;
@@ -279,7 +299,7 @@ void Sharer::finishRunDirect(RunSlot &slot) {
             for (int g = 0; g < kMaxGroups; g++) maxSurv = std::max(maxSurv, (size_t)h->nSurvivors[g]);
             survCap_ = std::max(survCap_ * 2, maxSurv + maxSurv / 4);
         }
-        if (flags & 2u) recCap_ = pow2AtLeast(std::max<size_t>(recCap_ * 2, (size_t)h->maxRec + h->maxRec / 4));
+        if (flags & 2u) recCap_ = pow2AtLeast(std::max<size_t>(recCap_ * 2, (size_t)h->maxRec + h->maxRec / 2));
         if (flags & 4u) {
             entryGuess_ = std::max<int64_t>(entryGuess_ * 2, h->nTotal + h->nTotal / 2);
             litGuess_ = std::max<int64_t>(litGuess_ * 2, h->litTotal + h->litTotal / 2);
@@ -322,7 +342,7 @@ void Sharer::bumpDirect(RunSlot &slot, unsigned int maxRec) {
     bumpFlagDev_.reserve(1, 0, stream_);
     bumpFlagHost_.resize(1);
     GSS_CUDA(cudaMemsetAsync(bumpFlagDev_.data(), 0, sizeof(int), stream_));
-    launchBumpFromRecs(slot.recKeys.data(), slot.recCap, slot.ctrDev.data(), slot.nSolvers, std::min(maxRec, slot.recCap),
+    launchBumpFromRecs(slot.recKeys.data(), slot.recCap, slot.solverInfo.data(), slot.nSolvers, std::min(maxRec, slot.recCap),
                        (const LenDir *)bumpDirDev_.data(), (int)dir.size(), db_->activityIncrement(), bumpFlagDev_.data(), stream_,
                        &launches_);
     GSS_CUDA(cudaMemcpyAsync(bumpFlagHost_.data(), bumpFlagDev_.data(), sizeof(int), cudaMemcpyDeviceToHost, stream_));

@@ -337,7 +337,7 @@ bool Sharer::launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly) {
     const bool recs = slot.direct && !dense;
     if (slot.direct && !recs) ensureResultBuffers();
     GSS_CUDA(cudaMemsetAsync(resDev_.data(), 0, sizeof(Counters), stream_));
-    if (recs) GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)kMaxSolvers * sizeof(unsigned long long), stream_));
+    if (recs) GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)kMaxSolvers * kRecShards * sizeof(unsigned long long), stream_));
     int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
     int lastGroup = -1;
     for (int g = 0; g < groups; g++)
@@ -1017,7 +1017,7 @@ double Sharer::timeCheck(int iters, int mode) {
         if (mode <= 2) {
             launchCheckKernels(slot, dense, filterOnly);
         } else if (mode == 3) {
-            if (slot.direct) GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)kMaxSolvers * sizeof(unsigned long long), stream_));
+            if (slot.direct) GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)kMaxSolvers * kRecShards * sizeof(unsigned long long), stream_));
             for (int g = 0; g < groups; g++)
                 if (slot.aggStart[g]) launchExactOnly(checkArgs(slot, g, slot.direct), dims_, numSMs_, stream_, &launches_);
         } else if (mode == 6) {

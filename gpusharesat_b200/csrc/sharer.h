@@ -129,13 +129,15 @@ private:
         bool checked = false;       // check kernels + k_emit were launched (some solver had a frozen slot)
         uint32_t seq = 0;           // what k_emit writes into the header last
         std::shared_ptr<RunBuf> runBuf;
-        DevBuf<unsigned long long> ctrDev;  // [kMaxSolvers] records | literals << 32
+        DevBuf<unsigned long long> ctrDev;  // [kMaxSolvers][kRecShards] records | literals << 32
+        DevBuf<EmitSolver> solverInfo;      // [kMaxSolvers] written by k_emit_sort
         DevBuf<unsigned long long> recKeys; // [nSolvers][recCap]
         DevBuf<uint32_t> recMasks;
         DevBuf<int32_t> recPos;             // [nSolvers][recCap + 1]
         DevBuf<unsigned int> ticketDev;     // 4 words
         unsigned int recCap = 0;
         size_t srcOff = 0;          // offset of the per-solver delta pointers in headHost / headDev
+        std::vector<std::pair<int, size_t>> staged; // solvers whose deltas are not page-locked: {solver, offset in updHost}
         const LenDir *dirDev() const { return (const LenDir *)headDev.data(); }
         const SolverRunParams *paramsDev() const { return (const SolverRunParams *)(headDev.data() + dirBytes); }
         size_t dirBytes = 0;
@@ -145,6 +147,8 @@ private:
     // page-locked buffers, results are written by the GPU into page-locked result buffers that the
     // solvers' ClauseBatches view in place ----
     bool startRunDirect(RunSlot &slot);
+    void collectDirect(RunSlot &slot, bool rebuild);
+    void launchDirect(RunSlot &slot, int64_t h2d);
     void launchDirectCheck(RunSlot &slot);
     void launchEmitFor(RunSlot &slot);
     void finishRunDirect(RunSlot &slot);
