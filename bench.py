@@ -68,6 +68,8 @@ def parse():
     p.add_argument("--dense-iters", type=int, default=3)
     p.add_argument("--prod-iters", type=int, default=20)
     p.add_argument("--filter-sweep", action="store_true", help="time every variant of the level-1 kernel")
+    p.add_argument("--devices", type=int, default=1,
+                   help="single process, GPUSHARE_DEVICES=N: the sharer itself shards over N devices (csrc/multi.cu)")
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                    help="N > 1: weak = --clauses per GPU (database grows with N), strong = --clauses in total")
     p.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -240,8 +242,10 @@ def workload_config(a):
                       f"{(1 - a.p_agree) * (1 - a.p_undef):.4f}/{a.p_undef}",
             "churn_per_assignment": a.churn,
             "l2_policy": "inputs larger than L2 (clause arenas + assignment tables > 126 MB)",
-            "parallelism": (f"clause tiles sharded x{a.gpus} ({a.scaling} scaling: {a.clauses} clauses in total), "
-                            f"assignments broadcast, exchange = {a.exchange}") if a.gpus > 1 else "single GPU"}
+            "parallelism": ((f"clause tiles sharded x{a.gpus} ({a.scaling} scaling: {a.clauses} clauses in total), " +
+                             ("one process, GPUSHARE_DEVICES: every device reads the batch from page-locked host memory and "
+                              "writes its results there" if getattr(a, "devices", 1) > 1 else
+                              f"assignments broadcast, exchange = {a.exchange}")) if a.gpus > 1 else "single GPU")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -472,6 +476,12 @@ def run_b200(a):
     from gpusharesat_b200 import GpuClauseSharer, GpuClauseSharerOptions
     rank, world, local, dist = 0, 1, 0, None
     os.environ.setdefault("GPUSHARE_DEVICE", "0")
+    if a.devices > 1:  # one process, N devices behind the one sharer
+        os.environ["GPUSHARE_DEVICES"] = str(a.devices)
+        a.gpus = a.devices
+        if a.scaling == "weak":
+            a.clauses *= a.devices
+        a.no_dense = a.no_ref_gpu = True
 
     sig, offsets, lits = make_inputs(a)
     L_total, A = int(offsets[-1]), a.solvers * a.slots
@@ -557,7 +567,7 @@ def run_b200(a):
         total_hits = sum(hits)
 
     out = {
-        "metric": METRIC, "value": L_total * A * a.steps / dev_s, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "metric": METRIC, "value": L_total * A * a.steps / dev_s, "unit": UNIT, "n_gpus": max(world, a.devices), "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(a),
         "e2e": {"value": L_total * A * a.steps / wall_s, "unit": UNIT, "ms_per_step": 1e3 * wall_s / a.steps,
@@ -580,6 +590,19 @@ def run_b200(a):
                           "gpu_runs": sh.getGlobalStat(3)},
     }
 
+    if a.devices > 1:
+        out["phases_us_per_step"]["note"] = "device times = the slowest device's (max over the devices of every phase)"
+        if not a.no_cpu and first_hits is not None:
+            from oracle_lib import check_db
+            d, t, start = batch_words(a, sig)
+            n_sample = min(a.clauses, a.parity_clauses)
+            off = offsets[: n_sample + 1]
+            cpu_hits = check_db(off, lits[: off[-1]], d, t, start, use_filter=1, nthreads=os.cpu_count() or 1, cap=1 << 22)
+            g = first_hits[first_hits["clause_id"] < n_sample]
+            out["parity_sample"] = {"clauses": int(n_sample), "gpu_hits": int(len(g)), "cpu_hits": int(len(cpu_hits)),
+                                    "identical": bool(np.array_equal(g, cpu_hits))}
+        print(json.dumps(out))
+        return
     if rank == 0 and world == 1:
         # kernel-only timings on the last batch (tables still resident)
         push_batch(sh, streams, a.slots, pool)

@@ -266,10 +266,29 @@ float ClauseDb::approxNthAct(int64_t n) const {
     return std::numeric_limits<float>::max();
 }
 
-void ClauseDb::reduceDb(cudaStream_t stream) {
+void ClauseDb::syncActivitiesFromDevice(cudaStream_t stream) {
     // apply host-decided rescales to the device copies, then bring the activities home
     applyPendingDeviceRescales(stream);
     downloadActivities(stream);
+}
+
+void ClauseDb::copyActivitiesFrom(const ClauseDb &other) {
+    GSS_CHECK(other.maxLen_ == maxLen_);
+    for (int s = 1; s <= maxLen_; s++) {
+        PerLen &pl = *perLen_[s];
+        const PerLen &po = *other.perLen_[s];
+        GSS_CHECK(pl.meta.size() == po.meta.size());
+        for (size_t i = 0; i < pl.meta.size(); i++) pl.meta[i].activity = po.meta[i].activity;
+    }
+    pendingDeviceRescales_ = 0; // the copied values are final
+}
+
+void ClauseDb::reduceDb(cudaStream_t stream) {
+    syncActivitiesFromDevice(stream);
+    reduceAfterSync(stream);
+}
+
+void ClauseDb::reduceAfterSync(cudaStream_t stream) {
     reduceHost();
     for (int s = maxLen_; s >= 3; s--) {
         PerLen &pl = *perLen_[s];

@@ -103,6 +103,11 @@ public:
 
     // reference HostClauses::reduceDb (actOnly), Clauses.cu:426-465 / 249-282
     void reduceDb(cudaStream_t stream);
+    // the two halves of reduceDb, and (several devices in one process: every device keeps the whole
+    // database, the activities are authoritative on the first one) taking the activities from a twin
+    void syncActivitiesFromDevice(cudaStream_t stream);
+    void reduceAfterSync(cudaStream_t stream);
+    void copyActivitiesFrom(const ClauseDb &other);
     void reduceHost(); // the host half: pick the threshold, compact the mirror (no device work)
     // Device-resident activities (product path): hits bump them on the GPU, the host copy is only
     // refreshed right before a reduceDb.

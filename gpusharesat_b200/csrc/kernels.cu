@@ -403,6 +403,41 @@ __device__ __forceinline__ void reportHits(const CheckArgs &a, uint32_t m, int s
 // load and one coalesced T2 row (8 B per lane).  (reference dCheckOneClauseAllSolvers /
 // dCheckOneClauseOneSolver, GpuRunner.cu:68-131: serial per thread, one solver after the other)
 // ---------------------------------------------------------------------------------------------
+// Direct pipeline: the hits a warp has staged go to PER-SOLVER record lists.  Lane l serves solver
+// groupBase + l: it counts its records among the staged ones (broadcast reads of shared memory),
+// reserves their slots and adds up their literals with ONE 64-bit atomic, and copies them.  The
+// atomics' round trips are paid once per ~64 staged hits, not once per warp step.  A solver's list is
+// split in kRecShards sub-lists, picked by warp, so that the appends of a solver spread over counters.
+__device__ __forceinline__ void flushRecs(const CheckArgs &a, WarpStage<HitRecord> &stage, int lane, unsigned int warp) {
+    const int n = stage.n;
+    if (n == 0) return;
+    __syncwarp();
+    const int mySolver = a.groupBase + lane;
+    unsigned int cnt = 0, lits = 0;
+    for (int i = 0; i < n; i++) {
+        const HitRecord r = stage.buf[i];
+        if (r.solver == mySolver) { cnt++; lits += (unsigned int)r.len; }
+    }
+    if (cnt) {
+        const unsigned int shard = warp & (kRecShards - 1), shardCap = a.recCap / kRecShards;
+        unsigned int slot = (unsigned int)atomicAdd(a.solverCtr + mySolver * kRecShards + shard,
+                                                    (unsigned long long)cnt | ((unsigned long long)lits << 32));
+        const size_t base = (size_t)mySolver * a.recCap + (size_t)shard * shardCap;
+        for (int i = 0; i < n; i++) {
+            const HitRecord r = stage.buf[i];
+            if (r.solver == mySolver) {
+                if (slot < shardCap) {
+                    a.recKeys[base + slot] = ((unsigned long long)(unsigned int)r.len << 32) | (unsigned int)r.idx;
+                    a.recMasks[base + slot] = r.mask;
+                }
+                slot++;
+            }
+        }
+    }
+    __syncwarp();
+    stage.n = 0;
+}
+
 // G = survivors a warp checks together (their row gathers are independent)
 template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS) k_exact_t(CheckArgs a) {
     const int lane = threadIdx.x & 31;
@@ -488,39 +523,21 @@ template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS
                 if (!__any_sync(FULL, any)) { dead = true; break; }
             }
         }
-        if (a.recKeys) {
-            // direct pipeline: lane = solver appends to ITS OWN record list; one 64-bit atomic per lane
-            // reserves the slots of all its hits of this step and adds their literal count
-            unsigned int cnt = 0, lits = 0;
 #pragma unroll
-            for (int g = 0; g < G; g++)
-                if (all[g] | one[g]) { cnt++; lits += (unsigned int)len[g]; }
-            // (a solver's list is split in kRecShards sub-lists, picked by warp: 145 k appends on 32
-            // counters took k_exact from 19 to 55 us)
-            const unsigned int shard = warp & (kRecShards - 1), shardCap = a.recCap / kRecShards;
-            unsigned int slot = 0;
-            if (cnt)
-                slot = (unsigned int)atomicAdd(a.solverCtr + solver * kRecShards + shard,
-                                               (unsigned long long)cnt | ((unsigned long long)lits << 32));
-            const size_t base = (size_t)solver * a.recCap + (size_t)shard * shardCap;
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                const int idx = (int)__shfl_sync(FULL, sv0.z, g);
-                const uint32_t m = all[g] | one[g];
+        for (int g = 0; g < G; g++) {
+            const int idx = (int)__shfl_sync(FULL, sv0.z, g);
+            const bool has = (all[g] | one[g]) != 0;
+            const HitRecord rec{all[g] | one[g], solver, len[g], idx};
+            if (a.recKeys) {
+                const unsigned m = __ballot_sync(FULL, has);
                 if (m) {
-                    if (slot < shardCap) {
-                        a.recKeys[base + slot] = ((unsigned long long)(unsigned int)len[g] << 32) | (unsigned int)idx;
-                        a.recMasks[base + slot] = m;
-                    }
-                    slot++;
+                    const int cnt = __popc(m);
+                    if (stage.n + cnt > kStageCap) flushRecs(a, stage, lane, warp);
+                    if (has) stage.buf[stage.n + __popc(m & ((1u << lane) - 1))] = rec;
+                    stage.n += cnt;
                 }
-            }
-        } else {
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                const int idx = (int)__shfl_sync(FULL, sv0.z, g);
-                stage.push((all[g] | one[g]) != 0, HitRecord{all[g] | one[g], solver, len[g], idx}, a.hits, &a.counters->nHits,
-                           a.hitCap, lane);
+            } else {
+                stage.push(has, rec, a.hits, &a.counters->nHits, a.hitCap, lane);
             }
         }
         sv0 = sv1;
@@ -528,7 +545,8 @@ template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS
 #pragma unroll
         for (int g = 0; g < G; g++) lit0[g] = lit1[g];
     }
-    stage.flush(a.hits, &a.counters->nHits, a.hitCap, lane);
+    if (a.recKeys) flushRecs(a, stage, lane, warp);
+    else stage.flush(a.hits, &a.counters->nHits, a.hitCap, lane);
     if (lane == 0 && tests) atomicAdd(&a.counters->exactTests, tests);
     if (a.peerDone) {
         // Multi-GPU: the hits went straight into this rank's slot of rank 0's gather window (peer
@@ -883,9 +901,12 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
         a.hdr->solver[s].n = max(es.n, 0);
         a.hdr->solver[s].nLits = es.nLits;
     }
+    // Completion is the kernel's: the host waits for the event behind it, which makes every store to
+    // host memory visible.  (A system-scope fence per block -- needed only if the host polled the header
+    // while the kernel runs -- drains the block's posted PCIe writes: 1184 of them cost ~200 us.)
     __syncthreads();
     if (tid == 0) {
-        __threadfence_system(); // this block's stores have been performed in host memory (cumulative over the barrier)
+        __threadfence();
         const unsigned int ticket = atomicAdd(a.ticket, 1u);
         if (ticket == gridDim.x * gridDim.y - 1) {
             __threadfence();
@@ -908,8 +929,7 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
             a.ticket[0] = 0u;
             a.ticket[1] = 0u;
             a.ticket[2] = 0u;
-            __threadfence_system();
-            *reinterpret_cast<volatile uint32_t *>(&a.hdr->seq) = a.seq;
+            a.hdr->seq = a.seq;
         }
     }
 }

@@ -123,6 +123,7 @@ void Sharer::collectDirect(RunSlot &slot, bool rebuild) {
     slot.aggOnDevice = false;
     slot.maxUpd = 0;
     slot.staged.clear();
+    slot.stagedOff.clear();
     PhaseTimer t(hostPhases_[3]);
     if (rebuild) {
         collectBatch(slot, true); // full update lists in slot.updHost, behind the payload prefix
@@ -131,7 +132,7 @@ void Sharer::collectDirect(RunSlot &slot, bool rebuild) {
         const VarUpdate *base = slot.updHost.data() + payloadPrefixRecords(S);
         for (int s = 0; s < S; s++) {
             src[s] = base + params[s].updStart;
-            if (!slot.updHost.pinned() && params[s].updCount > 0) slot.staged.push_back({s, (size_t)(src[s] - slot.updHost.data())});
+            if (!slot.updHost.pinned() && params[s].updCount > 0) slot.staged.push_back({s, src[s]});
             slot.aggStart[s / kMaxSolversPerGroup] |= params[s].usedAggBits;
             slot.maxUpd = std::max(slot.maxUpd, (int)params[s].updCount);
         }
@@ -157,7 +158,7 @@ void Sharer::collectDirect(RunSlot &slot, bool rebuild) {
         sa.unlock();
         const int n = params[s].updCount;
         if (!pinned && n > 0) { // ordinary memory (page-locked budget exhausted): stage it like the reference does
-            slot.staged.push_back({s, slot.updHost.size()});
+            slot.stagedOff.push_back({s, slot.updHost.size()}); // (updHost may still move: pointers once it is complete)
             memcpy(slot.updHost.append((size_t)n), src[s], (size_t)n * sizeof(VarUpdate));
         }
         total += n;
@@ -166,6 +167,8 @@ void Sharer::collectDirect(RunSlot &slot, bool rebuild) {
         slot.maxUpd = std::max(slot.maxUpd, n);
     }
     slot.nUpdates = total;
+    for (auto &so : slot.stagedOff) slot.staged.push_back({so.first, slot.updHost.data() + so.second});
+    slot.stagedOff.clear();
 }
 
 // Launch the run described by slot.headHost on this device: header H2D, deferred collapse of the
@@ -180,8 +183,7 @@ void Sharer::launchDirect(RunSlot &slot, int64_t h2d) {
     for (auto &st : slot.staged) { // deltas that are not in page-locked memory go up as ordinary copies
         const int s = st.first;
         VarUpdate *dst = slot.updDev.data() + params[s].updStart;
-        GSS_CUDA(cudaMemcpyAsync(dst, slot.updHost.data() + st.second, (size_t)params[s].updCount * sizeof(VarUpdate),
-                                 cudaMemcpyHostToDevice, stream_));
+        GSS_CUDA(cudaMemcpyAsync(dst, st.second, (size_t)params[s].updCount * sizeof(VarUpdate), cudaMemcpyHostToDevice, stream_));
         src[s] = dst;
     }
     slot.headDev.reserve(slot.headHost.size(), 0, stream_);
@@ -325,14 +327,17 @@ bool Sharer::waitBumpFlag() {
 }
 
 // reference: one host-side bump per hit record (Clauses.cu:231-237, GpuRunner.cu:375-378); here one
-// kernel over the sorted per-solver record lists, with the increment the reference would use at this
-// point (after the next batch of clauses has been drained)
-void Sharer::bumpDirect(RunSlot &slot, unsigned int maxRec) {
+// kernel per device over its sorted per-solver record lists, with the increment the reference would
+// use at this point (after the next batch of clauses has been drained).  The activities live on THIS
+// device; the record lists of other devices of the process are read in place through peer access.
+void Sharer::bumpDirect(const std::vector<DevicePart> &parts) {
     if (waitBumpFlag()) {
         db_->rescaleAfterDeviceOverflow();
         db_->applyPendingDeviceRescales(stream_);
     }
-    if (maxRec == 0) return;
+    bool any = false;
+    for (const DevicePart &p : parts) any = any || (p.slot->checked && p.slot->runBuf->hdr()->maxRec > 0);
+    if (!any) return;
     std::vector<LenDir> dir;
     db_->buildDirectory(dir);
     bumpDirHost_.resize(dir.size() * sizeof(LenDir));
@@ -342,34 +347,51 @@ void Sharer::bumpDirect(RunSlot &slot, unsigned int maxRec) {
     bumpFlagDev_.reserve(1, 0, stream_);
     bumpFlagHost_.resize(1);
     GSS_CUDA(cudaMemsetAsync(bumpFlagDev_.data(), 0, sizeof(int), stream_));
-    launchBumpFromRecs(slot.recKeys.data(), slot.recCap, slot.solverInfo.data(), slot.nSolvers, std::min(maxRec, slot.recCap),
-                       (const LenDir *)bumpDirDev_.data(), (int)dir.size(), db_->activityIncrement(), bumpFlagDev_.data(), stream_,
-                       &launches_);
+    for (const DevicePart &p : parts) {
+        RunSlot &slot = *p.slot;
+        if (!slot.checked) continue;
+        const unsigned int maxRec = slot.runBuf->hdr()->maxRec;
+        launchBumpFromRecs(slot.recKeys.data(), slot.recCap, slot.solverInfo.data(), slot.nSolvers, std::min(maxRec, slot.recCap),
+                           (const LenDir *)bumpDirDev_.data(), (int)dir.size(), db_->activityIncrement(), bumpFlagDev_.data(),
+                           stream_, &launches_);
+    }
     GSS_CUDA(cudaMemcpyAsync(bumpFlagHost_.data(), bumpFlagDev_.data(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
     if (!bumpFlagEv_) GSS_CUDA(cudaEventCreateWithFlags(&bumpFlagEv_, cudaEventDisableTiming));
-    GSS_CUDA(cudaEventRecord(bumpFlagEv_, stream_));
+    GSS_CUDA(cudaEventRecord(bumpFlagEv_, stream_)); // (also: the other devices' record lists have been read)
     bumpFlagPending_ = true;
 }
 
 void Sharer::processResultsDirect(RunSlot &slot) {
+    std::vector<DevicePart> parts{DevicePart{this, &slot}};
+    processResultsParts(slot, parts);
+}
+
+// parts[0] is this sharer's own slot; with several devices in one process (multi.cu) every device
+// contributes one slice per solver
+void Sharer::processResultsParts(RunSlot &slot, const std::vector<DevicePart> &parts) {
     // reference gatherGpuRunResults, GpuRunner.cu:360-383 (64-bit arithmetic)
     const int64_t clCount = db_->stats().clauses;
-    const RunHdr *h = slot.checked ? slot.runBuf->hdr() : nullptr;
+    int64_t nTotal = 0;
+    for (const DevicePart &p : parts)
+        if (p.slot->checked) nTotal += p.slot->runBuf->hdr()->nTotal;
     globalStats_[G_gpuRuns]++;
     globalStats_[G_totalAssigClauseTested] += (uint64_t)clCount * (uint64_t)slot.assigCount;
     globalStats_[G_clauseTestsOnGroups] += (uint64_t)clCount;
-    globalStats_[G_gpuReports] += h ? (uint64_t)h->nTotal : 0;
+    globalStats_[G_gpuReports] += (uint64_t)nTotal;
     lastHitsValid_ = false;
     lastDirect_ = &slot;
     bumpN_ = 0; // (nothing parked by the staged path)
-    bumpDirect(slot, h ? h->maxRec : 0u);
+    bumpDirect(parts);
     TimeAdder t(globalStats_[G_timeSpentFillingReported], opts_.quickProf != 0);
     std::vector<std::vector<ResultView>> views((size_t)slot.nSolvers);
-    if (h && h->nTotal > 0) {
-        RunBuf &rb = *slot.runBuf;
+    for (const DevicePart &p : parts) {
+        if (!p.slot->checked) continue;
+        const RunHdr *h = p.slot->runBuf->hdr();
+        if (h->nTotal <= 0) continue;
+        RunBuf &rb = *p.slot->runBuf;
         // safety valve: a solver that does not pop keeps its batches, and with them whole result buffers,
         // alive; past a bound the slices are copied out and the buffer goes back to the pool at once
-        const bool copyOut = runBufs_->outstanding() > 64;
+        const bool copyOut = p.sh->runBufs_->outstanding() > 64;
         for (int s = 0; s < slot.nSolvers; s++) {
             const RunHdr::PerSolver &ps = h->solver[s];
             if (ps.n <= 0) continue;
@@ -379,7 +401,7 @@ void Sharer::processResultsDirect(RunSlot &slot) {
                 v.ids = rb.ids() + ps.entryBase;
                 v.pos = rb.pos() + ps.entryBase + s;
                 v.lits = rb.lits() + ps.litBase;
-                v.owner = slot.runBuf;
+                v.owner = p.slot->runBuf;
             } else {
                 const size_t bytes = (size_t)ps.n * 8 + ((size_t)ps.n + 1) * 4 + (size_t)ps.nLits * 4;
                 std::shared_ptr<uint8_t> heap(new uint8_t[bytes + 8], std::default_delete<uint8_t[]>());
@@ -398,6 +420,24 @@ void Sharer::processResultsDirect(RunSlot &slot) {
         }
     }
     reported_->handOverViews(views, slot.ids, slot.nSolvers);
+}
+
+// (clause id, solver, mask) triples of a finished direct run on THIS device, appended to `out`
+void Sharer::appendDirectHits(RunSlot &slot, std::vector<gss_hit> &out) {
+    if (!slot.checked || !slot.runBuf) return;
+    useDevice();
+    const RunHdr *h = slot.runBuf->hdr();
+    std::vector<uint32_t> masks;
+    for (int s = 0; s < slot.nSolvers; s++) {
+        const RunHdr::PerSolver &ps = h->solver[s];
+        if (ps.n <= 0) continue;
+        masks.resize((size_t)ps.n);
+        GSS_CUDA(cudaMemcpyAsync(masks.data(), slot.recMasks.data() + (size_t)s * slot.recCap, (size_t)ps.n * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, stream_));
+        GSS_CUDA(cudaStreamSynchronize(stream_));
+        const int64_t *ids = slot.runBuf->ids() + ps.entryBase;
+        for (int32_t i = 0; i < ps.n; i++) out.push_back(gss_hit{ids[i], s, masks[(size_t)i]});
+    }
 }
 
 } // namespace gss

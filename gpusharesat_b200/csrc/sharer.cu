@@ -15,7 +15,8 @@ namespace gss {
 
 std::shared_ptr<Sharer::RunBufPool> makeRunBufPool(); // pipeline.cu
 
-Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
+Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx, int workerOfDevice) : opts_(o) {
+    isWorker_ = workerOfDevice >= 0;
     logger_.verbosity = o.verbosity;
     if (log) logger_.fn = [log, logCtx](const std::string &s) { log(s.c_str(), logCtx); };
 
@@ -25,7 +26,8 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
     if (e != cudaSuccess || nDev == 0)
         GSS_DIE(std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); gpushare_b200 has no CPU fallback");
     const char *envDev = getenv("GPUSHARE_DEVICE");
-    if (envDev) device_ = atoi(envDev);
+    if (isWorker_) device_ = workerOfDevice;
+    else if (envDev) device_ = atoi(envDev);
     else GSS_CUDA(cudaGetDevice(&device_));
     GSS_CUDA(cudaSetDevice(device_));
     cudaDeviceProp props;
@@ -82,9 +84,15 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx) : opts_(o) {
     runBufs_ = makeRunBufPool();
     directEnabled_ = getenv("GPUSHARE_LEGACY_PIPELINE") == nullptr;
     logger_.log(1, std::string("c gpushare_b200 on ") + props.name + ", " + std::to_string(numSMs_) + " SMs\n");
+    // several devices behind this one sharer (the factory keeps the reference's signature: the count
+    // comes from the environment)
+    if (!isWorker_)
+        if (const char *e = getenv("GPUSHARE_DEVICES"))
+            if (atoi(e) > 1) multiInit(atoi(e));
 }
 
 Sharer::~Sharer() {
+    multiShutdown();
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_); // nothing may still be using the buffers (or a peer's window)
     peerClose();
@@ -109,11 +117,13 @@ void Sharer::gpuMemInfo(size_t *freeB, size_t *totalB) {
 void Sharer::setVarCount(int n) {
     varCount_ = std::max(varCount_, n);
     assigs_->setVarCount(n);
+    for (auto &w : workers_) w->setVarCount(n);
 }
 
 void Sharer::setCpuSolverCount(int n) {
     // GpuClauseSharerImpl.cu:96-103
     if (n > kMaxGroups * kMaxSolversPerGroup) GSS_DIE("too many cpu solvers (max 256)");
+    for (auto &w : workers_) w->setCpuSolverCount(n);
     assigs_->growSolvers(n);
     for (int s = 0; s < assigs_->solverCount(); s++) assigs_->solver(s).setAllocDevice(device_);
     reported_->setSolverCount(n);
@@ -126,14 +136,27 @@ void Sharer::setCpuSolverCount(int n) {
 }
 
 int64_t Sharer::addClause(int solver, const int *lits, int n) {
-    int64_t id = db_->addClause(lits, n);
+    int64_t id;
+    if (workers_.empty()) {
+        id = db_->addClause(lits, n);
+    } else { // every device's database takes the clause, under one lock so that the ids agree
+        std::lock_guard<std::mutex> g(multiAddLock_);
+        id = db_->addClause(lits, n);
+        for (auto &w : workers_)
+            if (w->db_->addClause(lits, n) != id) GSS_DIE("the clause databases of a multi-device sharer disagree");
+    }
     // GpuClauseSharerImpl.cu:124-128 registers the echo suppression even for a rejected clause
     if (solver != -1) reported_->clauseWasAdded(solver, id);
     return id;
 }
 
 int64_t Sharer::addClausesBulk(const int64_t *offsets, const int *lits, int64_t n) {
-    return db_->addClausesBulk(offsets, lits, n);
+    if (workers_.empty()) return db_->addClausesBulk(offsets, lits, n);
+    std::lock_guard<std::mutex> g(multiAddLock_);
+    const int64_t id = db_->addClausesBulk(offsets, lits, n);
+    for (auto &w : workers_)
+        if (w->db_->addClausesBulk(offsets, lits, n) != id) GSS_DIE("the clause databases of a multi-device sharer disagree");
+    return id;
 }
 
 void Sharer::unsetPendingLocked(int solver) {
@@ -203,6 +226,11 @@ void Sharer::currentAssignment(int solver, uint8_t *assig) {
 
 int64_t Sharer::globalStat(int stat) {
     switch (stat) {
+    case G_clauseTestsOnAssigs: {
+        uint64_t v = globalStats_[stat];
+        for (auto &w : workers_) v += w->globalStats_[stat];
+        return (int64_t)v;
+    }
     case G_gpuClauses: return db_->stats().clauses;
     case G_gpuClauseLengthSum: return db_->stats().lengthSum;
     case G_gpuClausesAdded: return db_->stats().added;
@@ -230,11 +258,16 @@ void Sharer::reduceDb() {
     useDevice();
     materializeLastHits(); // clause indices are about to change
     TimeAdder t(globalStats_[G_timeSpentReduceGpuDb], true);
-    db_->reduceDb(stream_);
+    if (workers_.empty()) {
+        db_->reduceDb(stream_);
+    } else {
+        reduceDbMulti();
+    }
     lastStarted_ = -1;
 }
 
 void Sharer::wholeRun(bool canStart) {
+    if (!workers_.empty()) return wholeRunMulti(canStart);
     useDevice();
     RunSlot *prev = cur_ >= 0 ? &slots_[cur_] : nullptr;
     {
@@ -962,25 +995,12 @@ void Sharer::processResults(RunSlot &slot) {
 void Sharer::materializeLastHits() {
     if (lastHitsValid_) return;
     if (lastDirect_) {
-        // direct pipeline: ids are in the result buffer (host), the masks of the sorted record lists on the device
-        RunSlot &slot = *lastDirect_;
+        // direct pipeline: ids are in the result buffers (host), the masks of the sorted record lists on the device(s)
         lastHits_.clear();
-        if (slot.checked && slot.runBuf) {
-            useDevice();
-            const RunHdr *h = slot.runBuf->hdr();
-            lastHits_.resize((size_t)h->nTotal);
-            std::vector<uint32_t> masks;
-            for (int s = 0; s < slot.nSolvers; s++) {
-                const RunHdr::PerSolver &ps = h->solver[s];
-                if (ps.n <= 0) continue;
-                masks.resize((size_t)ps.n);
-                GSS_CUDA(cudaMemcpyAsync(masks.data(), slot.recMasks.data() + (size_t)s * slot.recCap, (size_t)ps.n * sizeof(uint32_t),
-                                         cudaMemcpyDeviceToHost, stream_));
-                GSS_CUDA(cudaStreamSynchronize(stream_));
-                const int64_t *ids = slot.runBuf->ids() + ps.entryBase;
-                for (int32_t i = 0; i < ps.n; i++) lastHits_[(size_t)ps.entryBase + i] = gss_hit{ids[i], s, masks[(size_t)i]};
-            }
-        }
+        const int idx = (int)(lastDirect_ - slots_);
+        appendDirectHits(*lastDirect_, lastHits_);
+        for (auto &w : workers_) w->appendDirectHits(w->slots_[idx], lastHits_);
+        useDevice();
     } else if (postValid_) {
         lastHits_.resize(postN_);
         for (size_t i = 0; i < postN_; i++)

@@ -10,6 +10,7 @@
 #include "stats.h"
 #include <chrono>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 namespace gss {
@@ -33,7 +34,8 @@ struct TimeAdder { // reference TimeGauge, gpuShareLib/Profiler.h:28-46
 
 class Sharer {
 public:
-    Sharer(const gss_options &opts, gss_log_fn log, void *logCtx);
+    // workerOfDevice >= 0: a device worker of another sharer of this process (multi.cu), on that device
+    Sharer(const gss_options &opts, gss_log_fn log, void *logCtx, int workerOfDevice = -1);
     ~Sharer();
 
     // ---- GpuClauseSharer.h API (see include/gpushare_b200.h for the line map) ----
@@ -59,7 +61,10 @@ public:
     // ---- parity / bench hooks ----
     int64_t lastHits(gss_hit *out, int64_t cap);
     int64_t addClausesBulk(const int64_t *offsets, const int *lits, int64_t n);
-    void setMaxClauseLen(int n) { db_->setMaxLen(n); }
+    void setMaxClauseLen(int n) {
+        db_->setMaxLen(n);
+        for (auto &w : workers_) w->db_->setMaxLen(n);
+    }
     void setDense(bool d) { dense_ = d; }
     double timeCheck(int iters, int mode);
     int lastRunTimes(double out[4]);
@@ -137,7 +142,8 @@ private:
         DevBuf<unsigned int> ticketDev;     // 4 words
         unsigned int recCap = 0;
         size_t srcOff = 0;          // offset of the per-solver delta pointers in headHost / headDev
-        std::vector<std::pair<int, size_t>> staged; // solvers whose deltas are not page-locked: {solver, offset in updHost}
+        std::vector<std::pair<int, const VarUpdate *>> staged; // solvers whose deltas are not page-locked: {solver, host copy}
+        std::vector<std::pair<int, size_t>> stagedOff;
         const LenDir *dirDev() const { return (const LenDir *)headDev.data(); }
         const SolverRunParams *paramsDev() const { return (const SolverRunParams *)(headDev.data() + dirBytes); }
         size_t dirBytes = 0;
@@ -153,9 +159,36 @@ private:
     void launchEmitFor(RunSlot &slot);
     void finishRunDirect(RunSlot &slot);
     void processResultsDirect(RunSlot &slot);
+    struct DevicePart { // one device's share of a run (several devices in one process: multi.cu)
+        Sharer *sh;
+        RunSlot *slot;
+    };
+    void processResultsParts(RunSlot &slot, const std::vector<DevicePart> &parts);
+    void appendDirectHits(RunSlot &slot, std::vector<gss_hit> &out);
     void ensureDirectBuffers(RunSlot &slot);
-    void bumpDirect(RunSlot &slot, unsigned int maxRec);
+    void bumpDirect(const std::vector<DevicePart> &parts);
     bool waitBumpFlag();
+    // ---- several devices in one process (GPUSHARE_DEVICES=N, multi.cu): this sharer is the front-end
+    // and device 0; workers_[r-1] drives device r.  Every device keeps the whole clause database and
+    // checks its share of the tiles; the batch reaches every device straight from the solver threads'
+    // page-locked buffers (every GPU reads them over its own PCIe link), every device writes its
+    // finished per-solver results into page-locked result buffers, the front-end stitches views ----
+    class WorkerThreads;
+    void multiInit(int nDevices);
+    void multiShutdown();
+    void wholeRunMulti(bool canStart);
+    void reduceDbMulti();
+    void workerStart(const RunSlot &rootSlot, const uint8_t *paramsAndSrc, int slotIdx, bool rebuild);
+    std::vector<uint8_t> multiSnap_;
+    void workerFinish(int slotIdx);
+    std::vector<std::unique_ptr<Sharer>> workers_;
+    WorkerThreads *wthreads_ = nullptr; // (owned; created / deleted in multi.cu)
+    std::mutex multiAddLock_;
+    bool isWorker_ = false;
+    cudaEvent_t peerReadEv_ = nullptr; // front-end: its bump kernels have read the workers' record lists
+    bool peerReadRecorded_ = false;
+    Sharer *root_ = nullptr;
+
     std::shared_ptr<RunBufPool> runBufs_;
     bool directEnabled_ = true;
     size_t recCap_ = 1024;       // per-solver record capacity (power of two)
