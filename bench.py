@@ -63,6 +63,7 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-dense", action="store_true")
+    p.add_argument("--no-latency", action="store_true", help="skip the import-latency harness (import_latency object)")
     p.add_argument("--no-ref-gpu", action="store_true", help="skip the reference GPU library leg (reference_gpu object)")
     p.add_argument("--ref-gpu-steps", type=int, default=5)
     p.add_argument("--dense-iters", type=int, default=3)
@@ -232,6 +233,20 @@ def run_reference_arm(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def import_latency():
+    """BASELINE config 5's shape (64 solver threads, clauses up to 200 literals) through the C ABI from
+    C++ threads (tests/latency/latency_harness.cc): add a falsified clause -> the target solver pops it"""
+    exe = os.path.join(ROOT, "tests", "latency", "latency_harness")
+    if not os.path.exists(exe):
+        return {"unavailable": "tests/latency/latency_harness not built"}
+    try:
+        r = subprocess.run([exe, "64", "200000", "1000000", "300"], capture_output=True, text=True, timeout=120)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+        return json.loads(line)
+    except Exception as e:  # the headline numbers do not depend on it
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def workload_config(a):
@@ -701,8 +716,10 @@ def run_b200(a):
         else:
             sh.gpuRun()
             drain()
+        sh.close()  # free the device: the latency harness and the reference library bring their own databases
+        if not a.no_latency:
+            out["import_latency"] = import_latency()
         if not a.no_ref_gpu:
-            sh.close()  # free the device before the reference library loads its own copy of the database
             out["reference_gpu"] = reference_gpu_numbers(a, sig, offsets, lits, a.ref_gpu_steps, 2)
             if "e2e" in out["reference_gpu"]:
                 out["reference_gpu"]["ours_over_reference"] = {

@@ -199,7 +199,12 @@ int ClauseDb::buildDirectory(std::vector<LenDir> &dir) const {
         const int64_t allTiles = (n + kTileClauses - 1) / kTileClauses;
         tiles += (int)localTiles(allTiles);
         dir.push_back(LenDir{pl.dev.data(), s, (int32_t)n, tiles, (int32_t)shardFirstTile(allTiles), pl.idsDev.data(),
-                             const_cast<float *>(pl.actsDev.data())});
+                             const_cast<float *>(pl.actsDev.data()), 0});
+    }
+    int64_t before = 0; // the directory is longest first: walk it backwards for the ascending prefix
+    for (size_t k = dir.size(); k-- > 0;) {
+        dir[k].ascStart = before;
+        before += dir[k].count;
     }
     return tiles;
 }

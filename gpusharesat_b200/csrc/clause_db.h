@@ -31,6 +31,7 @@ struct LenDir {
     int32_t firstTile; // first tile of this length that THIS DEVICE checks (multi-GPU: its contiguous share)
     const int64_t *ids; // device copy of the clause ids of this length, indexed by (global) clause index
     float *acts;        // device-resident clause activities (bumped by k_bump_activity), same indexing
+    int64_t ascStart;   // clauses of all SHORTER lengths: ascStart + index = position in the canonical order
 };
 
 struct DbStats {

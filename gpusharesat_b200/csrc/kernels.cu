@@ -403,39 +403,27 @@ __device__ __forceinline__ void reportHits(const CheckArgs &a, uint32_t m, int s
 // load and one coalesced T2 row (8 B per lane).  (reference dCheckOneClauseAllSolvers /
 // dCheckOneClauseOneSolver, GpuRunner.cu:68-131: serial per thread, one solver after the other)
 // ---------------------------------------------------------------------------------------------
-// Direct pipeline: the hits a warp has staged go to PER-SOLVER record lists.  Lane l serves solver
-// groupBase + l: it counts its records among the staged ones (broadcast reads of shared memory),
-// reserves their slots and adds up their literals with ONE 64-bit atomic, and copies them.  The
-// atomics' round trips are paid once per ~64 staged hits, not once per warp step.  A solver's list is
-// split in kRecShards sub-lists, picked by warp, so that the appends of a solver spread over counters.
-__device__ __forceinline__ void flushRecs(const CheckArgs &a, WarpStage<HitRecord> &stage, int lane, unsigned int warp) {
-    const int n = stage.n;
-    if (n == 0) return;
-    __syncwarp();
-    const int mySolver = a.groupBase + lane;
-    unsigned int cnt = 0, lits = 0;
-    for (int i = 0; i < n; i++) {
-        const HitRecord r = stage.buf[i];
-        if (r.solver == mySolver) { cnt++; lits += (unsigned int)r.len; }
+// Direct pipeline: append one hit to its solver's record list, in the bucket of the clause's position
+// in the canonical order (kernels.cuh: kRecBuckets).  One 64-bit atomic reserves the slot and adds the
+// clause's literals to the bucket's literal count.  sLen / sAsc: the directory's lengths (descending)
+// and ascending clause prefix in shared memory.
+__device__ __forceinline__ void appendRec(const CheckArgs &a, const int *sLen, const long long *sAsc, int nDir, int solver, int len,
+                                          int idx, uint32_t mask) {
+    int lo = 0, hi = nDir - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (sLen[mid] <= len) hi = mid; else lo = mid + 1;
     }
-    if (cnt) {
-        const unsigned int shard = warp & (kRecShards - 1), shardCap = a.recCap / kRecShards;
-        unsigned int slot = (unsigned int)atomicAdd(a.solverCtr + mySolver * kRecShards + shard,
-                                                    (unsigned long long)cnt | ((unsigned long long)lits << 32));
-        const size_t base = (size_t)mySolver * a.recCap + (size_t)shard * shardCap;
-        for (int i = 0; i < n; i++) {
-            const HitRecord r = stage.buf[i];
-            if (r.solver == mySolver) {
-                if (slot < shardCap) {
-                    a.recKeys[base + slot] = ((unsigned long long)(unsigned int)r.len << 32) | (unsigned int)r.idx;
-                    a.recMasks[base + slot] = r.mask;
-                }
-                slot++;
-            }
-        }
+    const unsigned long long g = (unsigned long long)(sAsc[lo] + idx);
+    const unsigned int bucket = (unsigned int)min((unsigned long long)(kRecBuckets - 1), g * kRecBuckets / (unsigned long long)a.totalClauses);
+    const unsigned int bucketCap = a.recCap / kRecBuckets;
+    const unsigned int slot = (unsigned int)atomicAdd(a.solverCtr + ((size_t)solver * kRecBuckets + bucket) * kCtrStride,
+                                                      1ull | ((unsigned long long)(unsigned int)len << 32));
+    if (slot < bucketCap) {
+        const size_t at = (size_t)solver * a.recCap + (size_t)bucket * bucketCap + slot;
+        a.recKeys[at] = ((unsigned long long)(unsigned int)len << 32) | (unsigned int)idx;
+        a.recMasks[at] = mask;
     }
-    __syncwarp();
-    stage.n = 0;
 }
 
 // G = survivors a warp checks together (their row gathers are independent)
@@ -458,6 +446,13 @@ template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS
     const uint2 ident = make_uint2(0u, 0u);
     __shared__ HitRecord sStage[kMaxWarpsPerBlock][kStageCap];
     WarpStage<HitRecord> stage{sStage[threadIdx.x >> 5], 0};
+    __shared__ int sDirLen[128];
+    __shared__ long long sDirAsc[128];
+    const int nDirS = min(a.nDir, 128);
+    if (a.recKeys) {
+        for (int i = threadIdx.x; i < nDirS; i += blockDim.x) { sDirLen[i] = a.dir[i].len; sDirAsc[i] = a.dir[i].ascStart; }
+        __syncthreads();
+    }
 
     // A warp takes G consecutive survivors at a time; lane g (< G) holds record g of the group.  The
     // chain per survivor is record -> literals -> T2 rows, each a dependent DRAM / L2 round trip:
@@ -529,13 +524,7 @@ template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS
             const bool has = (all[g] | one[g]) != 0;
             const HitRecord rec{all[g] | one[g], solver, len[g], idx};
             if (a.recKeys) {
-                const unsigned m = __ballot_sync(FULL, has);
-                if (m) {
-                    const int cnt = __popc(m);
-                    if (stage.n + cnt > kStageCap) flushRecs(a, stage, lane, warp);
-                    if (has) stage.buf[stage.n + __popc(m & ((1u << lane) - 1))] = rec;
-                    stage.n += cnt;
-                }
+                if (has) appendRec(a, sDirLen, sDirAsc, nDirS, solver, len[g], idx, rec.mask);
             } else {
                 stage.push(has, rec, a.hits, &a.counters->nHits, a.hitCap, lane);
             }
@@ -545,8 +534,7 @@ template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS
 #pragma unroll
         for (int g = 0; g < G; g++) lit0[g] = lit1[g];
     }
-    if (a.recKeys) flushRecs(a, stage, lane, warp);
-    else stage.flush(a.hits, &a.counters->nHits, a.hitCap, lane);
+    if (!a.recKeys) stage.flush(a.hits, &a.counters->nHits, a.hitCap, lane);
     if (lane == 0 && tests) atomicAdd(&a.counters->exactTests, tests);
     if (a.peerDone) {
         // Multi-GPU: the hits went straight into this rank's slot of rank 0's gather window (peer
@@ -706,8 +694,6 @@ __global__ void __launch_bounds__(256) k_apply_direct(const VarUpdate *const *__
 // copies (reference: Reporter.cuh:103-126 + Reported.cu:160-204).  The block that finishes last
 // writes the header and, after a system fence, the run's sequence number.
 // ---------------------------------------------------------------------------------------------
-constexpr int kEmitThreads = 1024;
-constexpr int kEmitSmemRecs = 8192; // records per solver sorted in shared memory
 constexpr int kWriteChunk = 256;    // entries per block step of k_emit_write
 
 __device__ __forceinline__ int dirOfLen(const int *sLen, int nDir, int len) { // directory: descending length
@@ -719,88 +705,75 @@ __device__ __forceinline__ int dirOfLen(const int *sLen, int nDir, int len) { //
     return lo;
 }
 
-__global__ void __launch_bounds__(kEmitThreads) k_emit_sort(EmitArgs a) {
-    extern __shared__ unsigned long long sDyn[];
-    __shared__ long long sPart[kEmitThreads / 32];
-    __shared__ long long sBase[2];
-    __shared__ unsigned int sShardOff[kRecShards + 1];
-    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned int shardCap = a.recCap / kRecShards;
+constexpr int kSortWarps = 8;        // buckets per block of k_emit_sort (a warp each)
+constexpr int kSortSmemRecs = 256;   // records per bucket sorted in shared memory
 
-    // this solver's sub-lists, and where its streams start (sum over the solvers before it)
-    if (wid == 0) {
-        long long e = 0, l = 0;
-        for (int t = lane; t < s * kRecShards; t += 32) {
-            const unsigned long long ct = a.solverCtr[t];
-            e += min((unsigned int)ct, shardCap);
-            l += (long long)(ct >> 32);
-        }
-        for (int o = 16; o; o >>= 1) {
-            e += __shfl_xor_sync(FULL, e, o);
-            l += __shfl_xor_sync(FULL, l, o);
-        }
-        if (lane == 0) { sBase[0] = e; sBase[1] = l; }
-    }
-    if (tid == 0) {
-        unsigned int off = 0;
-        for (int k = 0; k < kRecShards; k++) {
-            sShardOff[k] = off;
-            off += min((unsigned int)a.solverCtr[s * kRecShards + k], shardCap);
-        }
-        sShardOff[kRecShards] = off;
-    }
-    __syncthreads();
-    const long long entryBase = sBase[0], litBase = sBase[1];
-    const unsigned int n = sShardOff[kRecShards];
-    long long nLits = 0;
-    bool shardOverflow = false;
-    for (int k = 0; k < kRecShards; k++) {
-        const unsigned long long ct = a.solverCtr[s * kRecShards + k];
-        nLits += (long long)(ct >> 32);
-        shardOverflow = shardOverflow || (unsigned int)ct > shardCap;
-    }
-    const bool fits = !shardOverflow && entryBase + n <= a.entryCap && litBase + nLits <= a.litCap;
+// grid = (kRecBuckets / kSortWarps, solvers); warp w of block (x, s) owns bucket x * kSortWarps + w of solver s
+__global__ void __launch_bounds__(kSortWarps * 32) k_emit_sort(EmitArgs a) {
+    __shared__ unsigned long long sK[kSortWarps][kSortSmemRecs];
+    __shared__ uint32_t sM[kSortWarps][kSortSmemRecs];
+    __shared__ long long sRed[2][kSortWarps];
+    const int s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int bucket = blockIdx.x * kSortWarps + wid;
+    const unsigned int bucketCap = a.recCap / kRecBuckets;
+    auto ctrOf = [&](int solver, int b) { return a.solverCtr[((size_t)solver * kRecBuckets + b) * kCtrStride]; };
 
+    // Where this block's first bucket starts in the solver's sorted list and in the literal stream, and
+    // where the solver starts in the run's streams: sums over the counters before it (the whole block adds).
+    const int firstBucket = blockIdx.x * kSortWarps;
+    long long eSolver = 0, lSolver = 0, eBucket = 0, lBucket = 0; // before this solver / before this block's first bucket
+    for (int t = tid; t < s * kRecBuckets + firstBucket; t += blockDim.x) {
+        const unsigned long long ct = a.solverCtr[(size_t)t * kCtrStride];
+        const long long e = min((unsigned int)ct, bucketCap), l = (long long)(ct >> 32);
+        if (t < s * kRecBuckets) { eSolver += e; lSolver += l; } else { eBucket += e; lBucket += l; }
+    }
+    auto blockSum = [&](long long v, int slot) -> long long {
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        __syncthreads();
+        if (lane == 0) sRed[slot & 1][wid] = v;
+        __syncthreads();
+        long long r = 0;
+        for (int w = 0; w < kSortWarps; w++) r += sRed[slot & 1][w];
+        return r;
+    };
+    eSolver = blockSum(eSolver, 0);
+    lSolver = blockSum(lSolver, 1);
+    eBucket = blockSum(eBucket, 0);
+    lBucket = blockSum(lBucket, 1);
+    // the buckets of this block before this warp's
+    for (int w = 0; w < wid; w++) {
+        const unsigned long long ct = ctrOf(s, firstBucket + w);
+        eBucket += min((unsigned int)ct, bucketCap);
+        lBucket += (long long)(ct >> 32);
+    }
+    const unsigned long long mine = ctrOf(s, bucket);
+    const unsigned int nRaw = (unsigned int)mine, n = min(nRaw, bucketCap);
+    const long long nLits = (long long)(mine >> 32);
+
+    // sort this bucket by (length, index): bitonic network, one warp; in shared memory when it fits,
+    // else in place in the bucket's own storage (P <= bucketCap, a power of two)
     unsigned int P = 1;
     while (P < n) P <<= 1;
-    unsigned long long *const gK = a.recKeys + (size_t)s * a.recCap;
-    uint32_t *const gM = a.recMasks + (size_t)s * a.recCap;
-    int32_t *const gPos = a.recPos + (size_t)s * (a.recCap + 1);
+    unsigned long long *const gK = a.recKeys + (size_t)s * a.recCap + (size_t)bucket * bucketCap;
+    uint32_t *const gM = a.recMasks + (size_t)s * a.recCap + (size_t)bucket * bucketCap;
     unsigned long long *K;
     uint32_t *M;
-    const bool inSmem = P <= (unsigned int)kEmitSmemRecs;
-    if (inSmem) {
-        K = sDyn;
-        M = reinterpret_cast<uint32_t *>(sDyn + kEmitSmemRecs);
-        for (int k = 0; k < kRecShards; k++) {
-            const unsigned int o = sShardOff[k], c = sShardOff[k + 1] - o;
-            for (unsigned int i = tid; i < c; i += kEmitThreads) {
-                K[o + i] = gK[(size_t)k * shardCap + i];
-                M[o + i] = gM[(size_t)k * shardCap + i];
-            }
+    if (P <= (unsigned int)kSortSmemRecs) {
+        K = sK[wid];
+        M = sM[wid];
+        for (unsigned int i = lane; i < P; i += 32) {
+            K[i] = i < n ? gK[i] : ~0ull;
+            M[i] = i < n ? gM[i] : 0u;
         }
-        for (unsigned int i = n + tid; i < P; i += kEmitThreads) { K[i] = ~0ull; M[i] = 0u; }
-    } else { // compact the sub-lists towards the front (destination <= source, one sub-list after the other), P <= recCap
+    } else {
         K = gK;
         M = gM;
-        for (int k = 1; k < kRecShards; k++) {
-            const unsigned int o = sShardOff[k], c = sShardOff[k + 1] - o;
-            for (unsigned int i0 = 0; i0 < c; i0 += kEmitThreads) { // chunk by chunk: a chunk's reads finish before its writes start
-                const unsigned int i = i0 + tid;
-                unsigned long long kv = 0;
-                uint32_t mv = 0;
-                if (i < c) { kv = gK[(size_t)k * shardCap + i]; mv = gM[(size_t)k * shardCap + i]; }
-                __syncthreads();
-                if (i < c) { gK[o + i] = kv; gM[o + i] = mv; }
-                __syncthreads();
-            }
-        }
-        for (unsigned int i = n + tid; i < P; i += kEmitThreads) { K[i] = ~0ull; M[i] = 0u; }
+        for (unsigned int i = n + lane; i < P; i += 32) { K[i] = ~0ull; M[i] = 0u; }
     }
-    __syncthreads();
+    __syncwarp();
     for (unsigned int k = 2; k <= P; k <<= 1)
         for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-            for (unsigned int i = tid; i < P; i += kEmitThreads) {
+            for (unsigned int i = lane; i < P; i += 32) {
                 const unsigned int x = i ^ j;
                 if (x > i) {
                     const unsigned long long ki = K[i], kx = K[x];
@@ -810,51 +783,45 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_sort(EmitArgs a) {
                     }
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
-    // literal positions: exclusive sum of the lengths in sorted order (pos[n] = this solver's literal count)
-    const unsigned int per = (n + kEmitThreads - 1) / kEmitThreads;
-    const unsigned int i0 = min(n, tid * per), i1 = min(n, i0 + per);
-    long long mine = 0;
-    for (unsigned int i = i0; i < i1; i++) mine += (long long)(K[i] >> 32);
-    long long incl = mine;
-    for (int o = 1; o < 32; o <<= 1) {
-        const long long v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) sPart[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        long long v = sPart[lane], inc2 = v;
+    // the bucket's place in the solver's sorted list: records, masks, literal positions
+    unsigned long long *const oK = a.sortKeys + (size_t)s * a.recCap + eBucket;
+    uint32_t *const oM = a.sortMasks + (size_t)s * a.recCap + eBucket;
+    int32_t *const oPos = a.recPos + (size_t)s * (a.recCap + 1) + eBucket;
+    long long run = lBucket;
+    for (unsigned int i0 = 0; i0 < n; i0 += 32) {
+        const unsigned int i = i0 + lane;
+        const unsigned long long key = i < n ? K[i] : 0ull;
+        const long long len = i < n ? (long long)(key >> 32) : 0;
+        long long incl = len;
         for (int o = 1; o < 32; o <<= 1) {
-            const long long u = __shfl_up_sync(FULL, inc2, o);
-            if (lane >= o) inc2 += u;
+            const long long v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
         }
-        sPart[lane] = inc2 - v;
+        if (i < n) {
+            oK[i] = key;
+            oM[i] = M[i];
+            oPos[i] = (int32_t)(run + incl - len);
+        }
+        run += __shfl_sync(FULL, incl, 31);
     }
-    __syncthreads();
-    long long run = sPart[wid] + incl - mine;
-    for (unsigned int i = i0; i < i1; i++) {
-        gPos[i] = (int32_t)run;
-        run += (long long)(K[i] >> 32);
-    }
-    if (tid == 0) gPos[n] = (int32_t)nLits;
-    if (inSmem) // the sorted list stays on the device: k_emit_write, activity bumps, parity hooks
-        for (unsigned int i = tid; i < n; i += kEmitThreads) { gK[i] = K[i]; gM[i] = M[i]; }
-    if (tid == 0) {
-        EmitSolver &es = a.solverInfo[s];
-        es.entryBase = entryBase;
-        es.litBase = litBase;
-        es.n = fits ? (int32_t)n : -1; // -1: nothing of this solver is written (the run is repeated)
-        es.nLits = (int32_t)nLits;
-        es.nSorted = n;
-        unsigned int fl = 0;
-        if (shardOverflow) fl |= 2u;
-        else if (!fits) fl |= 4u;
-        if (fl) atomicOr(a.ticket + 1, fl);
-        unsigned int worst = 0; // what recCap would have had to be
-        for (int k = 0; k < kRecShards; k++) worst = max(worst, (unsigned int)a.solverCtr[s * kRecShards + k]);
-        atomicMax(a.ticket + 2, worst * kRecShards);
+    const bool lastBucket = bucket == kRecBuckets - 1;
+    if (lane == 0) {
+        if (lastBucket) {
+            // totals of this solver = what lies before its last bucket + that bucket
+            const long long nSolver = eBucket + n, litsSolver = lBucket + nLits;
+            a.recPos[(size_t)s * (a.recCap + 1) + nSolver] = (int32_t)litsSolver;
+            EmitSolver &es = a.solverInfo[s];
+            es.entryBase = eSolver;
+            es.litBase = lSolver;
+            es.nLits = (int32_t)litsSolver;
+            es.nSorted = (uint32_t)nSolver;
+            es.n = (eSolver + nSolver <= a.entryCap && lSolver + litsSolver <= a.litCap) ? (int32_t)nSolver : -1;
+            if (es.n < 0) atomicOr(a.ticket + 1, 4u);
+        }
+        if (nRaw > bucketCap) atomicOr(a.ticket + 1, 2u);
+        atomicMax(a.ticket + 2, nRaw); // (x kRecBuckets = what recCap would have had to be)
     }
 }
 
@@ -866,7 +833,7 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
     const int nDir = min(a.nDir, 128);
     for (int i = tid; i < nDir; i += blockDim.x) sLen[i] = a.dir[i].len;
     const EmitSolver es = a.solverInfo[s];
-    const unsigned long long *__restrict__ K = a.recKeys + (size_t)s * a.recCap;
+    const unsigned long long *__restrict__ K = a.sortKeys + (size_t)s * a.recCap;
     const int32_t *__restrict__ gPos = a.recPos + (size_t)s * (a.recCap + 1);
     const int n = es.n; // -1: this solver does not fit
     for (int c0 = blockIdx.x * kWriteChunk; c0 < n; c0 += gridDim.x * kWriteChunk) {
@@ -924,7 +891,7 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
             a.hdr->nTotal = tot;
             a.hdr->litTotal = lt;
             a.hdr->exactTests = cn->exactTests;
-            a.hdr->maxRec = *reinterpret_cast<volatile unsigned int *>(a.ticket + 2);
+            a.hdr->maxRec = *reinterpret_cast<volatile unsigned int *>(a.ticket + 2); // largest bucket
             a.hdr->flags = flags;
             a.ticket[0] = 0u;
             a.ticket[1] = 0u;
@@ -1293,15 +1260,7 @@ void launchApplyDirect(const VarUpdate *const *src, const SolverRunParams *param
 
 void launchEmit(const EmitArgs &a, cudaStream_t s, int64_t *launches) {
     if (a.nSolvers <= 0) return;
-    static const size_t smem = (size_t)kEmitSmemRecs * (sizeof(unsigned long long) + sizeof(uint32_t));
-    static bool configured[64] = {}; // per device: the attribute belongs to the function in that device's context
-    int dev = 0;
-    GSS_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !configured[dev]) {
-        GSS_CUDA(cudaFuncSetAttribute(k_emit_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
-    k_emit_sort<<<a.nSolvers, kEmitThreads, smem, s>>>(a);
+    k_emit_sort<<<dim3(kRecBuckets / kSortWarps, a.nSolvers, 1), kSortWarps * 32, 0, s>>>(a);
     // enough writers for PCIe: the blocks of a solver take chunks of its entries in turn
     const unsigned int perSolver = std::max(1u, std::min(64u, 1184u / (unsigned int)a.nSolvers));
     k_emit_write<<<dim3(perSolver, a.nSolvers, 1), 256, 0, s>>>(a);

@@ -24,7 +24,12 @@ struct DeviceTables {
 };
 
 constexpr int kMaxGroups = 8; // solver groups of 32 (256 solver threads)
-constexpr int kRecShards = 8; // sub-lists of a solver's hit record list (direct pipeline)
+// Direct pipeline: a solver's hit records are appended to kRecBuckets sub-lists, bucket = the hit
+// clause's position in the database's canonical order (length ascending, index ascending) scaled to
+// 0..kRecBuckets-1.  Sorting every bucket on its own (a warp each) and reading the buckets in order
+// gives the solver's hits in the canonical order; the appends of a solver spread over many counters.
+constexpr int kRecBuckets = 64;
+constexpr int kCtrStride = 4; // counters are 32 bytes apart: atomics on one L2 sector serialise
 
 // device-side counters of one run
 struct Counters {
@@ -65,11 +70,11 @@ struct CheckArgs {
     // direct pipeline: k_exact appends its hits to PER-SOLVER record lists instead of one global hit
     // buffer (lane = solver: one 64-bit atomicAdd per lane and warp step reserves the slots and adds up
     // the literal count of that solver's result stream).  recKeys == nullptr: global hit buffer.
-    // A solver's list is split in kRecShards sub-lists (shard = warp % kRecShards) of recCap / kRecShards.
-    unsigned long long *solverCtr = nullptr; // [solver][shard] records (low 32 bits) | literals (high 32 bits)
-    unsigned long long *recKeys = nullptr;   // [solver][shard][recCap / kRecShards]  clause length << 32 | clause index
+    unsigned long long *solverCtr = nullptr; // [solver][bucket] x kCtrStride: records (low 32 bits) | literals (high 32 bits)
+    unsigned long long *recKeys = nullptr;   // [solver][bucket][recCap / kRecBuckets]  clause length << 32 | clause index
     uint32_t *recMasks = nullptr;            // same shape: slot mask of the hit
-    unsigned int recCap = 0;                 // per solver, a power of two >= kRecShards
+    unsigned int recCap = 0;                 // per solver, a power of two >= kRecBuckets
+    long long totalClauses = 0;              // clauses in the database (bucket scaling)
 };
 
 void launchFillTables(const DeviceTables &t, int varFrom, cudaStream_t s, int64_t *launches);
@@ -179,9 +184,11 @@ struct EmitArgs {
     const LenDir *dir;
     int nDir;
     int nSolvers;
-    unsigned long long *solverCtr; // [solver][kRecShards]
-    unsigned long long *recKeys; // [solver][recCap]: sub-lists in, one sorted list out
+    unsigned long long *solverCtr; // [solver][kRecBuckets] x kCtrStride
+    unsigned long long *recKeys; // [solver][bucket][recCap / kRecBuckets]: the buckets k_exact filled (sorted in place when large)
     uint32_t *recMasks;
+    unsigned long long *sortKeys; // [solver][recCap]: the solver's records in canonical order
+    uint32_t *sortMasks;
     int32_t *recPos;             // [solver][recCap + 1] literal positions of the sorted list
     EmitSolver *solverInfo;      // [solver]
     unsigned int recCap;         // power of two

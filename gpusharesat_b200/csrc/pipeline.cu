@@ -94,17 +94,19 @@ static size_t pow2AtLeast(size_t x) {
 
 void Sharer::ensureDirectBuffers(RunSlot &slot) {
     const size_t S = (size_t)std::max(1, slot.nSolvers);
-    if (slot.ctrDev.capacity() < (size_t)kMaxSolvers * kRecShards) {
-        slot.ctrDev.reserve((size_t)kMaxSolvers * kRecShards, 0, stream_);
+    if (slot.ctrDev.capacity() < (size_t)kMaxSolvers * kRecBuckets * kCtrStride) {
+        slot.ctrDev.reserve((size_t)kMaxSolvers * kRecBuckets * kCtrStride, 0, stream_);
         slot.solverInfo.reserve(kMaxSolvers, 0, stream_);
         slot.ticketDev.reserve(4, 0, stream_);
-        GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)kMaxSolvers * kRecShards * sizeof(unsigned long long), stream_));
+        GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)kMaxSolvers * kRecBuckets * kCtrStride * sizeof(unsigned long long), stream_));
         GSS_CUDA(cudaMemsetAsync(slot.solverInfo.data(), 0, (size_t)kMaxSolvers * sizeof(EmitSolver), stream_));
         GSS_CUDA(cudaMemsetAsync(slot.ticketDev.data(), 0, 4 * sizeof(unsigned int), stream_));
     }
     slot.recCap = (unsigned int)recCap_;
     slot.recKeys.reserve(S * recCap_, 0, stream_);
     slot.recMasks.reserve(S * recCap_, 0, stream_);
+    slot.sortKeys.reserve(S * recCap_, 0, stream_);
+    slot.sortMasks.reserve(S * recCap_, 0, stream_);
     slot.recPos.reserve(S * (recCap_ + 1), 0, stream_);
     survDev_.reserve((size_t)std::max(1, tables_.nGroups) * survCap_, 0, stream_);
     resDev_.reserve(sizeof(Counters) + hitCap_ * sizeof(HitRecord), 0, stream_);
@@ -245,6 +247,8 @@ void Sharer::launchEmitFor(RunSlot &slot) {
     e.solverCtr = slot.ctrDev.data();
     e.recKeys = slot.recKeys.data();
     e.recMasks = slot.recMasks.data();
+    e.sortKeys = slot.sortKeys.data();
+    e.sortMasks = slot.sortMasks.data();
     e.recPos = slot.recPos.data();
     e.solverInfo = slot.solverInfo.data();
     e.recCap = slot.recCap;
@@ -301,7 +305,8 @@ void Sharer::finishRunDirect(RunSlot &slot) {
             for (int g = 0; g < kMaxGroups; g++) maxSurv = std::max(maxSurv, (size_t)h->nSurvivors[g]);
             survCap_ = std::max(survCap_ * 2, maxSurv + maxSurv / 4);
         }
-        if (flags & 2u) recCap_ = pow2AtLeast(std::max<size_t>(recCap_ * 2, (size_t)h->maxRec + h->maxRec / 2));
+        if (flags & 2u) // (maxRec = the fullest bucket of any solver)
+            recCap_ = pow2AtLeast(std::max<size_t>(recCap_ * 2, ((size_t)h->maxRec + h->maxRec / 2) * kRecBuckets));
         if (flags & 4u) {
             entryGuess_ = std::max<int64_t>(entryGuess_ * 2, h->nTotal + h->nTotal / 2);
             litGuess_ = std::max<int64_t>(litGuess_ * 2, h->litTotal + h->litTotal / 2);
@@ -350,8 +355,8 @@ void Sharer::bumpDirect(const std::vector<DevicePart> &parts) {
     for (const DevicePart &p : parts) {
         RunSlot &slot = *p.slot;
         if (!slot.checked) continue;
-        const unsigned int maxRec = slot.runBuf->hdr()->maxRec;
-        launchBumpFromRecs(slot.recKeys.data(), slot.recCap, slot.solverInfo.data(), slot.nSolvers, std::min(maxRec, slot.recCap),
+        if (slot.runBuf->hdr()->nTotal == 0) continue;
+        launchBumpFromRecs(slot.sortKeys.data(), slot.recCap, slot.solverInfo.data(), slot.nSolvers, slot.recCap,
                            (const LenDir *)bumpDirDev_.data(), (int)dir.size(), db_->activityIncrement(), bumpFlagDev_.data(),
                            stream_, &launches_);
     }
@@ -432,7 +437,7 @@ void Sharer::appendDirectHits(RunSlot &slot, std::vector<gss_hit> &out) {
         const RunHdr::PerSolver &ps = h->solver[s];
         if (ps.n <= 0) continue;
         masks.resize((size_t)ps.n);
-        GSS_CUDA(cudaMemcpyAsync(masks.data(), slot.recMasks.data() + (size_t)s * slot.recCap, (size_t)ps.n * sizeof(uint32_t),
+        GSS_CUDA(cudaMemcpyAsync(masks.data(), slot.sortMasks.data() + (size_t)s * slot.recCap, (size_t)ps.n * sizeof(uint32_t),
                                  cudaMemcpyDeviceToHost, stream_));
         GSS_CUDA(cudaStreamSynchronize(stream_));
         const int64_t *ids = slot.runBuf->ids() + ps.entryBase;

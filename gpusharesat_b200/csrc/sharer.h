@@ -134,10 +134,12 @@ private:
         bool checked = false;       // check kernels + k_emit were launched (some solver had a frozen slot)
         uint32_t seq = 0;           // what k_emit writes into the header last
         std::shared_ptr<RunBuf> runBuf;
-        DevBuf<unsigned long long> ctrDev;  // [kMaxSolvers][kRecShards] records | literals << 32
+        DevBuf<unsigned long long> ctrDev;  // [kMaxSolvers][kRecBuckets] x kCtrStride: records | literals << 32
         DevBuf<EmitSolver> solverInfo;      // [kMaxSolvers] written by k_emit_sort
-        DevBuf<unsigned long long> recKeys; // [nSolvers][recCap]
+        DevBuf<unsigned long long> recKeys; // [nSolvers][kRecBuckets][recCap / kRecBuckets] as k_exact appends them
         DevBuf<uint32_t> recMasks;
+        DevBuf<unsigned long long> sortKeys; // [nSolvers][recCap] every solver's records in canonical order (k_emit_sort)
+        DevBuf<uint32_t> sortMasks;
         DevBuf<int32_t> recPos;             // [nSolvers][recCap + 1]
         DevBuf<unsigned int> ticketDev;     // 4 words
         unsigned int recCap = 0;
@@ -191,6 +193,7 @@ private:
 
     std::shared_ptr<RunBufPool> runBufs_;
     bool directEnabled_ = true;
+    bool eagerResults_ = true; // surface a run's hits in the call that started it when it completes within minGpuLatencyMicros
     size_t recCap_ = 1024;       // per-solver record capacity (power of two)
     int64_t entryGuess_ = 4096, litGuess_ = 16384; // result buffer sizing (from previous runs)
     uint32_t directSeq_ = 0;

@@ -36,6 +36,10 @@ def make(devices, **opts):
         os.environ.pop("GPUSHARE_DEVICES", None)
 
 
+def model_clauses(model):
+    return len(model.clauses) if hasattr(model, "clauses") else 1 << 60
+
+
 def pop_all(sh, s):
     out = []
     while True:
@@ -86,11 +90,32 @@ def test_multi_device_equals_single_device_and_oracle(devices, nsolvers):
             # the hand-over order of a multi-device run is device-major: compare as sets
             assert sorted(pop_all(a, s)) == sorted(pop_all(b, s)), (r, s)
             assert a.getLastAssigAllReported(s) == b.getLastAssigAllReported(s)
-        if r == 4:  # reduceDb: the activities live on device 0, every device must compact identically
-            for sh in (a, b):
-                sh.reduceDb()
-            assert a.getGlobalStat(0) == b.getGlobalStat(0) and a.getGlobalStat(1) == b.getGlobalStat(1)
     assert total > 0
+    # reduceDb: the activities live on device 0, every device must compact identically (the oracle model
+    # keeps every clause, so from here on the two sharers are compared with each other only)
+    for r in range(3):
+        for sh in (a, b):
+            sh.reduceDb()
+        assert a.getGlobalStat(0) == b.getGlobalStat(0) and a.getGlobalStat(1) == b.getGlobalStat(1)
+        assert a.getGlobalStat(0) < model_clauses(model) if r == 0 else True
+        for s in range(nsolvers):
+            vs = rng.choice(nvars, size=nvars // 2, replace=False)
+            sets = [mkLit(int(v), bool(rng.random() < 0.8)) for v in vs]
+            for sh in (a, b):
+                sh.unsetSolverValues(s, [mkLit(v) for v in range(nvars)])
+                assert sh.trySetSolverValues(s, sets)
+                assert sh.trySendAssignment(s) >= 0
+        for sh in (a, b):
+            sh.gpuRun()
+            sh.gpuRun()
+        ha, hb = a.debugLastHits(), b.debugLastHits()
+        assert len(ha) > 0 and np.array_equal(ha, hb), r
+        for s in range(nsolvers):
+            assert sorted(pop_all(a, s)) == sorted(pop_all(b, s)), (r, s)
+        for _ in range(300):
+            n = int(rng.integers(3, 6))
+            lits = [mkLit(int(rng.integers(0, nvars)), bool(rng.integers(0, 2))) for _ in range(n)]
+            assert len({sh.addClause(-1, lits) for sh in (a, b)}) == 1
     for st in (0, 1, 2, 3, 4, 5, 6, 7, 8):
         assert a.getGlobalStat(st) == b.getGlobalStat(st), st
 
