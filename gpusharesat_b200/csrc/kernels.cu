@@ -364,10 +364,160 @@ __global__ void __launch_bounds__(256, MINBLOCKS) k_filter_t(CheckArgs a) {
     stage.flush(a.survivors, survCounter, a.survCap, lane);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Level 1, literal rows staged by TMA.  Same work split and arithmetic as k_filter_t (warp per tile,
+// lane = 4 clauses, contiguous run of tiles per warp), but rows 0 and 1 of a tile -- all a tile needs
+// 98 % of the time -- no longer travel through registers: one elected lane issues ONE 1-D bulk copy
+// (cp.async.bulk, 512 or 1024 contiguous bytes, L2 evict-first) per tile into the warp's private ring
+// in shared memory, kRing tiles ahead, completion on an mbarrier.  A warp therefore has the rows of
+// the next kRing tiles in flight at no register cost, and the per-tile dependent chain shrinks from
+// "row load -> gather -> vote -> gather -> vote" to "gather -> vote -> gather -> vote".  Rows >= 2
+// (12 % of the tiles of longer clauses) are fetched on demand with LDG.128 as before.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRing = 4;
+constexpr int kRingSlotBytes = 2 * kTileClauses * (int)sizeof(int32_t); // two literal rows
+
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulkLoad(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+}
+
+template <int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS) k_filter_tma_t(CheckArgs a) {
+    extern __shared__ __align__(128) unsigned char sDynRaw[];
+    // [ring: warps x kRing x 1 KB][mbarriers: warps x kRing x 8 B][cumulative tile counts: nDir ints]
+    const int warpsPerBlock = blockDim.x >> 5;
+    unsigned char *ringBase = sDynRaw;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sDynRaw + (size_t)warpsPerBlock * kRing * kRingSlotBytes);
+    int *sTileEnd = reinterpret_cast<int *>(bars + warpsPerBlock * kRing);
+    for (int i = threadIdx.x; i < a.nDir; i += blockDim.x) sTileEnd[i] = a.dir[i].tileEnd;
+    if ((int)threadIdx.x < warpsPerBlock * kRing) mbarInit(smemAddr(bars + threadIdx.x), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warp = blockIdx.x * warpsPerBlock + wib;
+    const int nWarps = gridDim.x * warpsPerBlock;
+    const uint2 *__restrict__ a1 = a.tables.a1 + (size_t)(a.groupBase / kMaxSolversPerGroup) * 2 * (size_t)a.tables.varCap;
+    const uint32_t start = groupAggStart(a, lane);
+    if (start == 0) return; // no frozen slot in this group
+    __shared__ Survivor sStage[kMaxWarpsPerBlock][kStageCap];
+    WarpStage<Survivor> stage{sStage[wib], 0};
+    unsigned int *survCounter = &a.counters->nSurvivors[a.groupBase / kMaxSolversPerGroup];
+    const unsigned char *myRing = ringBase + (size_t)wib * kRing * kRingSlotBytes;
+    const uint32_t myRingAddr = smemAddr(myRing), myBars = smemAddr(bars + wib * kRing);
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+
+    struct Cursor { // where a tile lives (every device holds the whole arena; this rank checks a contiguous share)
+        const int32_t *base; // the tile's first literal row
+        int len, c0;         // clause length; global index of the tile's first clause
+        int count;           // clauses of this length
+        int lenEnd;          // first (device-local) tile index of the next length
+    };
+    auto locate = [&](int tile) -> Cursor {
+        const int k = findDir(sTileEnd, a.nDir, tile);
+        const LenDir d = a.dir[k];
+        const int gTile = (tile - (k ? sTileEnd[k - 1] : 0)) + d.firstTile;
+        return Cursor{d.base + (size_t)gTile * kTileClauses * d.len, d.len, gTile * kTileClauses, d.count, sTileEnd[k]};
+    };
+    auto advance = [&](const Cursor &t, int tile) -> Cursor {
+        if (tile + 1 >= t.lenEnd) return locate(tile + 1);
+        return Cursor{t.base + (size_t)kTileClauses * t.len, t.len, t.c0 + kTileClauses, t.count, t.lenEnd};
+    };
+    const int per = (a.totalTiles + nWarps - 1) / nWarps;
+    const int first = warp * per, last = min(a.totalTiles, first + per);
+    if (first >= last) return;
+
+    auto issue = [&](const Cursor &t, int slot) { // rows 0 (and 1) of tile t -> ring slot
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)min(t.len, 2) * kTileClauses * (uint32_t)sizeof(int32_t);
+            const uint32_t bar = myBars + slot * 8;
+            mbarExpectTx(bar, bytes);
+            bulkLoad(myRingAddr + slot * kRingSlotBytes, t.base, bytes, bar, policy);
+        }
+    };
+    Cursor cur = locate(first), pf = cur;
+    int pfTile = first;
+    for (int k = 0; k < kRing && pfTile < last; k++) {
+        issue(pf, k);
+        if (pfTile + 1 < last) pf = advance(pf, pfTile);
+        pfTile++;
+    }
+    for (int tile = first; tile < last; tile++) {
+        const int n = tile - first, slot = n % kRing;
+        mbarWait(myBars + slot * 8, (uint32_t)(n / kRing) & 1u);
+        const int len = cur.len;
+        const int c0 = cur.c0 + lane, nValid = cur.count - c0; // clause c0 + 32q exists iff nValid > 32q
+        const int4 *sl = reinterpret_cast<const int4 *>(myRing + (size_t)slot * kRingSlotBytes) + lane;
+        uint32_t all0 = nValid > 0 ? start : 0u, all1 = nValid > 32 ? start : 0u;
+        uint32_t all2 = nValid > 64 ? start : 0u, all3 = nValid > 96 ? start : 0u;
+        uint32_t one0 = 0, one1 = 0, one2 = 0, one3 = 0;
+        int4 lits = sl[0];
+        uint32_t alive = 0;
+        const int32_t *row = cur.base + lane * 4;
+        for (int i = 0; i < len; i++) {
+            int4 next = lits;
+            if (i + 1 < len) next = i == 0 ? sl[kTileClauses / 4] : ldRow<0>(row + (size_t)(i + 1) * kTileClauses);
+            const uint2 dead = make_uint2(0u, 0u);
+            uint2 g0 = (all0 | one0) ? __ldg(a1 + lits.x) : dead;
+            uint2 g1 = (all1 | one1) ? __ldg(a1 + lits.y) : dead;
+            uint2 g2 = (all2 | one2) ? __ldg(a1 + lits.z) : dead;
+            uint2 g3 = (all3 | one3) ? __ldg(a1 + lits.w) : dead;
+            step(all0, one0, g0.x, g0.y);
+            step(all1, one1, g1.x, g1.y);
+            step(all2, one2, g2.x, g2.y);
+            step(all3, one3, g3.x, g3.y);
+            alive = (all0 | one0) | (all1 | one1) | (all2 | one2) | (all3 | one3);
+            if (!__any_sync(FULL, alive)) break;
+            lits = next;
+        }
+        // the slot is free again once every lane has read its words (generic-proxy reads ordered before the
+        // async-proxy write of the refill): refill it kRing tiles ahead
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (pfTile < last) {
+            issue(pf, slot);
+            if (pfTile + 1 < last) pf = advance(pf, pfTile);
+            pfTile++;
+        }
+        if (__any_sync(FULL, alive)) {
+            const uint64_t rowTag = (uint64_t)(uintptr_t)row | ((uint64_t)len << 48);
+            const uint32_t m0 = all0 | one0, m1 = all1 | one1, m2 = all2 | one2, m3 = all3 | one3;
+            stage.push(m0 != 0, Survivor{rowTag + 0 * sizeof(int32_t), c0 + 0, m0}, a.survivors, survCounter, a.survCap, lane);
+            stage.push(m1 != 0, Survivor{rowTag + 1 * sizeof(int32_t), c0 + 32, m1}, a.survivors, survCounter, a.survCap, lane);
+            stage.push(m2 != 0, Survivor{rowTag + 2 * sizeof(int32_t), c0 + 64, m2}, a.survivors, survCounter, a.survCap, lane);
+            stage.push(m3 != 0, Survivor{rowTag + 3 * sizeof(int32_t), c0 + 96, m3}, a.survivors, survCounter, a.survCap, lane);
+        }
+        if (tile + 1 < last) cur = advance(cur, tile);
+    }
+    stage.flush(a.survivors, survCounter, a.survCap, lane);
+}
+
 struct FilterVariant {
     void (*kernel)(CheckArgs);
     int threads;
     const char *name;
+    int ringBytesPerWarp = 0; // TMA variants: dynamic shared memory per warp (ring + mbarriers)
 };
 const FilterVariant kFilterVariants[] = {
     {k_filter_t<false, 0, 0, 0, 5>, 256, "strided tiles, 5 x 256 threads/SM"},
@@ -380,6 +530,9 @@ const FilterVariant kFilterVariants[] = {
     {k_filter_t<false, 2, 0, 0, 5>, 128, "contiguous per block, 10 x 128"},
     {k_filter_t<true, 1, 0, 0, 4>, 256, "contiguous per warp + ping-pong prefetch, 4 x 256"},
     {k_filter_t<true, 1, 0, 0, 5>, 256, "contiguous per warp + ping-pong prefetch, 5 x 256"},
+    {k_filter_tma_t<5>, 256, "rows 0-1 by TMA bulk copies into a per-warp ring (4 tiles ahead), 5 x 256", kRing *(kRingSlotBytes + 8)},
+    {k_filter_tma_t<6>, 256, "TMA ring, 6 x 256", kRing *(kRingSlotBytes + 8)},
+    {k_filter_tma_t<4>, 256, "TMA ring, 4 x 256", kRing *(kRingSlotBytes + 8)},
 };
 constexpr int kNumFilterVariants = (int)(sizeof(kFilterVariants) / sizeof(kFilterVariants[0]));
 int gFilterVariant = -1; // -1: not chosen yet (GSS_FILTER_VARIANT or the default)
@@ -424,6 +577,18 @@ __device__ __forceinline__ void appendRec(const CheckArgs &a, const int *sLen, c
         a.recKeys[at] = ((unsigned long long)(unsigned int)len << 32) | (unsigned int)idx;
         a.recMasks[at] = mask;
     }
+}
+
+__device__ __forceinline__ void flushRecs(const CheckArgs &a, WarpStage<HitRecord> &stage, const int *sLen, const long long *sAsc,
+                                          int nDir, int lane) {
+    if (stage.n == 0) return;
+    __syncwarp();
+    for (int i = lane; i < stage.n; i += 32) {
+        const HitRecord r = stage.buf[i];
+        appendRec(a, sLen, sAsc, nDir, r.solver, r.len, r.idx, r.mask);
+    }
+    __syncwarp();
+    stage.n = 0;
 }
 
 // G = survivors a warp checks together (their row gathers are independent)
@@ -524,7 +689,16 @@ template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS
             const bool has = (all[g] | one[g]) != 0;
             const HitRecord rec{all[g] | one[g], solver, len[g], idx};
             if (a.recKeys) {
-                if (has) appendRec(a, sDirLen, sDirAsc, nDirS, solver, len[g], idx, rec.mask);
+                // staged per warp like the global hit buffer; the flush appends them to the per-solver
+                // buckets with every lane's atomic in flight at once (an append per hit inside this loop
+                // put four dependent atomic round trips into every warp step: 19 -> 32 us)
+                const unsigned m = __ballot_sync(FULL, has);
+                if (m) {
+                    const int cnt = __popc(m);
+                    if (stage.n + cnt > kStageCap) flushRecs(a, stage, sDirLen, sDirAsc, nDirS, lane);
+                    if (has) stage.buf[stage.n + __popc(m & ((1u << lane) - 1))] = rec;
+                    stage.n += cnt;
+                }
             } else {
                 stage.push(has, rec, a.hits, &a.counters->nHits, a.hitCap, lane);
             }
@@ -534,7 +708,8 @@ template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS
 #pragma unroll
         for (int g = 0; g < G; g++) lit0[g] = lit1[g];
     }
-    if (!a.recKeys) stage.flush(a.hits, &a.counters->nHits, a.hitCap, lane);
+    if (a.recKeys) flushRecs(a, stage, sDirLen, sDirAsc, nDirS, lane);
+    else stage.flush(a.hits, &a.counters->nHits, a.hitCap, lane);
     if (lane == 0 && tests) atomicAdd(&a.counters->exactTests, tests);
     if (a.peerDone) {
         // Multi-GPU: the hits went straight into this rank's slot of rank 0's gather window (peer
@@ -846,9 +1021,11 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
             a.ids[es.entryBase + c0 + tid] = a.dir[dirOfLen(sLen, nDir, (int)(key >> 32))].ids[(unsigned int)key];
         }
         for (int i = tid; i < cnt + (c0 + cnt == n ? 1 : 0); i += blockDim.x) a.pos[es.entryBase + s + c0 + i] = sPos[i];
-        // literal stream of these entries: thread per literal (consecutive threads -> consecutive host addresses)
+        // Literal stream of these entries.  PCIe wants full, aligned lines: the body goes out as 16-byte
+        // vectors aligned in the HOST buffer (thread = four consecutive literals), the unaligned head and
+        // tail of the chunk as single words.
         const int q0 = sPos[0], q1 = sPos[cnt];
-        for (int q = q0 + tid; q < q1; q += blockDim.x) {
+        auto litAt = [&](int q) -> int32_t {
             int lo = 0, hi = cnt; // last i with sPos[i] <= q
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
@@ -858,8 +1035,21 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
             const int len = (int)(key >> 32), idx = (int)(unsigned int)key, j = q - sPos[lo];
             const int32_t *src = a.dir[dirOfLen(sLen, nDir, len)].base + (size_t)(idx / kTileClauses) * kTileClauses * len +
                                  tileSlot(idx % kTileClauses);
-            a.lits[es.litBase + q] = __ldg(src + (size_t)j * kTileClauses);
+            return __ldg(src + (size_t)j * kTileClauses);
+        };
+        const long long A0 = es.litBase + q0, A1 = es.litBase + q1; // absolute positions in the buffer's literal stream
+        const long long B0 = min(A1, (A0 + 3) & ~3ll), B1 = max(B0, A1 & ~3ll);
+        for (long long A = A0 + tid; A < B0; A += blockDim.x) a.lits[A] = litAt((int)(A - es.litBase));
+        for (long long A = B0 + 4ll * tid; A < B1; A += 4ll * blockDim.x) {
+            const int q = (int)(A - es.litBase);
+            int4 v;
+            v.x = litAt(q);
+            v.y = litAt(q + 1);
+            v.z = litAt(q + 2);
+            v.w = litAt(q + 3);
+            *reinterpret_cast<int4 *>(a.lits + A) = v;
         }
+        for (long long A = B1 + tid; A < A1; A += blockDim.x) a.lits[A] = litAt((int)(A - es.litBase));
     }
     if (n == 0 && blockIdx.x == 0 && tid == 0) a.pos[es.entryBase + s] = 0;
     if (blockIdx.x == 0 && tid == 0) {
@@ -1290,8 +1480,18 @@ void launchFilterOnly(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStrea
     }
     const FilterVariant &fv = kFilterVariants[gFilterVariant];
     int threads = std::min(dims.threads, fv.threads);
-    size_t smem = (size_t)a.nDir * sizeof(int);
     int warpsPerBlock = threads / 32;
+    size_t smem = (size_t)a.nDir * sizeof(int) + (size_t)fv.ringBytesPerWarp * warpsPerBlock;
+    if (fv.ringBytesPerWarp) { // the ring needs the large shared-memory carve-out (L1 hit rate of this kernel: 3 %)
+        static bool configured[64][16] = {};
+        int dev = 0;
+        GSS_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && gFilterVariant < 16 && !configured[dev][gFilterVariant]) {
+            GSS_CUDA(cudaFuncSetAttribute((const void *)fv.kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            GSS_CUDA(cudaFuncSetAttribute((const void *)fv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            configured[dev][gFilterVariant] = true;
+        }
+    }
     int blocks = resolveBlocks((const void *)fv.kernel, threads, smem, numSMs, dims.blocks,
                                ((long long)a.totalTiles + warpsPerBlock - 1) / warpsPerBlock);
     fv.kernel<<<blocks, threads, smem, s>>>(a);

@@ -120,6 +120,9 @@ int main(int argc, char **argv) {
     int lost = 0;
     const auto tStart = Clock::now();
     const int64_t runs0 = runs.load();
+    double ph0[6];
+    gss_debug_host_phases(h, ph0);
+    const int64_t reports0 = gss_get_global_stat(h, 8);
     for (int p = 0; p < nProbes; p++) {
         const int s = (int)(rng() % S);
         int len = (p % 4 == 3) ? 101 + (int)(rng() % 100) : 2 + (int)(rng() % 8);
@@ -143,6 +146,8 @@ int main(int argc, char **argv) {
     }
     const double wallS = usSince(tStart) * 1e-6;
     const int64_t nRuns = runs.load() - runs0;
+    double ph1[6];
+    gss_debug_host_phases(h, ph1);
     stop.store(true);
     for (auto &t : threads) t.join();
     gpu.join();
@@ -150,8 +155,12 @@ int main(int argc, char **argv) {
     auto q = [&](double f) { return lat.empty() ? -1.0 : lat[std::min(lat.size() - 1, (size_t)(f * lat.size()))]; };
     printf("{\"harness\": \"import_latency\", \"solvers\": %d, \"vars\": %d, \"clauses\": %lld, \"probes\": %d, \"lost\": %d, "
            "\"p50_us\": %.1f, \"p90_us\": %.1f, \"p99_us\": %.1f, \"max_us\": %.1f, \"gpu_runs_per_s\": %.0f, "
-           "\"min_gpu_latency_micros\": %d, \"long_clause_share\": 0.05, \"max_clause_len\": 200}\n",
-           S, V, (long long)C, nProbes, lost, q(0.5), q(0.9), q(0.99), lat.empty() ? -1.0 : lat.back(), nRuns / wallS, minLat);
+           "\"min_gpu_latency_micros\": %d, \"long_clause_share\": 0.05, \"max_clause_len\": 200, "
+           "\"host_us_per_run\": {\"finish_previous\": %.1f, \"start_next\": %.1f, \"hand_over\": %.1f, \"collect\": %.1f, "
+           "\"wait_for_gpu\": %.1f}, \"hits_reported_per_run\": %.0f}\n",
+           S, V, (long long)C, nProbes, lost, q(0.5), q(0.9), q(0.99), lat.empty() ? -1.0 : lat.back(), nRuns / wallS, minLat,
+           (ph1[0] - ph0[0]) / nRuns, (ph1[1] - ph0[1]) / nRuns, (ph1[2] - ph0[2]) / nRuns, (ph1[3] - ph0[3]) / nRuns,
+           (ph1[4] - ph0[4]) / nRuns, (double)(gss_get_global_stat(h, 8) - reports0) / nRuns);
     gss_destroy(h);
     return 0;
 }
