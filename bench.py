@@ -351,7 +351,7 @@ def run_b200_sharded(a):
         sub = sharded_pass(copy.copy(a), other, max(3, a.steps // 2), a.warmup, dist, torch, rank, world, local, device)
         if rank == 0:
             main[other + "_scaling"] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "scaling", "steps", "e2e", "hits_per_step",
-                                                            "phases_us_per_step", "parity_sample", "literals") if k in sub}
+                                                            "phases_us_per_step", "parity_sample", "literals", "e2e_host_us_per_step_rank0") if k in sub}
             main[other + "_scaling"]["clauses"] = sub["config"]["clauses"]
     if rank == 0:
         print(json.dumps(main))
@@ -418,6 +418,7 @@ def sharded_pass(a, scaling, steps, warmup, dist, torch, rank, world, local, dev
     if rank == 0:
         sampler.start()
     l0 = sh.debugKernelLaunches()
+    hp0 = sh.debugHostPhases()
     wall = dev = 0.0
     hits = upd = back = 0
     ex, tk, ck = [], [], []
@@ -430,6 +431,7 @@ def sharded_pass(a, scaling, steps, warmup, dist, torch, rank, world, local, dev
         upd += h2d
         back += d2h
     launches = sh.debugKernelLaunches() - l0
+    hp = [(b - a0) / a.steps for a0, b in zip(hp0, sh.debugHostPhases())]
     clocks = sampler.stop() if rank == 0 else None
     tt = torch.tensor([dev, wall], dtype=torch.float64, device=device)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -454,9 +456,10 @@ def sharded_pass(a, scaling, steps, warmup, dist, torch, rank, world, local, dev
         cfg = workload_config(a)
         cfg["clauses_per_gpu"] = a.clauses // world
         if a.exchange == "peer":
-            region = ("rank 0: batch resident in its HBM -> mailbox signal -> every rank: table kernels (deltas read over "
-                      "NVLink from rank 0), check kernels (hits stored over NVLink into rank 0) -> rank 0 has seen every "
-                      "rank's done flag; CUDA events on rank 0's stream, max over ranks")
+            region = ("every rank, on its own stream (CUDA events): batch resident in its HBM (rank 0: after the H2D; workers: "
+                      "after rank 0's push over NVLink has arrived) -> table kernels -> check kernels on the rank's share of "
+                      "the tiles -> per-solver sort and emission of the rank's finished results (ids, literal stream) into "
+                      "host memory over the rank's own PCIe link, plus the collapse; max over ranks")
             gap = "exchange_and_wait_for_slowest_rank"
         else:
             region = "NCCL broadcast of the batch, table + check kernels on every shard, NCCL all-gather of the hits; max over ranks"
@@ -468,15 +471,19 @@ def sharded_pass(a, scaling, steps, warmup, dist, torch, rank, world, local, dev
             "e2e": {"value": L_total * A * a.steps / wall, "unit": UNIT, "ms_per_step": 1e3 * wall / a.steps,
                     "h2d_bytes_per_step": int(upd / a.steps),
                     "d2h_bytes_per_step": int(back / a.steps),
-                    "timed_region": "rank 0 collect + H2D, exchange, table + check kernels on every shard, device-side sort / "
-                                    "resolve of the union, D2H, host hand-over on rank 0; wall clock, max over ranks"},
+                    "timed_region": "rank 0 collect + H2D, push to the workers, table + check + emit kernels on every rank (each "
+                                    "rank writes its finished per-solver results into shared host memory), rank 0 stitches "
+                                    "the per-rank slices into the solvers' batches (zero-copy); wall clock, max over ranks"},
             "gpu_launches": int(ll[0]), "clocks": clocks, "hits_per_step": hits / a.steps,
             "phases_us_per_step": {gap: float(np.mean(ex)), "table_kernels": float(np.mean(tk)),
                                    "check_kernels": float(np.mean(ck)),
                                    "per_rank_table_check_other": [[round(float(x), 1) for x in t.tolist()] for t in allph]},
             "literals": L_total, "assignments": A, "parity_sample": parity,
-            "note": "N > 1: value = " + region + "; e2e adds rank 0's collect, the payload H2D, the sort / resolve of the hits, "
-                    "their D2H and the host hand-over",
+            "e2e_host_us_per_step_rank0": {"enqueue": hp[1], "of_which_collect_deltas": hp[3], "finish": hp[0],
+                                           "of_which_wait_for_own_gpu": hp[4], "of_which_wait_for_workers": hp[5],
+                                           "of_which_hand_over": hp[2]},
+            "note": "N > 1: value = " + region + "; e2e adds rank 0's collect, the payload H2D, the wait for the slowest rank's "
+                    "publication and the host hand-over",
         })
     dist.barrier()
     del runner

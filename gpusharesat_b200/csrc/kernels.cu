@@ -902,6 +902,8 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_emit_sort(EmitArgs a) {
         const long long e = min((unsigned int)ct, bucketCap), l = (long long)(ct >> 32);
         if (t < s * kRecBuckets) { eSolver += e; lSolver += l; } else { eBucket += e; lBucket += l; }
     }
+    // (one bucket with more than kSortSmemRecs records sorts in global memory and decides the kernel's
+    // duration -- 64 buckets of ~70 records with a few of 300 took 53 us at config 3; 256 buckets keep them small)
     auto blockSum = [&](long long v, int slot) -> long long {
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
         __syncthreads();
@@ -1019,6 +1021,8 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
         if (tid < cnt) {
             const unsigned long long key = K[c0 + tid];
             a.ids[es.entryBase + c0 + tid] = a.dir[dirOfLen(sLen, nDir, (int)(key >> 32))].ids[(unsigned int)key];
+            if (a.keysOut) a.keysOut[es.entryBase + c0 + tid] = key;
+            if (a.masksOut) a.masksOut[es.entryBase + c0 + tid] = a.sortMasks[(size_t)s * a.recCap + c0 + tid];
         }
         for (int i = tid; i < cnt + (c0 + cnt == n ? 1 : 0); i += blockDim.x) a.pos[es.entryBase + s + c0 + i] = sPos[i];
         // Literal stream of these entries.  PCIe wants full, aligned lines: the body goes out as 16-byte
@@ -1456,6 +1460,29 @@ void launchEmit(const EmitArgs &a, cudaStream_t s, int64_t *launches) {
     k_emit_write<<<dim3(perSolver, a.nSolvers, 1), 256, 0, s>>>(a);
     checkLaunch("k_emit");
     *launches += 2;
+}
+
+__global__ void k_bump_keys(const unsigned long long *__restrict__ keys, long long n, const LenDir *__restrict__ dir, int nDir,
+                            float inc, int *overflow) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[i];
+        const int len = (int)(key >> 32), idx = (int)(unsigned int)key;
+        int lo = 0, hi = nDir - 1; // descending length
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (dir[mid].len <= len) hi = mid; else lo = mid + 1;
+        }
+        float old = atomicAdd(dir[lo].acts + idx, inc);
+        if (old + inc > 1e19f) *overflow = 1;
+    }
+}
+
+void launchBumpFromKeys(const unsigned long long *keys, long long n, const LenDir *dir, int nDir, float inc, int *overflow,
+                        cudaStream_t s, int64_t *launches) {
+    if (n <= 0) return;
+    k_bump_keys<<<(unsigned int)std::min<long long>((n + 255) / 256, 1184), 256, 0, s>>>(keys, n, dir, nDir, inc, overflow);
+    checkLaunch("k_bump_keys");
+    ++*launches;
 }
 
 void launchBumpFromRecs(const unsigned long long *recKeys, unsigned int recCap, const EmitSolver *solverInfo, int nSolvers,

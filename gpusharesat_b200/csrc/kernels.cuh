@@ -28,7 +28,7 @@ constexpr int kMaxGroups = 8; // solver groups of 32 (256 solver threads)
 // clause's position in the database's canonical order (length ascending, index ascending) scaled to
 // 0..kRecBuckets-1.  Sorting every bucket on its own (a warp each) and reading the buckets in order
 // gives the solver's hits in the canonical order; the appends of a solver spread over many counters.
-constexpr int kRecBuckets = 64;
+constexpr int kRecBuckets = 256;
 constexpr int kCtrStride = 4; // counters are 32 bytes apart: atomics on one L2 sector serialise
 
 // device-side counters of one run
@@ -203,6 +203,10 @@ struct EmitArgs {
     int32_t *pos;   // entryCap + nSolvers (one more position than entries per solver)
     int32_t *lits;  // litCap
     long long entryCap, litCap;
+    // optional (multi-process exchange): the sorted records themselves, next to the ids, for the
+    // front-end's activity bumps (keys) and parity hook (masks); nullptr: stay on the device only
+    unsigned long long *keysOut = nullptr; // entryCap
+    uint32_t *masksOut = nullptr;          // entryCap
 };
 // per-solver sort by (length, index) = the reproducible hand-over order, clause ids, literal positions and
 // the literal stream of every solver, written straight into the result buffer in host memory
@@ -213,6 +217,10 @@ void launchApplyDirect(const VarUpdate *const *src, const SolverRunParams *param
 // activity bumps from the sorted per-solver record lists of a finished run
 void launchBumpFromRecs(const unsigned long long *recKeys, unsigned int recCap, const EmitSolver *solverInfo, int nSolvers,
                         unsigned int maxCount, const LenDir *dir, int nDir, float inc, int *overflow, cudaStream_t s, int64_t *launches);
+
+// the same from a flat list of sorted record keys (length << 32 | index), e.g. another process's result
+void launchBumpFromKeys(const unsigned long long *keys, long long n, const LenDir *dir, int nDir, float inc, int *overflow,
+                        cudaStream_t s, int64_t *launches);
 
 // register-only LOP3 micro-benchmark: thread-level LOP3 per second on this device
 double measureLop3Peak(int numSMs, cudaStream_t s, int64_t *launches);

@@ -231,8 +231,8 @@ void Sharer::wholeRunMulti(bool canStart) {
     }
     if (prev) {
         PhaseTimer t(hostPhases_[2]);
-        std::vector<DevicePart> parts{DevicePart{this, prev}};
-        for (auto &w : workers_) parts.push_back(DevicePart{w.get(), &w->slots_[prevIdx]});
+        std::vector<DevicePart> parts{DevicePart{this, prev, nullptr}};
+        for (auto &w : workers_) parts.push_back(DevicePart{w.get(), &w->slots_[prevIdx], nullptr});
         processResultsParts(*prev, parts);
         GSS_CUDA(cudaEventRecord(peerReadEv_, stream_));
         peerReadRecorded_ = true;

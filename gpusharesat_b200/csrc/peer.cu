@@ -4,8 +4,7 @@
 // IPC; rank 0 (the front-end: solver threads, slot machines, hand-over) maps every worker's window,
 // the workers map rank 0's.  NVLink / NVSwitch then carries plain loads and stores:
 //
-//   rank 0 window   [control: done flag of every rank][payload: header, run parameters, deltas]
-//                   [gather: one slot per rank = 64 B header + hit records]
+//   rank 0 window   [control][payload: header, run parameters, deltas]
 //   worker window   [control: mailbox][payload]
 //
 // Data is always PUSHED (posted writes run at link speed; reading a peer's memory is latency-bound:
@@ -17,23 +16,33 @@
 //            transfers and a second stream both deliver the batch ~25 us later.)
 //   worker   stream waits for mailbox >= seq (cuStreamWaitValue32: nothing spins on an SM), then
 //            k_apply_updates (counts come from the payload itself, the host never reads it; it keeps
-//            a copy for the deferred collapse), k_filter / k_exact on this rank's tiles, which append
-//            the hits straight into this rank's slot of rank 0's gather area (peer stores); the block
-//            of k_exact that finishes last writes the slot header and the done flag.
+//            a copy for the deferred collapse), k_filter / k_exact on this rank's tiles (results: below)
 //   workers  as soon as a batch cannot be run again (no overflow), peerFinish enqueues its collapse
 //            (dSetAllAssigsToLast): off the critical path of the next batch, on a warm GPU.  Rank 0
 //            collapses right after the next push instead: it does not have to wait for the batch
 //            to arrive, so its collapse hides behind the workers' later start.
-//   rank 0   stream waits for every done flag, reads the headers (one small D2H), and sorts /
-//            resolves / hands over the union of the hits on its device (every rank holds the whole
-//            clause arena, so rank 0 can resolve any hit)
-// A rank whose survivor buffer overflowed flags it in its header (done = 2*seq-1), grows the buffer,
-// runs again and then reports done = 2*seq; rank 0 waits for that second flag.  Nothing is dropped.
+//   results  (round 2) every rank runs the direct pipeline's result path on its own device: per-solver
+//            record buckets, k_emit_sort, k_emit_write -- and k_emit_write writes the rank's FINISHED
+//            per-solver results (clause ids, literal positions, literal stream, plus the sorted
+//            records for rank 0's activity bumps) straight into HOST memory over the rank's own PCIe
+//            link: a ring of buffers in a POSIX shared-memory segment the rank owns and rank 0 maps.
+//            Rank 0 only stitches views: a solver's ClauseBatch views one slice per rank.  Nothing
+//            is funnelled through rank 0's GPU or its PCIe link any more (round 1: hits by peer stores
+//            into rank 0's window, then sort / resolve / D2H of the UNION on rank 0: e2e weak
+//            efficiency 0.31 at 8 GPUs).  A rank whose buffers overflowed repairs that by itself
+//            (re-launch with larger buffers) before it publishes; rank 0 just waits for it.
+//   hand-shake  a worker publishes (sequence number, buffer index) in its ring's control block after
+//            its own event has completed (so its GPU's writes are visible to every CPU); rank 0's
+//            host polls that word.
 //
 // (The reference drives one device only: gpuShareLib/GpuClauseSharerImpl.cu:52.)
 #include "sharer.h"
 #include <chrono>
 #include <cstring>
+#include <atomic>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <thread>
 #include <unistd.h>
 
@@ -61,6 +70,82 @@ static_assert(sizeof(PeerBlob) <= 128, "blob grew");
 
 inline size_t alignUp(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- a rank's result buffers in a POSIX shared-memory segment ----
+constexpr int kRingBufs = 4;
+constexpr uint32_t kRingMagic = 0x47535352u; // "GSSR"
+struct RingCtl {
+    uint32_t magic;
+    int32_t nBufs;
+    int64_t bufBytes, entryCap, litCap;
+    std::atomic<uint64_t> published; // (sequence number << 8) | buffer index, written by the owner after its event completed
+    uint8_t pad0[64 - 40];
+    struct {
+        std::atomic<uint32_t> state; // 0 free, 1 owned by the producer / still viewed by rank 0
+        uint8_t pad[60];
+    } buf[kRingBufs];
+};
+static_assert(sizeof(RingCtl) == 64 * (1 + kRingBufs), "control block layout");
+constexpr size_t kRingCtlBytes = 4096;
+
+struct ShmRing {
+    std::string name;
+    uint8_t *base = nullptr;
+    size_t bytes = 0;
+    bool owner = false, registered = false;
+    RingCtl *ctl() const { return reinterpret_cast<RingCtl *>(base); }
+    uint8_t *buf(int k) const { return base + kRingCtlBytes + (size_t)k * (size_t)ctl()->bufBytes; }
+
+    static std::string nameOf(int pid, int rank) { return "/gss_b200_" + std::to_string(pid) + "_" + std::to_string(rank); }
+    void create(int pid, int rank, int64_t entryCap, int64_t litCap) {
+        name = nameOf(pid, rank);
+        const size_t bufBytes = (Sharer::RunBuf::bytesFor(entryCap, litCap, true) + 4095) / 4096 * 4096;
+        bytes = kRingCtlBytes + kRingBufs * bufBytes;
+        shm_unlink(name.c_str());
+        int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+        // (posix_fallocate: a full /dev/shm must be an error here, not a SIGBUS on the first store)
+        if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0 || posix_fallocate(fd, 0, (off_t)bytes) != 0) {
+            if (fd >= 0) shm_unlink(name.c_str());
+            GSS_DIE("cannot create the shared-memory result ring " + name + " (" + std::to_string(bytes) + " bytes; is /dev/shm large enough?)");
+        }
+        map(fd);
+        memset(base, 0, kRingCtlBytes);
+        RingCtl *c = ctl();
+        c->nBufs = kRingBufs;
+        c->bufBytes = (int64_t)bufBytes;
+        c->entryCap = entryCap;
+        c->litCap = litCap;
+        c->magic = kRingMagic;
+        owner = true;
+    }
+    void open(int pid, int rank) {
+        name = nameOf(pid, rank);
+        int fd = shm_open(name.c_str(), O_RDWR, 0600);
+        if (fd < 0) GSS_DIE("cannot open the shared-memory result ring " + name);
+        struct stat st;
+        if (fstat(fd, &st) != 0) GSS_DIE("cannot stat " + name);
+        bytes = (size_t)st.st_size;
+        map(fd);
+        if (ctl()->magic != kRingMagic) GSS_DIE("shared-memory result ring " + name + " is not initialised");
+    }
+    void map(int fd) {
+        void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
+        ::close(fd);
+        if (p == MAP_FAILED) GSS_DIE("cannot map the shared-memory result ring " + name);
+        base = static_cast<uint8_t *>(p);
+        // page-locked + mapped: this process's device reads / writes it in place (unified addressing)
+        GSS_CUDA(cudaHostRegister(base, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+        registered = true;
+    }
+    ~ShmRing() { close(); }
+    void close() {
+        if (!base) return;
+        if (registered) cudaHostUnregister(base);
+        munmap(base, bytes);
+        if (owner) shm_unlink(name.c_str());
+        base = nullptr;
+    }
+};
+
 // driver entry point of the stream memory operation, resolved through the runtime (no libcuda link)
 using WaitValue32Fn = int (*)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
 
@@ -69,7 +154,7 @@ using WaitValue32Fn = int (*)(cudaStream_t, unsigned long long, uint32_t, unsign
 struct Sharer::PeerState {
     int rank = 0, world = 1;
     int64_t payloadCap = 0, slotHits = 0;
-    size_t slotBytes = 0, windowBytes = 0, payloadArea = 0;
+    size_t windowBytes = 0, payloadArea = 0;
     uint8_t *window = nullptr;          // this rank's window
     uint8_t *rootWindow = nullptr;      // rank 0's window (mapped on the workers)
     std::vector<uint8_t *> mapped;      // windows opened through IPC (to be closed)
@@ -78,7 +163,6 @@ struct Sharer::PeerState {
     uint32_t seq = 0;
     WaitValue32Fn waitFn = nullptr;
     bool connected = false;
-    HostBuf<long long> headsHost;       // rank 0: world x 8 int64
     HostBuf<int> errHost;
     double timeoutS = 120.0;
     cudaEvent_t evC0 = nullptr, evC1 = nullptr; // around the collapse of this batch (end of peerFinish)
@@ -86,9 +170,11 @@ struct Sharer::PeerState {
     bool collapsed = false, collapsePending = false;
     cudaEvent_t evWait = nullptr;               // workers: the mailbox wait has been satisfied
     bool trace = false;                         // GSS_PEER_TRACE: per-batch phase times on stderr
+    std::shared_ptr<ShmRing> ring;              // workers: this rank's result buffers
+    std::vector<std::shared_ptr<ShmRing>> rings; // rank 0: every worker's ring (index = rank; [0] unused)
+    int ringBuf = -1;                           // workers: buffer of the batch in flight (not yet published)
 
     uint8_t *payload() const { return (rank == 0 ? rootWindow : window) + kCtlBytes; } // this rank's copy of the batch
-    uint8_t *slot(int r) const { return rootWindow + kCtlBytes + payloadArea + (size_t)r * slotBytes; }
     uint32_t *done(int r) const { return reinterpret_cast<uint32_t *>(rootWindow + kDoneOff + (size_t)r * kFlagStride); }
     uint32_t *mailbox() const { return reinterpret_cast<uint32_t *>(window + kMailboxOff); }
     int *err() const { return reinterpret_cast<int *>(window + kErrOff); }
@@ -108,8 +194,7 @@ int64_t Sharer::peerInit(int rank, int world, int64_t payloadCap, int64_t slotHi
     P.payloadCap = payloadCap;
     P.slotHits = slotHits;
     P.payloadArea = alignUp((size_t)payloadCap, 256);
-    P.slotBytes = alignUp(64 + (size_t)slotHits * sizeof(HitRecord), 256);
-    P.windowBytes = kCtlBytes + P.payloadArea + (rank == 0 ? (size_t)world * P.slotBytes : 0);
+    P.windowBytes = kCtlBytes + P.payloadArea; // (round 1 also had one gather slot per rank here: results go to host memory now)
     GSS_CUDA(cudaMalloc(reinterpret_cast<void **>(&P.window), P.windowBytes));
     GSS_CUDA(cudaMemset(P.window, 0, kCtlBytes));
     GSS_CUDA(cudaDeviceSynchronize());
@@ -129,6 +214,10 @@ int64_t Sharer::peerInit(int rank, int world, int64_t payloadCap, int64_t slotHi
     logger_.log(1, std::string("c gpushare_b200 peer exchange: rank ") + std::to_string(rank) + "/" + std::to_string(world) +
                        (P.waitFn ? ", stream memory operations\n" : ", polling kernel\n"));
 
+    if (rank > 0) {
+        P.ring = std::make_shared<ShmRing>();
+        P.ring->create((int)getpid(), rank, slotHits, slotHits * 8);
+    }
     PeerBlob b;
     memset(&b, 0, sizeof(b));
     b.magic = kBlobMagic;
@@ -162,6 +251,12 @@ void Sharer::peerConnect(const void *blobs, int64_t blobBytes) {
         return static_cast<uint8_t *>(p);
     };
     if (P.rank == 0) {
+        P.rings.resize((size_t)P.world);
+        for (int r = 1; r < P.world; r++) {
+            P.rings[r] = std::make_shared<ShmRing>();
+            P.rings[r]->open(blobOf(r).pid, r);
+        }
+        foreignCopyOut_ = getenv("GPUSHARE_PEER_COPY_OUT") != nullptr;
         for (int r = 1; r < P.world; r++) {
             uint8_t *w = open(blobOf(r));
             P.push.dst[P.push.n] = reinterpret_cast<uint4 *>(w + kCtlBytes);
@@ -169,7 +264,6 @@ void Sharer::peerConnect(const void *blobs, int64_t blobBytes) {
             P.push.n++;
         }
         GSS_CUDA(cudaEventCreate(&P.evPushed));
-        P.headsHost.resize((size_t)P.world * 8);
     } else {
         P.rootWindow = open(blobOf(0));
     }
@@ -184,6 +278,10 @@ void Sharer::peerConnect(const void *blobs, int64_t blobBytes) {
 
 void Sharer::peerClose() {
     if (!peer_) return;
+    bumpOwners_.clear();
+    lastForeign_.clear();
+    peer_->ring.reset(); // (the mappings live until the last batch that views them has gone)
+    peer_->rings.clear();
     for (uint8_t *p : peer_->mapped) cudaIpcCloseMemHandle(p);
     if (peer_->evC0) cudaEventDestroy(peer_->evC0);
     if (peer_->evC1) cudaEventDestroy(peer_->evC1);
@@ -195,23 +293,37 @@ void Sharer::peerClose() {
     peer_ = nullptr;
 }
 
-void Sharer::peerLaunchCheckAndFinalize(RunSlot &slot) {
+// worker ranks: the batch's result buffer comes from the rank's shared-memory ring (rank 0 reads it there)
+bool Sharer::peerAcquireResultBuf(RunSlot &slot) {
     PeerState &P = *peer_;
-    uint8_t *mySlot = P.slot(P.rank);
-    hitsOverride_ = reinterpret_cast<HitRecord *>(mySlot + 64);
-    hitCapOverride_ = (unsigned int)P.slotHits;
-    fusedPublish_.peerHdr = reinterpret_cast<long long *>(mySlot);
-    fusedPublish_.peerDone = P.done(P.rank);
-    fusedPublish_.peerTicket = P.ticket();
-    fusedPublish_.peerSeq = P.seq;
-    const bool published = launchCheckKernels(slot, slot.dense);
-    hitsOverride_ = nullptr;
-    fusedPublish_.peerDone = nullptr;
-    if (published) return; // the last k_exact wrote the slot header and the done flag itself
-    // nothing was launched that could publish (no tile on this rank, no frozen slot, dense mode)
-    int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
-    launchPeerFinalize((const Counters *)resDev_.data(), (unsigned int)P.slotHits, (unsigned int)survCap_, groups,
-                       reinterpret_cast<long long *>(mySlot), P.done(P.rank), P.seq, stream_, &launches_);
+    if (P.rank == 0 || !P.ring) return false;
+    ShmRing &R = *P.ring;
+    RingCtl *c = R.ctl();
+    if (entryGuess_ > c->entryCap || litGuess_ > c->litCap)
+        GSS_DIE("peer exchange: the hits of rank " + std::to_string(P.rank) + " do not fit its result buffers (raise slot_hits)");
+    if (P.ringBuf >= 0) c->buf[P.ringBuf].state.store(0, std::memory_order_release); // a repeated batch: its first buffer was never published
+    P.ringBuf = -1;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        for (int k = 0; k < c->nBufs && P.ringBuf < 0; k++) {
+            uint32_t expect = 0;
+            if (c->buf[k].state.compare_exchange_strong(expect, 1u, std::memory_order_acq_rel)) P.ringBuf = k;
+        }
+        if (P.ringBuf >= 0) break;
+        // every buffer is still viewed by batches of rank 0's solvers: wait for one to be retired
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > P.timeoutS)
+            GSS_DIE("peer exchange: no free result buffer on rank " + std::to_string(P.rank) + " (rank 0's solvers do not pop)");
+        std::this_thread::yield();
+    }
+    RunBuf *b = new RunBuf();
+    b->base = R.buf(P.ringBuf);
+    b->bytes = (size_t)c->bufBytes;
+    b->entryCap = c->entryCap;
+    b->litCap = c->litCap;
+    b->withRecords = true;
+    std::shared_ptr<ShmRing> keep = P.ring;
+    slot.runBuf = std::shared_ptr<RunBuf>(b, [keep](RunBuf *q) { delete q; }); // (rank 0 frees the ring buffer)
+    return true;
 }
 
 // make the stream wait until *flag >= value (flag lives in THIS device's memory; another GPU stores it)
@@ -232,6 +344,7 @@ int Sharer::peerEnqueue() {
     GSS_CHECK(peer_ && peer_->connected && cur_ < 0 && mgpuPending_ < 0);
     PeerState &P = *peer_;
     const bool root = P.rank == 0;
+    PhaseTimer tEnqueue(hostPhases_[1]);
     db_->drainPending();
     if (db_->stats().clauses == 0) return -1;
     RunSlot &slot = slots_[nextSlot()];
@@ -256,7 +369,10 @@ int Sharer::peerEnqueue() {
     slot.headDev.reserve(slot.headHost.size(), 0, stream_);
 
     if (root) {
-        collectBatch(slot, rebuild);
+        {
+            PhaseTimer tCollect(hostPhases_[3]);
+            collectBatch(slot, rebuild);
+        }
         PayloadHeader hdr;
         memset(&hdr, 0, sizeof(hdr));
         hdr.magic = kPayloadMagic;
@@ -323,23 +439,12 @@ int Sharer::peerEnqueue() {
     launchApplyUpdates(reinterpret_cast<const VarUpdate *>(payload + PR * sizeof(VarUpdate)), paramsSrc, slot.nSolvers,
                        slot.maxUpd, slot.nUpdates, tables_, numSMs_, stream_, &launches_, slot.updDev.data(), paramsKeep);
     GSS_CUDA(cudaEventRecord(slot.evBeforeCheck, stream_));
-    peerLaunchCheckAndFinalize(slot);
+    // the direct pipeline's result path on this rank's own tiles: record buckets, k_emit_sort, k_emit_write into
+    // host memory (rank 0: a buffer of its pool; workers: a buffer of their shared-memory ring)
+    slot.direct = true;
+    launchDirectCheck(slot);
     GSS_CUDA(cudaEventRecord(slot.evAfterCheck, stream_));
-    if (root) {
-        if (P.world > 2) { // all workers' flags with one launch
-            PeerFlagList all{};
-            for (int r = 1; r < P.world; r++) all.p[all.n++] = P.done(r);
-            launchPeerWaitAll(all, 2u * P.seq - 1u, (unsigned long long)(P.timeoutS * 1e9), P.err(), stream_, &launches_);
-        } else if (P.world == 2) {
-            peerWaitFlag(P.done(1), 2u * P.seq - 1u);
-        }
-    }
-    GSS_CUDA(cudaEventRecord(P.evGathered, stream_)); // rank 0: the hits of every rank are in its memory
-    // (small copies cost ~10 us of latency each: they go after the point the batch is complete)
-    slot.resHost.resize(sizeof(Counters));
-    GSS_CUDA(cudaMemcpyAsync(slot.resHost.data(), resDev_.data(), sizeof(Counters), cudaMemcpyDeviceToHost, stream_));
-    if (root)
-        GSS_CUDA(cudaMemcpy2DAsync(P.headsHost.data(), 64, P.slot(0), P.slotBytes, 64, (size_t)P.world, cudaMemcpyDeviceToHost, stream_));
+    GSS_CUDA(cudaEventRecord(P.evGathered, stream_));
     GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
     slot.inFlight = true;
     P.collapsePending = slot.nUpdates != 0;
@@ -357,8 +462,10 @@ int64_t Sharer::peerFinish() {
     PeerState &P = *peer_;
     RunSlot &slot = slots_[cur_];
     const bool root = P.rank == 0;
-    auto waitEnd = [&]() {
+    PhaseTimer tFinish(hostPhases_[0]);
+    {
         // bounded wait: a protocol error must not hang the device box
+        PhaseTimer tWait(hostPhases_[4]);
         const auto t0 = std::chrono::steady_clock::now();
         for (;;) {
             cudaError_t e = cudaEventQuery(slot.evEnd);
@@ -368,133 +475,99 @@ int64_t Sharer::peerFinish() {
                 GSS_DIE("peer exchange timed out (rank " + std::to_string(P.rank) + ", batch " + std::to_string(P.seq) + ")");
             std::this_thread::yield();
         }
-        if (!P.waitFn || (root && P.world > 2)) {
+        if (!P.waitFn && !root) {
             GSS_CUDA(cudaMemcpyAsync(P.errHost.data(), P.err(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
             GSS_CUDA(cudaStreamSynchronize(stream_));
             if (P.errHost[0]) GSS_DIE("peer exchange timed out on the device (rank " + std::to_string(P.rank) + ")");
         }
-    };
-    waitEnd();
-
-    // this rank's own overflow: grow and run again (the tables are intact: collapse is deferred)
-    auto repairOwn = [&]() -> bool {
-        Counters c;
-        memcpy(&c, slot.resHost.data(), sizeof(c));
-        if ((int64_t)c.nHits > P.slotHits)
-            GSS_DIE("peer exchange: " + std::to_string(c.nHits) + " hits of rank " + std::to_string(P.rank) +
-                    " do not fit its gather slot (raise slot_hits)");
-        size_t maxSurv = 0;
-        for (int g = 0; g < kMaxGroups; g++) maxSurv = std::max(maxSurv, (size_t)c.nSurvivors[g]);
-        if (maxSurv <= survCap_) return false;
-        survCap_ = std::max(survCap_ * 2, maxSurv + maxSurv / 4);
-        ensureResultBuffers();
-        peerLaunchCheckAndFinalize(slot);
-        GSS_CUDA(cudaMemcpyAsync(slot.resHost.data(), resDev_.data(), sizeof(Counters), cudaMemcpyDeviceToHost, stream_));
-        return true;
-    };
-
-    // Once the batch cannot be run again, its tables are no longer needed: collapse every slot to the
-    // solver's last one right away (dSetAllAssigsToLast) -- the GPU is warm and otherwise idle while
-    // the host hands the hits over / rank 0 prepares the next batch.  Its time is charged to this batch.
+    }
     float msFirst[5] = {0, 0, 0, 0, 0}; // first attempt: copy, apply, check, total, tail
     cudaEventElapsedTime(&msFirst[0], slot.evStart, slot.evH2DDone);
     cudaEventElapsedTime(&msFirst[1], slot.evH2DDone, slot.evBeforeCheck);
     cudaEventElapsedTime(&msFirst[2], slot.evBeforeCheck, slot.evAfterCheck);
     cudaEventElapsedTime(&msFirst[3], slot.evStart, P.evGathered);
-    cudaEventElapsedTime(&msFirst[4], slot.evAfterCheck, P.evGathered);
-    auto collapseNow = [&]() {
-        if (root) { // rank 0: at the start of the next batch, behind the push (see peerEnqueue)
-            P.collapsed = false;
-            collapseSlot_ = P.collapsePending ? cur_ : -1;
-            P.collapsePending = false;
-            return;
-        }
-        P.collapsed = P.collapsePending;
-        if (!P.collapsed) return;
+    // this rank's own result: complete, or repaired here (overflow: larger buffers, same batch again --
+    // the tables are intact because the collapse is deferred)
+    finishRunDirect(slot);
+    const RunHdr *mine = slot.checked ? slot.runBuf->hdr() : nullptr;
+    int64_t total = mine ? mine->nTotal : 0;
+
+    if (!root) {
+        // publish: this rank's event has completed, so everything its GPU wrote is visible to rank 0's CPU
+        RingCtl *c = P.ring->ctl();
+        const uint64_t word = ((uint64_t)P.seq << 8) | (uint64_t)(slot.checked ? P.ringBuf : 0xFF);
+        P.ringBuf = -1;
+        slot.runBuf.reset(); // (rank 0 owns the buffer from here on)
+        c->published.store(word, std::memory_order_release);
+    }
+
+    // Once the batch cannot be run again, its tables are no longer needed: a worker collapses every slot
+    // to the solver's last one right away (dSetAllAssigsToLast; the GPU is warm and otherwise idle);
+    // rank 0 does it at the start of the next batch, behind the push (see peerEnqueue).
+    float msCollapse = 0;
+    if (root) {
+        collapseSlot_ = P.collapsePending ? cur_ : -1;
+    } else if (P.collapsePending) {
         GSS_CUDA(cudaEventRecord(P.evC0, stream_));
         launchCollapse(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, slot.nUpdates, tables_, numSMs_, stream_, &launches_);
         GSS_CUDA(cudaEventRecord(P.evC1, stream_));
-        P.collapsePending = false;
         collapseSlot_ = -1;
         lastStarted_ = -1; // the tables of this batch are gone
-    };
-    auto recordTimes = [&]() {
-        float msCollapse = 0;
-        if (P.collapsed) {
-            GSS_CUDA(cudaEventSynchronize(P.evC1));
-            cudaEventElapsedTime(&msCollapse, P.evC0, P.evC1);
-        }
-        // [0] prepare + H2D (+ wait for the batch on a worker), [1] table kernels (push on rank 0, apply,
-        // collapse), [2] check kernels, [3] everything from the start to "hits gathered" plus the
-        // collapse: [3] - [0] = device time of the batch on this rank
-        lastTimes_[0] = msFirst[0] * 1000.0;
-        lastTimes_[1] = (msFirst[1] + msCollapse) * 1000.0;
-        lastTimes_[2] = msFirst[2] * 1000.0;
-        lastTimes_[3] = (msFirst[3] + msCollapse) * 1000.0;
-        haveTimes_ = true;
-        if (opts_.quickProf) globalStats_[G_timeSpentTestingClauses] += (uint64_t)(msFirst[2] * 1000.0f);
-        if (P.trace) {
-            float msWait = 0, msAfterWait = 0, msPush = 0;
-            if (!root) {
-                cudaEventElapsedTime(&msWait, slot.evStart, P.evWait);
-                cudaEventElapsedTime(&msAfterWait, P.evWait, slot.evH2DDone);
-            } else if (P.push.n) {
-                cudaEventElapsedTime(&msPush, slot.evH2DDone, P.evPushed);
-            }
-            fprintf(stderr, "peer trace rank %d batch %u: start->batch-arrived %.1f | ->ready %.1f | push %.1f | push+apply %.1f | check %.1f | tail %.1f | collapse %.1f us\n",
-                    P.rank, P.seq, msWait * 1e3, msAfterWait * 1e3, msPush * 1e3, msFirst[1] * 1e3, msFirst[2] * 1e3, msFirst[4] * 1e3, msCollapse * 1e3);
-        }
-    };
-
-    int64_t total = 0;
-    if (!root) {
-        for (int attempt = 0; repairOwn(); attempt++) {
-            GSS_CHECK(attempt < 8);
-            GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
-            waitEnd();
-        }
-        collapseNow();
-        Counters c;
-        memcpy(&c, slot.resHost.data(), sizeof(c));
-        globalStats_[G_clauseTestsOnAssigs] += c.exactTests;
-        total = (int64_t)c.nHits;
-        slot.inFlight = false;
-        mgpuLast_ = cur_;
-        cur_ = -1;
-        recordTimes();
-        return total;
+        GSS_CUDA(cudaEventSynchronize(P.evC1));
+        cudaEventElapsedTime(&msCollapse, P.evC0, P.evC1);
     }
-
-    std::vector<int64_t> counts(P.world, 0);
-    for (int attempt = 0;; attempt++) {
-        GSS_CHECK(attempt < 16);
-        bool again = repairOwn();
-        for (int r = 1; r < P.world; r++) {
-            const long long flags = P.headsHost[(size_t)r * 8 + 1];
-            if (flags & 2) GSS_DIE("peer exchange: the hits of rank " + std::to_string(r) + " do not fit its gather slot (raise slot_hits)");
-            if (flags & 1) { // that rank is running again: its second flag follows
-                peerWaitFlag(P.done(r), 2u * P.seq);
-                again = true;
-            }
-        }
-        if (!again) break;
-        GSS_CUDA(cudaMemcpy2DAsync(P.headsHost.data(), 64, P.slot(0), P.slotBytes, 64, (size_t)P.world, cudaMemcpyDeviceToHost, stream_));
-        GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
-        waitEnd();
-    }
-    for (int r = 0; r < P.world; r++) {
-        GSS_CHECK(P.headsHost[(size_t)r * 8 + 3] == (long long)P.seq);
-        counts[r] = P.headsHost[(size_t)r * 8];
-        total += counts[r];
-        globalStats_[G_clauseTestsOnAssigs] += (uint64_t)P.headsHost[(size_t)r * 8 + 2];
-    }
-    collapseNow();
+    P.collapsePending = false;
+    // [0] prepare + H2D (+ wait for the batch on a worker), [1] table kernels (push on rank 0, apply, collapse),
+    // [2] check kernels + emit, [3] everything from the start to "this rank's results are in host memory" plus
+    // the collapse: [3] - [0] = device time of the batch on this rank
+    lastTimes_[0] = msFirst[0] * 1000.0;
+    lastTimes_[1] = (msFirst[1] + msCollapse) * 1000.0;
+    lastTimes_[2] = msFirst[2] * 1000.0;
+    lastTimes_[3] = (msFirst[3] + msCollapse) * 1000.0;
+    haveTimes_ = true;
+    if (P.trace)
+        fprintf(stderr, "peer trace rank %d batch %u: copies %.1f | tables %.1f | check+emit %.1f | collapse %.1f us\n", P.rank, P.seq,
+                msFirst[0] * 1e3, msFirst[1] * 1e3, msFirst[2] * 1e3, msCollapse * 1e3);
     slot.inFlight = false;
     mgpuLast_ = cur_;
     cur_ = -1;
-    finishedD2H_ = (int64_t)((size_t)P.world * 64 + sizeof(Counters));
-    mgpuImportGathered(P.slot(0), P.world, (int64_t)P.slotBytes, counts.data());
-    recordTimes();
+
+    if (!root) return total;
+
+    // rank 0: every rank's finished result, one slice per solver and rank
+    std::vector<DevicePart> parts{DevicePart{this, &slot, nullptr}};
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 1; r < P.world; r++) {
+        PhaseTimer tWorkers(hostPhases_[5]);
+        std::shared_ptr<ShmRing> ring = P.rings[r];
+        RingCtl *c = ring->ctl();
+        uint64_t word;
+        for (;;) {
+            word = c->published.load(std::memory_order_acquire);
+            if ((word >> 8) == (uint64_t)P.seq) break;
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > P.timeoutS)
+                GSS_DIE("peer exchange: rank " + std::to_string(r) + " did not publish batch " + std::to_string(P.seq));
+            std::this_thread::yield();
+        }
+        const int k = (int)(word & 0xFF);
+        if (k == 0xFF) continue; // that rank had nothing to check
+        RunBuf *b = new RunBuf();
+        b->base = ring->buf(k);
+        b->bytes = (size_t)c->bufBytes;
+        b->entryCap = c->entryCap;
+        b->litCap = c->litCap;
+        b->withRecords = true;
+        std::shared_ptr<RunBuf> buf(b, [ring, k](RunBuf *q) {
+            ring->ctl()->buf[k].state.store(0, std::memory_order_release); // the worker may fill it again
+            delete q;
+        });
+        total += b->hdr()->nTotal;
+        globalStats_[G_clauseTestsOnAssigs] += b->hdr()->exactTests;
+        finishedD2H_ += (int64_t)(sizeof(RunHdr) + (size_t)b->hdr()->nTotal * 24 + (size_t)b->hdr()->litTotal * 4);
+        parts.push_back(DevicePart{nullptr, nullptr, buf});
+    }
+    PhaseTimer tHandOver(hostPhases_[2]);
+    processResultsParts(slot, parts);
     return total;
 }
 

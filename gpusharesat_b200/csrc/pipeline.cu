@@ -232,7 +232,11 @@ void Sharer::launchDirectCheck(RunSlot &slot) {
     if (lastDirect_ == &slot) lastDirect_ = nullptr; // its record lists are about to be overwritten
     slot.seq = ++directSeq_;
     // capacities in powers of two: a released buffer fits the next run although the guesses drift
-    slot.runBuf = runBufs_->acquire((int64_t)pow2AtLeast((size_t)entryGuess_), (int64_t)pow2AtLeast((size_t)litGuess_));
+    if (peer_ && peerAcquireResultBuf(slot)) {
+        // (a worker rank of the multi-process exchange: a buffer of its shared-memory ring, which rank 0 reads)
+    } else {
+        slot.runBuf = runBufs_->acquire((int64_t)pow2AtLeast((size_t)entryGuess_), (int64_t)pow2AtLeast((size_t)litGuess_));
+    }
     launchCheckKernels(slot, false);
     launchEmitFor(slot);
 }
@@ -264,6 +268,10 @@ void Sharer::launchEmitFor(RunSlot &slot) {
     e.lits = rb.lits();
     e.entryCap = rb.entryCap;
     e.litCap = rb.litCap;
+    if (rb.withRecords) {
+        e.keysOut = rb.keys();
+        e.masksOut = rb.masks();
+    }
     launchEmit(e, stream_, &launches_);
 }
 
@@ -340,8 +348,9 @@ void Sharer::bumpDirect(const std::vector<DevicePart> &parts) {
         db_->rescaleAfterDeviceOverflow();
         db_->applyPendingDeviceRescales(stream_);
     }
+    bumpOwners_.clear(); // (the bump that read them has completed: waitBumpFlag)
     bool any = false;
-    for (const DevicePart &p : parts) any = any || (p.slot->checked && p.slot->runBuf->hdr()->maxRec > 0);
+    for (const DevicePart &p : parts) any = any || (p.view() && p.view()->hdr()->nTotal > 0);
     if (!any) return;
     std::vector<LenDir> dir;
     db_->buildDirectory(dir);
@@ -353,12 +362,18 @@ void Sharer::bumpDirect(const std::vector<DevicePart> &parts) {
     bumpFlagHost_.resize(1);
     GSS_CUDA(cudaMemsetAsync(bumpFlagDev_.data(), 0, sizeof(int), stream_));
     for (const DevicePart &p : parts) {
-        RunSlot &slot = *p.slot;
-        if (!slot.checked) continue;
-        if (slot.runBuf->hdr()->nTotal == 0) continue;
-        launchBumpFromRecs(slot.sortKeys.data(), slot.recCap, slot.solverInfo.data(), slot.nSolvers, slot.recCap,
-                           (const LenDir *)bumpDirDev_.data(), (int)dir.size(), db_->activityIncrement(), bumpFlagDev_.data(),
-                           stream_, &launches_);
+        const RunBuf *rb = p.view();
+        if (!rb || rb->hdr()->nTotal == 0) continue;
+        if (p.slot) {
+            RunSlot &slot = *p.slot;
+            launchBumpFromRecs(slot.sortKeys.data(), slot.recCap, slot.solverInfo.data(), slot.nSolvers, slot.recCap,
+                               (const LenDir *)bumpDirDev_.data(), (int)dir.size(), db_->activityIncrement(), bumpFlagDev_.data(),
+                               stream_, &launches_);
+        } else { // another process's result: its sorted record keys lie next to the ids, in host memory this device can read
+            launchBumpFromKeys(rb->keys(), rb->hdr()->nTotal, (const LenDir *)bumpDirDev_.data(), (int)dir.size(),
+                               db_->activityIncrement(), bumpFlagDev_.data(), stream_, &launches_);
+            bumpOwners_.push_back(p.buf);
+        }
     }
     GSS_CUDA(cudaMemcpyAsync(bumpFlagHost_.data(), bumpFlagDev_.data(), sizeof(int), cudaMemcpyDeviceToHost, stream_));
     if (!bumpFlagEv_) GSS_CUDA(cudaEventCreateWithFlags(&bumpFlagEv_, cudaEventDisableTiming));
@@ -367,7 +382,7 @@ void Sharer::bumpDirect(const std::vector<DevicePart> &parts) {
 }
 
 void Sharer::processResultsDirect(RunSlot &slot) {
-    std::vector<DevicePart> parts{DevicePart{this, &slot}};
+    std::vector<DevicePart> parts{DevicePart{this, &slot, nullptr}};
     processResultsParts(slot, parts);
 }
 
@@ -377,8 +392,11 @@ void Sharer::processResultsParts(RunSlot &slot, const std::vector<DevicePart> &p
     // reference gatherGpuRunResults, GpuRunner.cu:360-383 (64-bit arithmetic)
     const int64_t clCount = db_->stats().clauses;
     int64_t nTotal = 0;
-    for (const DevicePart &p : parts)
-        if (p.slot->checked) nTotal += p.slot->runBuf->hdr()->nTotal;
+    lastForeign_.clear();
+    for (const DevicePart &p : parts) {
+        if (p.view()) nTotal += p.view()->hdr()->nTotal;
+        if (!p.slot && p.buf) lastForeign_.push_back(p.buf);
+    }
     globalStats_[G_gpuRuns]++;
     globalStats_[G_totalAssigClauseTested] += (uint64_t)clCount * (uint64_t)slot.assigCount;
     globalStats_[G_clauseTestsOnGroups] += (uint64_t)clCount;
@@ -390,13 +408,14 @@ void Sharer::processResultsParts(RunSlot &slot, const std::vector<DevicePart> &p
     TimeAdder t(globalStats_[G_timeSpentFillingReported], opts_.quickProf != 0);
     std::vector<std::vector<ResultView>> views((size_t)slot.nSolvers);
     for (const DevicePart &p : parts) {
-        if (!p.slot->checked) continue;
-        const RunHdr *h = p.slot->runBuf->hdr();
+        if (!p.view()) continue;
+        const RunHdr *h = p.view()->hdr();
         if (h->nTotal <= 0) continue;
-        RunBuf &rb = *p.slot->runBuf;
+        const RunBuf &rb = *p.view();
         // safety valve: a solver that does not pop keeps its batches, and with them whole result buffers,
-        // alive; past a bound the slices are copied out and the buffer goes back to the pool at once
-        const bool copyOut = p.sh->runBufs_->outstanding() > 64;
+        // alive; past a bound the slices are copied out and the buffer goes back to its pool at once
+        // (another process's buffers come from a small ring: their slices are always copied out late)
+        const bool copyOut = p.sh ? p.sh->runBufs_->outstanding() > 64 : foreignCopyOut_;
         for (int s = 0; s < slot.nSolvers; s++) {
             const RunHdr::PerSolver &ps = h->solver[s];
             if (ps.n <= 0) continue;
@@ -406,7 +425,7 @@ void Sharer::processResultsParts(RunSlot &slot, const std::vector<DevicePart> &p
                 v.ids = rb.ids() + ps.entryBase;
                 v.pos = rb.pos() + ps.entryBase + s;
                 v.lits = rb.lits() + ps.litBase;
-                v.owner = p.slot->runBuf;
+                v.owner = p.owner();
             } else {
                 const size_t bytes = (size_t)ps.n * 8 + ((size_t)ps.n + 1) * 4 + (size_t)ps.nLits * 4;
                 std::shared_ptr<uint8_t> heap(new uint8_t[bytes + 8], std::default_delete<uint8_t[]>());

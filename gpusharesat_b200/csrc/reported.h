@@ -25,6 +25,7 @@ struct ResultView {
     const int32_t *pos = nullptr; // n + 1 entries, relative to lits
     int32_t *lits = nullptr;      // writable: callers permute the literals they are handed in place
     int32_t n = 0;
+    int32_t cur = 0;              // next entry to hand over (consumer side, ClauseBatch::pop)
     std::shared_ptr<void> owner;
 };
 
@@ -36,10 +37,12 @@ struct ClauseBatch {
     };
     std::vector<int> lits;
     std::vector<Entry> entries;
-    std::vector<ResultView> views; // zero-copy part (one view per device that contributed), after `entries`
+    // zero-copy part, after `entries`: one view per device that contributed, in device order.  Every view is
+    // in the canonical order (length, index) and a device's share of every length array lies before the next
+    // device's, so merging the views by clause length (ties: the earlier device) hands the clauses over in
+    // exactly the order of a single-device run.
+    std::vector<ResultView> views;
     size_t next = 0;
-    size_t viewAt = 0;
-    int32_t viewNext = 0;
     AssigIds ids;
     uint32_t hadSomeReported = 0;
     int64_t assigWhichKnowsAboutThese = 0;
@@ -49,8 +52,6 @@ struct ClauseBatch {
         entries.clear();
         views.clear(); // drops the references to the result buffers
         next = 0;
-        viewAt = 0;
-        viewNext = 0;
         hadSomeReported = 0;
     }
     bool pop(int *&outLits, int &count, int64_t &id) {
@@ -63,19 +64,22 @@ struct ClauseBatch {
             next++;
             return true;
         }
-        while (viewAt < views.size()) {
-            const ResultView &v = views[viewAt];
-            if (viewNext < v.n) {
-                outLits = v.lits + v.pos[viewNext];
-                count = v.pos[viewNext + 1] - v.pos[viewNext];
-                id = v.ids[viewNext];
-                viewNext++;
-                return true;
+        ResultView *best = nullptr;
+        int bestLen = 0;
+        for (ResultView &v : views) {
+            if (v.cur >= v.n) continue;
+            const int len = v.pos[v.cur + 1] - v.pos[v.cur];
+            if (!best || len < bestLen) {
+                best = &v;
+                bestLen = len;
             }
-            viewAt++;
-            viewNext = 0;
         }
-        return false;
+        if (!best) return false;
+        outLits = best->lits + best->pos[best->cur];
+        count = bestLen;
+        id = best->ids[best->cur];
+        best->cur++;
+        return true;
     }
     template <typename F> void forEachId(F f) const {
         for (const auto &e : entries) f(e.id);

@@ -1017,6 +1017,14 @@ void Sharer::materializeLastHits() {
         const int idx = (int)(lastDirect_ - slots_);
         appendDirectHits(*lastDirect_, lastHits_);
         for (auto &w : workers_) w->appendDirectHits(w->slots_[idx], lastHits_);
+        for (auto &fb : lastForeign_) { // other ranks' results (multi-process exchange): masks lie next to the ids
+            const RunHdr *h = fb->hdr();
+            for (int s = 0; s < kMaxSolvers; s++) {
+                const RunHdr::PerSolver &ps = h->solver[s];
+                for (int32_t i = 0; i < ps.n; i++)
+                    lastHits_.push_back(gss_hit{fb->ids()[ps.entryBase + i], s, fb->masks()[ps.entryBase + i]});
+            }
+        }
         useDevice();
     } else if (postValid_) {
         lastHits_.resize(postN_);

@@ -107,9 +107,14 @@ public:
         int64_t *ids() const { return reinterpret_cast<int64_t *>(base + hdrBytes()); }
         int32_t *pos() const { return reinterpret_cast<int32_t *>(base + hdrBytes() + (size_t)entryCap * 8); }
         int32_t *lits() const { return pos() + (size_t)entryCap + kMaxSolvers; }
+        // buffers another process reads (multi-process exchange, peer.cu) also carry the sorted records
+        bool withRecords = false;
+        unsigned long long *keys() const { return reinterpret_cast<unsigned long long *>(lits() + (size_t)litCap); }
+        uint32_t *masks() const { return reinterpret_cast<uint32_t *>(keys() + (size_t)entryCap); }
         static size_t hdrBytes() { return (sizeof(RunHdr) + 255) / 256 * 256; }
-        static size_t bytesFor(int64_t entryCap, int64_t litCap) {
-            return hdrBytes() + (size_t)entryCap * 8 + ((size_t)entryCap + kMaxSolvers) * 4 + (size_t)litCap * 4;
+        static size_t bytesFor(int64_t entryCap, int64_t litCap, bool withRecords = false) {
+            return hdrBytes() + (size_t)entryCap * 8 + ((size_t)entryCap + kMaxSolvers) * 4 + (size_t)litCap * 4 +
+                   (withRecords ? (size_t)entryCap * 12 : 0);
         }
     };
     class RunBufPool;
@@ -161,12 +166,21 @@ private:
     void launchEmitFor(RunSlot &slot);
     void finishRunDirect(RunSlot &slot);
     void processResultsDirect(RunSlot &slot);
-    struct DevicePart { // one device's share of a run (several devices in one process: multi.cu)
-        Sharer *sh;
-        RunSlot *slot;
+    // One device's share of a finished run: a result buffer in host memory (this process's or, in the
+    // multi-process exchange, another rank's shared-memory buffer) and where the sorted records are for
+    // the activity bumps / the parity hook: on a device of this process (slot) or next to the ids (buf).
+    struct DevicePart {
+        Sharer *sh = nullptr;        // the sharer whose pool the buffer came from (nullptr: another process)
+        RunSlot *slot = nullptr;     // device-resident record lists (nullptr: use buf->keys() / masks())
+        std::shared_ptr<RunBuf> buf; // nullptr: the slot's own (slot->runBuf), if it checked anything
+        const RunBuf *view() const { return buf ? buf.get() : (slot && slot->checked ? slot->runBuf.get() : nullptr); }
+        std::shared_ptr<RunBuf> owner() const { return buf ? buf : slot->runBuf; }
     };
     void processResultsParts(RunSlot &slot, const std::vector<DevicePart> &parts);
     void appendDirectHits(RunSlot &slot, std::vector<gss_hit> &out);
+    bool foreignCopyOut_ = false; // multi-process exchange: copy the slices of other ranks' results out of their ring buffers
+    std::vector<std::shared_ptr<RunBuf>> bumpOwners_;    // foreign result buffers a queued bump kernel still reads
+    std::vector<std::shared_ptr<RunBuf>> lastForeign_;   // foreign parts of the last processed run (parity hook)
     void ensureDirectBuffers(RunSlot &slot);
     void bumpDirect(const std::vector<DevicePart> &parts);
     bool waitBumpFlag();
@@ -194,7 +208,7 @@ private:
     std::shared_ptr<RunBufPool> runBufs_;
     bool directEnabled_ = true;
     bool eagerResults_ = true; // surface a run's hits in the call that started it when it completes within minGpuLatencyMicros
-    size_t recCap_ = 1024;       // per-solver record capacity (power of two)
+    size_t recCap_ = 4096;       // per-solver record capacity (power of two, >= kRecBuckets)
     int64_t entryGuess_ = 4096, litGuess_ = 16384; // result buffer sizing (from previous runs)
     uint32_t directSeq_ = 0;
     RunSlot *lastDirect_ = nullptr; // finished direct run whose records are still on the device (parity hook)
@@ -278,6 +292,7 @@ private:
     unsigned int hitCapOverride_ = 0;   // slot in rank 0's gather window) instead of resDev_
     CheckArgs fusedPublish_;            // peer mode: peerHdr / peerDone / peerTicket / peerSeq for the last k_exact
     void peerLaunchCheckAndFinalize(RunSlot &slot);
+    bool peerAcquireResultBuf(RunSlot &slot); // worker ranks: a buffer of the rank's shared-memory result ring
     void peerWaitFlag(const uint32_t *flag, uint32_t value);
 
     std::vector<HitRecord> hits_;   // hits of the run being processed

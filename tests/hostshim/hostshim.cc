@@ -154,7 +154,10 @@ double hs_hand_over_sorted(HostRig *r, const HitRecord *hits, int n) {
 // the direct pipeline's hand-over (Reported::handOverViews): per solver the result exactly as k_emit
 // lays it out in a result buffer -- ids, n + 1 positions, literal stream -- split in `parts` slices
 // (one per device in a multi-GPU run); the batches view the buffer, which lives until they let go
-double hs_hand_over_views(HostRig *r, const HitRecord *hits, int n, int parts) {
+// shareBound > 0: the slices are cut the way devices share the work -- part p holds the clauses of EVERY length
+// whose index falls into the p-th share [bound*p/parts, bound*(p+1)/parts) -- so the canonical order interleaves
+// the parts and the batch has to merge its views (ClauseBatch::pop)
+double hs_hand_over_views_shares(HostRig *r, const HitRecord *hits, int n, int parts, int shareBound) {
     std::vector<HitRecord> v(hits, hits + n);
     std::sort(v.begin(), v.end(), [](const HitRecord &a, const HitRecord &b) {
         if (a.solver != b.solver) return a.solver < b.solver;
@@ -173,10 +176,11 @@ double hs_hand_over_views(HostRig *r, const HitRecord *hits, int n, int parts) {
         while (i < v.size() && v[i].solver == s) i++;
         const size_t cnt = i - lo;
         for (int part = 0; part < parts; part++) {
-            const size_t a = lo + cnt * part / parts, b = lo + cnt * (part + 1) / parts;
+            const size_t a = shareBound > 0 ? lo : lo + cnt * part / parts, b = shareBound > 0 ? i : lo + cnt * (part + 1) / parts;
             auto buf = std::make_shared<Buf>();
             std::vector<int> tmp;
             for (size_t k = a; k < b; k++) {
+                if (shareBound > 0 && std::min(parts - 1, (int)((int64_t)v[k].idx * parts / shareBound)) != part) continue;
                 buf->pos.push_back((int32_t)buf->lits.size());
                 tmp.clear();
                 buf->ids.push_back(r->db.appendClause(v[k].len, v[k].idx, tmp));
@@ -187,7 +191,7 @@ double hs_hand_over_views(HostRig *r, const HitRecord *hits, int n, int parts) {
             rv.ids = buf->ids.data();
             rv.pos = buf->pos.data();
             rv.lits = buf->lits.data();
-            rv.n = (int32_t)(b - a);
+            rv.n = (int32_t)buf->ids.size();
             rv.owner = buf;
             views[s].push_back(std::move(rv));
         }
@@ -196,6 +200,7 @@ double hs_hand_over_views(HostRig *r, const HitRecord *hits, int n, int parts) {
     r->reported.handOverViews(views, r->ids, S);
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
 }
+double hs_hand_over_views(HostRig *r, const HitRecord *hits, int n, int parts) { return hs_hand_over_views_shares(r, hits, n, parts, 0); }
 int64_t hs_add_clauses_bulk(HostRig *r, const int64_t *offsets, const int *lits, int64_t n) { return r->db.addClausesBulk(offsets, lits, n); }
 int hs_pop(HostRig *r, int s, int *lits, int *count, int64_t *id) {
     int *l;

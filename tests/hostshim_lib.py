@@ -28,7 +28,7 @@ def load():
     sig = {
         "hs_create": (P, [I, I, C.c_double]), "hs_destroy": (None, [P]),
         "hs_available": (I, [P, I]), "hs_set_var": (None, [P, I, I, I]), "hs_send": (Q, [P, I]),
-        "hs_set_host_bumps": (None, [P, I]), "hs_collect": (I, [P, I]), "hs_collect_split": (I, [P]), "hs_collect_take": (I, [P]), "hs_hand_over_views": (C.c_double, [P, C.c_void_p, I, I]), "hs_hand_over_sorted": (C.c_double, [P, C.c_void_p, I]), "hs_get_params": (None, [P, I, C.POINTER(SolverRunParams)]),
+        "hs_set_host_bumps": (None, [P, I]), "hs_collect": (I, [P, I]), "hs_collect_split": (I, [P]), "hs_collect_take": (I, [P]), "hs_hand_over_views": (C.c_double, [P, C.c_void_p, I, I]), "hs_hand_over_views_shares": (C.c_double, [P, C.c_void_p, I, I, I]), "hs_hand_over_sorted": (C.c_double, [P, C.c_void_p, I]), "hs_get_params": (None, [P, I, C.POINTER(SolverRunParams)]),
         "hs_get_updates": (None, [P, C.c_void_p]), "hs_get_ids": (None, [P, I, C.POINTER(Q), IP]),
         "hs_add_clause": (Q, [P, IP, I]), "hs_drain": (None, [P]), "hs_count": (I, [P, I]),
         "hs_clause_id": (Q, [P, I, I]), "hs_activity": (C.c_float, [P, I, I]), "hs_bump": (None, [P, I, I]),
@@ -101,9 +101,10 @@ class Rig:
             params.append(p)
         return upd, params
 
-    def hand_over_views(self, hits, parts=1):
+    def hand_over_views(self, hits, parts=1, share_bound=0):
+        """share_bound > 0: slices cut like the devices' shares (every length's index range split `parts` ways)"""
         a = np.ascontiguousarray(hits, dtype=HIT)
-        return self.L.hs_hand_over_views(self.h, a.ctypes.data, a.size, parts)
+        return self.L.hs_hand_over_views_shares(self.h, a.ctypes.data, a.size, parts, share_bound)
 
     def hand_over_sorted(self, hits):
         a = np.ascontiguousarray(hits, dtype=HIT)

@@ -107,10 +107,25 @@ int main(int argc, char **argv) {
                 std::this_thread::sleep_for(std::chrono::microseconds(20));
             }
         });
+    // device phase times and bytes of the runs, accumulated by the GPU thread (the hooks are GPU-thread only)
+    double devSum[4] = {0, 0, 0, 0};
+    int64_t h2dSum = 0, d2hSum = 0, sampled = 0;
+    std::atomic<bool> sampling{false};
     std::thread gpu([&] {
         while (!stop.load(std::memory_order_relaxed)) {
             gss_gpu_run(h);
             runs.fetch_add(1);
+            if (sampling.load(std::memory_order_relaxed)) {
+                double t[4];
+                int64_t a = 0, b = 0;
+                if (gss_debug_last_run_times(h, t)) {
+                    for (int i = 0; i < 4; i++) devSum[i] += t[i];
+                    gss_debug_last_run_bytes(h, &a, &b);
+                    h2dSum += a;
+                    d2hSum += b;
+                    sampled++;
+                }
+            }
         }
     });
     while (ready.load() < S) std::this_thread::sleep_for(std::chrono::milliseconds(1));
@@ -119,6 +134,7 @@ int main(int argc, char **argv) {
     std::vector<double> lat;
     int lost = 0;
     const auto tStart = Clock::now();
+    sampling.store(true);
     const int64_t runs0 = runs.load();
     double ph0[6];
     gss_debug_host_phases(h, ph0);
@@ -151,16 +167,20 @@ int main(int argc, char **argv) {
     stop.store(true);
     for (auto &t : threads) t.join();
     gpu.join();
+    const double ns = sampled ? (double)sampled : 1.0;
     std::sort(lat.begin(), lat.end());
     auto q = [&](double f) { return lat.empty() ? -1.0 : lat[std::min(lat.size() - 1, (size_t)(f * lat.size()))]; };
     printf("{\"harness\": \"import_latency\", \"solvers\": %d, \"vars\": %d, \"clauses\": %lld, \"probes\": %d, \"lost\": %d, "
            "\"p50_us\": %.1f, \"p90_us\": %.1f, \"p99_us\": %.1f, \"max_us\": %.1f, \"gpu_runs_per_s\": %.0f, "
            "\"min_gpu_latency_micros\": %d, \"long_clause_share\": 0.05, \"max_clause_len\": 200, "
            "\"host_us_per_run\": {\"finish_previous\": %.1f, \"start_next\": %.1f, \"hand_over\": %.1f, \"collect\": %.1f, "
-           "\"wait_for_gpu\": %.1f}, \"hits_reported_per_run\": %.0f}\n",
+           "\"wait_for_gpu\": %.1f}, \"hits_reported_per_run\": %.0f, "
+           "\"device_us_per_run\": {\"copies\": %.1f, \"table_kernels\": %.1f, \"check_and_emit\": %.1f, \"total\": %.1f}, "
+           "\"h2d_bytes_per_run\": %.0f, \"d2h_bytes_per_run\": %.0f}\n",
            S, V, (long long)C, nProbes, lost, q(0.5), q(0.9), q(0.99), lat.empty() ? -1.0 : lat.back(), nRuns / wallS, minLat,
            (ph1[0] - ph0[0]) / nRuns, (ph1[1] - ph0[1]) / nRuns, (ph1[2] - ph0[2]) / nRuns, (ph1[3] - ph0[3]) / nRuns,
-           (ph1[4] - ph0[4]) / nRuns, (double)(gss_get_global_stat(h, 8) - reports0) / nRuns);
+           (ph1[4] - ph0[4]) / nRuns, (double)(gss_get_global_stat(h, 8) - reports0) / nRuns, devSum[0] / ns, devSum[1] / ns,
+           devSum[2] / ns, devSum[3] / ns, h2dSum / ns, d2hSum / ns);
     gss_destroy(h);
     return 0;
 }

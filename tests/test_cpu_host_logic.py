@@ -282,8 +282,8 @@ def test_take_collect_equals_single_pass_collect():
         assert [a.ids(s) for s in range(nsolvers)] == [b.ids(s) for s in range(nsolvers)]
 
 
-@pytest.mark.parametrize("parts", [1, 3])
-def test_view_hand_over_equals_host_hand_over(parts):
+@pytest.mark.parametrize("parts,share_bound", [(1, 0), (3, 0), (2, 40), (4, 40)])
+def test_view_hand_over_equals_host_hand_over(parts, share_bound):
     """the direct pipeline's zero-copy hand-over (Reported::handOverViews: every solver's batch views the
     ids / positions / literal stream the GPU wrote, one slice per device) hands over exactly what the
     host path does, including the re-report rules across runs and the empty progress-marker batches"""
@@ -314,7 +314,9 @@ def test_view_hand_over_equals_host_hand_over(parts):
         rec["solver"], rec["len"], rec["idx"] = hits[:, 0], hits[:, 1], hits[:, 2]
         rec["mask"] = rng.integers(1, 1 << 31, size=len(hits))
         a.hand_over(rec[rng.permutation(len(rec))])
-        b.hand_over_views(rec[rng.permutation(len(rec))], parts)
+        # share_bound: the slices are the devices' shares of every length (several devices behind one front-end):
+        # the batch merges them back into the single-device order
+        b.hand_over_views(rec[rng.permutation(len(rec))], parts, share_bound)
         for s in range(nsolvers):
             pa, pb = a.pop_all(s), b.pop_all(s)
             assert pa == pb
