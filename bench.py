@@ -63,6 +63,8 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-dense", action="store_true")
+    p.add_argument("--no-streamed", action="store_true", help="skip the streamed-database pass (streamed_db object)")
+    p.add_argument("--stream-chunk", type=int, default=100_000, help="clauses per run of the streamed-database pass")
     p.add_argument("--no-latency", action="store_true", help="skip the import-latency harness (import_latency object)")
     p.add_argument("--no-ref-gpu", action="store_true", help="skip the reference GPU library leg (reference_gpu object)")
     p.add_argument("--ref-gpu-steps", type=int, default=5)
@@ -492,6 +494,71 @@ def sharded_pass(a, scaling, steps, warmup, dist, torch, rank, world, local, dev
     return out
 
 
+def streamed_db_numbers(a, sig, offsets, lits, chunk):
+    """SURVEY 8(f1) / BASELINE configs[3] shape on this workload's database: the SAME clauses arrive `chunk` at a
+    time with a run between the chunks (2 fresh assignments per solver), the way solver threads feed the library --
+    never as one bulk load.  Reports the ingest rate including the runs, the distribution of gpuRun() wall times
+    while the arenas grow (in place: vmem.cc), the device-side re-sorts of the streamed tails (reduce.cu), what the
+    level-1 kernel costs on the streamed database against the bulk-loaded one, and reduceDb."""
+    from gpusharesat_b200 import GpuClauseSharer, GpuClauseSharerOptions, GlobalStats
+    n = len(offsets) - 1
+    sh = GpuClauseSharer(GpuClauseSharerOptions(minGpuLatencyMicros=0, verbosity=0))
+    sh.setVarCount(a.vars)
+    sh.setCpuSolverCount(a.solvers)
+    streams = make_streams(a, sig)
+    pool = ThreadPoolExecutor(max_workers=a.solvers)
+
+    def drain():
+        for s in range(a.solvers):
+            while sh.popReportedClause(s) is not None:
+                pass
+
+    run_ms, t_all = [], 0.0
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        off = offsets[lo:hi + 1] - offsets[lo]
+        part = lits[offsets[lo]:offsets[hi]]
+        t0 = time.perf_counter()
+        sh.addClausesBulk(off, part)
+        push_batch(sh, streams, 2, pool)
+        t1 = time.perf_counter()
+        sh.gpuRun()
+        t2 = time.perf_counter()
+        drain()
+        run_ms.append((t2 - t1) * 1e3)
+        t_all += t2 - t0
+    sh.gpuRun()
+    drain()
+    unsorted, resorts = sh.debugDbOrder()
+    push_batch(sh, streams, a.slots, pool)
+    sh.gpuRun()
+    t_filter = sh.debugTimeCheck(a.prod_iters, filter_only=True)
+    t_prod = sh.debugTimeCheck(a.prod_iters, dense=False)
+    sh.gpuRun()
+    drain()
+    before = sh.getGlobalStat(GlobalStats.gpuClauses)
+    t0 = time.perf_counter()
+    sh.reduceDb()
+    t_reduce = time.perf_counter() - t0
+    after = sh.getGlobalStat(GlobalStats.gpuClauses)
+    push_batch(sh, streams, a.slots, pool)
+    t0 = time.perf_counter()
+    sh.gpuRun(); sh.gpuRun()
+    t_after = time.perf_counter() - t0
+    drain()
+    oom = bool(sh.hasRunOutOfGpuMemoryOnce())
+    sh.close()
+    r = np.array(run_ms)
+    return {"workload": f"the same {n} clauses arriving {chunk} per run, {a.solvers} solvers x 2 assignments per run",
+            "ingest_clauses_per_s_incl_runs": n / t_all,
+            "gpu_run_ms_while_growing": {"p50": float(np.percentile(r, 50)), "p99": float(np.percentile(r, 99)), "max": float(r.max()),
+                                         "runs": len(run_ms)},
+            "device_resorts": int(resorts), "unsorted_clauses_at_the_end": int(unsorted),
+            "k_filter_us": t_filter, "check_kernels_us": t_prod,
+            "reduce_db_ms": t_reduce * 1e3, "clauses_before_after_reduce": [int(before), int(after)],
+            "first_batch_after_reduce_ms": t_after * 1e3, "out_of_memory": oom}
+
+
 def run_b200(a):
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         return run_b200_sharded(a)
@@ -724,6 +791,9 @@ def run_b200(a):
             sh.gpuRun()
             drain()
         sh.close()  # free the device: the latency harness and the reference library bring their own databases
+        if not a.no_streamed:
+            out["streamed_db"] = streamed_db_numbers(a, sig, offsets, lits, a.stream_chunk)
+            out["streamed_db"]["k_filter_us_bulk_loaded"] = t_filter
         if not a.no_latency:
             out["import_latency"] = import_latency()
         if not a.no_ref_gpu:

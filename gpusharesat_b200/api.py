@@ -87,6 +87,7 @@ SIGNATURES = {
     "gss_debug_last_run_bytes": (None, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "gss_debug_kernel_launches": (_L, [_P]),
     "gss_debug_db_size": (None, [_P, C.POINTER(_L), C.POINTER(_L)]),
+    "gss_debug_db_order": (None, [_P, C.POINTER(_L), C.POINTER(_L)]),
     "gss_set_shard": (None, [_P, _I, _I]),
     "gss_mgpu_collect": (_I, [_P, C.POINTER(C.c_void_p), C.POINTER(_L), C.POINTER(C.c_void_p), C.POINTER(_L)]),
     "gss_mgpu_run": (None, [_P, C.c_void_p, _L, C.c_void_p, _L, _I]),
@@ -446,6 +447,12 @@ class GpuClauseSharer:
     def mgpuImport(self, hits):
         a = np.ascontiguousarray(hits, dtype=RAW_HIT_DTYPE)
         self._lib.gss_mgpu_import(self._h, a.ctypes.data, int(a.size))
+
+    def debugDbOrder(self):
+        """(clauses behind the sorted part of their arena, device-side re-sorts so far)"""
+        a, b = C.c_int64(), C.c_int64()
+        self._lib.gss_debug_db_order(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def debugDbSize(self):
         a, b = C.c_int64(), C.c_int64()

@@ -96,6 +96,7 @@ double gss_debug_lop3_peak(gss_sharer *h) { return h->impl.lop3Peak(); }
 void gss_debug_last_run_bytes(gss_sharer *h, int64_t *h2d, int64_t *d2h) { h->impl.lastRunBytes(h2d, d2h); }
 int64_t gss_debug_kernel_launches(gss_sharer *h) { return h->impl.kernelLaunches(); }
 void gss_debug_db_size(gss_sharer *h, int64_t *nclauses, int64_t *nlits) { h->impl.dbSize(nclauses, nlits); }
+void gss_debug_db_order(gss_sharer *h, int64_t *unsorted_clauses, int64_t *resorts) { h->impl.dbOrder(unsorted_clauses, resorts); }
 void gss_set_shard(gss_sharer *h, int rank, int world) { h->impl.setShard(rank, world); }
 int gss_mgpu_collect(gss_sharer *h, const void **params, int64_t *params_bytes, const void **updates, int64_t *n_updates) {
     return h->impl.mgpuCollect(params, params_bytes, updates, n_updates);

@@ -12,6 +12,7 @@ static constexpr float kRescale = 1e19f; // reference RESCALE_CONST, Clauses.cuh
 ClauseDb::ClauseDb(double activityDecay, const Logger &logger, size_t pinnedLimitBytes)
     : logger_(logger), pinnedLimit_(pinnedLimitBytes), actDecay_((float)activityDecay) {
     setMaxLen(kDefaultMaxClauseLen);
+    if (const char *e = getenv("GPUSHARE_RESORT_MIN_CLAUSES")) resortMinClauses_ = std::max(1ll, atoll(e));
 }
 
 void ClauseDb::setMaxLen(int maxLen) {
@@ -24,8 +25,28 @@ void ClauseDb::setMaxLen(int maxLen) {
     perLen_.resize(maxLen_ + 1);
     for (int s = 0; s <= maxLen_; s++) {
         perLen_[s] = std::make_unique<PerLen>();
-        perLen_[s]->lits.setPinnedLimit(pinnedLimit_);
+        PerLen &pl = *perLen_[s];
+        pl.lits.setPinnedLimit(pinnedLimit_);
+        pl.ids.setPinnedLimit(pinnedLimit_);
+        pl.acts.setPinnedLimit(pinnedLimit_);
+        // the arenas grow for as long as the solvers learn: in place (vmem.cc), never by realloc + copy
+        pl.dev.setInPlace();
+        pl.idsDev.setInPlace();
+        pl.actsDev.setInPlace();
     }
+}
+
+ClauseDb::~ClauseDb() {
+    if (mirrorPending_ && mirrorEv_) cudaEventSynchronize(mirrorEv_);
+    if (mirrorEv_) cudaEventDestroy(mirrorEv_);
+    if (permuteDoneEv_) cudaEventDestroy(permuteDoneEv_);
+    if (mirrorStream_) cudaStreamDestroy(mirrorStream_);
+}
+
+void ClauseDb::waitMirror() const {
+    if (!mirrorPending_) return;
+    GSS_CUDA(cudaEventSynchronize(mirrorEv_));
+    mirrorPending_ = false;
 }
 
 void ClauseDb::setShard(int rank, int world) {
@@ -66,15 +87,20 @@ int64_t ClauseDb::addClausesBulk(const int64_t *offsets, const int *lits, int64_
 
 void ClauseDb::appendToMirror(const int *lits, int n, int64_t id) {
     PerLen &pl = *perLen_[n];
-    int64_t idx = (int64_t)pl.meta.size();
+    int64_t idx = pl.n;
     size_t need = wordsFor(n, idx + 1);
+    // (appending does not touch what an asynchronous mirror refresh writes, reallocating would)
+    if (mirrorPending_ && (need > pl.lits.capacity() || (size_t)idx + 1 > pl.ids.capacity() || (size_t)idx + 1 > pl.acts.capacity()))
+        waitMirror();
     if (need > pl.lits.size()) pl.lits.resize(need); // new tile, zero-filled
     for (int i = 0; i < n; i++) {
         pl.lits[wordPos(n, idx, i)] = lits[i];
         int v = litVar(lits[i]) + 1;
         if (v > maxVarPlusOne_) maxVarPlusOne_ = v;
     }
-    pl.meta.push_back(ClauseMeta{id, actIncr_});
+    pl.ids.push_back(id);
+    pl.acts.push_back(actIncr_);
+    pl.n++;
     stats_.clauses++;
     stats_.lengthSum += n;
     stats_.added++;
@@ -92,7 +118,7 @@ void ClauseDb::drainPending() {
         firstId = pendingFirstId_;
     }
     std::vector<char> wasEmpty(maxLen_ + 1, 0);
-    for (int s = 1; s <= maxLen_; s++) wasEmpty[s] = perLen_[s]->meta.empty();
+    for (int s = 1; s <= maxLen_; s++) wasEmpty[s] = perLen_[s]->n == 0;
     size_t pos = 0;
     for (size_t c = 0; c < lens.size(); c++) {
         // Clauses.cu:334 + Clauses.cuh:192: the increment decays once per added clause
@@ -102,12 +128,14 @@ void ClauseDb::drainPending() {
     }
     // bulk load into an empty arena: nothing refers to these clause indices yet, order them
     for (int s = 1; s <= maxLen_; s++)
-        if (wasEmpty[s] && perLen_[s]->meta.size() >= kSortMinClauses) sortArena(s);
+        if (wasEmpty[s] && perLen_[s]->n >= kSortMinClauses) sortArena(s);
 }
 
 void ClauseDb::sortArena(int len) {
+    waitMirror();
     PerLen &pl = *perLen_[len];
-    const int64_t n = (int64_t)pl.meta.size();
+    const int64_t n = pl.n;
+    pl.sortedN = n;
     if (n < 2) return;
     // counting sort by first literal (stable: equal literals keep arrival order)
     int32_t maxLit = 0;
@@ -116,11 +144,13 @@ void ClauseDb::sortArena(int len) {
     for (int64_t i = 0; i < n; i++) bucket[(size_t)pl.lits[wordPos(len, i, 0)] + 1]++;
     for (size_t b = 1; b < bucket.size(); b++) bucket[b] += bucket[b - 1];
     std::vector<int32_t> oldLits(pl.lits.data(), pl.lits.data() + pl.lits.size());
-    std::vector<ClauseMeta> oldMeta(pl.meta);
+    std::vector<int64_t> oldIds(pl.ids.data(), pl.ids.data() + n);
+    std::vector<float> oldActs(pl.acts.data(), pl.acts.data() + n);
     for (int64_t i = 0; i < n; i++) {
         int64_t to = bucket[(size_t)oldLits[wordPos(len, i, 0)]]++;
         for (int k = 0; k < len; k++) pl.lits[wordPos(len, to, k)] = oldLits[wordPos(len, i, k)];
-        pl.meta[to] = oldMeta[i];
+        pl.ids[(size_t)to] = oldIds[(size_t)i];
+        pl.acts[(size_t)to] = oldActs[(size_t)i];
     }
     pl.fullReupload = true;
     pl.dirtyFrom = 0;
@@ -140,7 +170,7 @@ bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
     applyPendingDeviceRescales(stream);
     for (int s = maxLen_; s >= 1; s--) {
         PerLen &pl = *perLen_[s];
-        int64_t n = (int64_t)pl.meta.size();
+        int64_t n = pl.n;
         if (!pl.fullReupload && pl.dirtyFrom >= n) continue;
         const size_t tileWords = (size_t)kTileClauses * s;
         const int64_t tiles = (n + kTileClauses - 1) / kTileClauses;
@@ -150,6 +180,9 @@ bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
             // arena (176 MB at 10 M clauses is nothing next to 180 GB), so any rank can resolve any
             // hit (ids, literals) on its device; a rank only checks its share of the tiles.
             size_t total = (size_t)tiles * tileWords, from = (size_t)firstTile * tileWords;
+            // (a device buffer that outgrows its address range is re-mapped: not under a mirror refresh)
+            if (mirrorPending_ && (total > pl.dev.capacity() || (size_t)n > pl.idsDev.capacity() || (size_t)n > pl.actsDev.capacity()))
+                waitMirror();
             if (total > 0) {
                 if (!pl.dev.tryReserve(total, pl.fullReupload ? 0 : from, stream)) return false;
                 GSS_CUDA(cudaMemcpyAsync(pl.dev.data() + from, pl.lits.data() + from, (total - from) * sizeof(int32_t),
@@ -160,22 +193,14 @@ bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
         // clause ids of the same dirty range
         {
             int64_t from = pl.fullReupload ? 0 : pl.dirtyFrom;
-            if (n > from) {
+            if (n > from) { // (the host arrays are the staging buffers: same element layout as on the device)
                 if (!pl.idsDev.tryReserve((size_t)n, (size_t)from, stream)) return false;
-                pl.idsStage.setPinnedLimit(pinnedLimit_);
-                pl.idsStage.clear();
-                pl.idsStage.resize((size_t)(n - from));
-                for (int64_t i = from; i < n; i++) pl.idsStage[(size_t)(i - from)] = pl.meta[(size_t)i].id;
-                GSS_CUDA(cudaMemcpyAsync(pl.idsDev.data() + from, pl.idsStage.data(), (size_t)(n - from) * sizeof(int64_t),
+                GSS_CUDA(cudaMemcpyAsync(pl.idsDev.data() + from, pl.ids.data() + from, (size_t)(n - from) * sizeof(int64_t),
                                          cudaMemcpyHostToDevice, stream));
                 if (bytesCopied) *bytesCopied += (n - from) * (int64_t)sizeof(int64_t);
                 if (deviceActs_) {
                     if (!pl.actsDev.tryReserve((size_t)n, (size_t)from, stream)) return false;
-                    pl.actsStage.setPinnedLimit(pinnedLimit_);
-                    pl.actsStage.clear();
-                    pl.actsStage.resize((size_t)(n - from));
-                    for (int64_t i = from; i < n; i++) pl.actsStage[(size_t)(i - from)] = pl.meta[(size_t)i].activity;
-                    GSS_CUDA(cudaMemcpyAsync(pl.actsDev.data() + from, pl.actsStage.data(), (size_t)(n - from) * sizeof(float),
+                    GSS_CUDA(cudaMemcpyAsync(pl.actsDev.data() + from, pl.acts.data() + from, (size_t)(n - from) * sizeof(float),
                                              cudaMemcpyHostToDevice, stream));
                     pl.actsOnDevice = n;
                 }
@@ -192,7 +217,7 @@ int ClauseDb::buildDirectory(std::vector<LenDir> &dir) const {
     int tiles = 0;
     for (int s = maxLen_; s >= 1; s--) { // longest first: the tail of the grid gets the cheap tiles
         const PerLen &pl = *perLen_[s];
-        int64_t n = (int64_t)pl.meta.size();
+        int64_t n = pl.n;
         if (n == 0) continue;
         // a length none of whose tiles is checked here still gets its entry: hits of other ranks
         // are resolved (ids, literals, activity bumps) through this directory
@@ -210,65 +235,105 @@ int ClauseDb::buildDirectory(std::vector<LenDir> &dir) const {
 }
 
 void ClauseDb::getClause(int len, int idx, std::vector<int> &lits, int64_t &id) const {
+    waitMirror();
     const PerLen &pl = *perLen_[len];
     lits.resize(len);
     for (int i = 0; i < len; i++) lits[i] = pl.lits[wordPos(len, idx, i)];
-    id = pl.meta[idx].id;
+    id = pl.ids[(size_t)idx];
 }
 
 void ClauseDb::bumpActivity(int len, int idx) {
-    float &a = perLen_[len]->meta[idx].activity;
+    float &a = perLen_[len]->acts[(size_t)idx];
     a += actIncr_;
     if (a > kRescale) rescaleActivity();
 }
 
 void ClauseDb::rescaleActivity() { // Clauses.cu:284-291
-    for (int s = 0; s <= maxLen_; s++)
-        for (auto &m : perLen_[s]->meta) m.activity /= kRescale;
+    waitMirror();
+    for (int s = 0; s <= maxLen_; s++) {
+        PerLen &pl = *perLen_[s];
+        for (int64_t i = 0; i < pl.n; i++) pl.acts[(size_t)i] /= kRescale;
+    }
     actIncr_ /= kRescale;
     if (deviceActs_) pendingDeviceRescales_++;
 }
 
 void ClauseDb::downloadActivities(cudaStream_t stream) {
     if (!deviceActs_) return;
-    std::vector<float> tmp;
+    waitMirror();
+    bool any = false;
     for (int s = 1; s <= maxLen_; s++) {
         PerLen &pl = *perLen_[s];
-        int64_t n = std::min<int64_t>(pl.actsOnDevice, (int64_t)pl.meta.size());
+        int64_t n = std::min<int64_t>(pl.actsOnDevice, pl.n);
         if (n <= 0) continue;
-        tmp.resize((size_t)n);
-        GSS_CUDA(cudaMemcpyAsync(tmp.data(), pl.actsDev.data(), (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
-        GSS_CUDA(cudaStreamSynchronize(stream));
-        for (int64_t i = 0; i < n; i++) pl.meta[(size_t)i].activity = tmp[(size_t)i];
+        GSS_CUDA(cudaMemcpyAsync(pl.acts.data(), pl.actsDev.data(), (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        any = true;
     }
+    if (any) GSS_CUDA(cudaStreamSynchronize(stream));
 }
 
-float ClauseDb::approxNthAct(int64_t n) const {
-    // Clauses.cu:492-525: 20000 log-scale buckets over the float range, rounded up.  The
-    // facade passes the clause length as LBD (GpuClauseSharerImpl.cu:125) and the range is
-    // [0, MAX_CL_SIZE), so clauses of exactly the maximum length are not counted.
-    if (n == 0) return 0.0f;
-    const int buckets = 20000;
-    std::vector<int64_t> counts(buckets, 0);
+// Clauses.cu:492-525: 20000 log-scale buckets over the float range.
+namespace {
+struct ActScale {
     float lowestLog = std::log(std::numeric_limits<float>::min());
     float largestLog = std::log(std::numeric_limits<float>::max());
-    float stepLog = (largestLog - lowestLog) / buckets;
-    for (int s = 1; s < maxLen_; s++) {
-        for (const auto &m : perLen_[s]->meta) {
-            int b = (int)std::floor(((double)std::log(m.activity) - (double)lowestLog) / (double)stepLog);
-            if (b < 0) b = 0;
-            if (b >= buckets) b = buckets - 1;
-            counts[b]++;
-        }
-    }
+    float stepLog = (largestLog - lowestLog) / ClauseDb::kActBuckets;
+};
+const ActScale kActScale;
+} // namespace
+
+int ClauseDb::actBucket(float activity) {
+    int b = (int)std::floor(((double)std::log(activity) - (double)kActScale.lowestLog) / (double)kActScale.stepLog);
+    if (b < 0) b = 0;
+    if (b >= kActBuckets) b = kActBuckets - 1;
+    return b;
+}
+
+float ClauseDb::thresholdFromHistogram(const int64_t *counts, int64_t n) {
+    if (n == 0) return 0.0f;
     int64_t seen = 0;
-    for (int b = 0; b < buckets; b++) {
+    for (int b = 0; b < kActBuckets; b++) {
         seen += counts[b];
-        if (seen >= n) return std::exp(lowestLog + (b + 1) * stepLog);
+        if (seen >= n) return std::exp(kActScale.lowestLog + (b + 1) * kActScale.stepLog); // rounded up
     }
     // more than half of the database has the maximum length: the reference aborts here
     // (bare `throw;`).  Removing every removable clause is the closest defined behaviour.
     return std::numeric_limits<float>::max();
+}
+
+// bounds[b] = bit pattern of the smallest non-negative float whose bucket is >= b (bounds[0] = 0), so that
+// bucket(x) = number of b in [1, kActBuckets) with bounds[b] <= bits(x): the device histogram (reduce.cu)
+// finds the bucket by binary search over this table and agrees with actBucket() bit for bit without
+// depending on the device's logarithm.  (actBucket is monotone; 31 evaluations per bound, once per process.)
+const std::vector<uint32_t> &ClauseDb::actBucketBounds() {
+    static const std::vector<uint32_t> bounds = [] {
+        std::vector<uint32_t> v((size_t)kActBuckets, 0u);
+        for (int b = 1; b < kActBuckets; b++) {
+            uint32_t lo = v[(size_t)b - 1], hi = 0x7F800000u; // +inf always reaches the last bucket
+            while (lo < hi) {
+                uint32_t mid = lo + (hi - lo) / 2;
+                float x;
+                memcpy(&x, &mid, 4);
+                if (actBucket(x) >= b) hi = mid; else lo = mid + 1;
+            }
+            v[(size_t)b] = lo;
+        }
+        return v;
+    }();
+    return bounds;
+}
+
+float ClauseDb::approxNthAct(int64_t n) const {
+    // The facade passes the clause length as LBD (GpuClauseSharerImpl.cu:125) and the range is
+    // [0, MAX_CL_SIZE), so clauses of exactly the maximum length are not counted.
+    if (n == 0) return 0.0f;
+    waitMirror();
+    std::vector<int64_t> counts(kActBuckets, 0);
+    for (int s = 1; s < maxLen_; s++) {
+        const PerLen &pl = *perLen_[s];
+        for (int64_t i = 0; i < pl.n; i++) counts[(size_t)actBucket(pl.acts[(size_t)i])]++;
+    }
+    return thresholdFromHistogram(counts.data(), n);
 }
 
 void ClauseDb::syncActivitiesFromDevice(cudaStream_t stream) {
@@ -279,18 +344,38 @@ void ClauseDb::syncActivitiesFromDevice(cudaStream_t stream) {
 
 void ClauseDb::copyActivitiesFrom(const ClauseDb &other) {
     GSS_CHECK(other.maxLen_ == maxLen_);
+    waitMirror();
+    other.waitMirror();
     for (int s = 1; s <= maxLen_; s++) {
         PerLen &pl = *perLen_[s];
         const PerLen &po = *other.perLen_[s];
-        GSS_CHECK(pl.meta.size() == po.meta.size());
-        for (size_t i = 0; i < pl.meta.size(); i++) pl.meta[i].activity = po.meta[i].activity;
+        GSS_CHECK(pl.n == po.n);
+        if (pl.n) memcpy(pl.acts.data(), po.acts.data(), (size_t)pl.n * sizeof(float));
     }
     pendingDeviceRescales_ = 0; // the copied values are final
 }
 
 void ClauseDb::reduceDb(cudaStream_t stream) {
+    if (deviceActs_ && deviceReduce_ && shardWorld_ == 1 && permuteOnDevice(stream, true)) return;
     syncActivitiesFromDevice(stream);
     reduceAfterSync(stream);
+}
+
+int64_t ClauseDb::unsortedClauses() const {
+    int64_t u = 0;
+    for (int s = 1; s <= maxLen_; s++) u += perLen_[s]->n - perLen_[s]->sortedN;
+    return u;
+}
+
+bool ClauseDb::resortDue() const {
+    if (!deviceActs_ || !deviceReduce_ || shardWorld_ != 1) return false;
+    const int64_t u = unsortedClauses();
+    return u >= resortMinClauses_ && u * kResortShare >= stats_.clauses;
+}
+
+void ClauseDb::resortOnDevice(cudaStream_t stream) {
+    if (!permuteOnDevice(stream, false)) // no memory for the second set of arenas: the tails stay unsorted
+        for (int s = 1; s <= maxLen_; s++) perLen_[s]->sortedN = perLen_[s]->n;
 }
 
 void ClauseDb::reduceAfterSync(cudaStream_t stream) {
@@ -298,7 +383,7 @@ void ClauseDb::reduceAfterSync(cudaStream_t stream) {
     for (int s = maxLen_; s >= 3; s--) {
         PerLen &pl = *perLen_[s];
         // give memory back when the arena is mostly empty (reference: CorrespArr.cu:103-113)
-        if (pl.dev.capacity() > 1024 && wordsFor(s, (int64_t)pl.meta.size()) * 3 < pl.dev.capacity()) {
+        if (pl.dev.capacity() > 1024 && wordsFor(s, pl.n) * 3 < pl.dev.capacity()) {
             GSS_CUDA(cudaStreamSynchronize(stream));
             pl.dev.free();
             pl.idsDev.free();
@@ -312,6 +397,7 @@ void ClauseDb::reduceAfterSync(cudaStream_t stream) {
 }
 
 void ClauseDb::reduceHost() {
+    waitMirror();
     addedAtLastReduce_ = stats_.added;
     reduceDbs_++;
     float act = approxNthAct(stats_.clauses / 2);
@@ -321,28 +407,31 @@ void ClauseDb::reduceHost() {
     // activity >= act.
     for (int s = maxLen_; s >= 3; s--) {
         PerLen &pl = *perLen_[s];
-        int64_t n = (int64_t)pl.meta.size(), to = 0;
+        int64_t n = pl.n, to = 0;
         if (n == 0) continue;
         for (int64_t idx = 0; idx < n; idx++) {
-            const ClauseMeta m = pl.meta[idx];
-            if (s < maxLen_ && m.activity >= act) {
+            const float a = pl.acts[(size_t)idx];
+            if (s < maxLen_ && a >= act) {
                 if (to != idx) {
                     for (int i = 0; i < s; i++) pl.lits[wordPos(s, to, i)] = pl.lits[wordPos(s, idx, i)];
-                    pl.meta[to] = m;
+                    pl.ids[(size_t)to] = pl.ids[(size_t)idx];
+                    pl.acts[(size_t)to] = a;
                 }
                 to++;
             }
         }
         stats_.clauses -= n - to;
         stats_.lengthSum -= (n - to) * s;
-        pl.meta.resize(to);
+        pl.n = to;
+        pl.ids.resize((size_t)to);
+        pl.acts.resize((size_t)to);
         pl.lits.resize(wordsFor(s, to));
         pl.fullReupload = true;
         pl.dirtyFrom = 0;
     }
-    // clause indices change anyway: put every arena back in first-literal order
-    for (int s = 1; s <= maxLen_; s++)
-        if ((int64_t)perLen_[s]->meta.size() >= kSortMinClauses) sortArena(s);
+    // clause indices change anyway: put every arena back in first-literal order (a stable sort of the
+    // stable compaction: the device-side reduce, reduce.cu, produces exactly the same order)
+    for (int s = 1; s <= maxLen_; s++) sortArena(s);
 }
 
 void ClauseDb::writeCnf(FILE *f, int varCount) const {

@@ -17,10 +17,6 @@
 
 namespace gss {
 
-struct ClauseMeta {
-    int64_t id;     // GpuClauseId handed out by addClause
-    float activity; // bumped per hit, decayed per added clause (Clauses.cu:200-237)
-};
 
 // One non-empty clause length, as the kernels see it.
 struct LenDir {
@@ -41,6 +37,7 @@ struct DbStats {
 class ClauseDb {
 public:
     ClauseDb(double activityDecay, const Logger &logger, size_t pinnedLimitBytes);
+    ~ClauseDb();
 
     void setMaxLen(int maxLen);
     int maxLen() const { return maxLen_; }
@@ -65,29 +62,30 @@ public:
     void getClause(int len, int idx, std::vector<int> &lits, int64_t &id) const;
     // append the literals to `out` (no temporary); returns the clause id
     int64_t appendClause(int len, int idx, std::vector<int> &out) const {
+        waitMirror();
         const PerLen &pl = *perLen_[len];
         size_t at = out.size();
         out.resize(at + len);
         const int32_t *p = pl.lits.data() + wordPos(len, idx, 0);
         for (int i = 0; i < len; i++) out[at + i] = p[(size_t)i * kTileClauses];
-        return pl.meta[idx].id;
+        return pl.ids[(size_t)idx];
     }
     // hint the caches about a clause that is about to be read (hits arrive sorted by index)
     void prefetchClause(int len, int idx) const {
         const PerLen &pl = *perLen_[len];
-        __builtin_prefetch(&pl.meta[idx]);
+        __builtin_prefetch(&pl.ids[(size_t)idx]);
         __builtin_prefetch(pl.lits.data() + wordPos(len, idx, 0));
         if (len > 1) __builtin_prefetch(pl.lits.data() + wordPos(len, idx, 1));
     }
-    void prefetchMeta(int len, int idx) const { __builtin_prefetch(&perLen_[len]->meta[idx]); }
-    int64_t clauseId(int len, int idx) const { return perLen_[len]->meta[idx].id; }
-    float activity(int len, int idx) const { return perLen_[len]->meta[idx].activity; }
+    void prefetchMeta(int len, int idx) const { __builtin_prefetch(&perLen_[len]->ids[(size_t)idx]); }
+    int64_t clauseId(int len, int idx) const { waitMirror(); return perLen_[len]->ids[(size_t)idx]; }
+    float activity(int len, int idx) const { waitMirror(); return perLen_[len]->acts[(size_t)idx]; }
     void bumpActivity(int len, int idx); // Clauses.cu:231-237
     // same bump from several threads at once (large hit lists are processed per solver in
     // parallel); returns true when the activity passed the rescale limit -- the caller then calls
     // rescaleIfNeeded() once the parallel section is over
     bool bumpActivityAtomic(int len, int idx) {
-        float *p = &perLen_[len]->meta[idx].activity;
+        float *p = &perLen_[len]->acts[(size_t)idx];
         uint32_t *bits = reinterpret_cast<uint32_t *>(p);
         uint32_t old = __atomic_load_n(bits, __ATOMIC_RELAXED), want;
         float nv;
@@ -100,10 +98,22 @@ public:
         return nv > 1e19f;
     }
     void rescaleIfNeeded(bool needed) { if (needed) rescaleActivity(); }
-    int count(int len) const { return len <= maxLen_ ? (int)perLen_[len]->meta.size() : 0; }
+    int count(int len) const { return len <= maxLen_ ? (int)perLen_[len]->n : 0; }
 
-    // reference HostClauses::reduceDb (actOnly), Clauses.cu:426-465 / 249-282
+    // reference HostClauses::reduceDb (actOnly), Clauses.cu:426-465 / 249-282.  With device-resident
+    // activities (the product path of a single-device sharer) the whole reduction runs on the device
+    // (reduce.cu): threshold from a device histogram, keep flags, stable sort by first literal, one
+    // permutation pass into fresh arenas -- the host mirror is refreshed by an asynchronous copy.
+    // Otherwise (several devices behind one front-end, CPU test rig): host compaction + re-upload.
     void reduceDb(cudaStream_t stream);
+    // Streamed clauses are appended behind the first-literal-sorted part of their arena; once the unsorted
+    // tails have grown past a share of the database the arenas are put back in order on the device
+    // (same permutation pass as reduceDb, nothing removed).  Clause indices change: the caller makes sure
+    // no run is in flight and nothing refers to indices any more, exactly as for reduceDb.
+    bool resortDue() const;
+    void resortOnDevice(cudaStream_t stream);
+    void setDeviceReduce(bool on) { deviceReduce_ = on; }
+    int64_t unsortedClauses() const;
     // the two halves of reduceDb, and (several devices in one process: every device keeps the whole
     // database, the activities are authoritative on the first one) taking the activities from a twin
     void syncActivitiesFromDevice(cudaStream_t stream);
@@ -120,8 +130,12 @@ public:
     void rescaleAfterDeviceOverflow() { rescaleActivity(); }
     // rescales decided on the host (drain, device overflow) that the device copies have not seen yet
     void applyPendingDeviceRescales(cudaStream_t stream);
-    // reference approxNthAct, Clauses.cu:492-525
+    // reference approxNthAct, Clauses.cu:492-525; its pieces are shared with the device-side reduce
     float approxNthAct(int64_t n) const;
+    static constexpr int kActBuckets = 20000;
+    static int actBucket(float activity);
+    static float thresholdFromHistogram(const int64_t *counts, int64_t n);
+    static const std::vector<uint32_t> &actBucketBounds();
     void writeCnf(FILE *f, int varCount) const; // Clauses.cu:527-549
 
     const DbStats &stats() const { return stats_; }
@@ -132,17 +146,28 @@ public:
 
 private:
     struct PerLen {
+        int64_t n = 0;            // clauses of this length
         HostBuf<int32_t> lits;    // tiled host mirror
-        std::vector<ClauseMeta> meta;
-        DevBuf<int32_t> dev;
-        DevBuf<int64_t> idsDev;   // clause ids (the GPU emits them with the hits of large result lists)
-        HostBuf<int64_t> idsStage;
+        HostBuf<int64_t> ids;     // GpuClauseId handed out by addClause, per clause
+        HostBuf<float> acts;      // activity: bumped per hit, decayed per added clause (Clauses.cu:200-237)
+        DevBuf<int32_t> dev;      // device arena (grows in place: vmem.cc)
+        DevBuf<int64_t> idsDev;   // clause ids (the GPU emits them with the hits)
         DevBuf<float> actsDev;    // clause activities live on the device between two reduceDb calls
-        HostBuf<float> actsStage;
         int64_t actsOnDevice = 0; // clauses [0, actsOnDevice) have their authoritative activity on the device
         int64_t dirtyFrom = 0;    // first clause index not yet on the device
+        int64_t sortedN = 0;      // clauses [0, sortedN) are in first-literal order
         bool fullReupload = false;
     };
+    // device-side reduce / re-sort (reduce.cu); false: could not get the memory, nothing changed
+    bool permuteOnDevice(cudaStream_t stream, bool dropByActivity);
+    // The host mirror of the clauses [0, n) of every length is being refreshed by an asynchronous
+    // device-to-host copy (after a device-side reduce / re-sort): wait for it before the host reads that
+    // part of the mirror or reallocates any of its buffers.
+    void waitMirror() const;
+    mutable bool mirrorPending_ = false;
+    cudaEvent_t mirrorEv_ = nullptr, permuteDoneEv_ = nullptr;
+    cudaStream_t mirrorStream_ = nullptr;
+    bool deviceReduce_ = true;
     static size_t wordsFor(int len, int64_t count) {
         return (size_t)((count + kTileClauses - 1) / kTileClauses) * kTileClauses * (size_t)len;
     }
@@ -168,6 +193,10 @@ private:
         return globalTiles * (shardRank_ + 1) / shardWorld_ - globalTiles * shardRank_ / shardWorld_;
     }
     static constexpr int64_t kSortMinClauses = 1024;
+    // re-sort on the device once the unsorted tails hold >= 64 k clauses and >= 1/8 of the database
+    // (GPUSHARE_RESORT_MIN_CLAUSES overrides the first bound: tests)
+    int64_t resortMinClauses_ = 65536;
+    static constexpr int64_t kResortShare = 8;
     int maxLen_ = kDefaultMaxClauseLen;
     int shardRank_ = 0, shardWorld_ = 1;
     std::vector<std::unique_ptr<PerLen>> perLen_;

@@ -3,7 +3,9 @@
 // buffers, one pinned-host, one device, both stream-ordered.
 #pragma once
 #include "common.h"
+#include <algorithm>
 #include <cstring>
+#include <vector>
 
 namespace gss {
 
@@ -69,24 +71,80 @@ public:
     T *append(size_t n) { reserve(size_ + n); T *r = p_ + size_; size_ += n; return r; }
 };
 
-// Growable device buffer.  Growth allocates a larger block and copies device-to-device on the
-// given stream; tryReserve returns false instead of dying when the device is out of memory
+// Device memory that grows in place: a reserved range of virtual addresses with physical chunks
+// mapped behind it as the buffer grows (vmem.cc).
+namespace vm {
+bool available(); // the driver's virtual memory management entry points could be resolved
+struct Block {
+    struct Chunk {
+        unsigned long long handle;
+        size_t bytes;
+    };
+    void *base = nullptr;
+    size_t reserved = 0, mapped = 0, gran = 0;
+    int device = 0;
+    std::vector<Chunk> chunks;
+    // make at least `bytes` usable; false: out of device memory (nothing changed).  The data never moves
+    // unless the reserved range itself is outgrown (then: same chunks, new addresses, after a stream sync).
+    bool grow(size_t bytes, cudaStream_t stream);
+    void release();
+
+private:
+    bool reserveRange(size_t bytes);
+    bool mapChunks(size_t from);
+};
+} // namespace vm
+
+// Growable device buffer.  tryReserve returns false instead of dying when the device is out of memory
 // (the caller then reduces the clause database like the reference, GpuRunner.cu:243-246).
+// Two growth strategies: the default allocates a larger block and copies device-to-device on the given
+// stream (small, short-lived buffers); setInPlace() buffers -- the clause arenas -- map more physical
+// memory behind the same addresses (vm::Block: no copy, no synchronisation, no free).
 template <typename T> class DevBuf {
     T *p_ = nullptr;
     size_t cap_ = 0;
+    bool wantInPlace_ = false, inPlace_ = false;
+    vm::Block block_;
+    // a mapping granule is 2 MB: buffers below this size stay ordinary allocations (a database has one
+    // arena per clause length, most of them tiny) and move behind a virtual range once, when they pass it
+    static constexpr size_t kInPlaceMinBytes = (size_t)8 << 20;
 
 public:
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    ~DevBuf() { if (p_) cudaFree(p_); }
+    ~DevBuf() { free(); }
+    // ignored when the driver lacks the entry points
+    void setInPlace() { wantInPlace_ = vm::available(); }
+    bool inPlace() const { return inPlace_; }
     T *data() { return p_; }
     const T *data() const { return p_; }
     size_t capacity() const { return cap_; }
+    void swap(DevBuf &o) {
+        std::swap(p_, o.p_);
+        std::swap(cap_, o.cap_);
+        std::swap(wantInPlace_, o.wantInPlace_);
+        std::swap(inPlace_, o.inPlace_);
+        std::swap(block_, o.block_);
+    }
     // keep = number of leading elements whose contents must survive the growth
     bool tryReserve(size_t n, size_t keep, cudaStream_t stream, bool exact = false) {
         if (n <= cap_) return true;
+        if (inPlace_ || (wantInPlace_ && n * sizeof(T) >= kInPlaceMinBytes)) {
+            if (!block_.grow(n * sizeof(T), stream)) return false;
+            T *q = static_cast<T *>(block_.base);
+            if (!inPlace_) { // the one move of this buffer's life
+                if (keep && p_) GSS_CUDA(cudaMemcpyAsync(q, p_, keep * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+                if (p_) {
+                    GSS_CUDA(cudaStreamSynchronize(stream));
+                    cudaFree(p_);
+                }
+                inPlace_ = true;
+            }
+            p_ = q;
+            cap_ = block_.mapped / sizeof(T);
+            return true;
+        }
         size_t nc = n;
         if (!exact) {
             nc = cap_ ? cap_ : 256;
@@ -108,7 +166,13 @@ public:
     void reserve(size_t n, size_t keep, cudaStream_t stream) {
         if (!tryReserve(n, keep, stream)) GSS_DIE("out of device memory");
     }
-    void free() { if (p_) cudaFree(p_); p_ = nullptr; cap_ = 0; }
+    void free() {
+        if (inPlace_) block_.release();
+        else if (p_) cudaFree(p_);
+        inPlace_ = false;
+        p_ = nullptr;
+        cap_ = 0;
+    }
 };
 
 } // namespace gss

@@ -178,11 +178,18 @@ void Sharer::workerFinish(int slotIdx) {
 // compacts its copy of the database the same way, in parallel
 void Sharer::reduceDbMulti() {
     db_->syncActivitiesFromDevice(stream_);
+    // (two steps: nobody may still be reading this device's activities when its own reduction rewrites them)
+    // (every device drains its pending clauses at the start of the same runs, never here: the mirrors are in step)
+    const std::function<void(int)> take = [&](int i) {
+        Sharer &w = *workers_[i];
+        w.useDevice();
+        w.db_->copyActivitiesFrom(*db_);
+    };
+    wthreads_->start(take);
+    wthreads_->wait();
     const std::function<void(int)> red = [&](int i) {
         Sharer &w = *workers_[i];
         w.useDevice();
-        w.db_->drainPending();
-        w.db_->copyActivitiesFrom(*db_);
         w.db_->reduceAfterSync(w.stream_);
         w.lastStarted_ = -1;
     };

@@ -42,7 +42,7 @@ public:
                     free_.pop_back();
                     break;
                 }
-            if (!b && free_.size() >= 4) { // too small for today's results: do not hoard them
+            if (!b && free_.size() >= 4) { // all too small for today's results: do not hoard them
                 for (RunBuf *f : free_) destroy(f);
                 free_.clear();
             }
@@ -235,7 +235,14 @@ void Sharer::launchDirectCheck(RunSlot &slot) {
     if (peer_ && peerAcquireResultBuf(slot)) {
         // (a worker rank of the multi-process exchange: a buffer of its shared-memory ring, which rank 0 reads)
     } else {
-        slot.runBuf = runBufs_->acquire((int64_t)pow2AtLeast((size_t)entryGuess_), (int64_t)pow2AtLeast((size_t)litGuess_));
+        // ... and sticky: a need that hovers around a power of two must not alternate between two buffer sizes
+        // (a miss is a page-locked allocation: tens of milliseconds); shrink only below a quarter
+        int64_t wantE = (int64_t)pow2AtLeast((size_t)entryGuess_), wantL = (int64_t)pow2AtLeast((size_t)litGuess_);
+        if (wantE < runCapE_ && wantE * 4 > runCapE_) wantE = runCapE_;
+        if (wantL < runCapL_ && wantL * 4 > runCapL_) wantL = runCapL_;
+        runCapE_ = wantE;
+        runCapL_ = wantL;
+        slot.runBuf = runBufs_->acquire(wantE, wantL);
     }
     launchCheckKernels(slot, false);
     launchEmitFor(slot);

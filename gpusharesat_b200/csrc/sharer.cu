@@ -79,6 +79,7 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx, int workerOfD
     reported_ = std::make_unique<Reported>(*db_, oneSolverStats_);
     reported_->setPool(&pool_);
     db_->setDeviceActivities(true);
+    if (getenv("GPUSHARE_HOST_REDUCE")) db_->setDeviceReduce(false); // round-1 reduceDb (host compaction + re-upload), for comparison
     reported_->setHostBumps(false);
     setCpuSolverCount(1);
     runBufs_ = makeRunBufPool();
@@ -247,6 +248,16 @@ int64_t Sharer::globalStat(int stat) {
 void Sharer::gpuRun() {
     // GpuClauseSharerImpl.cu:83-94
     int64_t t0 = nowMicros();
+    // clauses streamed in since the arenas were last put in first-literal order: once their share has grown
+    // enough, re-sort on the device (clause indices change: finish the run in flight first, as for reduceDb)
+    if (workers_.empty() && !peer_ && db_->resortDue()) {
+        wholeRun(false);
+        useDevice();
+        materializeLastHits();
+        db_->resortOnDevice(stream_);
+        lastStarted_ = -1;
+        resorts_++;
+    }
     wholeRun(true);
     // The reference sleeps until minGpuLatencyMicros have passed and surfaces the run's hits in the NEXT
     // call (GpuRunner.cu:233-242).  Here the waiting time is used: a run that completes within it is

@@ -92,6 +92,7 @@ public:
     void mgpuImport(const HitRecord *hits, int64_t n);
     void mgpuImportGathered(const void *devGathered, int world, int64_t slotBytes, const int64_t *counts);
     void dbSize(int64_t *ncl, int64_t *nlits) { *ncl = db_->stats().clauses; *nlits = db_->stats().lengthSum; }
+    void dbOrder(int64_t *unsorted, int64_t *resorts) { *unsorted = db_->unsortedClauses(); *resorts = resorts_; }
     // ---- multi-GPU over peer memory (CUDA IPC windows, no collective on the data path: peer.cu) ----
     int64_t peerInit(int rank, int world, int64_t payloadCap, int64_t slotHits, void *blobOut, int64_t blobCap);
     void peerConnect(const void *blobs, int64_t blobBytes);
@@ -206,10 +207,12 @@ private:
     Sharer *root_ = nullptr;
 
     std::shared_ptr<RunBufPool> runBufs_;
+    int64_t resorts_ = 0; // device-side re-sorts of streamed clauses (ClauseDb::resortOnDevice)
     bool directEnabled_ = true;
     bool eagerResults_ = true; // surface a run's hits in the call that started it when it completes within minGpuLatencyMicros
     size_t recCap_ = 4096;       // per-solver record capacity (power of two, >= kRecBuckets)
     int64_t entryGuess_ = 4096, litGuess_ = 16384; // result buffer sizing (from previous runs)
+    int64_t runCapE_ = 0, runCapL_ = 0;            // capacities of the previous run's result buffer
     uint32_t directSeq_ = 0;
     RunSlot *lastDirect_ = nullptr; // finished direct run whose records are still on the device (parity hook)
 

@@ -165,6 +165,10 @@ int64_t gss_debug_kernel_launches(gss_sharer *h);
 /* Sum of clause lengths / clause count currently in the database */
 void gss_debug_db_size(gss_sharer *h, int64_t *nclauses, int64_t *nlits);
 
+/* Clauses streamed in behind the first-literal-sorted part of their arena, and how often the arenas have
+ * been put back in order on the device so far (csrc/reduce.cu) */
+void gss_debug_db_order(gss_sharer *h, int64_t *unsorted_clauses, int64_t *resorts);
+
 /* ------------------------------------------------------------------------------------------
  * Multi-GPU (new functionality; the reference drives device 0 only, GpuClauseSharerImpl.cu:52).
  * One process per GPU.  Every rank creates a sharer, calls gss_set_shard(rank, world) and then

@@ -14,6 +14,7 @@ using namespace gss;
 // the host-only rig never has activities on a device (kernels.cu is not linked here)
 namespace gss {
 void scaleActivitiesOnDevice(float *, int64_t, float, cudaStream_t) {}
+bool ClauseDb::permuteOnDevice(cudaStream_t, bool) { return false; } // (reduce.cu is device code)
 } // namespace gss
 
 struct HostRig {

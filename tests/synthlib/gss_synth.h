@@ -36,6 +36,14 @@ const uint8_t *gss_synth_stream_values(gss_synth_stream *s);
  * assignment.  Both arrays need room for nvars entries. */
 void gss_synth_stream_next(gss_synth_stream *s, int32_t *set_lits, int32_t *n_set, int32_t *unset_lits, int32_t *n_unset);
 
+/* BASELINE configs[3]: a satisfiable CNF instance in DIMACS format for the reference's real solvers:
+ * nclauses clauses over nvars variables, lengths from len_weights (len_weights[k] = relative share of
+ * clauses with k + 2 literals, n_lens entries), distinct variables per clause, every literal true under
+ * the planted assignment with probability p_agree and every clause satisfied by it (one literal is
+ * flipped where the draw left none).  Returns 0, or -1 when the file cannot be written. */
+int gss_synth_write_cnf(const char *path, int nvars, int64_t nclauses, const double *len_weights, int n_lens,
+                        double p_agree, uint64_t seed);
+
 #ifdef __cplusplus
 }
 #endif

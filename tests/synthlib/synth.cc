@@ -2,6 +2,7 @@
 // host-only library (libgss_synth.so), so that input generation never loads the product library.
 #include "gss_synth.h"
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <thread>
 #include <vector>
@@ -157,4 +158,61 @@ void gss_synth_stream_next(gss_synth_stream *s, int32_t *set_lits, int32_t *n_se
     *n_unset = nu;
 }
 
+
+int gss_synth_write_cnf(const char *path, int nvars, int64_t nclauses, const double *len_weights, int n_lens,
+                        double p_agree, uint64_t seed) {
+    FILE *f = fopen(path, "w");
+    if (!f) return -1;
+    std::vector<uint8_t> sigma((size_t)nvars);
+    gss_synth_sigma(nvars, seed ^ 0x5151ull, sigma.data());
+    double total = 0;
+    for (int k = 0; k < n_lens; k++) total += len_weights[k];
+    SplitMix64 r(seed);
+    std::vector<char> buf;
+    buf.reserve(1 << 22);
+    fprintf(f, "p cnf %d %lld\n", nvars, (long long)nclauses);
+    int vars[64];
+    for (int64_t c = 0; c < nclauses; c++) {
+        double x = r.unit() * total;
+        int len = 2;
+        for (int k = 0; k < n_lens; k++) {
+            if (x < len_weights[k] || k == n_lens - 1) { len = k + 2; break; }
+            x -= len_weights[k];
+        }
+        if (len > 64) len = 64;
+        bool sat = false;
+        int signs[64];
+        for (int i = 0; i < len; i++) {
+            int v;
+            bool dup;
+            do {
+                v = (int)r.below((uint32_t)nvars);
+                dup = false;
+                for (int j = 0; j < i; j++) dup = dup || vars[j] == v;
+            } while (dup);
+            vars[i] = v;
+            const bool agree = r.unit() < p_agree;
+            const int trueSign = sigma[(size_t)v] == 0 ? 0 : 1;
+            signs[i] = agree ? trueSign : 1 - trueSign;
+            sat = sat || agree;
+        }
+        if (!sat) {
+            const int i = (int)r.below((uint32_t)len);
+            signs[i] = 1 - signs[i];
+        }
+        char tmp[16];
+        for (int i = 0; i < len; i++) {
+            int n = snprintf(tmp, sizeof(tmp), "%s%d ", signs[i] ? "-" : "", vars[i] + 1);
+            buf.insert(buf.end(), tmp, tmp + n);
+        }
+        buf.push_back('0');
+        buf.push_back('\n');
+        if (buf.size() > (1u << 22) - 1024) {
+            fwrite(buf.data(), 1, buf.size(), f);
+            buf.clear();
+        }
+    }
+    fwrite(buf.data(), 1, buf.size(), f);
+    return fclose(f) == 0 ? 0 : -1;
+}
 } // extern "C"
