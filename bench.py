@@ -41,6 +41,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# measured on this pool's B200 (profiles/probes, profiles/r02_probes.jsonl): 64-byte rows gathered at random from a
+# 64 MB table (L2 resident), 8 blocks x 256 threads per SM, useful bytes per second
+L2_GATHER_GBS = 10223.0
 METRIC = "clause_literal_x_assignment_checks_per_sec"
 UNIT = "checks/s"
 
@@ -243,12 +246,17 @@ def import_latency():
     exe = os.path.join(ROOT, "tests", "latency", "latency_harness")
     if not os.path.exists(exe):
         return {"unavailable": "tests/latency/latency_harness not built"}
-    try:
-        r = subprocess.run([exe, "64", "200000", "1000000", "300"], capture_output=True, text=True, timeout=120)
-        line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
-        return json.loads(line)
-    except Exception as e:  # the headline numbers do not depend on it
-        return {"unavailable": f"{type(e).__name__}: {e}"}
+    out = {}
+    # quiet: the solvers' assignments satisfy nearly every clause (a few background hits per run);
+    # saturated: ~1000 background hits per solver and run, re-reported run after run
+    for name, agree in (("quiet", "999"), ("saturated", "985")):
+        try:
+            r = subprocess.run([exe, "64", "200000", "1000000", "300", "-1", agree], capture_output=True, text=True, timeout=120)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+            out[name] = json.loads(line)
+        except Exception as e:  # the headline numbers do not depend on it
+            out[name] = {"unavailable": f"{type(e).__name__}: {e}"}
+    return out
 
 
 def workload_config(a):
@@ -513,19 +521,22 @@ def streamed_db_numbers(a, sig, offsets, lits, chunk):
             while sh.popReportedClause(s) is not None:
                 pass
 
-    run_ms, t_all = [], 0.0
+    run_ms, t_all, t_add, resort_at = [], 0.0, 0.0, []
+    sh.debugHostPhases()  # (GSS_HOST_PROF: start of this pass)
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)
         off = offsets[lo:hi + 1] - offsets[lo]
         part = lits[offsets[lo]:offsets[hi]]
         t0 = time.perf_counter()
         sh.addClausesBulk(off, part)
+        t_add += time.perf_counter() - t0
         push_batch(sh, streams, 2, pool)
         t1 = time.perf_counter()
         sh.gpuRun()
         t2 = time.perf_counter()
         drain()
         run_ms.append((t2 - t1) * 1e3)
+        resort_at.append(sh.debugDbOrder()[1])
         t_all += t2 - t0
     sh.gpuRun()
     drain()
@@ -537,6 +548,7 @@ def streamed_db_numbers(a, sig, offsets, lits, chunk):
     sh.gpuRun()
     drain()
     before = sh.getGlobalStat(GlobalStats.gpuClauses)
+    sh.debugHostPhases()  # (GSS_HOST_PROF: the streaming part ends here)
     t0 = time.perf_counter()
     sh.reduceDb()
     t_reduce = time.perf_counter() - t0
@@ -548,11 +560,18 @@ def streamed_db_numbers(a, sig, offsets, lits, chunk):
     drain()
     oom = bool(sh.hasRunOutOfGpuMemoryOnce())
     sh.close()
-    r = np.array(run_ms)
+    sh_phases = None
+    # the first run builds the assignment tables from scratch (every variable of every solver): reported on its own
+    r = np.array(run_ms[1:]) if len(run_ms) > 1 else np.array(run_ms)
+    with_resort = [run_ms[i] for i in range(1, len(run_ms)) if resort_at[i] != resort_at[i - 1]]
     return {"workload": f"the same {n} clauses arriving {chunk} per run, {a.solvers} solvers x 2 assignments per run",
             "ingest_clauses_per_s_incl_runs": n / t_all,
-            "gpu_run_ms_while_growing": {"p50": float(np.percentile(r, 50)), "p99": float(np.percentile(r, 99)), "max": float(r.max()),
-                                         "runs": len(run_ms)},
+            "add_clauses_bulk_ms_per_chunk": 1e3 * t_add / max(1, len(run_ms)),
+            "first_run_ms_table_build": run_ms[0],
+            "gpu_run_ms_while_growing": {"p50": float(np.percentile(r, 50)), "p90": float(np.percentile(r, 90)),
+                                         "p99": float(np.percentile(r, 99)), "max": float(r.max()), "runs": len(r),
+                                         "runs_with_a_resort_ms": [round(x, 2) for x in with_resort],
+                                         "all_ms": [round(x, 2) for x in run_ms]},
             "device_resorts": int(resorts), "unsorted_clauses_at_the_end": int(unsorted),
             "k_filter_us": t_filter, "check_kernels_us": t_prod,
             "reduce_db_ms": t_reduce * 1e3, "clauses_before_after_reduce": [int(before), int(after)],
@@ -754,6 +773,7 @@ def run_b200(a):
                            "frac": (fb + 2 * float(np.mean(h2d)) + 16.0 * float(np.mean(hits))) / (step_us * 1e-6) / 1e9 / hbm_peak}}
         if not a.no_dense:
             t_dense = sh.debugTimeCheck(a.dense_iters, dense=True)
+            t_slice = sh.debugTimeCheck(a.dense_iters, mode=7)
             sh.gpuRun()
             n_dense = len(sh.debugLastHits())
             drain()
@@ -771,7 +791,11 @@ def run_b200(a):
                 "peak": lop3 / 1e12 if bound_int else hbm_peak,
                 "unit": "TLOP3/s" if bound_int else "GB/s",
                 "frac": max(t_hbm, t_int) / (t_dense * 1e-6),
-                "traffic": traffic.get("k_check_dense"), "traffic_source": traffic_src,
+                # (sliced variant: one launch per slice of 8 solvers -> W/8... = ceil(solvers / 8) launches per sweep)
+                "traffic": (traffic.get("k_check_dense_sliced") * ((min(a.solvers, 32) + 7) // 8)
+                            if traffic.get("k_check_dense_sliced") and not os.environ.get("GSS_DENSE_FLAT") and a.solvers > 8
+                            else traffic.get("k_check_dense")),
+                "traffic_source": traffic_src,
                 "us_per_sweep": t_dense, "t_roof_us": max(t_hbm, t_int) * 1e6,
                 "t_hbm_us": t_hbm * 1e6, "t_int_us": t_int * 1e6,
                 "algorithmic_bytes": bytes_alg, "algorithmic_lop3": lop3_alg,
@@ -779,8 +803,18 @@ def run_b200(a):
                 "lop3_peak_source": "measured in this run (register-only LOP3 micro-benchmark, gss_debug_lop3_peak)",
                 "gather_view": {"table_bytes_gathered": 8.0 * L_total * W,
                                 "gathered_gbs": 8.0 * L_total * W / (t_dense * 1e-6) / 1e9,
+                                "l2_gather_ceiling_gbs": L2_GATHER_GBS,
+                                "t_l2_gather_us": 8.0 * L_total * W / (L2_GATHER_GBS * 1e9) * 1e6,
+                                "frac_of_l2_gather_ceiling": (8.0 * L_total * W / (L2_GATHER_GBS * 1e9)) / (t_dense * 1e-6),
                                 "note": "every (literal, word) pair gathers 8 B of table data that has no reuse "
-                                        "structure; this L2->SM stream, not LOP3 issue, bounds dense mode"},
+                                        "structure (random variables): 8*L*W bytes have to cross L2 -> SM whatever the "
+                                        "layout.  The ceiling is the measured rate of 64-byte row gathers from an "
+                                        "L2-resident 64 MB table on this GPU (profiles/r02_probes.jsonl, probe 'gather', "
+                                        "row64_u8); it, not LOP3 issue or HBM, bounds dense mode"},
+                "kernel_variant": ("k_check_dense_sliced: table cut into 8-solver slices of 64 MB that stay in L2, one sweep "
+                                   "of the clauses per slice" if not os.environ.get("GSS_DENSE_FLAT") and a.solvers > 8
+                                   else "k_check_dense: 256-byte rows of the whole table (mostly from HBM)"),
+                "slice_build_us_per_batch": t_slice,
                 "dense_hits": n_dense,
                 "production_speedup_over_dense": t_dense / t_prod,
                 # the production kernels do the same NOMINAL checks in t_prod: relative to the dense roofline

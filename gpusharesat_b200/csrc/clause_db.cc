@@ -45,6 +45,7 @@ ClauseDb::~ClauseDb() {
 
 void ClauseDb::waitMirror() const {
     if (!mirrorPending_) return;
+    HostProf hp("waitMirror (blocked)");
     GSS_CUDA(cudaEventSynchronize(mirrorEv_));
     mirrorPending_ = false;
 }
@@ -108,6 +109,7 @@ void ClauseDb::appendToMirror(const int *lits, int n, int64_t id) {
 }
 
 void ClauseDb::drainPending() {
+    HostProf hp("drainPending");
     std::vector<int> lits, lens;
     int64_t firstId;
     {
@@ -166,6 +168,7 @@ void ClauseDb::applyPendingDeviceRescales(cudaStream_t stream) {
 }
 
 bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
+    HostProf hp("uploadDirty");
     // rescales decided while draining (Clauses.cu:284-291) reach the device copies first
     applyPendingDeviceRescales(stream);
     for (int s = maxLen_; s >= 1; s--) {

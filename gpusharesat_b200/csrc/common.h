@@ -1,6 +1,7 @@
 // common.h -- shared types and helpers of the B200 clause sharer (host + device).
 #pragma once
 #include <cuda_runtime.h>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -105,5 +106,55 @@ struct Logger {
         if (e__ != cudaSuccess)                                                   \
             GSS_DIE(std::string("CUDA error ") + cudaGetErrorString(e__) + " in " + #call); \
     } while (0)
+
+// Fine-grained host profile of the run pipeline (GSS_HOST_PROF=1: mean microseconds per call of every
+// named scope, printed to stderr when the process exits).  Off: one predictable branch per scope.
+struct HostProf {
+    static constexpr int kMax = 32;
+    struct Entry {
+        const char *name;
+        double us;
+        long calls;
+    };
+    static bool enabled() {
+        static const bool on = getenv("GSS_HOST_PROF") != nullptr;
+        return on;
+    }
+    static Entry *table() {
+        static Entry t[kMax] = {};
+        static const bool registered = (atexit(&HostProf::dump), true);
+        (void)registered;
+        return t;
+    }
+    static void add(const char *name, double us) {
+        Entry *t = table();
+        for (int i = 0; i < kMax; i++) {
+            if (!t[i].name) t[i].name = name;
+            if (t[i].name == name) {
+                t[i].us += us;
+                t[i].calls++;
+                return;
+            }
+        }
+    }
+    static void reset() { // (bench: gss_debug_host_phases marks the start of a timed region)
+        Entry *t = table();
+        for (int i = 0; i < kMax; i++) t[i].us = 0, t[i].calls = 0;
+    }
+    static void dump() {
+        if (!enabled()) return;
+        Entry *t = table();
+        for (int i = 0; i < kMax && t[i].name; i++)
+            if (t[i].calls) fprintf(stderr, "host prof %-28s %9.2f us/call x %ld\n", t[i].name, t[i].us / (double)t[i].calls, t[i].calls);
+    }
+    const char *name;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostProf(const char *n) : name(n) {
+        if (enabled()) t0 = std::chrono::steady_clock::now();
+    }
+    ~HostProf() {
+        if (enabled()) add(name, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
 
 } // namespace gss

@@ -804,6 +804,85 @@ __global__ void __launch_bounds__(128) k_check_dense(CheckArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dense mode, L2-resident variant.  k_check_dense gathers 256-byte rows of a V x 32-solver table: 256 MB
+// at 1 M variables, twice the L2, so every row comes from HBM (ncu round 1: 6.67 GB of DRAM reads per
+// sweep against 0.43 GB algorithmic).  Here the table is cut into SLICES of 8 solvers -- slice g is a
+// dense [var][8] array of {def,tru} pairs, 64 MB at 1 M variables -- and the clauses are swept once per
+// slice (the literal rows are streamed evict-first, 176 MB per sweep), so the gathers of a sweep hit an
+// L2-resident table and DRAM only sees the literal stream plus one read of the table: ~1 GB.  What is
+// left is the L2 -> SM gather stream itself: 8 B per (literal, word) = 11.3 GB per pass over the database,
+// whatever the layout (measured ceiling of 64-byte row gathers from a 64 MB table: ~10 TB/s, profiles/).
+// A warp takes HALF a tile (64 clauses); lane = (c4 = lane / 8: one of four clauses, s = lane % 8: solver),
+// so one gather instruction fetches four 64-byte rows; 16 gathers (= 64 clauses) are in flight per literal row.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSliceSolvers = 8;
+
+__global__ void __launch_bounds__(256) k_slice_tables(DeviceTables t, int groupBase, int groupSolvers, uint2 *__restrict__ sliced) {
+    const int lane = threadIdx.x & 31; // solver of the group
+    const size_t nVars = (size_t)t.varCap;
+    for (size_t v = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < nVars; v += (size_t)gridDim.x * (blockDim.x >> 5)) {
+        uint2 e = make_uint2(0u, 0u);
+        if (lane < groupSolvers) e = t.t2[v * t.solverStride + groupBase + lane];
+        sliced[((size_t)(lane / kSliceSolvers) * nVars + v) * kSliceSolvers + (lane % kSliceSolvers)] = e;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_check_dense_sliced(CheckArgs a, const uint2 *__restrict__ slice, int sliceBase) {
+    extern __shared__ int sTileEnd[];
+    for (int i = threadIdx.x; i < a.nDir; i += blockDim.x) sTileEnd[i] = a.dir[i].tileEnd;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int sIdx = lane & (kSliceSolvers - 1), c4 = lane >> 3;
+    const int warpsPerBlock = blockDim.x >> 5;
+    const int warp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
+    const int nWarps = gridDim.x * warpsPerBlock;
+    const bool active = sliceBase + sIdx < a.groupSolvers;
+    const int solver = a.groupBase + (active ? sliceBase + sIdx : 0);
+    const uint32_t myStart = active ? a.params[solver].startVals : 0u;
+    const uint2 *__restrict__ t2 = slice + sIdx;
+
+    const long long nWork = (long long)a.totalTiles * 2;
+    for (long long w = warp; w < nWork; w += nWarps) {
+        const int tile = (int)(w >> 1), half = (int)(w & 1);
+        const int k = findDir(sTileEnd, a.nDir, tile);
+        const LenDir d = a.dir[k];
+        const int len = d.len;
+        const int gTile = tile - (k ? sTileEnd[k - 1] : 0) + d.firstTile;
+        const int nValid = d.count - gTile * kTileClauses; // clauses of this tile
+        if (nValid <= 64 * half) continue;
+        // lane l holds, of every literal row, the words of clauses 32 * (2 half) + l and 32 * (2 half + 1) + l
+        const int32_t *row = d.base + (size_t)gTile * kTileClauses * len + 4 * lane + 2 * half;
+
+        uint32_t all[16], one[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const int j = 32 * (2 * half + (c >> 3)) + 4 * (c & 7) + c4;
+            all[c] = j < nValid ? myStart : 0u;
+            one[c] = 0u;
+        }
+        int2 word = __ldcs(reinterpret_cast<const int2 *>(row));
+        for (int i = 0; i < len; i++) {
+            int2 nextWord = word;
+            if (i + 1 < len) nextWord = __ldcs(reinterpret_cast<const int2 *>(row + (size_t)(i + 1) * kTileClauses));
+            int lit[16];
+            uint2 e[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                lit[c] = __shfl_sync(FULL, (c >> 3) ? word.y : word.x, 4 * (c & 7) + c4);
+                e[c] = ldTable(t2 + (size_t)(lit[c] >> 1) * kSliceSolvers);
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c++) step(all[c], one[c], e[c].x & ((lit[c] & 1) ? e[c].y : ~e[c].y), ~e[c].x);
+            word = nextWord;
+        }
+#pragma unroll
+        for (int c = 0; c < 16; c++)
+            reportHits(a, all[c] | one[c], solver, len, gTile * kTileClauses + 32 * (2 * half + (c >> 3)) + 4 * (c & 7) + c4, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Direct pipeline.  k_apply_direct = k_apply_updates with the deltas of solver s read from src[s]:
 // the solver thread's own delta buffer in mapped pinned host memory (no staging copy on the host, no
 // separate H2D: the transfer IS the kernel's load stream) or device memory.  Records are 12 bytes:
@@ -1286,9 +1365,24 @@ __global__ void k_scale_acts(float *acts, long long n, float factor) {
 }
 
 int resolveBlocks(const void *kernel, int threads, size_t smem, int numSMs, int requested, long long work) {
-    int perSM = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, smem);
-    if (perSM < 1) perSM = 1;
+    // (the occupancy query is a driver call: asked once per kernel / shape, not once per launch)
+    struct Seen {
+        const void *kernel;
+        int threads;
+        size_t smem;
+        int perSM;
+    };
+    static thread_local Seen seen[16];
+    static thread_local int nSeen = 0;
+    int perSM = 0;
+    for (int i = 0; i < nSeen; i++)
+        if (seen[i].kernel == kernel && seen[i].threads == threads && seen[i].smem == smem) perSM = seen[i].perSM;
+    if (perSM == 0) {
+        perSM = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, smem);
+        if (perSM < 1) perSM = 1;
+        if (nSeen < 16) seen[nSeen++] = Seen{kernel, threads, smem, perSM};
+    }
     long long blocks = requested > 0 ? requested : (long long)perSM * numSMs;
     if (work >= 0 && blocks > work) blocks = work;
     if (blocks < 1) blocks = 1;
@@ -1563,6 +1657,26 @@ void launchCheck(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s
     if (a.totalTiles == 0) return;
     launchFilterOnly(a, dims, numSMs, s, launches);
     launchExactOnly(a, dims, numSMs, s, launches);
+}
+
+void launchSliceTables(const DeviceTables &t, int groupBase, int groupSolvers, uint2 *sliced, int numSMs, cudaStream_t s,
+                       int64_t *launches) {
+    k_slice_tables<<<numSMs * 8, 256, 0, s>>>(t, groupBase, groupSolvers, sliced);
+    checkLaunch("k_slice_tables");
+    ++*launches;
+}
+
+void launchCheckDenseSliced(const CheckArgs &a, const uint2 *sliced, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches) {
+    if (a.totalTiles == 0) return;
+    const int threads = 128;
+    const size_t smem = (size_t)a.nDir * sizeof(int);
+    const int blocks = resolveBlocks((const void *)k_check_dense_sliced, threads, smem, numSMs, dims.blocks,
+                                     ((long long)a.totalTiles * 2 + 3) / 4);
+    for (int base = 0; base < a.groupSolvers; base += kSliceSolvers) { // one sweep of the clauses per slice of 8 solvers
+        k_check_dense_sliced<<<blocks, threads, smem, s>>>(a, sliced + (size_t)(base / kSliceSolvers) * a.tables.varCap * kSliceSolvers, base);
+        checkLaunch("k_check_dense_sliced");
+        ++*launches;
+    }
 }
 
 void launchCheckDense(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches) {

@@ -98,6 +98,11 @@ const char *exactVariantName(int v);
 void setExactVariant(int v);
 // bench-only dense mode: no filter, no early exit
 void launchCheckDense(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
+// the same against an L2-resident table: `sliced` = the group's T2 rows cut into slices of 8 solvers
+// ([slice][var][8], 4 x varCap x 8 entries), one sweep of the clauses per slice
+void launchSliceTables(const DeviceTables &t, int groupBase, int groupSolvers, uint2 *sliced, int numSMs, cudaStream_t s,
+                       int64_t *launches);
+void launchCheckDenseSliced(const CheckArgs &a, const uint2 *sliced, LaunchDims dims, int numSMs, cudaStream_t s, int64_t *launches);
 
 // Post-processing of a large hit list on the device (the host hand-over is the bottleneck of a run
 // that returns 10^5 hits): radix-sort the hits by (solver, length, index) -- the reproducible

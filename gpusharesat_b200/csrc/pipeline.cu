@@ -179,6 +179,7 @@ void Sharer::launchDirect(RunSlot &slot, int64_t h2d) {
     const int S = slot.nSolvers;
     SolverRunParams *params = (SolverRunParams *)(slot.headHost.data() + slot.dirBytes);
     const VarUpdate **src = (const VarUpdate **)(slot.headHost.data() + slot.srcOff);
+    HostProf hpAll("launchDirect");
     slot.direct = true;
     slot.dense = false;
     slot.updDev.reserve((size_t)std::max<int64_t>(slot.nUpdates, 1), 0, stream_);
@@ -189,19 +190,29 @@ void Sharer::launchDirect(RunSlot &slot, int64_t h2d) {
         src[s] = dst;
     }
     slot.headDev.reserve(slot.headHost.size(), 0, stream_);
-    GSS_CUDA(cudaMemcpyAsync(slot.headDev.data(), slot.headHost.data(), slot.headHost.size(), cudaMemcpyHostToDevice, stream_));
+    {
+        HostProf hp("  head H2D");
+        GSS_CUDA(cudaMemcpyAsync(slot.headDev.data(), slot.headHost.data(), slot.headHost.size(), cudaMemcpyHostToDevice, stream_));
+    }
     h2d += (int64_t)slot.headHost.size() + slot.nUpdates * (int64_t)sizeof(VarUpdate);
-    ensureDirectBuffers(slot);
+    {
+        HostProf hp("  ensureDirectBuffers");
+        ensureDirectBuffers(slot);
+    }
     GSS_CUDA(cudaEventRecord(slot.evH2DDone, stream_));
 
     // the previous batch collapses to its last slot first (deferred dSetAllAssigsToLast)
     if (collapseSlot_ >= 0) {
+        HostProf hp("  launch collapse");
         RunSlot &c = slots_[collapseSlot_];
         launchCollapse(c.updDev.data(), c.paramsDev(), c.nSolvers, c.maxUpd, c.nUpdates, tables_, numSMs_, stream_, &launches_);
         collapseSlot_ = -1;
     }
-    launchApplyDirect((const VarUpdate *const *)(slot.headDev.data() + slot.srcOff), slot.paramsDev(), S, slot.maxUpd, tables_,
-                      slot.updDev.data(), numSMs_, stream_, &launches_);
+    {
+        HostProf hp("  launch apply");
+        launchApplyDirect((const VarUpdate *const *)(slot.headDev.data() + slot.srcOff), slot.paramsDev(), S, slot.maxUpd, tables_,
+                          slot.updDev.data(), numSMs_, stream_, &launches_);
+    }
     GSS_CUDA(cudaEventRecord(slot.evBeforeCheck, stream_));
     launchDirectCheck(slot);
     GSS_CUDA(cudaEventRecord(slot.evAfterCheck, stream_));
@@ -215,8 +226,14 @@ void Sharer::launchDirect(RunSlot &slot, int64_t h2d) {
 bool Sharer::startRunDirect(RunSlot &slot) {
     int64_t h2d = 0;
     bool rebuild = false;
-    if (!prepareRun(slot, rebuild, h2d)) return false;
-    collectDirect(slot, rebuild);
+    {
+        HostProf hp("prepareRun");
+        if (!prepareRun(slot, rebuild, h2d)) return false;
+    }
+    {
+        HostProf hp("collectDirect");
+        collectDirect(slot, rebuild);
+    }
     launchDirect(slot, h2d);
     return true;
 }
@@ -228,6 +245,7 @@ void Sharer::launchDirectCheck(RunSlot &slot) {
     for (int g = 0; g < groups; g++) any = any || slot.aggStart[g] != 0;
     slot.checked = any && slot.totalTiles > 0;
     if (!slot.checked) return;
+    HostProf hpAll("  launchDirectCheck");
     ensureDirectBuffers(slot);
     if (lastDirect_ == &slot) lastDirect_ = nullptr; // its record lists are about to be overwritten
     slot.seq = ++directSeq_;
@@ -242,9 +260,14 @@ void Sharer::launchDirectCheck(RunSlot &slot) {
         if (wantL < runCapL_ && wantL * 4 > runCapL_) wantL = runCapL_;
         runCapE_ = wantE;
         runCapL_ = wantL;
+        HostProf hp("    acquire result buffer");
         slot.runBuf = runBufs_->acquire(wantE, wantL);
     }
-    launchCheckKernels(slot, false);
+    {
+        HostProf hp("    launch filter+exact");
+        launchCheckKernels(slot, false);
+    }
+    HostProf hp("    launch emit");
     launchEmitFor(slot);
 }
 
@@ -351,6 +374,7 @@ bool Sharer::waitBumpFlag() {
 // use at this point (after the next batch of clauses has been drained).  The activities live on THIS
 // device; the record lists of other devices of the process are read in place through peer access.
 void Sharer::bumpDirect(const std::vector<DevicePart> &parts) {
+    HostProf hpAll("bumpDirect");
     if (waitBumpFlag()) {
         db_->rescaleAfterDeviceOverflow();
         db_->applyPendingDeviceRescales(stream_);
@@ -413,6 +437,7 @@ void Sharer::processResultsParts(RunSlot &slot, const std::vector<DevicePart> &p
     bumpN_ = 0; // (nothing parked by the staged path)
     bumpDirect(parts);
     TimeAdder t(globalStats_[G_timeSpentFillingReported], opts_.quickProf != 0);
+    HostProf hpViews("handOverViews");
     std::vector<std::vector<ResultView>> views((size_t)slot.nSolvers);
     for (const DevicePart &p : parts) {
         if (!p.view()) continue;

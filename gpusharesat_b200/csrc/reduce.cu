@@ -87,10 +87,17 @@ __global__ void __launch_bounds__(256) k_reduce_permute(const PermLen *__restric
                                                         const int *__restrict__ kept) {
     const PermLen l = L[blockIdx.y];
     const int n = kept[blockIdx.y];
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    if (l.mode == 2) return;
+    // (the unused slots of the last tile are zeroed: literal 0 is a valid table index for kernels that do not mask)
+    const int nPad = (n + kTileClauses - 1) / kTileClauses * kTileClauses;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nPad; j += gridDim.x * blockDim.x) {
+        int32_t *d = l.dst + wordPosDev(l.len, j, 0);
+        if (j >= n) {
+            for (int i = 0; i < l.len; i++) d[(size_t)i * kTileClauses] = 0;
+            continue;
+        }
         const int old = (int)order[l.off + j];
         const int32_t *s = l.src + wordPosDev(l.len, old, 0);
-        int32_t *d = l.dst + wordPosDev(l.len, j, 0);
         for (int i = 0; i < l.len; i++) d[(size_t)i * kTileClauses] = s[(size_t)i * kTileClauses];
         l.idsDst[j] = l.idsSrc[old];
         l.actsDst[j] = l.actsSrc[old];
@@ -106,6 +113,7 @@ template <typename T> struct Scratch { // plain device scratch, freed on scope e
 } // namespace
 
 bool ClauseDb::permuteOnDevice(cudaStream_t stream, bool dropByActivity) {
+    HostProf hpAll(dropByActivity ? "reduce on device" : "re-sort on device");
     waitMirror();
     applyPendingDeviceRescales(stream);
     {
@@ -150,6 +158,7 @@ bool ClauseDb::permuteOnDevice(cudaStream_t stream, bool dropByActivity) {
     const int nL = (int)lens.size();
 
     // memory first: when any of it is missing nothing has changed yet (the caller takes the host path / gives up)
+    auto hpAlloc = std::make_unique<HostProf>("  permute: allocate");
     std::vector<std::unique_ptr<DevBuf<int32_t>>> newDev((size_t)nL);
     std::vector<std::unique_ptr<DevBuf<int64_t>>> newIds((size_t)nL);
     std::vector<std::unique_ptr<DevBuf<float>>> newActs((size_t)nL);
@@ -182,6 +191,8 @@ bool ClauseDb::permuteOnDevice(cudaStream_t stream, bool dropByActivity) {
         !valsB.alloc((size_t)total) || !keptDev.alloc((size_t)nL) || !cubTmp.alloc(cubBytes) ||
         (dropByActivity && (!boundsDev.alloc(kActBuckets) || !histDev.alloc(kActBuckets))))
         return false;
+    hpAlloc.reset();
+    auto hpKernels = std::make_unique<HostProf>("  permute: kernels + sync");
     GSS_CUDA(cudaMemcpyAsync(lensDev.p, lens.data(), (size_t)nL * sizeof(PermLen), cudaMemcpyHostToDevice, stream));
     GSS_CUDA(cudaMemsetAsync(keptDev.p, 0, (size_t)nL * sizeof(int), stream));
     const dim3 grid((unsigned int)std::min<long long>((maxN + 255) / 256, 2368), (unsigned int)nL);
@@ -213,6 +224,8 @@ bool ClauseDb::permuteOnDevice(cudaStream_t stream, bool dropByActivity) {
     GSS_CUDA(cudaStreamSynchronize(stream));
     GSS_CUDA(cudaGetLastError());
 
+    hpKernels.reset();
+    HostProf hpSwap("  permute: swap + mirror + free");
     // swap the arena sets, shrink the host mirror, start its refresh
     if (!mirrorStream_) {
         GSS_CUDA(cudaStreamCreateWithFlags(&mirrorStream_, cudaStreamNonBlocking));

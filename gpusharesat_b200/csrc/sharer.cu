@@ -79,6 +79,7 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx, int workerOfD
     reported_ = std::make_unique<Reported>(*db_, oneSolverStats_);
     reported_->setPool(&pool_);
     db_->setDeviceActivities(true);
+    denseSliced_ = getenv("GSS_DENSE_FLAT") == nullptr; // (bench: the round-1 dense kernel, 256-byte rows from HBM)
     if (getenv("GPUSHARE_HOST_REDUCE")) db_->setDeviceReduce(false); // round-1 reduceDb (host compaction + re-upload), for comparison
     reported_->setHostBumps(false);
     setCpuSolverCount(1);
@@ -408,7 +409,21 @@ bool Sharer::launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly) {
         if (slot.aggStart[g] == 0) continue; // no frozen slot in this group
         CheckArgs a = checkArgs(slot, g, recs);
         if (filterOnly) launchFilterOnly(a, dims_, numSMs_, stream_, &launches_);
-        else if (dense) launchCheckDense(a, dims_, numSMs_, stream_, &launches_);
+        else if (dense) {
+            if (denseSliced_ && a.groupSolvers > 8) {
+                // slices of this batch's tables, built once per batch and group (a real dense-mode library
+                // would have k_apply_updates write this layout; here it is a copy, timed by gss_debug_time_check mode 7)
+                const size_t per = (size_t)tables_.varCap * 32;
+                t2Sliced_.reserve(per * (size_t)groups, 0, stream_);
+                if (!(denseSlicesValid_ & (1u << g))) {
+                    launchSliceTables(tables_, a.groupBase, a.groupSolvers, t2Sliced_.data() + per * (size_t)g, numSMs_, stream_, &launches_);
+                    denseSlicesValid_ |= 1u << g;
+                }
+                launchCheckDenseSliced(a, t2Sliced_.data() + per * (size_t)g, dims_, numSMs_, stream_, &launches_);
+            } else {
+                launchCheckDense(a, dims_, numSMs_, stream_, &launches_);
+            }
+        }
         else {
             if (fusedPublish_.peerDone && g == lastGroup && a.totalTiles > 0) {
                 a.peerHdr = fusedPublish_.peerHdr;
@@ -435,6 +450,8 @@ void Sharer::enqueueResultCopy(RunSlot &slot) {
 bool Sharer::prepareRun(RunSlot &slot, bool &rebuild, int64_t &h2d) {
     GSS_CUDA(cudaEventRecord(slot.evStart, stream_));
     rebuild = false;
+    denseSlicesValid_ = 0; // a new batch: the tables are about to change
+    HostProf hpUp("  prepare: tables+upload+dir");
     // Removing clauses cannot make room for the assignment tables (V x S words): fail loudly instead
     // of reducing the database run after run.  Clause arenas that do not fit take the reduceDb path.
     if (!ensureTables(rebuild))
@@ -1078,6 +1095,9 @@ double Sharer::timeCheck(int iters, int mode) {
                 if (slot.aggStart[g]) launchExactOnly(checkArgs(slot, g, slot.direct), dims_, numSMs_, stream_, &launches_);
         } else if (mode == 6) {
             launchEmitFor(slot);
+        } else if (mode == 7) {
+            t2Sliced_.reserve((size_t)tables_.varCap * 32 * (size_t)groups, 0, stream_);
+            launchSliceTables(tables_, 0, std::min(kMaxSolversPerGroup, slot.nSolvers), t2Sliced_.data(), numSMs_, stream_, &launches_);
         } else if (mode == 4) {
             launchApplyUpdates(slot.updDev.data(), slot.paramsDev(), slot.nSolvers, slot.maxUpd, slot.nUpdates, tables_, numSMs_,
                                stream_, &launches_);

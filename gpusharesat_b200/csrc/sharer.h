@@ -75,7 +75,14 @@ public:
     // device-side sort/resolve + D2H), [1] start the next run (drain, upload, collect, enqueue),
     // [2] hand-over, [3] collect alone (part of 1), [4] wait for the GPU alone (part of 0),
     // [5] sort/resolve/D2H of a large hit list (part of 0)
-    void hostPhases(double out[6]) const { for (int i = 0; i < 6; i++) out[i] = hostPhases_[i]; }
+    void hostPhases(double out[6]) const {
+        for (int i = 0; i < 6; i++) out[i] = hostPhases_[i];
+        if (HostProf::enabled()) {
+            HostProf::dump();
+            fprintf(stderr, "host prof ---- (reset)\n");
+            HostProf::reset();
+        }
+    }
     // ---- multi-GPU (see include/gpushare_b200.h) ----
     void setShard(int rank, int world) { db_->setShard(rank, world); }
     int mgpuCollect(const void **params, int64_t *paramsBytes, const void **updates, int64_t *nUpdates);
@@ -207,6 +214,9 @@ private:
     Sharer *root_ = nullptr;
 
     std::shared_ptr<RunBufPool> runBufs_;
+    DevBuf<uint2> t2Sliced_;          // dense mode (bench): the level-2 table cut into L2-sized slices of 8 solvers
+    uint32_t denseSlicesValid_ = 0;   // per solver group: the slices match the current tables
+    bool denseSliced_ = true;
     int64_t resorts_ = 0; // device-side re-sorts of streamed clauses (ClauseDb::resortOnDevice)
     bool directEnabled_ = true;
     bool eagerResults_ = true; // surface a run's hits in the call that started it when it completes within minGpuLatencyMicros

@@ -7,7 +7,7 @@ once against the reference's own GPU library recompiled for sm_100a (glucose-gpu
 time.  Prints one JSON object with the last periodic statistics of both (GPU runs, clause tests, reports,
 clauses on the GPU, reduceDbs, imports per solver).
 
-usage (GPU box): python profiles/bench_config4_glucose.py [--seconds 40] > gpurun_out/config4_glucose.json"""
+usage (GPU box): python profiles/bench_config4_glucose.py [--seconds 75] > gpurun_out/config4_glucose.json"""
 import argparse
 import ctypes as C
 import json
@@ -53,7 +53,7 @@ def last_stats(text):
 def run(exe, cnf, threads, seconds, env=None):
     t0 = time.time()
     p = subprocess.run(["timeout", "-s", "INT", str(seconds), exe, f"-thread-count={threads}", "-verb=1",
-                        "-write-stats-period-sec=5", "-max-memory=40000", "-mem-lim=60000", cnf],
+                        "-write-stats-period-sec=5", "-max-memory=40000", "-mem-lim=60000", "-no-pre", cnf],
                        capture_output=True, text=True, env=env)
     wall = time.time() - t0
     verdict = re.search(r"^s (\w+)", p.stdout, re.M)
@@ -84,7 +84,7 @@ def main():
     ap.add_argument("--vars", type=int, default=2_000_000)
     ap.add_argument("--clauses", type=int, default=8_000_000)
     ap.add_argument("--threads", type=int, default=32)
-    ap.add_argument("--seconds", type=int, default=40)
+    ap.add_argument("--seconds", type=int, default=75)
     ap.add_argument("--cnf", default="/tmp/gss_config4.cnf")
     a = ap.parse_args()
     t0 = time.time()

@@ -25,7 +25,7 @@ def main():
     raw = os.path.join(out_dir, f"{tag}_launches_raw.csv")
     cmd = ["ncu", "--metrics", "gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
            "-c", "600", "--csv", "--log-file", raw, sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3",
-           "--no-cpu", "--no-ref-gpu", "--prod-iters", "2", "--dense-iters", "1"] + sys.argv[2:]
+           "--no-cpu", "--no-ref-gpu", "--no-streamed", "--no-latency", "--prod-iters", "2", "--dense-iters", "1"] + sys.argv[2:]
     subprocess.run(cmd, check=True, stdout=open(os.path.join(out_dir, f"{tag}_traffic_bench.log"), "w"), stderr=subprocess.STDOUT)
     rows = [r for r in csv.reader(open(raw)) if r]
     hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)

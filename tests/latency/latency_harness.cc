@@ -35,6 +35,10 @@ int main(int argc, char **argv) {
     const int64_t C = argc > 3 ? atoll(argv[3]) : 1000000;
     const int nProbes = argc > 4 ? atoi(argv[4]) : 300;
     const int minLat = argc > 5 ? atoi(argv[5]) : -1;
+    // share (per mille) of the database's literals that are TRUE under the solvers' assignments: 999 = the solvers
+    // satisfy nearly every learned clause (a handful of background hits per run: the latency of an otherwise
+    // quiet pipeline); 985 = ~65 k background hits per run with 64 solvers (the pipeline saturated by reports)
+    const int agreePerMille = argc > 6 ? atoi(argv[6]) : 999;
     const int kStable = 4096; // variables [0, kStable) are never unset by the solver threads: probes use them
 
     gss_options o;
@@ -63,7 +67,7 @@ int main(int argc, char **argv) {
             else len = 4 + (int)(rng() % 27);
             for (int i = 0; i < len; i++) {
                 const int v = (int)(rng() % V);
-                const bool agree = (rng() % 1000) < 985;
+                const bool agree = (int)(rng() % 1000) < agreePerMille;
                 const int sign = agree ? sigma[v] : 1 - sigma[v]; // literal true under sigma iff sign == sigma (sign 1 = negated)
                 lits.push_back(2 * v + sign);
             }
@@ -132,7 +136,7 @@ int main(int argc, char **argv) {
     std::this_thread::sleep_for(std::chrono::milliseconds(300)); // first runs: table rebuild, buffer growth
 
     std::vector<double> lat;
-    int lost = 0;
+    int lost = 0, lostLong = 0;
     const auto tStart = Clock::now();
     sampling.store(true);
     const int64_t runs0 = runs.load();
@@ -156,7 +160,10 @@ int main(int argc, char **argv) {
         const auto w0 = Clock::now();
         while (!probe.done.load(std::memory_order_acquire) && usSince(w0) < 1e6) std::this_thread::yield();
         if (probe.done.load()) lat.push_back(probe.latencyUs);
-        else lost++;
+        else {
+            lost++;
+            if (len > 100) lostLong++;
+        }
         probe.target.store(-1);
         std::this_thread::sleep_for(std::chrono::microseconds(200));
     }
@@ -170,14 +177,14 @@ int main(int argc, char **argv) {
     const double ns = sampled ? (double)sampled : 1.0;
     std::sort(lat.begin(), lat.end());
     auto q = [&](double f) { return lat.empty() ? -1.0 : lat[std::min(lat.size() - 1, (size_t)(f * lat.size()))]; };
-    printf("{\"harness\": \"import_latency\", \"solvers\": %d, \"vars\": %d, \"clauses\": %lld, \"probes\": %d, \"lost\": %d, "
+    printf("{\"harness\": \"import_latency\", \"solvers\": %d, \"vars\": %d, \"clauses\": %lld, \"probes\": %d, \"lost\": %d, \"lost_long\": %d, \"true_literals_per_mille\": %d, "
            "\"p50_us\": %.1f, \"p90_us\": %.1f, \"p99_us\": %.1f, \"max_us\": %.1f, \"gpu_runs_per_s\": %.0f, "
            "\"min_gpu_latency_micros\": %d, \"long_clause_share\": 0.05, \"max_clause_len\": 200, "
            "\"host_us_per_run\": {\"finish_previous\": %.1f, \"start_next\": %.1f, \"hand_over\": %.1f, \"collect\": %.1f, "
            "\"wait_for_gpu\": %.1f}, \"hits_reported_per_run\": %.0f, "
            "\"device_us_per_run\": {\"copies\": %.1f, \"table_kernels\": %.1f, \"check_and_emit\": %.1f, \"total\": %.1f}, "
            "\"h2d_bytes_per_run\": %.0f, \"d2h_bytes_per_run\": %.0f}\n",
-           S, V, (long long)C, nProbes, lost, q(0.5), q(0.9), q(0.99), lat.empty() ? -1.0 : lat.back(), nRuns / wallS, minLat,
+           S, V, (long long)C, nProbes, lost, lostLong, agreePerMille, q(0.5), q(0.9), q(0.99), lat.empty() ? -1.0 : lat.back(), nRuns / wallS, minLat,
            (ph1[0] - ph0[0]) / nRuns, (ph1[1] - ph0[1]) / nRuns, (ph1[2] - ph0[2]) / nRuns, (ph1[3] - ph0[3]) / nRuns,
            (ph1[4] - ph0[4]) / nRuns, (double)(gss_get_global_stat(h, 8) - reports0) / nRuns, devSum[0] / ns, devSum[1] / ns,
            devSum[2] / ns, devSum[3] / ns, h2dSum / ns, d2hSum / ns);
