@@ -29,11 +29,19 @@ void ClauseDb::setMaxLen(int maxLen) {
         pl.lits.setPinnedLimit(pinnedLimit_);
         pl.ids.setPinnedLimit(pinnedLimit_);
         pl.acts.setPinnedLimit(pinnedLimit_);
+        // the host mirror grows in place too (address space now, page-locked chunk by chunk: mem.h)
+        pl.lits.setInPlace((size_t)8 << 30);
+        pl.ids.setInPlace((size_t)2 << 30);
+        pl.acts.setInPlace((size_t)1 << 30);
         // the arenas grow for as long as the solvers learn: in place (vmem.cc), never by realloc + copy
         pl.dev.setInPlace();
         pl.idsDev.setInPlace();
         pl.actsDev.setInPlace();
+        pl.devAlt.setInPlace();
+        pl.idsAlt.setInPlace();
+        pl.actsAlt.setInPlace();
     }
+    initPermScratch();
 }
 
 ClauseDb::~ClauseDb() {
@@ -94,11 +102,13 @@ void ClauseDb::appendToMirror(const int *lits, int n, int64_t id) {
     if (mirrorPending_ && (need > pl.lits.capacity() || (size_t)idx + 1 > pl.ids.capacity() || (size_t)idx + 1 > pl.acts.capacity()))
         waitMirror();
     if (need > pl.lits.size()) pl.lits.resize(need); // new tile, zero-filled
+    int32_t *dst = pl.lits.data() + wordPos(n, idx, 0);
+    int maxLit = 0;
     for (int i = 0; i < n; i++) {
-        pl.lits[wordPos(n, idx, i)] = lits[i];
-        int v = litVar(lits[i]) + 1;
-        if (v > maxVarPlusOne_) maxVarPlusOne_ = v;
+        dst[(size_t)i * kTileClauses] = lits[i];
+        maxLit = std::max(maxLit, lits[i]);
     }
+    if (litVar(maxLit) + 1 > maxVarPlusOne_) maxVarPlusOne_ = litVar(maxLit) + 1;
     pl.ids.push_back(id);
     pl.acts.push_back(actIncr_);
     pl.n++;
@@ -188,8 +198,7 @@ bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
                 waitMirror();
             if (total > 0) {
                 if (!pl.dev.tryReserve(total, pl.fullReupload ? 0 : from, stream)) return false;
-                GSS_CUDA(cudaMemcpyAsync(pl.dev.data() + from, pl.lits.data() + from, (total - from) * sizeof(int32_t),
-                                         cudaMemcpyHostToDevice, stream));
+                pl.lits.copyToDevice(pl.dev.data() + from, from, total - from, stream);
                 if (bytesCopied) *bytesCopied += (int64_t)((total - from) * sizeof(int32_t));
             }
         }
@@ -198,13 +207,11 @@ bool ClauseDb::uploadDirty(cudaStream_t stream, int64_t *bytesCopied) {
             int64_t from = pl.fullReupload ? 0 : pl.dirtyFrom;
             if (n > from) { // (the host arrays are the staging buffers: same element layout as on the device)
                 if (!pl.idsDev.tryReserve((size_t)n, (size_t)from, stream)) return false;
-                GSS_CUDA(cudaMemcpyAsync(pl.idsDev.data() + from, pl.ids.data() + from, (size_t)(n - from) * sizeof(int64_t),
-                                         cudaMemcpyHostToDevice, stream));
+                pl.ids.copyToDevice(pl.idsDev.data() + from, (size_t)from, (size_t)(n - from), stream);
                 if (bytesCopied) *bytesCopied += (n - from) * (int64_t)sizeof(int64_t);
                 if (deviceActs_) {
                     if (!pl.actsDev.tryReserve((size_t)n, (size_t)from, stream)) return false;
-                    GSS_CUDA(cudaMemcpyAsync(pl.actsDev.data() + from, pl.acts.data() + from, (size_t)(n - from) * sizeof(float),
-                                             cudaMemcpyHostToDevice, stream));
+                    pl.acts.copyToDevice(pl.actsDev.data() + from, (size_t)from, (size_t)(n - from), stream);
                     pl.actsOnDevice = n;
                 }
             }
@@ -269,7 +276,7 @@ void ClauseDb::downloadActivities(cudaStream_t stream) {
         PerLen &pl = *perLen_[s];
         int64_t n = std::min<int64_t>(pl.actsOnDevice, pl.n);
         if (n <= 0) continue;
-        GSS_CUDA(cudaMemcpyAsync(pl.acts.data(), pl.actsDev.data(), (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        pl.acts.copyFromDevice(pl.actsDev.data(), 0, (size_t)n, stream);
         any = true;
     }
     if (any) GSS_CUDA(cudaStreamSynchronize(stream));
@@ -311,15 +318,21 @@ float ClauseDb::thresholdFromHistogram(const int64_t *counts, int64_t n) {
 const std::vector<uint32_t> &ClauseDb::actBucketBounds() {
     static const std::vector<uint32_t> bounds = [] {
         std::vector<uint32_t> v((size_t)kActBuckets, 0u);
+        auto bucketOfBits = [](uint32_t bits) {
+            float x;
+            memcpy(&x, &bits, 4);
+            return actBucket(x);
+        };
         for (int b = 1; b < kActBuckets; b++) {
-            uint32_t lo = v[(size_t)b - 1], hi = 0x7F800000u; // +inf always reaches the last bucket
-            while (lo < hi) {
-                uint32_t mid = lo + (hi - lo) / 2;
-                float x;
-                memcpy(&x, &mid, 4);
-                if (actBucket(x) >= b) hi = mid; else lo = mid + 1;
-            }
-            v[(size_t)b] = lo;
+            // start from the analytic boundary exp(lowest + b * step) and walk the few float neighbours to the
+            // exact one (positive floats are ordered like their bit patterns; +inf always reaches the last bucket)
+            const float guess = std::exp(kActScale.lowestLog + (float)b * kActScale.stepLog);
+            uint32_t bits;
+            memcpy(&bits, &guess, 4);
+            bits = std::min(std::max(bits, v[(size_t)b - 1]), 0x7F800000u);
+            while (bits > v[(size_t)b - 1] && bucketOfBits(bits - 1) >= b) bits--;
+            while (bits < 0x7F800000u && bucketOfBits(bits) < b) bits++;
+            v[(size_t)b] = bits;
         }
         return v;
     }();
@@ -382,6 +395,7 @@ void ClauseDb::resortOnDevice(cudaStream_t stream) {
 }
 
 void ClauseDb::reduceAfterSync(cudaStream_t stream) {
+    releaseSpare(stream); // (the host path re-uploads into the primary arenas; the spare set would only hold memory)
     reduceHost();
     for (int s = maxLen_; s >= 3; s--) {
         PerLen &pl = *perLen_[s];

@@ -153,6 +153,9 @@ private:
         DevBuf<int32_t> dev;      // device arena (grows in place: vmem.cc)
         DevBuf<int64_t> idsDev;   // clause ids (the GPU emits them with the hits)
         DevBuf<float> actsDev;    // clause activities live on the device between two reduceDb calls
+        DevBuf<int32_t> devAlt;   // the second set of arenas: a device-side reduce / re-sort permutes into it and swaps
+        DevBuf<int64_t> idsAlt;
+        DevBuf<float> actsAlt;
         int64_t actsOnDevice = 0; // clauses [0, actsOnDevice) have their authoritative activity on the device
         int64_t dirtyFrom = 0;    // first clause index not yet on the device
         int64_t sortedN = 0;      // clauses [0, sortedN) are in first-literal order
@@ -160,6 +163,13 @@ private:
     };
     // device-side reduce / re-sort (reduce.cu); false: could not get the memory, nothing changed
     bool permuteOnDevice(cudaStream_t stream, bool dropByActivity);
+    struct PermScratch; // key / value / histogram arrays of the pass, kept between passes (reduce.cu)
+    struct PermScratchDeleter {
+        void operator()(PermScratch *p) const;
+    };
+    std::unique_ptr<PermScratch, PermScratchDeleter> permScratch_;
+    void initPermScratch();
+    void releaseSpare(cudaStream_t stream);
     // The host mirror of the clauses [0, n) of every length is being refreshed by an asynchronous
     // device-to-host copy (after a device-side reduce / re-sort): wait for it before the host reads that
     // part of the mirror or reallocates any of its buffers.

@@ -889,12 +889,24 @@ __global__ void __launch_bounds__(128) k_check_dense_sliced(CheckArgs a, const u
 // a block pulls 256 of them as 768 coalesced words through shared memory, so PCIe sees full lines.
 // A copy of every record goes to `keep` (the deferred collapse and re-timed launches read it).
 // ---------------------------------------------------------------------------------------------
+// Side jobs (ApplyExtra): this is the first kernel of a run, so it also (a) brings the run header -- directory,
+// run parameters, delta pointers; ~10 KB -- from page-locked host memory into the slot's device copy, which
+// the kernels that follow read (its own blocks read their parameters from the host copy), and (b) zeroes the
+// run's counters.  That is one host-to-device copy and two memsets fewer to issue per run (~30 us of host time
+// on the GPU boxes of this pool, where every asynchronous call costs 5-10 us).
 __global__ void __launch_bounds__(256) k_apply_direct(const VarUpdate *const *__restrict__ src,
                                                       const SolverRunParams *__restrict__ params, DeviceTables t,
-                                                      VarUpdate *__restrict__ keep) {
+                                                      VarUpdate *__restrict__ keep, ApplyExtra x) {
     __shared__ uint32_t sAgg[kSlots], sSlot[kSlots];
     __shared__ uint32_t sWords[3 * 256];
     const int s = blockIdx.y;
+    if (x.headWords | x.zeroAWords | x.zeroBWords) {
+        const int nBlocks = gridDim.x * gridDim.y, me = blockIdx.y * gridDim.x + blockIdx.x;
+        for (int i = me * blockDim.x + threadIdx.x; i < x.headWords; i += nBlocks * blockDim.x) x.headDev[i] = x.headHost[i];
+        for (int i = me * blockDim.x + threadIdx.x; i < x.zeroBWords; i += nBlocks * blockDim.x) x.zeroB[i] = 0u;
+        if (me == 0)
+            for (int i = threadIdx.x; i < x.zeroAWords; i += blockDim.x) x.zeroA[i] = 0u;
+    }
     const SolverRunParams &p = params[s];
     const int n = p.updCount, nGroups = p.nGroups, updStart = p.updStart;
     if (n <= 0) return;
@@ -1247,6 +1259,45 @@ __global__ void __launch_bounds__(256) k_peer_push(const uint4 *__restrict__ src
     }
 }
 
+// root, direct variant: the deltas do not pass through a staging buffer and a host-to-device copy first.  Row s
+// of the grid reads solver s's records where the solver thread left them (src[s]: page-locked host memory, as
+// in k_apply_direct) and stores them -- ONE pass over PCIe -- into this rank's payload area and into every
+// worker's window; row nSolvers forwards the prefix ([header][run parameters], uploaded with the run header).
+// The block that finishes last signals the mailboxes.
+__global__ void __launch_bounds__(256) k_peer_push_direct(const VarUpdate *const *__restrict__ src,
+                                                          const SolverRunParams *__restrict__ params, int nSolvers,
+                                                          uint32_t *__restrict__ local, const uint32_t *__restrict__ prefix,
+                                                          long long prefixWords, PeerPushList L, uint32_t seq, unsigned int *ticket) {
+    const long long stride = (long long)gridDim.x * blockDim.x, first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)blockIdx.y == nSolvers) {
+        for (long long i = first; i < prefixWords; i += stride) {
+            const uint32_t v = prefix[i];
+            local[i] = v;
+            for (int r = 0; r < L.n; r++) reinterpret_cast<uint32_t *>(L.dst[r])[i] = v;
+        }
+    } else {
+        const SolverRunParams &p = params[blockIdx.y];
+        const long long nw = 3ll * p.updCount, base = prefixWords + 3ll * p.updStart;
+        const uint32_t *__restrict__ w = reinterpret_cast<const uint32_t *>(src[blockIdx.y]);
+        const bool inPlace = w == local + base; // (a delta buffer that was not page-locked went up as an ordinary copy)
+        for (long long k = first; k < nw; k += stride) {
+            const uint32_t v = w[k];
+            if (!inPlace) local[base + k] = v;
+            for (int r = 0; r < L.n; r++) reinterpret_cast<uint32_t *>(L.dst[r])[base + k] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x * gridDim.y - 1) {
+            *ticket = 0u;
+            __threadfence_system();
+            for (int r = 0; r < L.n; r++) *reinterpret_cast<volatile uint32_t *>(L.mailbox[r]) = seq;
+        }
+    }
+}
+
 // every rank, when no k_exact launch could publish the result itself (see k_exact): result header into its slot of the root's gather window, then
 // the done flag.  The hits themselves were appended to the slot by k_exact (peer stores), which has
 // completed.  flag = 2*seq when the result is complete, 2*seq-1 when a survivor / hit buffer
@@ -1483,6 +1534,17 @@ void launchPeerPush(const void *src, long long bytes, const PeerPushList &L, uin
     ++*launches;
 }
 
+void launchPeerPushDirect(const VarUpdate *const *src, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver, void *local,
+                          const void *prefix, long long prefixWords, const PeerPushList &L, uint32_t seq, unsigned int *ticket,
+                          int numSMs, cudaStream_t s, int64_t *launches) {
+    // enough blocks per solver to keep PCIe full (every block has 3 KB in flight), few enough to stay in one wave
+    const int perSolver = std::max(1, std::min((3 * maxUpdPerSolver + 767) / 768, std::max(1, numSMs * 8 / (nSolvers + 1))));
+    k_peer_push_direct<<<dim3((unsigned int)perSolver, (unsigned int)nSolvers + 1), 256, 0, s>>>(
+        src, params, nSolvers, static_cast<uint32_t *>(local), static_cast<const uint32_t *>(prefix), prefixWords, L, seq, ticket);
+    checkLaunch("k_peer_push_direct");
+    ++*launches;
+}
+
 void launchPeerFinalize(const Counters *counters, unsigned int hitCap, unsigned int survCap, int groups, long long *hdr,
                         uint32_t *doneFlag, uint32_t seq, cudaStream_t s, int64_t *launches) {
     k_peer_finalize<<<1, 32, 0, s>>>(counters, hitCap, survCap, groups, hdr, doneFlag, seq);
@@ -1539,9 +1601,10 @@ void launchCollapse(const VarUpdate *upd, const SolverRunParams *params, int nSo
 }
 
 void launchApplyDirect(const VarUpdate *const *src, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
-                       const DeviceTables &t, VarUpdate *keep, int numSMs, cudaStream_t s, int64_t *launches) {
-    if (nSolvers == 0 || maxUpdPerSolver == 0) return;
-    k_apply_direct<<<updateGrid(nSolvers, maxUpdPerSolver, numSMs), 256, 0, s>>>(src, params, t, keep);
+                       const DeviceTables &t, VarUpdate *keep, int numSMs, cudaStream_t s, int64_t *launches, const ApplyExtra &x) {
+    const bool extra = (x.headWords | x.zeroAWords | x.zeroBWords) != 0;
+    if (nSolvers == 0 || (maxUpdPerSolver == 0 && !extra)) return;
+    k_apply_direct<<<updateGrid(nSolvers, std::max(1, maxUpdPerSolver), numSMs), 256, 0, s>>>(src, params, t, keep, x);
     checkLaunch("k_apply_direct");
     ++*launches;
 }

@@ -152,6 +152,11 @@ struct PeerPushList {
 // copy `bytes` of the batch to every worker and then store seq into every mailbox (one launch)
 void launchPeerPush(const void *src, long long bytes, const PeerPushList &L, uint32_t seq, unsigned int *ticket, int numSMs,
                     cudaStream_t s, int64_t *launches);
+// the same without a staging copy: the deltas are read from the solvers' page-locked buffers (src[s]) and stored into
+// this rank's payload area (`local`) and every worker's window in one pass; `prefix` = [header][run parameters]
+void launchPeerPushDirect(const VarUpdate *const *src, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver, void *local,
+                          const void *prefix, long long prefixWords, const PeerPushList &L, uint32_t seq, unsigned int *ticket,
+                          int numSMs, cudaStream_t s, int64_t *launches);
 void launchPeerFinalize(const Counters *counters, unsigned int hitCap, unsigned int survCap, int groups, long long *hdr,
                         uint32_t *doneFlag, uint32_t seq, cudaStream_t s, int64_t *launches);
 void launchPeerWaitAll(const PeerFlagList &flags, uint32_t value, unsigned long long timeoutNs, int *err, cudaStream_t s,
@@ -217,8 +222,19 @@ struct EmitArgs {
 // the literal stream of every solver, written straight into the result buffer in host memory
 void launchEmit(const EmitArgs &a, cudaStream_t s, int64_t *launches);
 // deltas of every solver read from src[s] (mapped pinned host memory or device memory), a copy kept in `keep`
+// side jobs of the run's first kernel: fetch the run header from page-locked host memory, zero the run's counters
+struct ApplyExtra {
+    const uint32_t *headHost = nullptr;
+    uint32_t *headDev = nullptr;
+    int headWords = 0;
+    uint32_t *zeroA = nullptr; // Counters
+    int zeroAWords = 0;
+    uint32_t *zeroB = nullptr; // per-solver record counters
+    int zeroBWords = 0;
+};
 void launchApplyDirect(const VarUpdate *const *src, const SolverRunParams *params, int nSolvers, int maxUpdPerSolver,
-                       const DeviceTables &t, VarUpdate *keep, int numSMs, cudaStream_t s, int64_t *launches);
+                       const DeviceTables &t, VarUpdate *keep, int numSMs, cudaStream_t s, int64_t *launches,
+                       const ApplyExtra &x = ApplyExtra());
 // activity bumps from the sorted per-solver record lists of a finished run
 void launchBumpFromRecs(const unsigned long long *recKeys, unsigned int recCap, const EmitSolver *solverInfo, int nSolvers,
                         unsigned int maxCount, const LenDir *dir, int nDir, float inc, int *overflow, cudaStream_t s, int64_t *launches);

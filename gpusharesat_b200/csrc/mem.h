@@ -9,13 +9,38 @@
 
 namespace gss {
 
+// address space for a host buffer that grows in place (vmem.cc: anonymous mapping, untouched pages cost nothing)
+void *hostReserve(size_t bytes); // nullptr: not available
+void hostUnreserve(void *p, size_t bytes);
+
 // Growable host buffer, page-locked when the allocation is below the pinned budget
 // (reference option maxPageLockedMemory, GpuClauseSharer.h:44-47).
+// Two growth strategies.  Default: a larger block, copy, free (small, short-lived buffers).  setInPlace(): the
+// host mirror of a clause arena grows for as long as the solvers learn, and re-allocating page-locked memory
+// is expensive (allocating 100 MB of it takes tens of milliseconds, and the old contents have to be copied:
+// measured as 0.3 - 1.5 s gpuRun() spikes while 10 M clauses streamed in).  Such a buffer reserves address
+// space once (anonymous mapping, no memory behind it until touched) and page-locks it CHUNK BY CHUNK
+// (cudaHostRegister) as it grows: the data never moves, only new memory is ever pinned.  Copies between such a
+// buffer and the device are split at chunk boundaries (copyToDevice / copyFromDevice), so every piece lies
+// inside one registered range.
 template <typename T> class HostBuf {
     T *p_ = nullptr;
     size_t size_ = 0, cap_ = 0;
     bool pinned_ = false;
     size_t pinnedLimitBytes_ = (size_t)1 << 40;
+    // in-place mode
+    bool inPlace_ = false;
+    size_t reservedBytes_ = 0, usableBytes_ = 0, registeredBytes_ = 0;
+    // chunks: [0, 64 KB), then doubling up to 8 MB, then 8 MB each (a database has one mirror per clause
+    // length, most of them tiny: the first chunk must be small; large mirrors must not need many registrations)
+    static constexpr size_t kFirstChunk = (size_t)64 << 10, kChunkBytes = (size_t)8 << 20;
+    static size_t chunkEnd(size_t off) { // end of the chunk that contains byte `off`
+        if (off < kFirstChunk) return kFirstChunk;
+        if (off >= kChunkBytes) return (off / kChunkBytes + 1) * kChunkBytes;
+        size_t e = kFirstChunk;
+        while (e <= off) e *= 2;
+        return e;
+    }
 
     static T *alloc(size_t n, size_t limit, bool &pinned) {
         if (n == 0) return nullptr;
@@ -35,13 +60,62 @@ template <typename T> class HostBuf {
         if (!q) return;
         if (pinned) cudaFreeHost(q); else free(q);
     }
+    void releaseAll() {
+        if (inPlace_) {
+            uint8_t *base = reinterpret_cast<uint8_t *>(p_);
+            for (size_t off = 0; off < registeredBytes_; off = chunkEnd(off)) cudaHostUnregister(base + off);
+            if (p_) hostUnreserve(p_, reservedBytes_);
+            inPlace_ = false;
+            reservedBytes_ = usableBytes_ = registeredBytes_ = 0;
+        } else {
+            release(p_, pinned_);
+        }
+        p_ = nullptr;
+        cap_ = 0;
+    }
+    // make [0, bytes) usable (and page-locked while the budget lasts); false: beyond the reserved range
+    bool growInPlace(size_t bytes) {
+        if (bytes > reservedBytes_) return false;
+        uint8_t *base = reinterpret_cast<uint8_t *>(p_);
+        while (usableBytes_ < bytes) {
+            const size_t len = std::min(chunkEnd(usableBytes_), reservedBytes_) - usableBytes_;
+            if (registeredBytes_ == usableBytes_ && usableBytes_ + len <= pinnedLimitBytes_) {
+                if (cudaHostRegister(base + usableBytes_, len, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess)
+                    registeredBytes_ += len;
+                else
+                    cudaGetLastError(); // (no device, or out of lockable memory: ordinary memory from here on)
+            }
+            usableBytes_ += len;
+        }
+        pinned_ = registeredBytes_ == usableBytes_;
+        cap_ = usableBytes_ / sizeof(T);
+        return true;
+    }
+    template <typename F> void forEachPiece(size_t firstElem, size_t nElems, F f) const {
+        size_t off = firstElem * sizeof(T), end = off + nElems * sizeof(T);
+        while (off < end) {
+            const size_t stop = inPlace_ ? std::min(end, chunkEnd(off)) : end;
+            f(off, stop - off);
+            off = stop;
+        }
+    }
 
 public:
     HostBuf() = default;
     HostBuf(const HostBuf &) = delete;
     HostBuf &operator=(const HostBuf &) = delete;
-    ~HostBuf() { release(p_, pinned_); }
+    ~HostBuf() { releaseAll(); }
     void setPinnedLimit(size_t bytes) { pinnedLimitBytes_ = bytes; }
+    // before the first element: reserve maxBytes of address space and grow inside it (falls back to the default
+    // strategy when the address space cannot be reserved, or later when the buffer outgrows it)
+    void setInPlace(size_t maxBytes) {
+        if (p_ || inPlace_) return;
+        void *q = hostReserve(maxBytes);
+        if (!q) return;
+        p_ = static_cast<T *>(q);
+        inPlace_ = true;
+        reservedBytes_ = maxBytes;
+    }
     T *data() { return p_; }
     const T *data() const { return p_; }
     size_t size() const { return size_; }
@@ -53,6 +127,18 @@ public:
     void clear() { size_ = 0; }
     void reserve(size_t n) {
         if (n <= cap_) return;
+        if (inPlace_) {
+            if (growInPlace(n * sizeof(T))) return;
+            // outgrown the reserved range: one move into an ordinary block, default strategy from here on
+            size_t nc = cap_ ? cap_ : 64;
+            while (nc < n) nc *= 2;
+            bool pinned;
+            T *q = alloc(nc, pinnedLimitBytes_, pinned);
+            if (size_) memcpy(q, p_, size_ * sizeof(T));
+            releaseAll();
+            p_ = q; cap_ = nc; pinned_ = pinned;
+            return;
+        }
         size_t nc = cap_ ? cap_ : 64;
         while (nc < n) nc *= 2;
         bool pinned;
@@ -69,6 +155,21 @@ public:
     }
     void push_back(const T &v) { reserve(size_ + 1); p_[size_++] = v; }
     T *append(size_t n) { reserve(size_ + n); T *r = p_ + size_; size_ += n; return r; }
+    // asynchronous copies of elements [firstElem, firstElem + nElems) to / from device memory
+    void copyToDevice(void *dev, size_t firstElem, size_t nElems, cudaStream_t stream) const {
+        const uint8_t *h = reinterpret_cast<const uint8_t *>(p_);
+        const size_t base = firstElem * sizeof(T);
+        forEachPiece(firstElem, nElems, [&](size_t off, size_t len) {
+            GSS_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(dev) + (off - base), h + off, len, cudaMemcpyHostToDevice, stream));
+        });
+    }
+    void copyFromDevice(const void *dev, size_t firstElem, size_t nElems, cudaStream_t stream) {
+        uint8_t *h = reinterpret_cast<uint8_t *>(p_);
+        const size_t base = firstElem * sizeof(T);
+        forEachPiece(firstElem, nElems, [&](size_t off, size_t len) {
+            GSS_CUDA(cudaMemcpyAsync(h + off, static_cast<const uint8_t *>(dev) + (off - base), len, cudaMemcpyDeviceToHost, stream));
+        });
+    }
 };
 
 // Device memory that grows in place: a reserved range of virtual addresses with physical chunks

@@ -173,6 +173,7 @@ struct Sharer::PeerState {
     std::shared_ptr<ShmRing> ring;              // workers: this rank's result buffers
     std::vector<std::shared_ptr<ShmRing>> rings; // rank 0: every worker's ring (index = rank; [0] unused)
     int ringBuf = -1;                           // workers: buffer of the batch in flight (not yet published)
+    bool directPush = true;                     // rank 0: deltas read in place by the push kernel (GPUSHARE_PEER_STAGED: staged copy + H2D)
 
     uint8_t *payload() const { return (rank == 0 ? rootWindow : window) + kCtlBytes; } // this rank's copy of the batch
     uint32_t *done(int r) const { return reinterpret_cast<uint32_t *>(rootWindow + kDoneOff + (size_t)r * kFlagStride); }
@@ -273,6 +274,7 @@ void Sharer::peerConnect(const void *blobs, int64_t blobBytes) {
     GSS_CUDA(cudaEventCreate(&P.evGathered));
     GSS_CUDA(cudaEventCreate(&P.evWait));
     P.trace = getenv("GSS_PEER_TRACE") != nullptr;
+    P.directPush = directEnabled_ && getenv("GPUSHARE_PEER_STAGED") == nullptr;
     P.connected = true;
 }
 
@@ -367,8 +369,48 @@ int Sharer::peerEnqueue() {
     const int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
     slot.dense = dense_;
     slot.headDev.reserve(slot.headHost.size(), 0, stream_);
+    bool pushedDirect = false;
 
-    if (root) {
+    if (root && P.directPush) {
+        // Direct variant (default): no staging copy, no separate H2D of the deltas.  The solvers' delta buffers are
+        // swapped out (collectDirect) and k_peer_push_direct reads them in place over PCIe, storing every record into
+        // this rank's payload area AND every worker's window in the same pass.
+        collectDirect(slot, rebuild); // slot.headHost = [directory][run parameters][per-solver delta pointers]
+        const int S = slot.nSolvers;
+        const size_t prefixOff = alignUp(slot.headHost.size(), 16), prefixBytes = PR * sizeof(VarUpdate);
+        slot.headHost.resize(prefixOff + prefixBytes); // (may move the buffer: pointers into it are taken below)
+        SolverRunParams *params = (SolverRunParams *)(slot.headHost.data() + slot.dirBytes);
+        const VarUpdate **src = (const VarUpdate **)(slot.headHost.data() + slot.srcOff);
+        PayloadHeader hdr;
+        memset(&hdr, 0, sizeof(hdr));
+        hdr.magic = kPayloadMagic;
+        hdr.status = rebuild ? 1 : 0;
+        hdr.nSolvers = S;
+        hdr.prefixRecords = (int32_t)PR;
+        hdr.nUpdates = slot.nUpdates;
+        hdr.totalBytes = (int64_t)((PR + (size_t)slot.nUpdates) * sizeof(VarUpdate));
+        if (hdr.totalBytes > P.payloadCap) GSS_DIE("peer exchange: the batch does not fit the payload area (raise payload_cap)");
+        memcpy(slot.headHost.data() + prefixOff, &hdr, sizeof(hdr));
+        memcpy(slot.headHost.data() + prefixOff + sizeof(hdr), params, (size_t)S * sizeof(SolverRunParams));
+        VarUpdate *updLocal = reinterpret_cast<VarUpdate *>(payload) + PR;
+        for (auto &st : slot.staged) { // delta buffers outside page-locked memory go up as ordinary copies, straight into place
+            VarUpdate *dst = updLocal + params[st.first].updStart;
+            GSS_CUDA(cudaMemcpyAsync(dst, st.second, (size_t)params[st.first].updCount * sizeof(VarUpdate), cudaMemcpyHostToDevice, stream_));
+            src[st.first] = dst;
+        }
+        for (int sIdx = 0; sIdx < S; sIdx++)
+            if (!src[sIdx]) src[sIdx] = updLocal + params[sIdx].updStart; // (a skipped solver: zero records)
+        slot.headDev.reserve(slot.headHost.size(), 0, stream_);
+        GSS_CUDA(cudaMemcpyAsync(slot.headDev.data(), slot.headHost.data(), slot.headHost.size(), cudaMemcpyHostToDevice, stream_));
+        h2d += (int64_t)slot.headHost.size() + hdr.totalBytes;
+        peerPayloadBytes_ = hdr.totalBytes;
+        GSS_CUDA(cudaEventRecord(slot.evH2DDone, stream_));
+        launchPeerPushDirect((const VarUpdate *const *)(slot.headDev.data() + slot.srcOff), slot.paramsDev(), S, slot.maxUpd, payload,
+                             slot.headDev.data() + prefixOff, (long long)(prefixBytes / 4), P.push, P.seq, P.pushTicket(), numSMs_,
+                             stream_, &launches_);
+        GSS_CUDA(cudaEventRecord(P.evPushed, stream_));
+        pushedDirect = true;
+    } else if (root) {
         {
             PhaseTimer tCollect(hostPhases_[3]);
             collectBatch(slot, rebuild);
@@ -419,8 +461,8 @@ int Sharer::peerEnqueue() {
     }
     slot.updDev.reserve((size_t)std::max<int64_t>(slot.nUpdates, 1), 0, stream_);
     ensureResultBuffers();
-    GSS_CUDA(cudaEventRecord(slot.evH2DDone, stream_));
-    if (root && P.push.n) {
+    if (!pushedDirect) GSS_CUDA(cudaEventRecord(slot.evH2DDone, stream_));
+    if (root && P.push.n && !pushedDirect) {
         // push the batch into every worker's window and signal: one kernel, FIRST on rank 0's stream
         // (on a second stream it reached the workers ~25 us later: it competed with rank 0's own table
         // kernels).  The workers start ~12 us after rank 0 and have no push to do: the ranks finish

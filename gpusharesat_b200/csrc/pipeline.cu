@@ -190,7 +190,11 @@ void Sharer::launchDirect(RunSlot &slot, int64_t h2d) {
         src[s] = dst;
     }
     slot.headDev.reserve(slot.headHost.size(), 0, stream_);
-    {
+    // The run header travels inside the first kernel (k_apply_direct reads it from page-locked host memory and
+    // leaves the device copy behind) and the same kernel zeroes the run's counters; only a header that is not
+    // page-locked goes up as an ordinary copy.
+    const bool fused = fuseHeader_ && slot.headHost.pinned();
+    if (!fused) {
         HostProf hp("  head H2D");
         GSS_CUDA(cudaMemcpyAsync(slot.headDev.data(), slot.headHost.data(), slot.headHost.size(), cudaMemcpyHostToDevice, stream_));
     }
@@ -210,11 +214,25 @@ void Sharer::launchDirect(RunSlot &slot, int64_t h2d) {
     }
     {
         HostProf hp("  launch apply");
-        launchApplyDirect((const VarUpdate *const *)(slot.headDev.data() + slot.srcOff), slot.paramsDev(), S, slot.maxUpd, tables_,
-                          slot.updDev.data(), numSMs_, stream_, &launches_);
+        ApplyExtra x;
+        const uint8_t *head = slot.headDev.data();
+        if (fused) {
+            head = slot.headHost.data(); // (this kernel's own blocks read their parameters where the host wrote them)
+            x.headHost = reinterpret_cast<const uint32_t *>(slot.headHost.data());
+            x.headDev = reinterpret_cast<uint32_t *>(slot.headDev.data());
+            x.headWords = (int)((slot.headHost.size() + 3) / 4);
+            x.zeroA = reinterpret_cast<uint32_t *>(resDev_.data());
+            x.zeroAWords = (int)(sizeof(Counters) / 4);
+            x.zeroB = reinterpret_cast<uint32_t *>(slot.ctrDev.data());
+            x.zeroBWords = (int)((size_t)S * kRecBuckets * kCtrStride * sizeof(unsigned long long) / 4);
+            slot.countersZeroed = true;
+        }
+        launchApplyDirect((const VarUpdate *const *)(head + slot.srcOff), (const SolverRunParams *)(head + slot.dirBytes), S,
+                          slot.maxUpd, tables_, slot.updDev.data(), numSMs_, stream_, &launches_, x);
     }
     GSS_CUDA(cudaEventRecord(slot.evBeforeCheck, stream_));
     launchDirectCheck(slot);
+    slot.countersZeroed = false; // (only the check launched right behind the apply may rely on it)
     GSS_CUDA(cudaEventRecord(slot.evAfterCheck, stream_));
     GSS_CUDA(cudaEventRecord(slot.evEnd, stream_));
     slot.inFlight = true;

@@ -104,13 +104,29 @@ __global__ void __launch_bounds__(256) k_reduce_permute(const PermLen *__restric
     }
 }
 
-template <typename T> struct Scratch { // plain device scratch, freed on scope exit
-    T *p = nullptr;
-    bool alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) == cudaSuccess || (cudaGetLastError(), false); }
-    ~Scratch() { if (p) cudaFree(p); }
+} // namespace
+
+struct ClauseDb::PermScratch {
+    DevBuf<uint8_t> lens, cubTmp;
+    DevBuf<uint32_t> keysA, keysB, valsA, valsB, bounds;
+    DevBuf<unsigned long long> hist;
+    DevBuf<int> kept;
 };
 
-} // namespace
+void ClauseDb::PermScratchDeleter::operator()(PermScratch *p) const { delete p; }
+
+void ClauseDb::initPermScratch() { permScratch_.reset(new PermScratch()); }
+
+// give the spare arenas and the scratch arrays back (host-path reduce, out of device memory)
+void ClauseDb::releaseSpare(cudaStream_t stream) {
+    GSS_CUDA(cudaStreamSynchronize(stream));
+    for (int s = 0; s <= maxLen_; s++) {
+        perLen_[s]->devAlt.free();
+        perLen_[s]->idsAlt.free();
+        perLen_[s]->actsAlt.free();
+    }
+    initPermScratch();
+}
 
 bool ClauseDb::permuteOnDevice(cudaStream_t stream, bool dropByActivity) {
     HostProf hpAll(dropByActivity ? "reduce on device" : "re-sort on device");
@@ -157,40 +173,41 @@ bool ClauseDb::permuteOnDevice(cudaStream_t stream, bool dropByActivity) {
     const uint32_t dropKey = 1u << litBits;
     const int nL = (int)lens.size();
 
-    // memory first: when any of it is missing nothing has changed yet (the caller takes the host path / gives up)
+    // Memory first: when any of it is missing nothing has changed yet (the caller takes the host path / gives up).
+    // The second set of arenas and the scratch arrays are kept between passes (they only ever grow, in place):
+    // in steady state a pass allocates and frees nothing -- cudaMalloc / cudaFree synchronise the whole device
+    // and cost tens of milliseconds for arrays of this size (measured: 58 + ~200 ms per pass at 10 M clauses).
     auto hpAlloc = std::make_unique<HostProf>("  permute: allocate");
-    std::vector<std::unique_ptr<DevBuf<int32_t>>> newDev((size_t)nL);
-    std::vector<std::unique_ptr<DevBuf<int64_t>>> newIds((size_t)nL);
-    std::vector<std::unique_ptr<DevBuf<float>>> newActs((size_t)nL);
     for (int k = 0; k < nL; k++) {
-        newDev[k] = std::make_unique<DevBuf<int32_t>>();
-        newIds[k] = std::make_unique<DevBuf<int64_t>>();
-        newActs[k] = std::make_unique<DevBuf<float>>();
-        newDev[k]->setInPlace();
-        newIds[k]->setInPlace();
-        newActs[k]->setInPlace();
+        PerLen &pl = *perLen_[lenOf[k]];
         if (lens[k].mode == 2) continue; // nothing of this length survives
-        if (!newDev[k]->tryReserve(wordsFor(lens[k].len, lens[k].n), 0, stream, true) ||
-            !newIds[k]->tryReserve((size_t)lens[k].n, 0, stream, true) || !newActs[k]->tryReserve((size_t)lens[k].n, 0, stream, true))
+        if (!pl.devAlt.tryReserve(wordsFor(lens[k].len, lens[k].n), 0, stream) ||
+            !pl.idsAlt.tryReserve((size_t)lens[k].n, 0, stream) || !pl.actsAlt.tryReserve((size_t)lens[k].n, 0, stream))
             return false;
-        lens[k].dst = newDev[k]->data();
-        lens[k].idsDst = newIds[k]->data();
-        lens[k].actsDst = newActs[k]->data();
+        lens[k].dst = pl.devAlt.data();
+        lens[k].idsDst = pl.idsAlt.data();
+        lens[k].actsDst = pl.actsAlt.data();
     }
-    Scratch<PermLen> lensDev;
-    Scratch<uint32_t> keysA, keysB, valsA, valsB, boundsDev;
-    Scratch<unsigned long long> histDev;
-    Scratch<int> keptDev;
-    Scratch<uint8_t> cubTmp;
     size_t cubBytes = 0;
     int32_t maxN = 0;
     for (const PermLen &l : lens) maxN = std::max(maxN, l.n);
     cub::DeviceRadixSort::SortPairs(nullptr, cubBytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
                                     (uint32_t *)nullptr, maxN, 0, litBits + 1, stream);
-    if (!lensDev.alloc((size_t)nL) || !keysA.alloc((size_t)total) || !keysB.alloc((size_t)total) || !valsA.alloc((size_t)total) ||
-        !valsB.alloc((size_t)total) || !keptDev.alloc((size_t)nL) || !cubTmp.alloc(cubBytes) ||
-        (dropByActivity && (!boundsDev.alloc(kActBuckets) || !histDev.alloc(kActBuckets))))
+    PermScratch &sc = *permScratch_;
+    const bool needBounds = dropByActivity && sc.bounds.capacity() == 0;
+    if (!sc.lens.tryReserve((size_t)nL * sizeof(PermLen), 0, stream) || !sc.keysA.tryReserve((size_t)total, 0, stream) ||
+        !sc.keysB.tryReserve((size_t)total, 0, stream) || !sc.valsA.tryReserve((size_t)total, 0, stream) ||
+        !sc.valsB.tryReserve((size_t)total, 0, stream) || !sc.kept.tryReserve((size_t)nL, 0, stream) ||
+        !sc.cubTmp.tryReserve(cubBytes, 0, stream) ||
+        (dropByActivity && (!sc.bounds.tryReserve(kActBuckets, 0, stream, true) || !sc.hist.tryReserve(kActBuckets, 0, stream, true))))
         return false;
+    struct { // (the names the rest of the pass uses)
+        PermLen *p;
+    } lensDev{reinterpret_cast<PermLen *>(sc.lens.data())};
+    struct { uint32_t *p; } keysA{sc.keysA.data()}, keysB{sc.keysB.data()}, valsA{sc.valsA.data()}, valsB{sc.valsB.data()}, boundsDev{sc.bounds.data()};
+    struct { unsigned long long *p; } histDev{sc.hist.data()};
+    struct { int *p; } keptDev{sc.kept.data()};
+    struct { uint8_t *p; } cubTmp{sc.cubTmp.data()};
     hpAlloc.reset();
     auto hpKernels = std::make_unique<HostProf>("  permute: kernels + sync");
     GSS_CUDA(cudaMemcpyAsync(lensDev.p, lens.data(), (size_t)nL * sizeof(PermLen), cudaMemcpyHostToDevice, stream));
@@ -201,8 +218,10 @@ bool ClauseDb::permuteOnDevice(cudaStream_t stream, bool dropByActivity) {
     if (dropByActivity) {
         addedAtLastReduce_ = stats_.added;
         reduceDbs_++;
-        const std::vector<uint32_t> &bounds = actBucketBounds();
-        GSS_CUDA(cudaMemcpyAsync(boundsDev.p, bounds.data(), (size_t)kActBuckets * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        if (needBounds) { // (once per database: the table never changes)
+            const std::vector<uint32_t> &bounds = actBucketBounds();
+            GSS_CUDA(cudaMemcpyAsync(boundsDev.p, bounds.data(), (size_t)kActBuckets * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        }
         GSS_CUDA(cudaMemsetAsync(histDev.p, 0, (size_t)kActBuckets * sizeof(unsigned long long), stream));
         k_act_hist<<<grid, 256, 0, stream>>>(lensDev.p, boundsDev.p, kActBuckets, histDev.p);
         std::vector<int64_t> hist((size_t)kActBuckets);
@@ -239,9 +258,9 @@ bool ClauseDb::permuteOnDevice(cudaStream_t stream, bool dropByActivity) {
         GSS_CHECK(to <= pl.n && (lens[k].mode != 0 || to == pl.n));
         stats_.clauses -= pl.n - to;
         stats_.lengthSum -= (pl.n - to) * s;
-        pl.dev.swap(*newDev[k]); // (the old set is freed with newDev / newIds / newActs: the stream has drained)
-        pl.idsDev.swap(*newIds[k]);
-        pl.actsDev.swap(*newActs[k]);
+        pl.dev.swap(pl.devAlt); // (the old set is the spare set of the next pass)
+        pl.idsDev.swap(pl.idsAlt);
+        pl.actsDev.swap(pl.actsAlt);
         pl.n = to;
         pl.sortedN = to;
         pl.actsOnDevice = to;
@@ -254,9 +273,7 @@ bool ClauseDb::permuteOnDevice(cudaStream_t stream, bool dropByActivity) {
         // the last, partial tile now (new clauses are appended into it), the full tiles on the side stream
         const size_t tileWords = (size_t)kTileClauses * s;
         const size_t fullWords = (size_t)(to / kTileClauses) * tileWords;
-        if (to % kTileClauses)
-            GSS_CUDA(cudaMemcpyAsync(pl.lits.data() + fullWords, pl.dev.data() + fullWords, tileWords * sizeof(int32_t),
-                                     cudaMemcpyDeviceToHost, stream));
+        if (to % kTileClauses) pl.lits.copyFromDevice(pl.dev.data() + fullWords, fullWords, tileWords, stream);
     }
     GSS_CUDA(cudaEventRecord(permuteDoneEv_, stream));
     GSS_CUDA(cudaStreamWaitEvent(mirrorStream_, permuteDoneEv_, 0));
@@ -265,10 +282,9 @@ bool ClauseDb::permuteOnDevice(cudaStream_t stream, bool dropByActivity) {
         PerLen &pl = *perLen_[s];
         if (pl.n == 0) continue;
         const size_t fullWords = (size_t)(pl.n / kTileClauses) * kTileClauses * (size_t)s;
-        if (fullWords)
-            GSS_CUDA(cudaMemcpyAsync(pl.lits.data(), pl.dev.data(), fullWords * sizeof(int32_t), cudaMemcpyDeviceToHost, mirrorStream_));
-        GSS_CUDA(cudaMemcpyAsync(pl.ids.data(), pl.idsDev.data(), (size_t)pl.n * sizeof(int64_t), cudaMemcpyDeviceToHost, mirrorStream_));
-        GSS_CUDA(cudaMemcpyAsync(pl.acts.data(), pl.actsDev.data(), (size_t)pl.n * sizeof(float), cudaMemcpyDeviceToHost, mirrorStream_));
+        if (fullWords) pl.lits.copyFromDevice(pl.dev.data(), 0, fullWords, mirrorStream_);
+        pl.ids.copyFromDevice(pl.idsDev.data(), 0, (size_t)pl.n, mirrorStream_);
+        pl.acts.copyFromDevice(pl.actsDev.data(), 0, (size_t)pl.n, mirrorStream_);
     }
     GSS_CUDA(cudaEventRecord(mirrorEv_, mirrorStream_));
     mirrorPending_ = true;

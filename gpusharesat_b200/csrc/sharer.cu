@@ -80,6 +80,7 @@ Sharer::Sharer(const gss_options &o, gss_log_fn log, void *logCtx, int workerOfD
     reported_->setPool(&pool_);
     db_->setDeviceActivities(true);
     denseSliced_ = getenv("GSS_DENSE_FLAT") == nullptr; // (bench: the round-1 dense kernel, 256-byte rows from HBM)
+    fuseHeader_ = getenv("GPUSHARE_NO_FUSED_HEADER") == nullptr;
     if (getenv("GPUSHARE_HOST_REDUCE")) db_->setDeviceReduce(false); // round-1 reduceDb (host compaction + re-upload), for comparison
     reported_->setHostBumps(false);
     setCpuSolverCount(1);
@@ -398,8 +399,12 @@ bool Sharer::launchCheckKernels(RunSlot &slot, bool dense, bool filterOnly) {
     // direct pipeline: k_exact appends to per-solver record lists (dense mode always uses the global hit buffer)
     const bool recs = slot.direct && !dense;
     if (slot.direct && !recs) ensureResultBuffers();
-    GSS_CUDA(cudaMemsetAsync(resDev_.data(), 0, sizeof(Counters), stream_));
-    if (recs) GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)slot.nSolvers * kRecBuckets * kCtrStride * sizeof(unsigned long long), stream_));
+    if (slot.countersZeroed && recs) {
+        slot.countersZeroed = false; // (k_apply_direct of this run has done it)
+    } else {
+        GSS_CUDA(cudaMemsetAsync(resDev_.data(), 0, sizeof(Counters), stream_));
+        if (recs) GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)slot.nSolvers * kRecBuckets * kCtrStride * sizeof(unsigned long long), stream_));
+    }
     int groups = (slot.nSolvers + kMaxSolversPerGroup - 1) / kMaxSolversPerGroup;
     int lastGroup = -1;
     for (int g = 0; g < groups; g++)

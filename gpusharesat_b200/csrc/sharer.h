@@ -145,6 +145,7 @@ private:
         // ---- direct pipeline (pipeline.cu) ----
         bool direct = false;        // this run used the direct pipeline (per-solver records, k_emit into host memory)
         bool checked = false;       // check kernels + k_emit were launched (some solver had a frozen slot)
+        bool countersZeroed = false; // this run's k_apply_direct has reset the counters: no memsets before the check
         uint32_t seq = 0;           // what k_emit writes into the header last
         std::shared_ptr<RunBuf> runBuf;
         DevBuf<unsigned long long> ctrDev;  // [kMaxSolvers][kRecBuckets] x kCtrStride: records | literals << 32
@@ -217,6 +218,7 @@ private:
     DevBuf<uint2> t2Sliced_;          // dense mode (bench): the level-2 table cut into L2-sized slices of 8 solvers
     uint32_t denseSlicesValid_ = 0;   // per solver group: the slices match the current tables
     bool denseSliced_ = true;
+    bool fuseHeader_ = true; // direct pipeline: the run header and the counter reset ride in k_apply_direct
     int64_t resorts_ = 0; // device-side re-sorts of streamed clauses (ClauseDb::resortOnDevice)
     bool directEnabled_ = true;
     bool eagerResults_ = true; // surface a run's hits in the call that started it when it completes within minGpuLatencyMicros

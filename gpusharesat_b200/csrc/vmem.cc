@@ -15,8 +15,17 @@
 #include "mem.h"
 #include <cuda.h>
 #include <mutex>
+#include <sys/mman.h>
 
 namespace gss {
+
+void *hostReserve(size_t bytes) {
+    if (getenv("GPUSHARE_NO_VMM")) return nullptr;
+    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    return p == MAP_FAILED ? nullptr : p;
+}
+void hostUnreserve(void *p, size_t bytes) { munmap(p, bytes); }
+
 namespace vm {
 
 namespace {

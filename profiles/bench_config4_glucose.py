@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE configs[3] as stated: the reference's REAL GPU portfolio solver (glucose-syrup/gpu, unmodified
 sources) with 32 solver threads on a synthetic SAT-competition-shaped instance (2 M variables, 8 M clauses:
-planted satisfiable, 35 % binary / 45 % ternary / 20 % longer clauses), the learned clauses streaming into
+planted satisfiable, 88 % ternary clauses at a clause / variable ratio of 4, the rest of length 2 and 4-9), the learned clauses streaming into
 the GPU clause database -- once linked against libgpushare_b200.so through the shim (glucose-gpu-b200) and
 once against the reference's own GPU library recompiled for sm_100a (glucose-gpu-ref), for the same wall
 time.  Prints one JSON object with the last periodic statistics of both (GPU runs, clause tests, reports,
@@ -26,13 +26,14 @@ def write_cnf(path, nvars, nclauses, seed):
     L = synth.load_library()
     L.gss_synth_write_cnf.restype = C.c_int
     L.gss_synth_write_cnf.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_uint64]
-    w = [0.35, 0.45, 0.08, 0.05, 0.03, 0.02, 0.01, 0.01]  # lengths 2..9
+    w = [0.02, 0.88, 0.04, 0.03, 0.01, 0.01, 0.005, 0.005]  # lengths 2..9: 3-SAT dominated, clause / variable ratio 4
     arr = (C.c_double * len(w))(*w)
-    assert L.gss_synth_write_cnf(path.encode(), nvars, nclauses, arr, len(w), 0.45, seed) == 0
+    assert L.gss_synth_write_cnf(path.encode(), nvars, nclauses, arr, len(w), 0.5, seed) == 0
 
 
 def last_stats(text):
-    """the last {"type": "periodicStats" ...} object the solver printed"""
+    """the last {"type": "periodicStats" ...} object the solver printed (every line carries the comment prefix "c")"""
+    text = re.sub(r"^c ?", "", text, flags=re.M)
     best = None
     for m in re.finditer(r'\{\s*"type"\s*:\s*"periodicStats"', text):
         depth, i = 0, m.start()
@@ -84,12 +85,12 @@ def main():
     ap.add_argument("--vars", type=int, default=2_000_000)
     ap.add_argument("--clauses", type=int, default=8_000_000)
     ap.add_argument("--threads", type=int, default=32)
-    ap.add_argument("--seconds", type=int, default=75)
+    ap.add_argument("--seconds", type=int, default=110)
     ap.add_argument("--cnf", default="/tmp/gss_config4.cnf")
     a = ap.parse_args()
     t0 = time.time()
     write_cnf(a.cnf, a.vars, a.clauses, 41)
-    res = {"config": "BASELINE configs[3]", "instance": f"{a.vars} vars, {a.clauses} clauses, planted, lengths 2-9 (35/45/20 %)",
+    res = {"config": "BASELINE configs[3]", "instance": f"{a.vars} vars, {a.clauses} clauses, planted, 88 % ternary, lengths 2-9",
            "threads": a.threads, "seconds": a.seconds, "host_cores": os.cpu_count(), "cnf_write_s": time.time() - t0}
     for name in ("glucose-gpu-b200", "glucose-gpu-ref"):
         exe = os.path.join(ROOT, "oracle", "_ref", name)

@@ -14,7 +14,12 @@ using namespace gss;
 // the host-only rig never has activities on a device (kernels.cu is not linked here)
 namespace gss {
 void scaleActivitiesOnDevice(float *, int64_t, float, cudaStream_t) {}
-bool ClauseDb::permuteOnDevice(cudaStream_t, bool) { return false; } // (reduce.cu is device code)
+// (reduce.cu is device code)
+struct ClauseDb::PermScratch {};
+void ClauseDb::PermScratchDeleter::operator()(PermScratch *p) const { delete p; }
+void ClauseDb::initPermScratch() {}
+void ClauseDb::releaseSpare(cudaStream_t) {}
+bool ClauseDb::permuteOnDevice(cudaStream_t, bool) { return false; }
 } // namespace gss
 
 struct HostRig {

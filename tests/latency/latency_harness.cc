@@ -40,6 +40,10 @@ int main(int argc, char **argv) {
     // quiet pipeline); 985 = ~65 k background hits per run with 64 solvers (the pipeline saturated by reports)
     const int agreePerMille = argc > 6 ? atoi(argv[6]) : 999;
     const int kStable = 4096; // variables [0, kStable) are never unset by the solver threads: probes use them
+    if (nProbes > kStable / 2) {
+        fprintf(stderr, "at most %d probes\n", kStable / 2);
+        return 2;
+    }
 
     gss_options o;
     gss_options_default(&o);
@@ -78,6 +82,10 @@ int main(int argc, char **argv) {
 
     std::atomic<bool> stop{false};
     std::atomic<int64_t> runs{0};
+    // A solver that imports a clause stops falsifying it (it backtracks).  Probe p therefore contains the false
+    // literal of variable p, and once the probe is over every solver thread flips variable p: the clause is
+    // satisfied from then on and does not come back run after run as a background hit.
+    std::atomic<int> flipUpTo{0};
     Probe probe;
     std::vector<std::thread> threads;
     std::atomic<int> ready{0};
@@ -90,8 +98,20 @@ int main(int argc, char **argv) {
             while (!gss_try_set_solver_values(h, s, set.data(), (int)set.size())) std::this_thread::yield();
             while (gss_try_send_assignment(h, s) < 0) std::this_thread::yield();
             ready.fetch_add(1);
-            std::vector<int> flip;
+            std::vector<int> flip, fix;
+            int myFlips = 0;
             while (!stop.load(std::memory_order_relaxed)) {
+                const int upTo = flipUpTo.load(std::memory_order_acquire);
+                if (myFlips < upTo) {
+                    flip.clear();
+                    fix.clear();
+                    for (int v = myFlips; v < upTo; v++) {
+                        flip.push_back(2 * v + sigma[v]);
+                        fix.push_back(2 * v + (1 - sigma[v]));
+                    }
+                    gss_unset_solver_values(h, s, flip.data(), (int)flip.size());
+                    if (gss_try_set_solver_values(h, s, fix.data(), (int)fix.size())) myFlips = upTo;
+                }
                 // a little trail churn: unset and re-set a handful of (non-stable) variables, then export
                 flip.clear();
                 for (int k = 0; k < 8; k++) {
@@ -136,7 +156,8 @@ int main(int argc, char **argv) {
     std::this_thread::sleep_for(std::chrono::milliseconds(300)); // first runs: table rebuild, buffer growth
 
     std::vector<double> lat;
-    int lost = 0, lostLong = 0;
+    int lost = 0, lostLong = 0, lostByLen[16] = {0};
+
     const auto tStart = Clock::now();
     sampling.store(true);
     const int64_t runs0 = runs.load();
@@ -147,8 +168,9 @@ int main(int argc, char **argv) {
         const int s = (int)(rng() % S);
         int len = (p % 4 == 3) ? 101 + (int)(rng() % 100) : 2 + (int)(rng() % 8);
         std::vector<int> lits;
-        for (int i = 0; i < len; i++) {
-            const int v = (int)(rng() % kStable);
+        lits.push_back(2 * p + (1 - sigma[p])); // the variable the solvers flip once the probe is over
+        for (int i = 1; i < len; i++) {
+            const int v = nProbes + (int)(rng() % (kStable - nProbes));
             lits.push_back(2 * v + (1 - sigma[v])); // false under every solver's assignment
         }
         probe.done.store(0);
@@ -163,8 +185,10 @@ int main(int argc, char **argv) {
         else {
             lost++;
             if (len > 100) lostLong++;
+            if (len < 16) lostByLen[len]++;
         }
         probe.target.store(-1);
+        flipUpTo.store(p + 1, std::memory_order_release);
         std::this_thread::sleep_for(std::chrono::microseconds(200));
     }
     const double wallS = usSince(tStart) * 1e-6;
@@ -177,14 +201,15 @@ int main(int argc, char **argv) {
     const double ns = sampled ? (double)sampled : 1.0;
     std::sort(lat.begin(), lat.end());
     auto q = [&](double f) { return lat.empty() ? -1.0 : lat[std::min(lat.size() - 1, (size_t)(f * lat.size()))]; };
-    printf("{\"harness\": \"import_latency\", \"solvers\": %d, \"vars\": %d, \"clauses\": %lld, \"probes\": %d, \"lost\": %d, \"lost_long\": %d, \"true_literals_per_mille\": %d, "
+    printf("{\"harness\": \"import_latency\", \"solvers\": %d, \"vars\": %d, \"clauses\": %lld, \"probes\": %d, \"lost\": %d, \"lost_long\": %d, \"lost_by_len_2_to_9\": [%d,%d,%d,%d,%d,%d,%d,%d], \"true_literals_per_mille\": %d, "
            "\"p50_us\": %.1f, \"p90_us\": %.1f, \"p99_us\": %.1f, \"max_us\": %.1f, \"gpu_runs_per_s\": %.0f, "
            "\"min_gpu_latency_micros\": %d, \"long_clause_share\": 0.05, \"max_clause_len\": 200, "
            "\"host_us_per_run\": {\"finish_previous\": %.1f, \"start_next\": %.1f, \"hand_over\": %.1f, \"collect\": %.1f, "
            "\"wait_for_gpu\": %.1f}, \"hits_reported_per_run\": %.0f, "
            "\"device_us_per_run\": {\"copies\": %.1f, \"table_kernels\": %.1f, \"check_and_emit\": %.1f, \"total\": %.1f}, "
            "\"h2d_bytes_per_run\": %.0f, \"d2h_bytes_per_run\": %.0f}\n",
-           S, V, (long long)C, nProbes, lost, lostLong, agreePerMille, q(0.5), q(0.9), q(0.99), lat.empty() ? -1.0 : lat.back(), nRuns / wallS, minLat,
+           S, V, (long long)C, nProbes, lost, lostLong, lostByLen[2], lostByLen[3], lostByLen[4], lostByLen[5], lostByLen[6], lostByLen[7], lostByLen[8],
+           lostByLen[9], agreePerMille, q(0.5), q(0.9), q(0.99), lat.empty() ? -1.0 : lat.back(), nRuns / wallS, minLat,
            (ph1[0] - ph0[0]) / nRuns, (ph1[1] - ph0[1]) / nRuns, (ph1[2] - ph0[2]) / nRuns, (ph1[3] - ph0[3]) / nRuns,
            (ph1[4] - ph0[4]) / nRuns, (double)(gss_get_global_stat(h, 8) - reports0) / nRuns, devSum[0] / ns, devSum[1] / ns,
            devSum[2] / ns, devSum[3] / ns, h2dSum / ns, d2hSum / ns);
