@@ -1,7 +1,11 @@
 // reported.h -- host side hand-over of hits to the solver threads (reference Reported /
 // ClauseBatch / ConcurrentQueue, gpuShareLib/Reported.{cuh,cu}, ConcurrentQueue.h; rules
 // restated in SURVEY.md Appendix B).  Pure CPU logic; observable behaviour follows the
-// reference call for call, including its re-report suppression rules.
+// reference call for call, including its re-report suppression rules -- with ONE deliberate
+// deviation that is the default: a clause that was already handed over is skipped and the rest of
+// its batch is still delivered, where the reference falls through and discards the rest of the
+// batch (Reported.cu:113-129).  GPUSHARE_REFERENCE_DUP_QUIRK=1 restores the reference behaviour;
+// tests/test_cpu_host_logic.py covers both settings.
 #pragma once
 #include "assigs.h"
 #include "clause_db.h"

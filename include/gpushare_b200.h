@@ -221,23 +221,28 @@ int     gss_mgpu_finish(gss_sharer *h);
  * (world blocks of slot_bytes, each [64 B header][hits]; counts[r] = hits of rank r).  Large
  * unions are sorted and resolved on the device like the hits of a local run. */
 void    gss_mgpu_import_gathered(gss_sharer *h, const void *dev_gathered, int world, int64_t slot_bytes, const int64_t *counts);
-/* ---- multi-GPU over peer memory: no collective on the data path (csrc/peer.cu) ----
- * Every rank exports a window of its device memory with CUDA IPC; workers read the batch straight
- * out of rank 0's memory and append their hits straight into rank 0's memory over NVLink; streams
- * wait on flags with stream memory operations.  Setup (once, after gss_set_shard):
- *   gss_peer_init     allocates this rank's window and writes an opaque blob (<= 128 bytes) to
- *                     blob_out; returns the blob size.  payload_cap: bytes reserved for one batch
- *                     (64 B + 288 B per solver + 12 B per variable delta); slot_hits: hit records
- *                     each rank may return per batch.  Same values on every rank.
+/* ---- multi-GPU, one process per GPU: no collective on the data path (csrc/peer.cu) ----
+ * Every rank exports a window of its device memory with CUDA IPC.  Rank 0 pushes every batch into
+ * the workers' windows with peer stores over NVLink (straight from the solver threads' page-locked
+ * delta buffers) and signals a mailbox; the workers' streams wait on it with stream memory
+ * operations.  Every rank sorts and emits its OWN hits into a ring of result buffers in a POSIX
+ * shared-memory segment it owns (over its own PCIe link); rank 0 maps the rings and hands every
+ * solver one slice per rank, merged into the single-device order.  Setup (once, after gss_set_shard):
+ *   gss_peer_init     allocates this rank's window (and, on workers, its result ring: 4 buffers of
+ *                     about slot_hits x 52 bytes in /dev/shm) and writes an opaque blob (<= 128
+ *                     bytes) to blob_out; returns the blob size.  payload_cap: bytes reserved for one
+ *                     batch (64 B + 288 B per solver + 12 B per variable delta); slot_hits: hit
+ *                     records each rank may return per batch.  Same values on every rank.
  *   [exchange the blobs, e.g. torch.distributed.all_gather_object]
  *   gss_peer_connect  blobs of all ranks in rank order, blob_bytes apart.
  * Per batch, on every rank (SPMD, like the clause stream):
- *   gss_peer_enqueue  rank 0: collect the batch (gss_mgpu_collect semantics), one H2D, signal the
- *                     workers, check its own tiles.  Workers: enqueue wait + kernels, never read the
- *                     batch on the host.  Returns -1 no clause yet, 1 tables rebuilt, else 0.
- *   gss_peer_finish   waits; a rank whose survivor buffer overflowed runs again (rank 0 waits for
- *                     it); rank 0 then sorts / resolves / hands over the union of the hits on its
- *                     device.  Returns the number of hit records (rank 0: of all ranks). */
+ *   gss_peer_enqueue  rank 0: collect the batch (buffer swap per solver), push it, check its own
+ *                     tiles.  Workers: enqueue wait + kernels, never read the batch on the host.
+ *                     Returns -1 no clause yet, 1 tables rebuilt, else 0.
+ *   gss_peer_finish   waits for this rank's result (a rank whose buffers overflowed runs again by
+ *                     itself before it publishes); rank 0 then waits for every rank's publication
+ *                     and hands the results over.  Returns the number of hit records (rank 0: of
+ *                     all ranks). */
 int64_t gss_peer_init(gss_sharer *h, int rank, int world, int64_t payload_cap, int64_t slot_hits, void *blob_out, int64_t blob_cap);
 void    gss_peer_connect(gss_sharer *h, const void *blobs, int64_t blob_bytes);
 int     gss_peer_enqueue(gss_sharer *h);
