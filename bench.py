@@ -150,6 +150,8 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        if os.environ.get("GSS_NO_CLOCK_SAMPLER"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -171,6 +173,48 @@ class ClockSampler:
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
+
+
+class HostWatch:
+    """What happened to the HOST during a timed region: involuntary context switches of the timing thread
+    (it was descheduled), vCPU time stolen by the hypervisor (/proc/stat), load average."""
+
+    @staticmethod
+    def _steal():
+        try:
+            f = open("/proc/stat").readline().split()
+            return float(f[8]), float(sum(map(float, f[1:9])))
+        except Exception:
+            return 0.0, 0.0
+
+    def __init__(self):
+        import resource
+        self.res = resource
+        who = getattr(resource, "RUSAGE_THREAD", resource.RUSAGE_SELF)
+        self.who = who
+        self.ru0 = resource.getrusage(who)
+        self.st0 = self._steal()
+
+    def stop(self, timed_seconds):
+        ru = self.res.getrusage(self.who)
+        st = self._steal()
+        nivcsw = ru.ru_nivcsw - self.ru0.ru_nivcsw
+        dt = st[1] - self.st0[1]
+        steal = (st[0] - self.st0[0]) / dt if dt > 0 else 0.0
+        try:
+            load = float(open("/proc/loadavg").read().split()[0])
+        except Exception:
+            load = None
+        out = {"involuntary_context_switches_of_timing_thread": int(nivcsw), "steal_fraction": round(steal, 4),
+               "loadavg_1min": load, "cpus": os.cpu_count()}
+        why = []
+        # a descheduled thread loses a scheduler slice (milliseconds) per switch; the timed calls last ~0.1-1 ms
+        if nivcsw > 0 and nivcsw * 1e-3 > 0.05 * timed_seconds:
+            why.append(f"host:timing thread descheduled {nivcsw}x")
+        if steal > 0.02:
+            why.append(f"host:steal {steal:.3f}")
+        out["disturbed"] = why
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -629,32 +673,54 @@ def run_b200(a):
             first_hits = sh.debugLastHits().copy()
         drain()
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = sh.debugKernelLaunches()
-    hp0 = sh.debugHostPhases()
-    wall, dev_tables, dev_check, dev_total, hits, h2d, d2h = [], [], [], [], [], [], []
-    collapse_us = []
-    barrier()
-    for it in range(a.steps):
-        push_batch(sh, streams, a.slots, pool)
+    def timed_region():
+        """W warm-up steps are done; times exactly a.steps steps.  Also watches the HOST while it times: a thread
+        that was descheduled, or vCPU time stolen by the hypervisor, makes the wall-clock (e2e) number a
+        measurement of the neighbours, not of the path."""
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = sh.debugKernelLaunches()
+        hp0 = sh.debugHostPhases()
+        wall, dev_tables, dev_check, dev_total, hits, h2d, d2h = [], [], [], [], [], [], []
+        collapse_us = []
+        host0 = HostWatch()
         barrier()
-        t0 = time.perf_counter()
-        sh.gpuRun()                       # starts this batch's run (and gathers the empty run before it)
-        prev = sh.debugLastRunTimes()     # phases of the empty run: holds the deferred collapse of the previous batch
-        b1 = sh.debugLastRunBytes()
-        sh.gpuRun()                       # gathers it: hits are on the host, handed to the solver queues
-        dt = time.perf_counter() - t0
-        ph = sh.debugLastRunTimes()
-        wall.append(dt)
-        collapse_us.append(prev[1] if prev else 0.0)
-        dev_tables.append(ph[1]); dev_check.append(ph[2]); dev_total.append(ph[3])
-        hits.append(len(sh.debugLastHits()))
-        h2d.append(b1[0]); d2h.append(sh.debugLastRunBytes()[1])
-        drain()
-    launches = sh.debugKernelLaunches() - launches0
-    hp = [(b - a0) / a.steps for a0, b in zip(hp0, sh.debugHostPhases())]
-    clocks = sampler.stop()
+        for it in range(a.steps):
+            push_batch(sh, streams, a.slots, pool)
+            barrier()
+            t0 = time.perf_counter()
+            sh.gpuRun()                       # starts this batch's run (and gathers the empty run before it)
+            prev = sh.debugLastRunTimes()     # phases of the empty run: holds the deferred collapse of the previous batch
+            b1 = sh.debugLastRunBytes()
+            sh.gpuRun()                       # gathers it: hits are on the host, handed to the solver queues
+            dt = time.perf_counter() - t0
+            ph = sh.debugLastRunTimes()
+            wall.append(dt)
+            collapse_us.append(prev[1] if prev else 0.0)
+            dev_tables.append(ph[1]); dev_check.append(ph[2]); dev_total.append(ph[3])
+            hits.append(len(sh.debugLastHits()))
+            h2d.append(b1[0]); d2h.append(sh.debugLastRunBytes()[1])
+            drain()
+        host = host0.stop(sum(wall))
+        launches = sh.debugKernelLaunches() - launches0
+        hp = [(b - a0) / a.steps for a0, b in zip(hp0, sh.debugHostPhases())]
+        clocks = sampler.stop()
+        return dict(wall=wall, dev_tables=dev_tables, dev_check=dev_check, dev_total=dev_total, hits=hits, h2d=h2d, d2h=d2h,
+                    collapse_us=collapse_us, launches=launches, hp=hp, clocks=clocks, host=host)
+
+    # Re-measure ONCE when the region was disturbed -- the GPU throttled (contract) or the host thread lost its
+    # core (involuntary context switches of the timing thread / stolen vCPU time); both attempts are reported.
+    attempts = []
+    for attempt in range(2):
+        r = timed_region()
+        bad = [x for x in r["clocks"].get("reasons", []) if x != "sw_power_cap"]
+        r["rejected"] = (["gpu:" + x for x in bad] + r["host"]["disturbed"]) if attempt == 0 else []
+        attempts.append(r)
+        if not r["rejected"]:
+            break
+    r = attempts[-1]
+    wall, dev_tables, dev_check, dev_total, hits, h2d, d2h = (r[k] for k in ("wall", "dev_tables", "dev_check", "dev_total", "hits", "h2d", "d2h"))
+    collapse_us, launches, hp, clocks = r["collapse_us"], r["launches"], r["hp"], r["clocks"]
     # the collapse of batch k runs at the start of the following run: charge it to batch k
     sh.gpuRun()
     tail = sh.debugLastRunTimes()
@@ -679,11 +745,16 @@ def run_b200(a):
         "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload_config(a),
         "e2e": {"value": L_total * A * a.steps / wall_s, "unit": UNIT, "ms_per_step": 1e3 * wall_s / a.steps,
+                "ms_every_step": [round(1e3 * w, 3) for w in wall],
                 "h2d_bytes_per_step": int(np.mean(h2d)), "d2h_bytes_per_step": int(np.mean(d2h)),
                 "timed_region": "gss_gpu_run() x 2 per batch: collect (buffer swap), header H2D, k_apply_direct reading the deltas "
                                 "from page-locked host memory, check kernels, k_emit writing ids + literals into page-locked "
                                 "host memory, zero-copy hand-over to the solver queues"},
         "gpu_launches": int(launches), "clocks": clocks,
+        "host_during_timed_region": r["host"],
+        "remeasured": ([{"rejected_because": x["rejected"], "e2e_ms_per_step": 1e3 * sum(x["wall"]) / a.steps,
+                         "device_ms_per_step": 1e-3 * float(np.mean(x["dev_tables"]) + np.mean(x["dev_check"]))}
+                        for x in attempts[:-1]] or None),
         "hits_per_step": total_hits / a.steps,
         "phases_us_per_step": {"table_kernels": float(np.mean(dev_tables) + np.mean(collapse)),
                                "check_kernels": float(np.mean(dev_check)), "h2d_to_d2h_total": float(np.mean(dev_total))},

@@ -8,6 +8,7 @@
 #include <functional>
 #include <sstream>
 #include <string>
+#include <sys/resource.h>
 
 namespace gss {
 
@@ -113,8 +114,8 @@ struct HostProf {
     static constexpr int kMax = 32;
     struct Entry {
         const char *name;
-        double us;
-        long calls;
+        double us, maxUs;
+        long calls, ctxSwitches, pageFaults; // (of the calling thread, inside the scope: getrusage)
     };
     static bool enabled() {
         static const bool on = getenv("GSS_HOST_PROF") != nullptr;
@@ -126,34 +127,53 @@ struct HostProf {
         (void)registered;
         return t;
     }
-    static void add(const char *name, double us) {
+    static void add(const char *name, double us, long ctx, long faults) {
         Entry *t = table();
         for (int i = 0; i < kMax; i++) {
             if (!t[i].name) t[i].name = name;
             if (t[i].name == name) {
                 t[i].us += us;
+                t[i].maxUs = us > t[i].maxUs ? us : t[i].maxUs;
                 t[i].calls++;
+                t[i].ctxSwitches += ctx;
+                t[i].pageFaults += faults;
                 return;
             }
         }
     }
     static void reset() { // (bench: gss_debug_host_phases marks the start of a timed region)
         Entry *t = table();
-        for (int i = 0; i < kMax; i++) t[i].us = 0, t[i].calls = 0;
+        for (int i = 0; i < kMax; i++) t[i].us = t[i].maxUs = 0, t[i].calls = t[i].ctxSwitches = t[i].pageFaults = 0;
     }
     static void dump() {
         if (!enabled()) return;
         Entry *t = table();
         for (int i = 0; i < kMax && t[i].name; i++)
-            if (t[i].calls) fprintf(stderr, "host prof %-28s %9.2f us/call x %ld\n", t[i].name, t[i].us / (double)t[i].calls, t[i].calls);
+            if (t[i].calls)
+                fprintf(stderr, "host prof %-28s %9.2f us/call x %ld  (max %.1f us; %ld context switches, %ld page faults)\n", t[i].name,
+                        t[i].us / (double)t[i].calls, t[i].calls, t[i].maxUs, t[i].ctxSwitches, t[i].pageFaults);
     }
     const char *name;
     std::chrono::steady_clock::time_point t0;
+    long ctx0 = 0, flt0 = 0;
+    static void usage(long &ctx, long &flt) {
+        struct rusage ru;
+        getrusage(RUSAGE_THREAD, &ru);
+        ctx = ru.ru_nivcsw + ru.ru_nvcsw;
+        flt = ru.ru_minflt + ru.ru_majflt;
+    }
     explicit HostProf(const char *n) : name(n) {
-        if (enabled()) t0 = std::chrono::steady_clock::now();
+        if (enabled()) {
+            usage(ctx0, flt0);
+            t0 = std::chrono::steady_clock::now();
+        }
     }
     ~HostProf() {
-        if (enabled()) add(name, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+        if (!enabled()) return;
+        const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        long ctx, flt;
+        usage(ctx, flt);
+        add(name, us, ctx - ctx0, flt - flt0);
     }
 };
 

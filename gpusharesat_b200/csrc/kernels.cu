@@ -898,7 +898,7 @@ __global__ void __launch_bounds__(256) k_apply_direct(const VarUpdate *const *__
                                                       const SolverRunParams *__restrict__ params, DeviceTables t,
                                                       VarUpdate *__restrict__ keep, ApplyExtra x) {
     __shared__ uint32_t sAgg[kSlots], sSlot[kSlots];
-    __shared__ uint32_t sWords[3 * 256];
+    __shared__ __align__(16) uint32_t sWords[3 * 256];
     const int s = blockIdx.y;
     if (x.headWords | x.zeroAWords | x.zeroBWords) {
         const int nBlocks = gridDim.x * gridDim.y, me = blockIdx.y * gridDim.x + blockIdx.x;
@@ -920,12 +920,16 @@ __global__ void __launch_bounds__(256) k_apply_direct(const VarUpdate *const *__
     for (int c0 = blockIdx.x * 256; c0 < n; c0 += gridDim.x * 256) {
         const int cnt = min(256, n - c0), nw = 3 * cnt;
         __syncthreads();
-        for (int k = threadIdx.x; k < nw; k += 256) {
-            const uint32_t v = w[(size_t)3 * c0 + k];
-            sWords[k] = v;
-            kw[(size_t)3 * c0 + k] = v;
-        }
+        // (a chunk starts 3072 * k bytes into the solver's buffer: 16-byte loads whenever the buffers are
+        // aligned -- they are, page-locked allocations -- so that PCIe sees 512-byte requests per warp)
+        const uint32_t *cw = w + (size_t)3 * c0;
+        uint32_t *ck = kw + (size_t)3 * c0;
+        const int nv = ((uintptr_t)cw & 15) == 0 ? nw >> 2 : 0;
+        for (int k = threadIdx.x; k < nv; k += 256)
+            *reinterpret_cast<uint4 *>(sWords + 4 * k) = *reinterpret_cast<const uint4 *>(cw + 4 * k);
+        for (int k = 4 * nv + threadIdx.x; k < nw; k += 256) sWords[k] = cw[k];
         __syncthreads();
+        for (int k = threadIdx.x; k < nw; k += 256) ck[k] = sWords[k]; // (the kept copy starts wherever the solver's share starts)
         if ((int)threadIdx.x < cnt) {
             VarUpdate vu;
             vu.var = (int32_t)sWords[3 * threadIdx.x];
@@ -974,49 +978,90 @@ __device__ __forceinline__ int dirOfLen(const int *sLen, int nDir, int len) { //
 constexpr int kSortWarps = 8;        // buckets per block of k_emit_sort (a warp each)
 constexpr int kSortSmemRecs = 256;   // records per bucket sorted in shared memory
 
+// k_emit_scan, ONE block: where every (solver, bucket) list starts in the run's entry and literal streams =
+// the exclusive prefix over all the bucket counters in canonical order (solver-major).  Also what the
+// host wants to know about every solver (EmitSolver) and about overflows.  (Round-2 profile: with every
+// block of k_emit_sort adding up "all the counters before mine" the kernel read 4.3 M sectors and took 34 us.)
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) k_emit_scan(EmitArgs a) {
+    __shared__ long long sE[kScanThreads / 32], sL[kScanThreads / 32];
+    __shared__ unsigned int sMax[kScanThreads / 32], sOver[kScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int total = a.nSolvers * kRecBuckets;
+    const int per = (total + kScanThreads - 1) / kScanThreads;
+    const int t0 = min(total, tid * per), t1 = min(total, t0 + per);
+    const unsigned int bucketCap = a.recCap / kRecBuckets;
+    long long e = 0, l = 0;
+    unsigned int mx = 0, over = 0;
+    for (int t = t0; t < t1; t++) {
+        const unsigned long long ct = a.solverCtr[(size_t)t * kCtrStride];
+        const unsigned int nRaw = (unsigned int)ct;
+        e += min(nRaw, bucketCap);
+        l += (long long)(ct >> 32);
+        mx = max(mx, nRaw);
+        over |= nRaw > bucketCap ? 1u : 0u;
+    }
+    long long ie = e, il = l; // inclusive scan over the threads
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long ve = __shfl_up_sync(FULL, ie, o), vl = __shfl_up_sync(FULL, il, o);
+        if (lane >= o) { ie += ve; il += vl; }
+    }
+    mx = __reduce_max_sync(FULL, mx);
+    over = __reduce_or_sync(FULL, over);
+    if (lane == 31) { sE[wid] = ie; sL[wid] = il; }
+    if (lane == 0) { sMax[wid] = mx; sOver[wid] = over; }
+    __syncthreads();
+    long long be = 0, bl = 0;
+    for (int w = 0; w < wid; w++) { be += sE[w]; bl += sL[w]; }
+    long long re = be + ie - e, rl = bl + il - l; // exclusive prefix of this thread's first counter
+    for (int t = t0; t < t1; t++) {
+        a.bucketBase[2 * (size_t)t] = re;
+        a.bucketBase[2 * (size_t)t + 1] = rl;
+        const unsigned long long ct = a.solverCtr[(size_t)t * kCtrStride];
+        re += min((unsigned int)ct, bucketCap);
+        rl += (long long)(ct >> 32);
+    }
+    if (t0 < total && t1 == total) { // the end of the last list = the totals
+        a.bucketBase[2 * (size_t)total] = re;
+        a.bucketBase[2 * (size_t)total + 1] = rl;
+    }
+    __syncthreads();
+    // per solver: totals, does it fit the result buffer
+    for (int sv = tid; sv < a.nSolvers; sv += kScanThreads) {
+        const long long eS = a.bucketBase[2 * (size_t)sv * kRecBuckets], lS = a.bucketBase[2 * (size_t)sv * kRecBuckets + 1];
+        const long long nS = a.bucketBase[2 * (size_t)(sv + 1) * kRecBuckets] - eS;
+        const long long litsS = a.bucketBase[2 * (size_t)(sv + 1) * kRecBuckets + 1] - lS;
+        a.recPos[(size_t)sv * (a.recCap + 1) + nS] = (int32_t)litsS;
+        EmitSolver &es = a.solverInfo[sv];
+        es.entryBase = eS;
+        es.litBase = lS;
+        es.nLits = (int32_t)litsS;
+        es.nSorted = (uint32_t)nS;
+        es.n = (eS + nS <= a.entryCap && lS + litsS <= a.litCap) ? (int32_t)nS : -1;
+        if (es.n < 0) atomicOr(a.ticket + 1, 4u);
+    }
+    if (tid == 0) {
+        unsigned int m = 0, o = 0;
+        for (int w = 0; w < kScanThreads / 32; w++) { m = max(m, sMax[w]); o |= sOver[w]; }
+        if (o) atomicOr(a.ticket + 1, 2u);
+        atomicMax(a.ticket + 2, m); // (x kRecBuckets = what recCap would have had to be)
+    }
+}
+
 // grid = (kRecBuckets / kSortWarps, solvers); warp w of block (x, s) owns bucket x * kSortWarps + w of solver s
 __global__ void __launch_bounds__(kSortWarps * 32) k_emit_sort(EmitArgs a) {
     __shared__ unsigned long long sK[kSortWarps][kSortSmemRecs];
     __shared__ uint32_t sM[kSortWarps][kSortSmemRecs];
-    __shared__ long long sRed[2][kSortWarps];
     const int s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int bucket = blockIdx.x * kSortWarps + wid;
     const unsigned int bucketCap = a.recCap / kRecBuckets;
     auto ctrOf = [&](int solver, int b) { return a.solverCtr[((size_t)solver * kRecBuckets + b) * kCtrStride]; };
-
-    // Where this block's first bucket starts in the solver's sorted list and in the literal stream, and
-    // where the solver starts in the run's streams: sums over the counters before it (the whole block adds).
-    const int firstBucket = blockIdx.x * kSortWarps;
-    long long eSolver = 0, lSolver = 0, eBucket = 0, lBucket = 0; // before this solver / before this block's first bucket
-    for (int t = tid; t < s * kRecBuckets + firstBucket; t += blockDim.x) {
-        const unsigned long long ct = a.solverCtr[(size_t)t * kCtrStride];
-        const long long e = min((unsigned int)ct, bucketCap), l = (long long)(ct >> 32);
-        if (t < s * kRecBuckets) { eSolver += e; lSolver += l; } else { eBucket += e; lBucket += l; }
-    }
-    // (one bucket with more than kSortSmemRecs records sorts in global memory and decides the kernel's
-    // duration -- 64 buckets of ~70 records with a few of 300 took 53 us at config 3; 256 buckets keep them small)
-    auto blockSum = [&](long long v, int slot) -> long long {
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        __syncthreads();
-        if (lane == 0) sRed[slot & 1][wid] = v;
-        __syncthreads();
-        long long r = 0;
-        for (int w = 0; w < kSortWarps; w++) r += sRed[slot & 1][w];
-        return r;
-    };
-    eSolver = blockSum(eSolver, 0);
-    lSolver = blockSum(lSolver, 1);
-    eBucket = blockSum(eBucket, 0);
-    lBucket = blockSum(lBucket, 1);
-    // the buckets of this block before this warp's
-    for (int w = 0; w < wid; w++) {
-        const unsigned long long ct = ctrOf(s, firstBucket + w);
-        eBucket += min((unsigned int)ct, bucketCap);
-        lBucket += (long long)(ct >> 32);
-    }
+    // where this bucket starts in the solver's sorted list and in its literal stream (k_emit_scan)
+    const size_t me = (size_t)s * kRecBuckets + bucket;
+    const long long eBucket = a.bucketBase[2 * me] - a.bucketBase[2 * (size_t)s * kRecBuckets];
+    const long long lBucket = a.bucketBase[2 * me + 1] - a.bucketBase[2 * (size_t)s * kRecBuckets + 1];
     const unsigned long long mine = ctrOf(s, bucket);
     const unsigned int nRaw = (unsigned int)mine, n = min(nRaw, bucketCap);
-    const long long nLits = (long long)(mine >> 32);
 
     // sort this bucket by (length, index): bitonic network, one warp; in shared memory when it fits,
     // else in place in the bucket's own storage (P <= bucketCap, a power of two)
@@ -1073,23 +1118,6 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_emit_sort(EmitArgs a) {
             oPos[i] = (int32_t)(run + incl - len);
         }
         run += __shfl_sync(FULL, incl, 31);
-    }
-    const bool lastBucket = bucket == kRecBuckets - 1;
-    if (lane == 0) {
-        if (lastBucket) {
-            // totals of this solver = what lies before its last bucket + that bucket
-            const long long nSolver = eBucket + n, litsSolver = lBucket + nLits;
-            a.recPos[(size_t)s * (a.recCap + 1) + nSolver] = (int32_t)litsSolver;
-            EmitSolver &es = a.solverInfo[s];
-            es.entryBase = eSolver;
-            es.litBase = lSolver;
-            es.nLits = (int32_t)litsSolver;
-            es.nSorted = (uint32_t)nSolver;
-            es.n = (eSolver + nSolver <= a.entryCap && lSolver + litsSolver <= a.litCap) ? (int32_t)nSolver : -1;
-            if (es.n < 0) atomicOr(a.ticket + 1, 4u);
-        }
-        if (nRaw > bucketCap) atomicOr(a.ticket + 1, 2u);
-        atomicMax(a.ticket + 2, nRaw); // (x kRecBuckets = what recCap would have had to be)
     }
 }
 
@@ -1611,12 +1639,13 @@ void launchApplyDirect(const VarUpdate *const *src, const SolverRunParams *param
 
 void launchEmit(const EmitArgs &a, cudaStream_t s, int64_t *launches) {
     if (a.nSolvers <= 0) return;
+    k_emit_scan<<<1, kScanThreads, 0, s>>>(a);
     k_emit_sort<<<dim3(kRecBuckets / kSortWarps, a.nSolvers, 1), kSortWarps * 32, 0, s>>>(a);
     // enough writers for PCIe: the blocks of a solver take chunks of its entries in turn
     const unsigned int perSolver = std::max(1u, std::min(64u, 1184u / (unsigned int)a.nSolvers));
     k_emit_write<<<dim3(perSolver, a.nSolvers, 1), 256, 0, s>>>(a);
     checkLaunch("k_emit");
-    *launches += 2;
+    *launches += 3;
 }
 
 __global__ void k_bump_keys(const unsigned long long *__restrict__ keys, long long n, const LenDir *__restrict__ dir, int nDir,

@@ -200,6 +200,7 @@ struct EmitArgs {
     unsigned long long *sortKeys; // [solver][recCap]: the solver's records in canonical order
     uint32_t *sortMasks;
     int32_t *recPos;             // [solver][recCap + 1] literal positions of the sorted list
+    long long *bucketBase;       // [nSolvers * kRecBuckets + 1][2]: entries / literals before every (solver, bucket) list (k_emit_scan)
     EmitSolver *solverInfo;      // [solver]
     unsigned int recCap;         // power of two
     Counters *counters;

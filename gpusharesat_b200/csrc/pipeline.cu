@@ -103,11 +103,13 @@ void Sharer::ensureDirectBuffers(RunSlot &slot) {
         GSS_CUDA(cudaMemsetAsync(slot.ticketDev.data(), 0, 4 * sizeof(unsigned int), stream_));
     }
     slot.recCap = (unsigned int)recCap_;
+    HostProf hpR("    edb: reserves");
     slot.recKeys.reserve(S * recCap_, 0, stream_);
     slot.recMasks.reserve(S * recCap_, 0, stream_);
     slot.sortKeys.reserve(S * recCap_, 0, stream_);
     slot.sortMasks.reserve(S * recCap_, 0, stream_);
     slot.recPos.reserve(S * (recCap_ + 1), 0, stream_);
+    slot.bucketBase.reserve(2 * (S * kRecBuckets + 1), 0, stream_);
     survDev_.reserve((size_t)std::max(1, tables_.nGroups) * survCap_, 0, stream_);
     resDev_.reserve(sizeof(Counters) + hitCap_ * sizeof(HitRecord), 0, stream_);
 }
@@ -182,14 +184,20 @@ void Sharer::launchDirect(RunSlot &slot, int64_t h2d) {
     HostProf hpAll("launchDirect");
     slot.direct = true;
     slot.dense = false;
-    slot.updDev.reserve((size_t)std::max<int64_t>(slot.nUpdates, 1), 0, stream_);
+    {
+        HostProf hp("  updDev reserve");
+        slot.updDev.reserve((size_t)std::max<int64_t>(slot.nUpdates, 1), 0, stream_);
+    }
     for (auto &st : slot.staged) { // deltas that are not in page-locked memory go up as ordinary copies
         const int s = st.first;
         VarUpdate *dst = slot.updDev.data() + params[s].updStart;
         GSS_CUDA(cudaMemcpyAsync(dst, st.second, (size_t)params[s].updCount * sizeof(VarUpdate), cudaMemcpyHostToDevice, stream_));
         src[s] = dst;
     }
-    slot.headDev.reserve(slot.headHost.size(), 0, stream_);
+    {
+        HostProf hp("  headDev reserve");
+        slot.headDev.reserve(slot.headHost.size(), 0, stream_);
+    }
     // The run header travels inside the first kernel (k_apply_direct reads it from page-locked host memory and
     // leaves the device copy behind) and the same kernel zeroes the run's counters; only a header that is not
     // page-locked goes up as an ordinary copy.
@@ -203,7 +211,10 @@ void Sharer::launchDirect(RunSlot &slot, int64_t h2d) {
         HostProf hp("  ensureDirectBuffers");
         ensureDirectBuffers(slot);
     }
-    GSS_CUDA(cudaEventRecord(slot.evH2DDone, stream_));
+    {
+        HostProf hp("  event record");
+        GSS_CUDA(cudaEventRecord(slot.evH2DDone, stream_));
+    }
 
     // the previous batch collapses to its last slot first (deferred dSetAllAssigsToLast)
     if (collapseSlot_ >= 0) {
@@ -212,7 +223,12 @@ void Sharer::launchDirect(RunSlot &slot, int64_t h2d) {
         launchCollapse(c.updDev.data(), c.paramsDev(), c.nSolvers, c.maxUpd, c.nUpdates, tables_, numSMs_, stream_, &launches_);
         collapseSlot_ = -1;
     }
-    {
+    // A run with nothing new -- no delta, no frozen assignment (a GPU thread that calls gpuRun() faster than the
+    // solvers export) -- has nothing to apply and nothing to check: only the deferred collapse above was due.
+    bool anyFrozen = false;
+    for (uint32_t g : slot.aggStart) anyFrozen = anyFrozen || g != 0;
+    const bool idleRun = slot.nUpdates == 0 && !anyFrozen && slot.staged.empty();
+    if (!idleRun) {
         HostProf hp("  launch apply");
         ApplyExtra x;
         const uint8_t *head = slot.headDev.data();
@@ -302,6 +318,7 @@ void Sharer::launchEmitFor(RunSlot &slot) {
     e.sortKeys = slot.sortKeys.data();
     e.sortMasks = slot.sortMasks.data();
     e.recPos = slot.recPos.data();
+    e.bucketBase = slot.bucketBase.data();
     e.solverInfo = slot.solverInfo.data();
     e.recCap = slot.recCap;
     e.counters = (Counters *)resDev_.data();
