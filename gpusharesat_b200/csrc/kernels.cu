@@ -158,6 +158,28 @@ template <typename T> struct WarpStage {
         __syncwarp();
         n = 0;
     }
+    // every lane contributes up to four records (r0..r3, quarter after quarter): four ballots, ONE capacity check
+    __device__ __forceinline__ void push4(bool h0, bool h1, bool h2, bool h3, const T &r0, const T &r1, const T &r2, const T &r3, T *out,
+                                          unsigned int *counter, unsigned int cap, int lane) {
+        const unsigned m0 = __ballot_sync(FULL, h0), m1 = __ballot_sync(FULL, h1), m2 = __ballot_sync(FULL, h2), m3 = __ballot_sync(FULL, h3);
+        const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
+        const int cnt = c0 + c1 + c2 + c3;
+        if (cnt == 0) return;
+        if (cnt > kStageCap) { // (more than the stage holds: the plain path, one quarter at a time)
+            push(h0, r0, out, counter, cap, lane);
+            push(h1, r1, out, counter, cap, lane);
+            push(h2, r2, out, counter, cap, lane);
+            push(h3, r3, out, counter, cap, lane);
+            return;
+        }
+        if (n + cnt > kStageCap) flush(out, counter, cap, lane);
+        const unsigned below = (1u << lane) - 1;
+        if (h0) buf[n + __popc(m0 & below)] = r0;
+        if (h1) buf[n + c0 + __popc(m1 & below)] = r1;
+        if (h2) buf[n + c0 + c1 + __popc(m2 & below)] = r2;
+        if (h3) buf[n + c0 + c1 + c2 + __popc(m3 & below)] = r3;
+        n += cnt;
+    }
     // every lane contributes at most one record
     __device__ __forceinline__ void push(bool has, const T &rec, T *out, unsigned int *counter, unsigned int cap, int lane) {
         const unsigned m = __ballot_sync(FULL, has);
@@ -199,7 +221,7 @@ __device__ __forceinline__ int findDir(const int *sTileEnd, int nDir, int tile) 
 //   CONTIG    0: a warp takes every nWarps-th tile; 1: a contiguous run of tiles per warp; 2: a
 //             contiguous run per block, the block's warps interleaved inside it
 //   ROWMODE   literal rows: 0 = ld.global.cs (evict-first), 1 = ld.global.L1::no_allocate
-//   GMODE     level-1 gathers: 0 = ld.global.nc (L1 + L2), 1 = ld.global.cg (L2 only)
+//   GMODE     level-1 gathers: 0 = ld.global.nc (L1 + L2), 1 = ld.global.cg (L2 only), 2 = 0 + lean addressing / staging
 template <int ROWMODE> __device__ __forceinline__ int4 ldRow(const int32_t *p) {
     if constexpr (ROWMODE == 0) {
         return __ldcs(reinterpret_cast<const int4 *>(p));
@@ -212,8 +234,8 @@ template <int ROWMODE> __device__ __forceinline__ int4 ldRow(const int32_t *p) {
     }
 }
 template <int GMODE> __device__ __forceinline__ uint2 ldGather(const uint2 *p) {
-    if constexpr (GMODE == 0) return __ldg(p);
-    else return __ldcg(p);
+    if constexpr (GMODE == 1) return __ldcg(p);
+    else return __ldg(p);
 }
 
 template <bool PREFETCH, int CONTIG, int ROWMODE, int GMODE, int MINBLOCKS>
@@ -226,7 +248,11 @@ __global__ void __launch_bounds__(256, MINBLOCKS) k_filter_t(CheckArgs a) {
     const int warpsPerBlock = blockDim.x >> 5;
     const int warp = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
     const int nWarps = gridDim.x * warpsPerBlock;
-    const uint2 *__restrict__ a1 = a.tables.a1 + (size_t)(a.groupBase / kMaxSolversPerGroup) * 2 * (size_t)a.tables.varCap;
+    const uint2 *a1 = a.tables.a1 + (size_t)(a.groupBase / kMaxSolversPerGroup) * 2 * (size_t)a.tables.varCap;
+    // GMODE 2 ("lean"): the group's table base is made opaque to the compiler, so that it stays ONE 64-bit register
+    // pair and a gather address is one IMAD.WIDE.U32 (left to itself the compiler re-adds the group offset to every
+    // literal: 4-5 instructions per gather, 16-20 of the ~64 of a row step); survivors are staged with one push4
+    if constexpr (GMODE == 2) asm volatile("" : "+l"(a1));
     const uint32_t start = groupAggStart(a, lane);
     if (start == 0) return; // no frozen slot in this group
     __shared__ Survivor sStage[kMaxWarpsPerBlock][kStageCap];
@@ -298,10 +324,18 @@ __global__ void __launch_bounds__(256, MINBLOCKS) k_filter_t(CheckArgs a) {
             // a dead clause stays dead: gather only for the live ones (every gather costs a 32 B
             // L2 sector, and after the first literal ~97 % of the clauses are dead)
             const uint2 dead = make_uint2(0u, 0u);
-            uint2 g0 = (all0 | one0) ? ldGather<GMODE>(a1 + lits.x) : dead;
-            uint2 g1 = (all1 | one1) ? ldGather<GMODE>(a1 + lits.y) : dead;
-            uint2 g2 = (all2 | one2) ? ldGather<GMODE>(a1 + lits.z) : dead;
-            uint2 g3 = (all3 | one3) ? ldGather<GMODE>(a1 + lits.w) : dead;
+            uint2 g0, g1, g2, g3;
+            if constexpr (GMODE == 2) { // (a literal is never negative: unsigned index = no sign extension)
+                g0 = (all0 | one0) ? ldGather<GMODE>(a1 + (uint32_t)lits.x) : dead;
+                g1 = (all1 | one1) ? ldGather<GMODE>(a1 + (uint32_t)lits.y) : dead;
+                g2 = (all2 | one2) ? ldGather<GMODE>(a1 + (uint32_t)lits.z) : dead;
+                g3 = (all3 | one3) ? ldGather<GMODE>(a1 + (uint32_t)lits.w) : dead;
+            } else {
+                g0 = (all0 | one0) ? ldGather<GMODE>(a1 + lits.x) : dead;
+                g1 = (all1 | one1) ? ldGather<GMODE>(a1 + lits.y) : dead;
+                g2 = (all2 | one2) ? ldGather<GMODE>(a1 + lits.z) : dead;
+                g3 = (all3 | one3) ? ldGather<GMODE>(a1 + lits.w) : dead;
+            }
             step(all0, one0, g0.x, g0.y);
             step(all1, one1, g1.x, g1.y);
             step(all2, one2, g2.x, g2.y);
@@ -315,10 +349,16 @@ __global__ void __launch_bounds__(256, MINBLOCKS) k_filter_t(CheckArgs a) {
             const uint64_t rowTag = (uint64_t)(uintptr_t)row | ((uint64_t)len << 48);
             const int c0 = cur.c0;
             const uint32_t m0 = all0 | one0, m1 = all1 | one1, m2 = all2 | one2, m3 = all3 | one3;
-            stage.push(m0 != 0, Survivor{rowTag + 0 * sizeof(int32_t), c0 + 0, m0}, a.survivors, survCounter, a.survCap, lane);
-            stage.push(m1 != 0, Survivor{rowTag + 1 * sizeof(int32_t), c0 + 32, m1}, a.survivors, survCounter, a.survCap, lane);
-            stage.push(m2 != 0, Survivor{rowTag + 2 * sizeof(int32_t), c0 + 64, m2}, a.survivors, survCounter, a.survCap, lane);
-            stage.push(m3 != 0, Survivor{rowTag + 3 * sizeof(int32_t), c0 + 96, m3}, a.survivors, survCounter, a.survCap, lane);
+            if constexpr (GMODE == 2) {
+                stage.push4(m0 != 0, m1 != 0, m2 != 0, m3 != 0, Survivor{rowTag + 0 * sizeof(int32_t), c0 + 0, m0},
+                            Survivor{rowTag + 1 * sizeof(int32_t), c0 + 32, m1}, Survivor{rowTag + 2 * sizeof(int32_t), c0 + 64, m2},
+                            Survivor{rowTag + 3 * sizeof(int32_t), c0 + 96, m3}, a.survivors, survCounter, a.survCap, lane);
+            } else {
+                stage.push(m0 != 0, Survivor{rowTag + 0 * sizeof(int32_t), c0 + 0, m0}, a.survivors, survCounter, a.survCap, lane);
+                stage.push(m1 != 0, Survivor{rowTag + 1 * sizeof(int32_t), c0 + 32, m1}, a.survivors, survCounter, a.survCap, lane);
+                stage.push(m2 != 0, Survivor{rowTag + 2 * sizeof(int32_t), c0 + 64, m2}, a.survivors, survCounter, a.survCap, lane);
+                stage.push(m3 != 0, Survivor{rowTag + 3 * sizeof(int32_t), c0 + 96, m3}, a.survivors, survCounter, a.survCap, lane);
+            }
         }
     };
     auto following = [&](const Tile &t, int tile) -> Tile { // the tile this warp takes after `tile`
@@ -533,6 +573,9 @@ const FilterVariant kFilterVariants[] = {
     {k_filter_tma_t<5>, 256, "rows 0-1 by TMA bulk copies into a per-warp ring (4 tiles ahead), 5 x 256", kRing *(kRingSlotBytes + 8)},
     {k_filter_tma_t<6>, 256, "TMA ring, 6 x 256", kRing *(kRingSlotBytes + 8)},
     {k_filter_tma_t<4>, 256, "TMA ring, 4 x 256", kRing *(kRingSlotBytes + 8)},
+    {k_filter_t<false, 1, 0, 2, 5>, 256, "contiguous per warp, lean (one-instruction gather addresses, one push4), 5 x 256"},
+    {k_filter_t<false, 1, 0, 2, 4>, 256, "contiguous per warp, lean, 4 x 256"},
+    {k_filter_t<true, 1, 0, 2, 4>, 256, "contiguous per warp + ping-pong prefetch, lean, 4 x 256"},
 };
 constexpr int kNumFilterVariants = (int)(sizeof(kFilterVariants) / sizeof(kFilterVariants[0]));
 int gFilterVariant = -1; // -1: not chosen yet (GSS_FILTER_VARIANT or the default)
@@ -978,74 +1021,85 @@ __device__ __forceinline__ int dirOfLen(const int *sLen, int nDir, int len) { //
 constexpr int kSortWarps = 8;        // buckets per block of k_emit_sort (a warp each)
 constexpr int kSortSmemRecs = 256;   // records per bucket sorted in shared memory
 
-// k_emit_scan, ONE block: where every (solver, bucket) list starts in the run's entry and literal streams =
-// the exclusive prefix over all the bucket counters in canonical order (solver-major).  Also what the
-// host wants to know about every solver (EmitSolver) and about overflows.  (Round-2 profile: with every
-// block of k_emit_sort adding up "all the counters before mine" the kernel read 4.3 M sectors and took 34 us.)
-constexpr int kScanThreads = 1024;
-__global__ void __launch_bounds__(kScanThreads) k_emit_scan(EmitArgs a) {
-    __shared__ long long sE[kScanThreads / 32], sL[kScanThreads / 32];
-    __shared__ unsigned int sMax[kScanThreads / 32], sOver[kScanThreads / 32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int total = a.nSolvers * kRecBuckets;
-    const int per = (total + kScanThreads - 1) / kScanThreads;
-    const int t0 = min(total, tid * per), t1 = min(total, t0 + per);
+// k_emit_scan, one block per solver, a thread per bucket: where every bucket's list starts in its solver's sorted list
+// and literal stream (exclusive prefix over the solver's bucket counters); the block that finishes last adds up the
+// solvers (where a solver starts in the run's streams, does it fit the result buffer: EmitSolver) and the overflow
+// flags.  (Round-2 profile: with every block of k_emit_sort adding up "all the counters before mine" that kernel read
+// 4.3 M sectors and took 34 us; a single-block scan over all the counters took 26 us -- three dependent global round
+// trips by one block.)
+__global__ void __launch_bounds__(kRecBuckets) k_emit_scan(EmitArgs a) {
+    __shared__ long long sE[kRecBuckets / 32], sL[kRecBuckets / 32];
+    __shared__ unsigned int sMax[kRecBuckets / 32], sOver[kRecBuckets / 32];
+    __shared__ bool sLast;
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned int bucketCap = a.recCap / kRecBuckets;
-    long long e = 0, l = 0;
-    unsigned int mx = 0, over = 0;
-    for (int t = t0; t < t1; t++) {
-        const unsigned long long ct = a.solverCtr[(size_t)t * kCtrStride];
-        const unsigned int nRaw = (unsigned int)ct;
-        e += min(nRaw, bucketCap);
-        l += (long long)(ct >> 32);
-        mx = max(mx, nRaw);
-        over |= nRaw > bucketCap ? 1u : 0u;
-    }
-    long long ie = e, il = l; // inclusive scan over the threads
-    for (int o = 1; o < 32; o <<= 1) {
-        const long long ve = __shfl_up_sync(FULL, ie, o), vl = __shfl_up_sync(FULL, il, o);
-        if (lane >= o) { ie += ve; il += vl; }
-    }
-    mx = __reduce_max_sync(FULL, mx);
-    over = __reduce_or_sync(FULL, over);
-    if (lane == 31) { sE[wid] = ie; sL[wid] = il; }
+    long long *const solverTot = a.bucketBase + 2 * (size_t)a.nSolvers * kRecBuckets; // [solver][2]
+    const size_t me = (size_t)s * kRecBuckets + tid;
+    const unsigned long long ct = a.solverCtr[me * kCtrStride];
+    const unsigned int nRaw = (unsigned int)ct;
+    const long long e = min(nRaw, bucketCap), l = (long long)(ct >> 32);
+    auto blockExclusive = [&](long long ve, long long vl, long long &outE, long long &outL, long long &totE, long long &totL) {
+        long long ie = ve, il = vl;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long xe = __shfl_up_sync(FULL, ie, o), xl = __shfl_up_sync(FULL, il, o);
+            if (lane >= o) { ie += xe; il += xl; }
+        }
+        __syncthreads();
+        if (lane == 31) { sE[wid] = ie; sL[wid] = il; }
+        __syncthreads();
+        long long be = 0, bl = 0;
+        totE = totL = 0;
+        for (int w = 0; w < kRecBuckets / 32; w++) {
+            if (w < wid) { be += sE[w]; bl += sL[w]; }
+            totE += sE[w];
+            totL += sL[w];
+        }
+        outE = be + ie - ve;
+        outL = bl + il - vl;
+    };
+    long long exE, exL, totE, totL;
+    blockExclusive(e, l, exE, exL, totE, totL);
+    a.bucketBase[2 * me] = exE;
+    a.bucketBase[2 * me + 1] = exL;
+    const unsigned int mx = __reduce_max_sync(FULL, nRaw), over = __reduce_or_sync(FULL, nRaw > bucketCap ? 1u : 0u);
     if (lane == 0) { sMax[wid] = mx; sOver[wid] = over; }
     __syncthreads();
-    long long be = 0, bl = 0;
-    for (int w = 0; w < wid; w++) { be += sE[w]; bl += sL[w]; }
-    long long re = be + ie - e, rl = bl + il - l; // exclusive prefix of this thread's first counter
-    for (int t = t0; t < t1; t++) {
-        a.bucketBase[2 * (size_t)t] = re;
-        a.bucketBase[2 * (size_t)t + 1] = rl;
-        const unsigned long long ct = a.solverCtr[(size_t)t * kCtrStride];
-        re += min((unsigned int)ct, bucketCap);
-        rl += (long long)(ct >> 32);
-    }
-    if (t0 < total && t1 == total) { // the end of the last list = the totals
-        a.bucketBase[2 * (size_t)total] = re;
-        a.bucketBase[2 * (size_t)total + 1] = rl;
-    }
-    __syncthreads();
-    // per solver: totals, does it fit the result buffer
-    for (int sv = tid; sv < a.nSolvers; sv += kScanThreads) {
-        const long long eS = a.bucketBase[2 * (size_t)sv * kRecBuckets], lS = a.bucketBase[2 * (size_t)sv * kRecBuckets + 1];
-        const long long nS = a.bucketBase[2 * (size_t)(sv + 1) * kRecBuckets] - eS;
-        const long long litsS = a.bucketBase[2 * (size_t)(sv + 1) * kRecBuckets + 1] - lS;
-        a.recPos[(size_t)sv * (a.recCap + 1) + nS] = (int32_t)litsS;
-        EmitSolver &es = a.solverInfo[sv];
-        es.entryBase = eS;
-        es.litBase = lS;
-        es.nLits = (int32_t)litsS;
-        es.nSorted = (uint32_t)nS;
-        es.n = (eS + nS <= a.entryCap && lS + litsS <= a.litCap) ? (int32_t)nS : -1;
-        if (es.n < 0) atomicOr(a.ticket + 1, 4u);
-    }
     if (tid == 0) {
         unsigned int m = 0, o = 0;
-        for (int w = 0; w < kScanThreads / 32; w++) { m = max(m, sMax[w]); o |= sOver[w]; }
+        for (int w = 0; w < kRecBuckets / 32; w++) { m = max(m, sMax[w]); o |= sOver[w]; }
         if (o) atomicOr(a.ticket + 1, 2u);
         atomicMax(a.ticket + 2, m); // (x kRecBuckets = what recCap would have had to be)
+        solverTot[2 * s] = totE;
+        solverTot[2 * s + 1] = totL;
+        a.recPos[(size_t)s * (a.recCap + 1) + totE] = (int32_t)totL; // the position behind the solver's last entry
+        __threadfence();
+        sLast = atomicAdd(a.ticket + 3, 1u) == gridDim.x - 1;
     }
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+    // the last block: the solvers one after the other in the run's entry and literal streams
+    long long carryE = 0, carryL = 0;
+    for (int base = 0; base < a.nSolvers; base += kRecBuckets) {
+        const int sv = base + tid;
+        const long long nS = sv < a.nSolvers ? __ldcg(solverTot + 2 * sv) : 0, litsS = sv < a.nSolvers ? __ldcg(solverTot + 2 * sv + 1) : 0;
+        long long eS, lS, tE, tL;
+        blockExclusive(nS, litsS, eS, lS, tE, tL);
+        eS += carryE;
+        lS += carryL;
+        if (sv < a.nSolvers) {
+            EmitSolver &es = a.solverInfo[sv];
+            es.entryBase = eS;
+            es.litBase = lS;
+            es.nLits = (int32_t)litsS;
+            es.nSorted = (uint32_t)nS;
+            es.n = (eS + nS <= a.entryCap && lS + litsS <= a.litCap) ? (int32_t)nS : -1;
+            if (es.n < 0) atomicOr(a.ticket + 1, 4u);
+        }
+        carryE += tE;
+        carryL += tL;
+    }
+    if (tid == 0) a.ticket[3] = 0u;
 }
 
 // grid = (kRecBuckets / kSortWarps, solvers); warp w of block (x, s) owns bucket x * kSortWarps + w of solver s
@@ -1058,8 +1112,7 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_emit_sort(EmitArgs a) {
     auto ctrOf = [&](int solver, int b) { return a.solverCtr[((size_t)solver * kRecBuckets + b) * kCtrStride]; };
     // where this bucket starts in the solver's sorted list and in its literal stream (k_emit_scan)
     const size_t me = (size_t)s * kRecBuckets + bucket;
-    const long long eBucket = a.bucketBase[2 * me] - a.bucketBase[2 * (size_t)s * kRecBuckets];
-    const long long lBucket = a.bucketBase[2 * me + 1] - a.bucketBase[2 * (size_t)s * kRecBuckets + 1];
+    const long long eBucket = a.bucketBase[2 * me], lBucket = a.bucketBase[2 * me + 1];
     const unsigned long long mine = ctrOf(s, bucket);
     const unsigned int nRaw = (unsigned int)mine, n = min(nRaw, bucketCap);
 
@@ -1639,7 +1692,7 @@ void launchApplyDirect(const VarUpdate *const *src, const SolverRunParams *param
 
 void launchEmit(const EmitArgs &a, cudaStream_t s, int64_t *launches) {
     if (a.nSolvers <= 0) return;
-    k_emit_scan<<<1, kScanThreads, 0, s>>>(a);
+    k_emit_scan<<<a.nSolvers, kRecBuckets, 0, s>>>(a);
     k_emit_sort<<<dim3(kRecBuckets / kSortWarps, a.nSolvers, 1), kSortWarps * 32, 0, s>>>(a);
     // enough writers for PCIe: the blocks of a solver take chunks of its entries in turn
     const unsigned int perSolver = std::max(1u, std::min(64u, 1184u / (unsigned int)a.nSolvers));
@@ -1696,10 +1749,10 @@ void launchFilterOnly(const CheckArgs &a, LaunchDims dims, int numSMs, cudaStrea
     int warpsPerBlock = threads / 32;
     size_t smem = (size_t)a.nDir * sizeof(int) + (size_t)fv.ringBytesPerWarp * warpsPerBlock;
     if (fv.ringBytesPerWarp) { // the ring needs the large shared-memory carve-out (L1 hit rate of this kernel: 3 %)
-        static bool configured[64][16] = {};
+        static bool configured[64][32] = {};
         int dev = 0;
         GSS_CUDA(cudaGetDevice(&dev));
-        if (dev >= 0 && dev < 64 && gFilterVariant < 16 && !configured[dev][gFilterVariant]) {
+        if (dev >= 0 && dev < 64 && gFilterVariant < 32 && !configured[dev][gFilterVariant]) {
             GSS_CUDA(cudaFuncSetAttribute((const void *)fv.kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             GSS_CUDA(cudaFuncSetAttribute((const void *)fv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             configured[dev][gFilterVariant] = true;

@@ -200,13 +200,13 @@ struct EmitArgs {
     unsigned long long *sortKeys; // [solver][recCap]: the solver's records in canonical order
     uint32_t *sortMasks;
     int32_t *recPos;             // [solver][recCap + 1] literal positions of the sorted list
-    long long *bucketBase;       // [nSolvers * kRecBuckets + 1][2]: entries / literals before every (solver, bucket) list (k_emit_scan)
+    long long *bucketBase;       // [nSolvers * kRecBuckets][2]: entries / literals of the solver before every bucket's list, then [nSolvers][2] totals (k_emit_scan)
     EmitSolver *solverInfo;      // [solver]
     unsigned int recCap;         // power of two
     Counters *counters;
     unsigned int survCap;
     int groups;
-    unsigned int *ticket;        // finished-block counter + flag word (2 x uint32)
+    unsigned int *ticket;        // [0] finished blocks of k_emit_write, [1] flag word, [2] fullest bucket, [3] finished blocks of k_emit_scan
     uint32_t seq;
     // result buffer in mapped pinned host memory
     RunHdr *hdr;

@@ -109,7 +109,7 @@ void Sharer::ensureDirectBuffers(RunSlot &slot) {
     slot.sortKeys.reserve(S * recCap_, 0, stream_);
     slot.sortMasks.reserve(S * recCap_, 0, stream_);
     slot.recPos.reserve(S * (recCap_ + 1), 0, stream_);
-    slot.bucketBase.reserve(2 * (S * kRecBuckets + 1), 0, stream_);
+    slot.bucketBase.reserve(2 * (S * kRecBuckets + S), 0, stream_);
     survDev_.reserve((size_t)std::max(1, tables_.nGroups) * survCap_, 0, stream_);
     resDev_.reserve(sizeof(Counters) + hitCap_ * sizeof(HitRecord), 0, stream_);
 }

@@ -155,7 +155,7 @@ private:
         DevBuf<unsigned long long> sortKeys; // [nSolvers][recCap] every solver's records in canonical order (k_emit_sort)
         DevBuf<uint32_t> sortMasks;
         DevBuf<int32_t> recPos;             // [nSolvers][recCap + 1]
-        DevBuf<long long> bucketBase;       // [nSolvers * kRecBuckets + 1][2] (k_emit_scan)
+        DevBuf<long long> bucketBase;       // [nSolvers * kRecBuckets + nSolvers][2] (k_emit_scan)
         DevBuf<unsigned int> ticketDev;     // 4 words
         unsigned int recCap = 0;
         size_t srcOff = 0;          // offset of the per-solver delta pointers in headHost / headDev
