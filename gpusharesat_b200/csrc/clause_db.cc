@@ -236,12 +236,30 @@ int ClauseDb::buildDirectory(std::vector<LenDir> &dir) const {
         dir.push_back(LenDir{pl.dev.data(), s, (int32_t)n, tiles, (int32_t)shardFirstTile(allTiles), pl.idsDev.data(),
                              const_cast<float *>(pl.actsDev.data()), 0});
     }
-    int64_t before = 0; // the directory is longest first: walk it backwards for the ascending prefix
+    // Canonical position (length ascending, index ascending) of a clause among THIS DEVICE's clauses: the
+    // directory is longest first, walk it backwards for the ascending prefix.  (With the whole database as the
+    // scale, a device that checks 1/N of every length would use 1/N of the record buckets: N times fuller
+    // buckets, sorted in global memory -- 8 GPUs: check + emit 168 -> 490 us.)
+    int64_t before = 0;
     for (size_t k = dir.size(); k-- > 0;) {
-        dir[k].ascStart = before;
-        before += dir[k].count;
+        const int64_t first = (int64_t)dir[k].firstTile * kTileClauses;
+        dir[k].ascStart = before - first;
+        before += localClausesOf(dir[k].count);
     }
     return tiles;
+}
+
+int64_t ClauseDb::localClausesOf(int64_t n) const {
+    const int64_t allTiles = (n + kTileClauses - 1) / kTileClauses;
+    const int64_t first = shardFirstTile(allTiles) * kTileClauses, mine = localTiles(allTiles) * kTileClauses;
+    return std::max<int64_t>(0, std::min(n - first, mine));
+}
+
+int64_t ClauseDb::localClauses() const {
+    int64_t total = 0;
+    for (int s = 1; s <= maxLen_; s++)
+        if (perLen_[s] && perLen_[s]->n) total += localClausesOf(perLen_[s]->n);
+    return total;
 }
 
 void ClauseDb::getClause(int len, int idx, std::vector<int> &lits, int64_t &id) const {

@@ -27,7 +27,7 @@ struct LenDir {
     int32_t firstTile; // first tile of this length that THIS DEVICE checks (multi-GPU: its contiguous share)
     const int64_t *ids; // device copy of the clause ids of this length, indexed by (global) clause index
     float *acts;        // device-resident clause activities (bumped by k_bump_activity), same indexing
-    int64_t ascStart;   // clauses of all SHORTER lengths: ascStart + index = position in the canonical order
+    int64_t ascStart;   // ascStart + index = position of a clause of THIS DEVICE's share among the device's clauses in the canonical order
 };
 
 struct DbStats {
@@ -58,6 +58,8 @@ public:
     bool uploadDirty(cudaStream_t stream, int64_t *bytesCopied);
     // directory of non-empty lengths, longest first; returns the total tile count
     int buildDirectory(std::vector<LenDir> &dir) const;
+    int64_t localClausesOf(int64_t n) const; // of a length with n clauses: how many lie in this device's tiles
+    int64_t localClauses() const;            // clauses this device checks
 
     void getClause(int len, int idx, std::vector<int> &lits, int64_t &id) const;
     // append the literals to `out` (no temporary); returns the clause id

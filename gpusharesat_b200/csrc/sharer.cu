@@ -374,7 +374,7 @@ CheckArgs Sharer::checkArgs(const RunSlot &slot, int g, bool recs) const {
         a.recKeys = const_cast<unsigned long long *>(slot.recKeys.data());
         a.recMasks = const_cast<uint32_t *>(slot.recMasks.data());
         a.recCap = slot.recCap;
-        a.totalClauses = std::max<int64_t>(1, db_->stats().clauses);
+        a.totalClauses = std::max<int64_t>(1, db_->localClauses());
     }
     a.dir = slot.dirDev();
     a.nDir = slot.nDir;
