@@ -9,21 +9,28 @@ of every clause against every assignment, hits back on the host.  checks per ste
 (L = literals in the database), nominal: early exits do not reduce the count.
 
 Numbers on the JSON line
-  value      L*A*N / device time of a step with the batch already resident in HBM
-             (table kernels + check kernels, CUDA events on the library's stream, max over ranks)
-  e2e        same metric through the C ABI with HOST buffers: timed region = gss_gpu_run() x 2
-             (the reference's execute(): delta H2D, kernels, hit D2H, host hand-over)
-  roofline   the dominant kernel of the timed region (k_filter, level 1) against measured HBM
-             bandwidth: algorithmic bytes per launch / its duration (CUDA events, this run)
-  roofline_dense  dense mode (no filter, no early exit: every (literal, 32-slot word) pair
-             evaluated), BASELINE.json's own definition; bound = slower of HBM bytes and LOP3 issue,
-             the LOP3 peak measured on this box by a register-only micro-benchmark
-  cpu_baseline  the reference algorithm (two-level filter, 32 slots bit-parallel) ported to C
-             (oracle/), all host cores, on a bounded sample of the same clause database
+  value      L*A*steps / device time of the steps (CUDA events on the library's stream, max over ranks): everything
+             the device does for a batch -- k_apply_direct (which pulls the deltas over PCIe), collapse, k_filter,
+             k_exact, k_emit_* (which write the results into page-locked host memory)
+  e2e        same metric through the C ABI with HOST buffers: timed region = gss_gpu_run() x 2 per batch
+             (collect, launches, wait, activity bumps, hand-over to the solver queues); ms_every_step lists the steps
+  roofline   the contract's figure: dense mode (no filter, no early exit: every (literal, 32-slot
+             word) pair evaluated) against the slower of HBM bytes and LOP3 issue; LOP3 peak measured in this run,
+             HBM peak from MEASURED_PEAKS.json, DRAM traffic from the ncu capture of this command
+             (profiles/capture_traffic.py); gather_view = the same sweep against the measured L2 gather ceiling
+  roofline_k_filter  the dominant production kernel against HBM (nominal and moved bytes)
+  device_step_complete  first event to last event of a step
+  cpu_baseline  the reference algorithm (two-level filter, 32 slots bit-parallel) ported to C (oracle/), all host
+             cores, on a bounded sample of the same clause database; parity_sample = first batch == that port
+  reference_gpu  the reference's own GPU library recompiled for sm_100a (oracle/_ref), same inputs and call pattern
+  streamed_db / import_latency  SURVEY 8(f1) / 8(f2)
+  host_during_timed_region / remeasured  involuntary context switches of the timing thread inside the timed calls
+             and stolen vCPU time; a disturbed region (or a throttled GPU) is measured once more, both attempts kept
 
---impl reference runs that CPU port as its own arm (the reference has no CPU implementation of
-this path).  --impl reference-gpu times the reference's own GPU library
-(oracle/_ref) on the same inputs, for context.
+--impl reference runs the CPU port as its own arm (the reference has no CPU implementation of this path;
+SURVEY.md 8d).  --impl reference-gpu times the reference's own GPU library on the same inputs.  N > 1 (torchrun):
+one process per GPU, --scaling weak (default) on the line and strong as a sub-object (or the other way round),
+parity_sample in both.
 """
 import argparse
 import ctypes as C

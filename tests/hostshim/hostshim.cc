@@ -221,4 +221,34 @@ int hs_pop(HostRig *r, int s, int *lits, int *count, int64_t *id) {
 int64_t hs_last_all_reported(HostRig *r, int s) { return r->reported.lastAssigAllReported(s); }
 int64_t hs_solver_stat(HostRig *r, int s, int stat) { return (int64_t)r->stats[s][stat]; }
 
+
+// ---- directory of a device's share (multi-GPU): one row per non-empty length, longest first ----
+// counts[i] clauses of length lens[i] are added to a fresh database with shard (rank, world); out = rows of
+// {len, count, firstTile, localTiles, ascStart}; returns the number of rows, *localTotal = clauses the device checks
+int hs_shard_directory(int rank, int world, const int *lens, const int *counts, int n, int64_t *out, int64_t *localTotal) {
+    Logger logger;
+    logger.verbosity = 0;
+    ClauseDb db(0.999, logger, 0);
+    db.setShard(rank, world);
+    std::vector<int> lits;
+    for (int i = 0; i < n; i++) {
+        lits.assign((size_t)lens[i], 2);
+        for (int c = 0; c < counts[i]; c++) db.addClause(lits.data(), lens[i]);
+    }
+    db.drainPending();
+    std::vector<LenDir> dir;
+    db.buildDirectory(dir);
+    int prevEnd = 0;
+    for (size_t k = 0; k < dir.size(); k++) {
+        out[5 * k] = dir[k].len;
+        out[5 * k + 1] = dir[k].count;
+        out[5 * k + 2] = dir[k].firstTile;
+        out[5 * k + 3] = dir[k].tileEnd - prevEnd;
+        out[5 * k + 4] = dir[k].ascStart;
+        prevEnd = dir[k].tileEnd;
+    }
+    *localTotal = db.localClauses();
+    return (int)dir.size();
+}
+
 } // extern "C"

@@ -39,11 +39,22 @@ def load():
         "hs_add_clauses_bulk": (Q, [P, C.POINTER(Q), IP, Q]),
         "hs_pop": (I, [P, I, IP, IP, C.POINTER(Q)]), "hs_last_all_reported": (Q, [P, I]),
         "hs_solver_stat": (Q, [P, I, I]),
+        "hs_shard_directory": (I, [I, I, IP, IP, I, C.POINTER(Q), C.POINTER(Q)]),
     }
     for n, (r, a) in sig.items():
         f = getattr(L, n)
         f.restype, f.argtypes = r, a
     return L
+
+
+def shard_directory(rank, world, lens, counts):
+    """rows (len, count, firstTile, localTiles, ascStart) of a device's directory and the clauses it checks"""
+    L = load()
+    n = len(lens)
+    la, ca = (C.c_int * n)(*lens), (C.c_int * n)(*counts)
+    out, tot = (C.c_int64 * (5 * n))(), C.c_int64(0)
+    k = L.hs_shard_directory(rank, world, la, ca, n, out, C.byref(tot))
+    return [tuple(out[5 * i: 5 * i + 5]) for i in range(k)], tot.value
 
 
 class Rig:

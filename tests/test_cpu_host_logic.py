@@ -544,3 +544,26 @@ def test_activity_only_threshold_with_huge_differences():
     assert a0 < thr <= a0 * 1.1
     thr = r.approx_nth_act(2)
     assert a1 < thr <= a1 * 1.1
+
+
+def test_record_buckets_scale_with_the_devices_own_share():
+    """Multi-GPU: a device checks a contiguous share of the tiles of every length.  The position that picks a hit's
+    record bucket (LenDir::ascStart + index, kernels.cu: appendRec) must run over THAT share -- 0 .. localClauses-1 in
+    the canonical order (length ascending, index ascending) -- or a device would use 1/N of its buckets."""
+    from hostshim_lib import shard_directory
+    lens, counts = [2, 3, 5, 9], [1000, 700, 385, 130]
+    tile = 128
+    for world in (1, 2, 3, 8):
+        seen_total = 0
+        for rank in range(world):
+            rows, local = shard_directory(rank, world, lens, counts)
+            assert [r[0] for r in rows] == sorted(lens, reverse=True)  # longest first
+            pos = []
+            for ln, count, first_tile, local_tiles, asc in sorted(rows):  # ascending length = canonical order
+                lo, hi = first_tile * tile, min(count, (first_tile + local_tiles) * tile)
+                pos += [asc + idx for idx in range(lo, hi)]
+            assert pos == list(range(local)), (world, rank)
+            seen_total += local
+            if local >= 256:  # every bucket of the 256 is in use
+                assert {p * 256 // local for p in pos} == set(range(256))
+        assert seen_total == sum(counts)
