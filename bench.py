@@ -457,7 +457,8 @@ def sharded_pass(a, scaling, steps, warmup, dist, torch, rank, world, local, dev
     # the first batch rebuilds the tables: it lists every variable of every solver
     payload_cap = a.solvers * a.vars * 12 + (4 << 20)
     if a.exchange == "peer":
-        runner = mgpu.PeerRunner(sh, dist, rank, world, payload_cap=payload_cap, slot_hits=a.slot_hits)
+        # the parity batch (first warm-up step) needs every rank's masks on rank 0; the timed steps run the default
+        runner = mgpu.PeerRunner(sh, dist, rank, world, payload_cap=payload_cap, slot_hits=a.slot_hits, records=True)
     else:
         runner = mgpu.ShardedRunner(sh, dist, rank, world, device, payload_cap=payload_cap)
 
@@ -481,6 +482,8 @@ def sharded_pass(a, scaling, steps, warmup, dist, torch, rank, world, local, dev
         step_out = step()
         if w == 0 and rank == 0:
             first_hits = sh.debugLastHits().copy()  # the union of every rank's hits of the first batch
+        if w == 0 and a.exchange == "peer":
+            runner.set_records(False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

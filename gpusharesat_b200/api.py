@@ -104,6 +104,7 @@ SIGNATURES = {
     "gss_peer_connect": (None, [_P, C.c_void_p, _L]),
     "gss_peer_enqueue": (_I, [_P]),
     "gss_peer_finish": (_L, [_P]),
+    "gss_debug_set_peer_records": (None, [_P, _I]),
     "gss_set_stream": (None, [_P, C.c_void_p]),
     "gss_mgpu_import": (None, [_P, C.c_void_p, _L]),
     "gss_version": (C.c_char_p, []),
@@ -424,6 +425,9 @@ class GpuClauseSharer:
 
     def peerFinish(self):
         return self._lib.gss_peer_finish(self._h)
+
+    def debugSetPeerRecords(self, on):
+        self._lib.gss_debug_set_peer_records(self._h, 1 if on else 0)
 
     def mgpuFinish(self):
         return self._lib.gss_mgpu_finish(self._h)

@@ -120,6 +120,7 @@ int64_t gss_peer_init(gss_sharer *h, int rank, int world, int64_t payload_cap, i
 void gss_peer_connect(gss_sharer *h, const void *blobs, int64_t blob_bytes) { h->impl.peerConnect(blobs, blob_bytes); }
 int gss_peer_enqueue(gss_sharer *h) { return h->impl.peerEnqueue(); }
 int64_t gss_peer_finish(gss_sharer *h) { return h->impl.peerFinish(); }
+void gss_debug_set_peer_records(gss_sharer *h, int on) { h->impl.setPeerRecords(on != 0); }
 void gss_set_stream(gss_sharer *h, void *cuda_stream) { h->impl.setStream(cuda_stream); }
 int64_t gss_mgpu_wait(gss_sharer *h, const gss_raw_hit **hits) {
     if (!hits) return h->impl.mgpuWait(nullptr);

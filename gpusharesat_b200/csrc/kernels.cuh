@@ -174,7 +174,7 @@ struct RunHdr {
     int64_t litTotal; // literals of all solvers
     uint64_t exactTests;
     uint32_t maxRec;  // largest per-solver record count (before clipping)
-    uint32_t pad;
+    uint32_t hasRecords; // multi-process exchange: the sorted record keys and masks lie next to the ids (written by the owning rank's host)
     uint32_t nSurvivors[kMaxGroups];
     struct PerSolver {
         int64_t entryBase; // first entry of this solver in ids[]; its positions start at pos[entryBase + solver]

@@ -173,6 +173,7 @@ struct Sharer::PeerState {
     std::shared_ptr<ShmRing> ring;              // workers: this rank's result buffers
     std::vector<std::shared_ptr<ShmRing>> rings; // rank 0: every worker's ring (index = rank; [0] unused)
     int ringBuf = -1;                           // workers: buffer of the batch in flight (not yet published)
+    bool exportRecords = false;                 // workers: sorted record keys + masks go out with the results (GPUSHARE_PEER_RECORDS=1, gss_debug_set_peer_records)
     bool directPush = true;                     // rank 0: deltas read in place by the push kernel (GPUSHARE_PEER_STAGED: staged copy + H2D)
 
     uint8_t *payload() const { return (rank == 0 ? rootWindow : window) + kCtlBytes; } // this rank's copy of the batch
@@ -275,6 +276,8 @@ void Sharer::peerConnect(const void *blobs, int64_t blobBytes) {
     GSS_CUDA(cudaEventCreate(&P.evWait));
     P.trace = getenv("GSS_PEER_TRACE") != nullptr;
     P.directPush = directEnabled_ && getenv("GPUSHARE_PEER_STAGED") == nullptr;
+    if (const char *r = getenv("GPUSHARE_PEER_RECORDS")) P.exportRecords = atoi(r) != 0;
+    if (peerRecordsWanted_ >= 0) P.exportRecords = peerRecordsWanted_ != 0;
     P.connected = true;
 }
 
@@ -293,6 +296,13 @@ void Sharer::peerClose() {
     if (peer_->window) cudaFree(peer_->window);
     delete peer_;
     peer_ = nullptr;
+}
+
+// Workers: also write the sorted record keys and masks next to the results (rank 0 then bumps the activities of every
+// rank's hits on its device and gss_debug_last_hits covers every rank); off: every rank bumps its own hits.
+void Sharer::setPeerRecords(bool on) {
+    peerRecordsWanted_ = on ? 1 : 0;
+    if (peer_) peer_->exportRecords = on;
 }
 
 // worker ranks: the batch's result buffer comes from the rank's shared-memory ring (rank 0 reads it there)
@@ -322,7 +332,7 @@ bool Sharer::peerAcquireResultBuf(RunSlot &slot) {
     b->bytes = (size_t)c->bufBytes;
     b->entryCap = c->entryCap;
     b->litCap = c->litCap;
-    b->withRecords = true;
+    b->withRecords = P.exportRecords;
     std::shared_ptr<ShmRing> keep = P.ring;
     slot.runBuf = std::shared_ptr<RunBuf>(b, [keep](RunBuf *q) { delete q; }); // (rank 0 frees the ring buffer)
     return true;
@@ -535,6 +545,17 @@ int64_t Sharer::peerFinish() {
     int64_t total = mine ? mine->nTotal : 0;
 
     if (!root) {
+        if (slot.checked) {
+            // with the records: rank 0 bumps the activities of every rank's hits (on its device).  Without (1.7 MB per
+            // step and rank less to write into host memory, 12 of the 32 bytes per hit): every rank bumps the activities
+            // of its own hits on its own device.
+            const bool exported = slot.runBuf->withRecords;
+            const_cast<RunHdr *>(mine)->hasRecords = exported ? 1u : 0u;
+            if (!exported && mine->nTotal > 0) {
+                std::vector<DevicePart> own{DevicePart{this, &slot, nullptr}};
+                bumpDirect(own);
+            }
+        }
         // publish: this rank's event has completed, so everything its GPU wrote is visible to rank 0's CPU
         RingCtl *c = P.ring->ctl();
         const uint64_t word = ((uint64_t)P.seq << 8) | (uint64_t)(slot.checked ? P.ringBuf : 0xFF);
@@ -598,14 +619,14 @@ int64_t Sharer::peerFinish() {
         b->bytes = (size_t)c->bufBytes;
         b->entryCap = c->entryCap;
         b->litCap = c->litCap;
-        b->withRecords = true;
+        b->withRecords = b->hdr()->hasRecords != 0;
         std::shared_ptr<RunBuf> buf(b, [ring, k](RunBuf *q) {
             ring->ctl()->buf[k].state.store(0, std::memory_order_release); // the worker may fill it again
             delete q;
         });
         total += b->hdr()->nTotal;
         globalStats_[G_clauseTestsOnAssigs] += b->hdr()->exactTests;
-        finishedD2H_ += (int64_t)(sizeof(RunHdr) + (size_t)b->hdr()->nTotal * 24 + (size_t)b->hdr()->litTotal * 4);
+        finishedD2H_ += (int64_t)(sizeof(RunHdr) + (size_t)b->hdr()->nTotal * (b->withRecords ? 24 : 12) + (size_t)b->hdr()->litTotal * 4);
         parts.push_back(DevicePart{nullptr, nullptr, buf});
     }
     PhaseTimer tHandOver(hostPhases_[2]);

@@ -435,7 +435,7 @@ void Sharer::bumpDirect(const std::vector<DevicePart> &parts) {
             launchBumpFromRecs(slot.sortKeys.data(), slot.recCap, slot.solverInfo.data(), slot.nSolvers, slot.recCap,
                                (const LenDir *)bumpDirDev_.data(), (int)dir.size(), db_->activityIncrement(), bumpFlagDev_.data(),
                                stream_, &launches_);
-        } else { // another process's result: its sorted record keys lie next to the ids, in host memory this device can read
+        } else if (rb->withRecords) { // another process's result: its sorted record keys lie next to the ids, in host memory this device can read
             launchBumpFromKeys(rb->keys(), rb->hdr()->nTotal, (const LenDir *)bumpDirDev_.data(), (int)dir.size(),
                                db_->activityIncrement(), bumpFlagDev_.data(), stream_, &launches_);
             bumpOwners_.push_back(p.buf);

@@ -1052,6 +1052,7 @@ void Sharer::materializeLastHits() {
         for (auto &w : workers_) w->appendDirectHits(w->slots_[idx], lastHits_);
         for (auto &fb : lastForeign_) { // other ranks' results (multi-process exchange): masks lie next to the ids
             const RunHdr *h = fb->hdr();
+            if (!fb->withRecords) continue; // (that rank kept its masks: gss_debug_set_peer_records)
             for (int s = 0; s < kMaxSolvers; s++) {
                 const RunHdr::PerSolver &ps = h->solver[s];
                 for (int32_t i = 0; i < ps.n; i++)

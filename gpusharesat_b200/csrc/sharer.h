@@ -105,6 +105,7 @@ public:
     void peerConnect(const void *blobs, int64_t blobBytes);
     int peerEnqueue();
     int64_t peerFinish();
+    void setPeerRecords(bool on);
     void peerClose();
 
     struct RunBuf { // one run's result buffer in page-locked host memory, written by k_emit (pipeline.cu)
@@ -271,6 +272,7 @@ private:
     DevBuf<uint8_t> resDev_; // [Counters][HitRecord x hitCap]
     DevBuf<Survivor> survDev_; // [nGroups][survCap]
     size_t hitCap_ = 0, survCap_ = 0;
+    int peerRecordsWanted_ = -1; // -1: GPUSHARE_PEER_RECORDS / the default decides
 
     RunSlot slots_[2];
     int cur_ = -1;          // slot of the run in flight

@@ -211,8 +211,10 @@ class PeerRunner:
 
     SPMD: every rank calls step() for every batch (like the clause stream, which every rank sees)."""
 
-    def __init__(self, sh, dist, rank, world, payload_cap=64 << 20, slot_hits=1 << 20):
+    def __init__(self, sh, dist, rank, world, payload_cap=64 << 20, slot_hits=1 << 20, records=None):
         self.sh, self.rank, self.world = sh, rank, world
+        if records is not None:  # (None: the library's default / GPUSHARE_PEER_RECORDS)
+            sh.debugSetPeerRecords(records)
         blob = sh.peerInit(rank, world, payload_cap, slot_hits)
         blobs = [None] * world
         if world > 1:
@@ -222,6 +224,11 @@ class PeerRunner:
         sh.peerConnect(blobs)
         if world > 1:
             dist.barrier()
+
+    def set_records(self, on):
+        """workers export their sorted record keys + masks (rank 0: activity bumps for every rank's hits, debugLastHits
+        over every rank) or every rank bumps its own hits; call on every rank between two batches"""
+        self.sh.debugSetPeerRecords(on)
 
     def step(self):
         """one batch; rank 0 returns the number of hits handed over, workers their own count, None

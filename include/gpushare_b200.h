@@ -247,6 +247,11 @@ int64_t gss_peer_init(gss_sharer *h, int rank, int world, int64_t payload_cap, i
 void    gss_peer_connect(gss_sharer *h, const void *blobs, int64_t blob_bytes);
 int     gss_peer_enqueue(gss_sharer *h);
 int64_t gss_peer_finish(gss_sharer *h);
+/* Workers also write their sorted record keys and masks (12 B per hit) next to their results: rank 0 then bumps the clause
+ * activities of every rank's hits on its own device and gss_debug_last_hits covers the hits of every rank (the parity
+ * hook of the tests and of bench.py).  Off (default; GPUSHARE_PEER_RECORDS=1 turns it on at start-up): every rank bumps
+ * the activities of its own hits on its own device.  Same setting on every rank, between two batches. */
+void    gss_debug_set_peer_records(gss_sharer *h, int on);
 /* Make the library enqueue everything on the caller's CUDA stream (e.g. torch's current stream,
  * so that its work is ordered with the NCCL collectives without host synchronisation). */
 void    gss_set_stream(gss_sharer *h, void *cuda_stream);
