@@ -390,6 +390,16 @@ void Sharer::finishRunDirect(RunSlot &slot) {
     }
     const RunHdr *h = slot.runBuf->hdr();
     globalStats_[G_clauseTestsOnAssigs] += h->exactTests;
+    // Head room for the batches to come: an overflow is repaired by a second pass over the same batch plus larger
+    // buffers (tens of milliseconds of cudaMalloc / cudaFree / synchronisation) -- with capacities that follow the
+    // observed counts closely, one batch in a few hundred overflowed by fluctuation alone (a 60 ms hiccup in the middle
+    // of a timed region, profiles/r02o_bench.json).  Grow ahead, while the counts are still far from the capacities.
+    {
+        size_t maxSurv = 0;
+        for (int g = 0; g < kMaxGroups; g++) maxSurv = std::max(maxSurv, (size_t)h->nSurvivors[g]);
+        if (maxSurv * 2 > survCap_) survCap_ = maxSurv * 3;
+        if ((size_t)h->maxRec * 3 > recCap_ / kRecBuckets) recCap_ = pow2AtLeast((size_t)h->maxRec * 4 * kRecBuckets);
+    }
     // size the next result buffer from this result (with head room), the hit buffer guess follows the trend
     entryGuess_ = std::max<int64_t>(4096, std::max(h->nTotal + h->nTotal / 2, entryGuess_ - entryGuess_ / 16));
     litGuess_ = std::max<int64_t>(16384, std::max(h->litTotal + h->litTotal / 2, litGuess_ - litGuess_ / 16));
