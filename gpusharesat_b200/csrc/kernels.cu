@@ -1102,12 +1102,11 @@ __global__ void __launch_bounds__(kRecBuckets) k_emit_scan(EmitArgs a) {
     if (tid == 0) a.ticket[3] = 0u;
 }
 
-// grid = (kRecBuckets / kSortWarps, solvers); warp w of block (x, s) owns bucket x * kSortWarps + w of solver s
-__global__ void __launch_bounds__(kSortWarps * 32) k_emit_sort(EmitArgs a) {
-    __shared__ unsigned long long sK[kSortWarps][kSortSmemRecs];
-    __shared__ uint32_t sM[kSortWarps][kSortSmemRecs];
-    const int s = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int bucket = blockIdx.x * kSortWarps + wid;
+// block bx of solver s sorts the solver's buckets bx * kSortWarps .. + kSortWarps - 1, a warp each
+__device__ __forceinline__ void emitSortBuckets(const EmitArgs &a, int s, int bx, unsigned long long (*sK)[kSortSmemRecs],
+                                                uint32_t (*sM)[kSortSmemRecs]) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int bucket = bx * kSortWarps + wid;
     const unsigned int bucketCap = a.recCap / kRecBuckets;
     auto ctrOf = [&](int solver, int b) { return a.solverCtr[((size_t)solver * kRecBuckets + b) * kCtrStride]; };
     // where this bucket starts in the solver's sorted list and in its literal stream (k_emit_scan)
@@ -1174,27 +1173,33 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_emit_sort(EmitArgs a) {
     }
 }
 
-// blockIdx.y = solver; the blocks of a solver take chunks of kWriteChunk entries in turn
-__global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
-    __shared__ int sLen[128];
-    __shared__ int32_t sPos[kWriteChunk + 1];
-    const int s = blockIdx.y, tid = threadIdx.x;
+// grid = (kRecBuckets / kSortWarps, solvers)
+__global__ void __launch_bounds__(kSortWarps * 32) k_emit_sort(EmitArgs a) {
+    __shared__ unsigned long long sK[kSortWarps][kSortSmemRecs];
+    __shared__ uint32_t sM[kSortWarps][kSortSmemRecs];
+    emitSortBuckets(a, blockIdx.y, blockIdx.x, sK, sM);
+}
+
+// block bx of the nbx blocks of solver s: the blocks of a solver take chunks of kWriteChunk entries in turn; nBlocks = all
+// the blocks of the launch (the one that finishes last writes the header)
+__device__ __forceinline__ void emitWriteSolver(const EmitArgs &a, int s, int bx, int nbx, unsigned int nBlocks, int *sLen, int32_t *sPos) {
+    const int tid = threadIdx.x;
     const int nDir = min(a.nDir, 128);
     for (int i = tid; i < nDir; i += blockDim.x) sLen[i] = a.dir[i].len;
     const EmitSolver es = a.solverInfo[s];
     const unsigned long long *__restrict__ K = a.sortKeys + (size_t)s * a.recCap;
     const int32_t *__restrict__ gPos = a.recPos + (size_t)s * (a.recCap + 1);
     const int n = es.n; // -1: this solver does not fit
-    for (int c0 = blockIdx.x * kWriteChunk; c0 < n; c0 += gridDim.x * kWriteChunk) {
+    for (int c0 = bx * kWriteChunk; c0 < n; c0 += nbx * kWriteChunk) {
         const int cnt = min(kWriteChunk, n - c0);
         __syncthreads();
-        for (int i = tid; i <= cnt; i += blockDim.x) sPos[i] = gPos[c0 + i];
+        for (int i = tid; i <= cnt; i += blockDim.x) sPos[i] = __ldcg(gPos + c0 + i); // (ld.cg: k_emit_fused reads what other blocks just wrote)
         __syncthreads();
         if (tid < cnt) {
-            const unsigned long long key = K[c0 + tid];
+            const unsigned long long key = __ldcg(K + c0 + tid);
             a.ids[es.entryBase + c0 + tid] = a.dir[dirOfLen(sLen, nDir, (int)(key >> 32))].ids[(unsigned int)key];
             if (a.keysOut) a.keysOut[es.entryBase + c0 + tid] = key;
-            if (a.masksOut) a.masksOut[es.entryBase + c0 + tid] = a.sortMasks[(size_t)s * a.recCap + c0 + tid];
+            if (a.masksOut) a.masksOut[es.entryBase + c0 + tid] = __ldcg(a.sortMasks + (size_t)s * a.recCap + c0 + tid);
         }
         for (int i = tid; i < cnt + (c0 + cnt == n ? 1 : 0); i += blockDim.x) a.pos[es.entryBase + s + c0 + i] = sPos[i];
         // Literal stream of these entries.  PCIe wants full, aligned lines: the body goes out as 16-byte
@@ -1207,7 +1212,7 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
                 const int mid = (lo + hi) >> 1;
                 if (sPos[mid] <= q) lo = mid; else hi = mid;
             }
-            const unsigned long long key = K[c0 + lo];
+            const unsigned long long key = __ldcg(K + c0 + lo);
             const int len = (int)(key >> 32), idx = (int)(unsigned int)key, j = q - sPos[lo];
             const int32_t *src = a.dir[dirOfLen(sLen, nDir, len)].base + (size_t)(idx / kTileClauses) * kTileClauses * len +
                                  tileSlot(idx % kTileClauses);
@@ -1227,8 +1232,8 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
         }
         for (long long A = B1 + tid; A < A1; A += blockDim.x) a.lits[A] = litAt((int)(A - es.litBase));
     }
-    if (n == 0 && blockIdx.x == 0 && tid == 0) a.pos[es.entryBase + s] = 0;
-    if (blockIdx.x == 0 && tid == 0) {
+    if (n == 0 && bx == 0 && tid == 0) a.pos[es.entryBase + s] = 0;
+    if (bx == 0 && tid == 0) {
         a.hdr->solver[s].entryBase = es.entryBase;
         a.hdr->solver[s].litBase = es.litBase;
         a.hdr->solver[s].n = max(es.n, 0);
@@ -1241,7 +1246,7 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
     if (tid == 0) {
         __threadfence();
         const unsigned int ticket = atomicAdd(a.ticket, 1u);
-        if (ticket == gridDim.x * gridDim.y - 1) {
+        if (ticket == nBlocks - 1) {
             __threadfence();
             const volatile Counters *cn = a.counters;
             unsigned int flags = *reinterpret_cast<volatile unsigned int *>(a.ticket + 1);
@@ -1262,9 +1267,47 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
             a.ticket[0] = 0u;
             a.ticket[1] = 0u;
             a.ticket[2] = 0u;
+            a.ticket[3] = 0u; // (k_emit_fused: the start-order counter)
+            if (a.solverDone)
+                for (int t = 0; t < a.nSolvers; t++) a.solverDone[t] = 0u;
             a.hdr->seq = a.seq;
         }
     }
+}
+
+// grid = (blocks per solver, solvers)
+__global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
+    __shared__ int sLen[128];
+    __shared__ int32_t sPos[kWriteChunk + 1];
+    emitWriteSolver(a, blockIdx.y, blockIdx.x, gridDim.x, gridDim.x * gridDim.y, sLen, sPos);
+}
+
+// k_emit_fused = k_emit_sort + k_emit_write in one launch, so that the PCIe writes of the first solvers run while the
+// last buckets are still being sorted (sort ~20 us, write ~70 us back to back).  kRecBuckets / kSortWarps = 32 blocks per
+// solver: a block sorts its 8 buckets, then waits for the solver's other blocks and takes its share of the solver's
+// entries.  Waiting on other blocks is safe because a block's place is its START order (a ticket), not its block index:
+// the blocks of a solver are then the 32 that started one after the other, at most one solver is ever started in part,
+// and every other resident block belongs to a solver whose blocks have all started and therefore finish.
+__global__ void __launch_bounds__(256) k_emit_fused(EmitArgs a) {
+    __shared__ unsigned long long sK[kSortWarps][kSortSmemRecs];
+    __shared__ uint32_t sM[kSortWarps][kSortSmemRecs];
+    __shared__ int sLen[128];
+    __shared__ int32_t sPos[kWriteChunk + 1];
+    __shared__ unsigned int sPlace;
+    constexpr int kPerSolver = kRecBuckets / kSortWarps;
+    if (threadIdx.x == 0) sPlace = atomicAdd(a.ticket + 3, 1u);
+    __syncthreads();
+    const int s = (int)(sPlace / kPerSolver), bx = (int)(sPlace % kPerSolver);
+    emitSortBuckets(a, s, bx, sK, sM);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence(); // this block's part of the sorted list is visible before it says so
+        atomicAdd(a.solverDone + s, 1u);
+        while (*reinterpret_cast<volatile unsigned int *>(a.solverDone + s) < (unsigned int)kPerSolver) __nanosleep(100);
+        __threadfence();
+    }
+    __syncthreads();
+    emitWriteSolver(a, s, bx, kPerSolver, gridDim.x, sLen, sPos);
 }
 
 // activity bumps straight from the sorted per-solver record lists (blockIdx.y = solver)
@@ -1693,6 +1736,13 @@ void launchApplyDirect(const VarUpdate *const *src, const SolverRunParams *param
 void launchEmit(const EmitArgs &a, cudaStream_t s, int64_t *launches) {
     if (a.nSolvers <= 0) return;
     k_emit_scan<<<a.nSolvers, kRecBuckets, 0, s>>>(a);
+    static const bool split = getenv("GSS_EMIT_SPLIT") != nullptr; // the two-kernel form, for comparison
+    if (a.solverDone && !split) {
+        k_emit_fused<<<(kRecBuckets / kSortWarps) * a.nSolvers, 256, 0, s>>>(a);
+        checkLaunch("k_emit");
+        *launches += 2;
+        return;
+    }
     k_emit_sort<<<dim3(kRecBuckets / kSortWarps, a.nSolvers, 1), kSortWarps * 32, 0, s>>>(a);
     // enough writers for PCIe: the blocks of a solver take chunks of its entries in turn
     const unsigned int perSolver = std::max(1u, std::min(64u, 1184u / (unsigned int)a.nSolvers));

@@ -206,7 +206,8 @@ struct EmitArgs {
     Counters *counters;
     unsigned int survCap;
     int groups;
-    unsigned int *ticket;        // [0] finished blocks of k_emit_write, [1] flag word, [2] fullest bucket, [3] finished blocks of k_emit_scan
+    unsigned int *solverDone = nullptr; // [nSolvers] k_emit_fused: blocks of the solver whose buckets are sorted (nullptr: two kernels)
+    unsigned int *ticket;        // [0] finished blocks of k_emit_write, [1] flag word, [2] fullest bucket, [3] finished blocks of k_emit_scan, then start order of k_emit_fused
     uint32_t seq;
     // result buffer in mapped pinned host memory
     RunHdr *hdr;

@@ -98,6 +98,8 @@ void Sharer::ensureDirectBuffers(RunSlot &slot) {
         slot.ctrDev.reserve((size_t)kMaxSolvers * kRecBuckets * kCtrStride, 0, stream_);
         slot.solverInfo.reserve(kMaxSolvers, 0, stream_);
         slot.ticketDev.reserve(4, 0, stream_);
+        slot.solverDone.reserve(kMaxSolvers, 0, stream_);
+        GSS_CUDA(cudaMemsetAsync(slot.solverDone.data(), 0, (size_t)kMaxSolvers * sizeof(unsigned int), stream_));
         GSS_CUDA(cudaMemsetAsync(slot.ctrDev.data(), 0, (size_t)kMaxSolvers * kRecBuckets * kCtrStride * sizeof(unsigned long long), stream_));
         GSS_CUDA(cudaMemsetAsync(slot.solverInfo.data(), 0, (size_t)kMaxSolvers * sizeof(EmitSolver), stream_));
         GSS_CUDA(cudaMemsetAsync(slot.ticketDev.data(), 0, 4 * sizeof(unsigned int), stream_));
@@ -325,6 +327,7 @@ void Sharer::launchEmitFor(RunSlot &slot) {
     e.survCap = (unsigned int)survCap_;
     e.groups = groups;
     e.ticket = slot.ticketDev.data();
+    e.solverDone = slot.solverDone.data();
     e.seq = slot.seq;
     RunBuf &rb = *slot.runBuf;
     e.hdr = rb.hdr();

@@ -156,6 +156,7 @@ private:
         DevBuf<unsigned long long> sortKeys; // [nSolvers][recCap] every solver's records in canonical order (k_emit_sort)
         DevBuf<uint32_t> sortMasks;
         DevBuf<int32_t> recPos;             // [nSolvers][recCap + 1]
+        DevBuf<unsigned int> solverDone;    // [kMaxSolvers] (k_emit_fused)
         DevBuf<long long> bucketBase;       // [nSolvers * kRecBuckets + nSolvers][2] (k_emit_scan)
         DevBuf<unsigned int> ticketDev;     // 4 words
         unsigned int recCap = 0;
