@@ -603,14 +603,26 @@ __device__ __forceinline__ void reportHits(const CheckArgs &a, uint32_t m, int s
 // in the canonical order (kernels.cuh: kRecBuckets).  One 64-bit atomic reserves the slot and adds the
 // clause's literals to the bucket's literal count.  sLen / sAsc: the directory's lengths (descending)
 // and ascending clause prefix in shared memory.
-__device__ __forceinline__ void appendRec(const CheckArgs &a, const int *sLen, const long long *sAsc, int nDir, int solver, int len,
-                                          int idx, uint32_t mask) {
+// The directory (one entry per non-empty clause length, longest first) is searched by length from shared memory;
+// a database with more distinct lengths than the cache holds (GPUSHARE_MAX_CLAUSE_LEN above kDirCache) reads the
+// entries past it from the directory itself.  (Up to round 2 the searches simply stopped at 128 entries: with 129
+// distinct lengths -- the import-latency harness: 2-30 and 101-200 -- every hit on the SHORTEST length was resolved
+// against the next one's arena.)
+constexpr int kDirCache = 128;
+__device__ __forceinline__ int dirLenAt(const LenDir *dir, const int *sLen, int i) { return i < kDirCache ? sLen[i] : dir[i].len; }
+__device__ __forceinline__ int dirIndexOfLen(const LenDir *dir, const int *sLen, int nDir, int len) { // descending length
     int lo = 0, hi = nDir - 1;
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
-        if (sLen[mid] <= len) hi = mid; else lo = mid + 1;
+        if (dirLenAt(dir, sLen, mid) <= len) hi = mid; else lo = mid + 1;
     }
-    const unsigned long long g = (unsigned long long)(sAsc[lo] + idx);
+    return lo;
+}
+
+__device__ __forceinline__ void appendRec(const CheckArgs &a, const int *sLen, const long long *sAsc, int nDir, int solver, int len,
+                                          int idx, uint32_t mask) {
+    const int lo = dirIndexOfLen(a.dir, sLen, nDir, len);
+    const unsigned long long g = (unsigned long long)((lo < kDirCache ? sAsc[lo] : a.dir[lo].ascStart) + idx);
     const unsigned int bucket = (unsigned int)min((unsigned long long)(kRecBuckets - 1), g * kRecBuckets / (unsigned long long)a.totalClauses);
     const unsigned int bucketCap = a.recCap / kRecBuckets;
     const unsigned int slot = (unsigned int)atomicAdd(a.solverCtr + ((size_t)solver * kRecBuckets + bucket) * kCtrStride,
@@ -654,11 +666,11 @@ template <int G, int MINBLOCKS> __global__ void __launch_bounds__(256, MINBLOCKS
     const uint2 ident = make_uint2(0u, 0u);
     __shared__ HitRecord sStage[kMaxWarpsPerBlock][kStageCap];
     WarpStage<HitRecord> stage{sStage[threadIdx.x >> 5], 0};
-    __shared__ int sDirLen[128];
-    __shared__ long long sDirAsc[128];
-    const int nDirS = min(a.nDir, 128);
+    __shared__ int sDirLen[kDirCache];
+    __shared__ long long sDirAsc[kDirCache];
+    const int nDirS = a.nDir; // (entries past the cache are read from the directory)
     if (a.recKeys) {
-        for (int i = threadIdx.x; i < nDirS; i += blockDim.x) { sDirLen[i] = a.dir[i].len; sDirAsc[i] = a.dir[i].ascStart; }
+        for (int i = threadIdx.x; i < min(nDirS, kDirCache); i += blockDim.x) { sDirLen[i] = a.dir[i].len; sDirAsc[i] = a.dir[i].ascStart; }
         __syncthreads();
     }
 
@@ -1009,14 +1021,6 @@ __global__ void __launch_bounds__(256) k_apply_direct(const VarUpdate *const *__
 // ---------------------------------------------------------------------------------------------
 constexpr int kWriteChunk = 256;    // entries per block step of k_emit_write
 
-__device__ __forceinline__ int dirOfLen(const int *sLen, int nDir, int len) { // directory: descending length
-    int lo = 0, hi = nDir - 1;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (sLen[mid] <= len) hi = mid; else lo = mid + 1;
-    }
-    return lo;
-}
 
 constexpr int kSortWarps = 8;        // buckets per block of k_emit_sort (a warp each)
 constexpr int kSortSmemRecs = 256;   // records per bucket sorted in shared memory
@@ -1184,8 +1188,8 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_emit_sort(EmitArgs a) {
 // the blocks of the launch (the one that finishes last writes the header)
 __device__ __forceinline__ void emitWriteSolver(const EmitArgs &a, int s, int bx, int nbx, unsigned int nBlocks, int *sLen, int32_t *sPos) {
     const int tid = threadIdx.x;
-    const int nDir = min(a.nDir, 128);
-    for (int i = tid; i < nDir; i += blockDim.x) sLen[i] = a.dir[i].len;
+    const int nDir = a.nDir;
+    for (int i = tid; i < min(nDir, kDirCache); i += blockDim.x) sLen[i] = a.dir[i].len;
     const EmitSolver es = a.solverInfo[s];
     const unsigned long long *__restrict__ K = a.sortKeys + (size_t)s * a.recCap;
     const int32_t *__restrict__ gPos = a.recPos + (size_t)s * (a.recCap + 1);
@@ -1197,7 +1201,7 @@ __device__ __forceinline__ void emitWriteSolver(const EmitArgs &a, int s, int bx
         __syncthreads();
         if (tid < cnt) {
             const unsigned long long key = __ldcg(K + c0 + tid);
-            a.ids[es.entryBase + c0 + tid] = a.dir[dirOfLen(sLen, nDir, (int)(key >> 32))].ids[(unsigned int)key];
+            a.ids[es.entryBase + c0 + tid] = a.dir[dirIndexOfLen(a.dir, sLen, nDir, (int)(key >> 32))].ids[(unsigned int)key];
             if (a.keysOut) a.keysOut[es.entryBase + c0 + tid] = key;
             if (a.masksOut) a.masksOut[es.entryBase + c0 + tid] = __ldcg(a.sortMasks + (size_t)s * a.recCap + c0 + tid);
         }
@@ -1214,7 +1218,7 @@ __device__ __forceinline__ void emitWriteSolver(const EmitArgs &a, int s, int bx
             }
             const unsigned long long key = __ldcg(K + c0 + lo);
             const int len = (int)(key >> 32), idx = (int)(unsigned int)key, j = q - sPos[lo];
-            const int32_t *src = a.dir[dirOfLen(sLen, nDir, len)].base + (size_t)(idx / kTileClauses) * kTileClauses * len +
+            const int32_t *src = a.dir[dirIndexOfLen(a.dir, sLen, nDir, len)].base + (size_t)(idx / kTileClauses) * kTileClauses * len +
                                  tileSlot(idx % kTileClauses);
             return __ldg(src + (size_t)j * kTileClauses);
         };
@@ -1277,7 +1281,7 @@ __device__ __forceinline__ void emitWriteSolver(const EmitArgs &a, int s, int bx
 
 // grid = (blocks per solver, solvers)
 __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
-    __shared__ int sLen[128];
+    __shared__ int sLen[kDirCache];
     __shared__ int32_t sPos[kWriteChunk + 1];
     emitWriteSolver(a, blockIdx.y, blockIdx.x, gridDim.x, gridDim.x * gridDim.y, sLen, sPos);
 }
@@ -1291,7 +1295,7 @@ __global__ void __launch_bounds__(256) k_emit_write(EmitArgs a) {
 __global__ void __launch_bounds__(256) k_emit_fused(EmitArgs a) {
     __shared__ unsigned long long sK[kSortWarps][kSortSmemRecs];
     __shared__ uint32_t sM[kSortWarps][kSortSmemRecs];
-    __shared__ int sLen[128];
+    __shared__ int sLen[kDirCache];
     __shared__ int32_t sPos[kWriteChunk + 1];
     __shared__ unsigned int sPlace;
     constexpr int kPerSolver = kRecBuckets / kSortWarps;

@@ -333,3 +333,31 @@ def test_large_hit_list_parallel_hand_over():
         assert [p[1] for p in pops] == expect           # handed over in clause order
         assert pops[0][0] == [mkLit(expect[0]), mkLit((expect[0] + 1) % n, True)]
     assert len(hits) > 8192
+
+
+def test_more_distinct_clause_lengths_than_the_kernels_cache():
+    """The kernels search the length directory from shared memory (128 entries) and read what lies past it from the
+    directory itself.  150 distinct lengths, every clause falsified: each solver must get every clause back with its
+    own id and literals -- the shortest lengths are the directory's LAST entries (up to round 2 their hits were
+    resolved against another length's arena: the import-latency harness lost every binary probe)."""
+    nlen, nsolvers = 150, 2
+    sh = make(400, nsolvers)
+    sh.setMaxClauseLen(200)
+    want = {}
+    for ln in range(1, nlen + 1):
+        for rep in range(2):
+            lits = [mkLit((7 * ln + 13 * rep + i) % 397) for i in range(ln)]
+            cid = sh.addClause(-1, lits)
+            assert cid >= 0
+            want[cid] = lits
+    for s in range(nsolvers):
+        assert sh.trySetSolverValues(s, [mkLit(v, True) for v in range(400)])
+        assert sh.trySendAssignment(s) >= 0
+    execute(sh)
+    hits = sh.debugLastHits()
+    assert sorted(hits["clause_id"].tolist()) == sorted(list(want) * nsolvers)
+    for s in range(nsolvers):
+        got = {}
+        while (x := sh.popReportedClause(s)) is not None:
+            got[int(x[1])] = [int(l) for l in x[0]]
+        assert got == want
