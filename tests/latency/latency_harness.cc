@@ -40,7 +40,7 @@ int main(int argc, char **argv) {
     // quiet pipeline); 985 = ~65 k background hits per run with 64 solvers (the pipeline saturated by reports)
     const int agreePerMille = argc > 6 ? atoi(argv[6]) : 999;
     const int kStable = 4096; // variables [0, kStable) are never unset by the solver threads: probes use them
-    if (nProbes > kStable / 2) {
+    if (nProbes + 100 > kStable / 2) {
         fprintf(stderr, "at most %d probes\n", kStable / 2);
         return 2;
     }
@@ -86,6 +86,8 @@ int main(int argc, char **argv) {
     // literal of variable p, and once the probe is over every solver thread flips variable p: the clause is
     // satisfied from then on and does not come back run after run as a background hit.
     std::atomic<int> flipUpTo{0};
+    std::vector<std::atomic<int>> flipsDone(S); // per solver thread: flips applied (and exported) so far
+    for (auto &f : flipsDone) f.store(0);
     Probe probe;
     std::vector<std::thread> threads;
     std::atomic<int> ready{0};
@@ -112,6 +114,7 @@ int main(int argc, char **argv) {
                     gss_unset_solver_values(h, s, flip.data(), (int)flip.size());
                     if (gss_try_set_solver_values(h, s, fix.data(), (int)fix.size())) myFlips = upTo;
                 }
+                const int flipsBefore = myFlips;
                 // a little trail churn: unset and re-set a handful of (non-stable) variables, then export
                 flip.clear();
                 for (int k = 0; k < 8; k++) {
@@ -119,7 +122,8 @@ int main(int argc, char **argv) {
                     flip.push_back(2 * v + sigma[v]);
                 }
                 gss_unset_solver_values(h, s, flip.data(), (int)flip.size());
-                if (gss_try_set_solver_values(h, s, flip.data(), (int)flip.size())) gss_try_send_assignment(h, s);
+                if (gss_try_set_solver_values(h, s, flip.data(), (int)flip.size()) && gss_try_send_assignment(h, s) >= 0)
+                    flipsDone[s].store(flipsBefore, std::memory_order_release); // an assignment with those flips is on its way
                 int *lits, count;
                 int64_t id;
                 while (gss_pop_reported_clause(h, s, &lits, &count, &id)) {
@@ -158,19 +162,28 @@ int main(int argc, char **argv) {
     std::vector<double> lat;
     int lost = 0, lostLong = 0, lostByLen[16] = {0};
 
-    const auto tStart = Clock::now();
-    sampling.store(true);
-    const int64_t runs0 = runs.load();
+    // The first kWarm probes are not measured: they take the library through its start-up transients (buffers that grow
+    // to the workload's hit counts, result buffers of the right size in the pool, arenas of every probe length).
+    const int kWarm = 100;
+    auto tStart = Clock::now();
+    int64_t runs0 = runs.load();
     double ph0[6];
     gss_debug_host_phases(h, ph0);
-    const int64_t reports0 = gss_get_global_stat(h, 8);
-    for (int p = 0; p < nProbes; p++) {
+    int64_t reports0 = gss_get_global_stat(h, 8);
+    for (int p = 0; p < nProbes + kWarm; p++) {
+        if (p == kWarm) {
+            tStart = Clock::now();
+            runs0 = runs.load();
+            gss_debug_host_phases(h, ph0);
+            reports0 = gss_get_global_stat(h, 8);
+            sampling.store(true);
+        }
         const int s = (int)(rng() % S);
         int len = (p % 4 == 3) ? 101 + (int)(rng() % 100) : 2 + (int)(rng() % 8);
         std::vector<int> lits;
         lits.push_back(2 * p + (1 - sigma[p])); // the variable the solvers flip once the probe is over
         for (int i = 1; i < len; i++) {
-            const int v = nProbes + (int)(rng() % (kStable - nProbes));
+            const int v = nProbes + kWarm + (int)(rng() % (kStable - nProbes - kWarm));
             lits.push_back(2 * v + (1 - sigma[v])); // false under every solver's assignment
         }
         probe.done.store(0);
@@ -181,7 +194,9 @@ int main(int argc, char **argv) {
         probe.id.store(id, std::memory_order_release);
         const auto w0 = Clock::now();
         while (!probe.done.load(std::memory_order_acquire) && usSince(w0) < 1e6) std::this_thread::yield();
-        if (probe.done.load()) lat.push_back(probe.latencyUs);
+        if (p < kWarm) {
+            // (not measured)
+        } else if (probe.done.load()) lat.push_back(probe.latencyUs);
         else {
             lost++;
             if (len > 100) lostLong++;
@@ -189,6 +204,11 @@ int main(int argc, char **argv) {
         }
         probe.target.store(-1);
         flipUpTo.store(p + 1, std::memory_order_release);
+        // the next probe starts once every solver has exported an assignment that satisfies this one (bounded wait):
+        // otherwise the probes of the last milliseconds come back as background hits of every solver, run after run
+        const auto f0 = Clock::now();
+        for (int t = 0; t < S; t++)
+            while (flipsDone[t].load(std::memory_order_acquire) < p + 1 && usSince(f0) < 50e3) std::this_thread::yield();
         std::this_thread::sleep_for(std::chrono::microseconds(200));
     }
     const double wallS = usSince(tStart) * 1e-6;
