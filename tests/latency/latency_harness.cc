@@ -100,7 +100,7 @@ int main(int argc, char **argv) {
             while (!gss_try_set_solver_values(h, s, set.data(), (int)set.size())) std::this_thread::yield();
             while (gss_try_send_assignment(h, s) < 0) std::this_thread::yield();
             ready.fetch_add(1);
-            std::vector<int> flip, fix;
+            std::vector<int> flip, fix, churn;
             int myFlips = 0;
             while (!stop.load(std::memory_order_relaxed)) {
                 const int upTo = flipUpTo.load(std::memory_order_acquire);
@@ -115,15 +115,23 @@ int main(int argc, char **argv) {
                     if (gss_try_set_solver_values(h, s, fix.data(), (int)fix.size())) myFlips = upTo;
                 }
                 const int flipsBefore = myFlips;
-                // a little trail churn: unset and re-set a handful of (non-stable) variables, then export
-                flip.clear();
-                for (int k = 0; k < 8; k++) {
-                    const int v = kStable + (int)(r() % (V - kStable));
-                    flip.push_back(2 * v + sigma[v]);
+                // a little trail churn: unset and re-set a handful of (non-stable) variables, then export.  When no
+                // assignment slot is free the unset is buffered and the set fails: the SAME variables are set again in the
+                // next round (picking new ones instead would leave eight more variables undefined for good each time --
+                // tens of thousands after a second, and every binary clause with one of them and a false literal a unit
+                // hit of this solver, run after run)
+                if (churn.empty()) {
+                    for (int k = 0; k < 8; k++) {
+                        const int v = kStable + (int)(r() % (V - kStable));
+                        churn.push_back(2 * v + sigma[v]);
+                    }
+                    gss_unset_solver_values(h, s, churn.data(), (int)churn.size());
                 }
-                gss_unset_solver_values(h, s, flip.data(), (int)flip.size());
-                if (gss_try_set_solver_values(h, s, flip.data(), (int)flip.size()) && gss_try_send_assignment(h, s) >= 0)
-                    flipsDone[s].store(flipsBefore, std::memory_order_release); // an assignment with those flips is on its way
+                if (gss_try_set_solver_values(h, s, churn.data(), (int)churn.size())) {
+                    churn.clear();
+                    if (gss_try_send_assignment(h, s) >= 0)
+                        flipsDone[s].store(flipsBefore, std::memory_order_release); // an assignment with those flips is on its way
+                }
                 int *lits, count;
                 int64_t id;
                 while (gss_pop_reported_clause(h, s, &lits, &count, &id)) {
